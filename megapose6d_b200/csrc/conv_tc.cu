@@ -1,0 +1,515 @@
+// Implicit-GEMM convolution for sm_100a: TMA im2col (activations) + TMA tiled (weights) ->
+// 128B-swizzled shared memory -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> fused epilogue
+// (folded-BN bias, residual add, ReLU) -> bf16 NHWC.
+//
+// Replaces the cuDNN convolutions issued by every nn.Conv2d + BatchNorm2d + ReLU (+ residual) of the
+// reference backbone (reference: src/megapose/models/torchvision_resnet.py:74-120 BasicBlock.forward,
+// :298-311 ResNet._forward_impl).
+//
+// GEMM view:  D[M, N] = A[M, K] * B[N, K]^T
+//   M = n_img * P * Q output pixels (flattened NHW, what TMA im2col walks natively)
+//   N = C_out
+//   K = R * S * C_in, ordered (r, s, c);  one K-block = 64 channels of one filter tap
+//
+// Persistent, warp-specialised CTA (256 threads):
+//   warp 0   : TMA producer (one elected lane)
+//   warp 1   : tcgen05.mma issuer (one elected lane)
+//   warp 2   : TMEM allocator / deallocator
+//   warps 4-7: epilogue (TMEM -> registers -> global), one TMEM lane quarter each
+// Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue).
+#include <cuda.h>
+#include "mpx_common.cuh"
+
+namespace mpx {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+      printf("mpx conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                                   int c, int w, int h, int n, uint16_t off_w,
+                                                   uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers bf16 inputs with fp32 accumulation.
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart).
+// Field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version [46,48) = 1, layout_type [61,64) = 2 for SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1) << 16;   // LBO (ignored for swizzled K-major)
+  d |= static_cast<uint64_t>(64) << 32;  // SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;   // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
+  return d;
+}
+
+struct ConvParams {
+  int M_total;  // n_img * P * Q
+  int P, Q;     // output height / width
+  int C_out;
+  int S;         // filter width (taps are ordered r-major)
+  int stride;
+  int pad_h, pad_w;  // lower padding
+  int cblocks;       // C_in / 64
+  int num_k_blocks;  // R * S * cblocks
+  int m_tiles, n_tiles;
+  int relu;
+  const float* bias;                // [C_out] folded BN shift
+  const __nv_bfloat16* residual;    // [M_total, C_out] or nullptr
+  __nv_bfloat16* out;               // [M_total, C_out]
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kATileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int pq = p.P * p.Q;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int m0 = m_tile * kBlockM;
+        const int img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int p0 = rem / p.Q;
+        const int q0 = rem - p0 * p.Q;
+        const int base_w = q0 * p.stride - p.pad_w;
+        const int base_h = p0 * p.stride - p.pad_h;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int r = tap / p.S;
+          const int s = tap - r * p.S;
+          tma_load_im2col_4d(smem_a + stage * kATileBytes, &map_a, &full_bar[stage], cb * kBlockK,
+                             base_w, base_h, img, static_cast<uint16_t>(s),
+                             static_cast<uint16_t>(r));
+          tma_load_2d(smem_b + stage * Cfg::kBTileBytes, &map_b, &full_bar[stage], kb * kBlockK,
+                      n_tile * BLOCK_N);
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tap;
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // InstrDescriptor (cute/arch/mma_sm100_desc.hpp): c_format F32 [4,6)=1, a/b format BF16
+      // [7,10)=[10,13)=1, a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                                 (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+                                 (static_cast<uint32_t>(kBlockM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * kATileBytes));
+          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * Cfg::kBTileBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+            tc_mma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q4 = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q4 * 32 + lane;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long m = static_cast<long long>(m_tile) * kBlockM + row;
+      const bool valid = m < p.M_total;
+      const int n0 = n_tile * BLOCK_N;
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tc_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+        tc_wait_ld();
+        if (valid) {
+          const size_t off = static_cast<size_t>(m) * p.C_out + n0 + c;
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
+          uint4 res[4];
+          if (p.residual != nullptr) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) res[i] = __ldg(r4 + i);
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float f[8];
+            const float4 b0 = __ldg(bias4 + 2 * i);
+            const float4 b1 = __ldg(bias4 + 2 * i + 1);
+            f[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
+            f[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
+            f[2] = __uint_as_float(v[8 * i + 2]) + b0.z;
+            f[3] = __uint_as_float(v[8 * i + 3]) + b0.w;
+            f[4] = __uint_as_float(v[8 * i + 4]) + b1.x;
+            f[5] = __uint_as_float(v[8 * i + 5]) + b1.y;
+            f[6] = __uint_as_float(v[8 * i + 6]) + b1.z;
+            f[7] = __uint_as_float(v[8 * i + 7]) + b1.w;
+            if (p.residual != nullptr) {
+              const uint32_t rr[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = unpack_bf16x2(rr[j]);
+                f[2 * j] += t.x;
+                f[2 * j + 1] += t.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            o4[i] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                     cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled g_encode_tiled = nullptr;
+static PFN_encodeIm2col g_encode_im2col = nullptr;
+
+// libcuda is reached through the runtime so the library loads (and its symbols can be listed) on a
+// machine without a driver.
+static int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return MPX_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  MPX_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+  MPX_REQUIRE(f != nullptr && q == cudaDriverEntryPointSuccess,
+              "cuTensorMapEncodeTiled not available from the driver");
+  g_encode_tiled = reinterpret_cast<PFN_encodeTiled>(f);
+  f = nullptr;
+  MPX_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q));
+  MPX_REQUIRE(f != nullptr && q == cudaDriverEntryPointSuccess,
+              "cuTensorMapEncodeIm2col not available from the driver");
+  g_encode_im2col = reinterpret_cast<PFN_encodeIm2col>(f);
+  return MPX_OK;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p,
+                       cudaStream_t stream, int max_ctas) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MPX_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  int cap = max_ctas > 0 ? max_ctas : sm_count();
+  if (grid > cap) grid = cap;
+  conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  MPX_CHECK_CUDA(cudaGetLastError());
+  return MPX_OK;
+}
+
+int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride) {
+  return (in + pad_lo + pad_hi - k) / stride + 1;
+}
+
+// x: [n_img, H, W, C_in] bf16; w: [C_out, R*S*C_in] bf16 ((r,s,c) ordered); bias fp32 [C_out];
+// residual/out: [n_img, P, Q, C_out] bf16.
+int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,
+                 const void* residual, void* out, int block_n_override, int max_ctas,
+                 cudaStream_t stream) {
+  MPX_REQUIRE(d.C_in % 64 == 0 && d.C_in >= 64, "conv: C_in=%d must be a multiple of 64", d.C_in);
+  MPX_REQUIRE(d.C_out % 64 == 0, "conv: C_out=%d must be a multiple of 64", d.C_out);
+  MPX_REQUIRE(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
+  MPX_REQUIRE(d.R >= 1 && d.R <= 8 && d.S >= 1 && d.S <= 8, "conv: filter %dx%d unsupported", d.R,
+              d.S);
+  int rc = load_driver_entry_points();
+  if (rc != MPX_OK) return rc;
+
+  const int P = conv_out_dim(d.H, d.pad_lo_h, d.pad_hi_h, d.R, d.stride);
+  const int Q = conv_out_dim(d.W, d.pad_lo_w, d.pad_hi_w, d.S, d.stride);
+  MPX_REQUIRE(P > 0 && Q > 0, "conv: empty output");
+  const long long M_total = static_cast<long long>(d.n_img) * P * Q;
+  MPX_REQUIRE(M_total > 0 && M_total < (1LL << 31), "conv: M=%lld out of range", M_total);
+
+  int block_n = block_n_override;
+  if (block_n <= 0) block_n = d.C_out >= 256 ? 256 : d.C_out;
+  MPX_REQUIRE((block_n == 64 || block_n == 128 || block_n == 256) && d.C_out % block_n == 0,
+              "conv: BLOCK_N=%d invalid for C_out=%d", block_n, d.C_out);
+
+  // --- activation map (im2col). Dims are innermost-first: {C, W, H, N}.
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.C_in), static_cast<cuuint64_t>(d.W),
+                          static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.n_img)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.C_in) * 2,
+                             static_cast<cuuint64_t>(d.W) * d.C_in * 2,
+                             static_cast<cuuint64_t>(d.H) * d.W * d.C_in * 2};
+    // Bounding box of the filter's *base* pixel (CUTLASS: lower = -pad_lo,
+    // upper = pad_hi - (filter-1)*dilation; cutlass/conv/collective/detail.hpp).
+    int lower[2] = {-d.pad_lo_w, -d.pad_lo_h};
+    int upper[2] = {d.pad_hi_w - (d.S - 1), d.pad_hi_h - (d.R - 1)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
+    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x),
+                                 dims, strides, lower, upper, /*channelsPerPixel=*/kBlockK,
+                                 /*pixelsPerColumn=*/kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d)", static_cast<int>(r));
+    // Driver quirk (<= 13.1) for im2col maps over tensors smaller than 128 KiB: same fix-up as
+    // cute/atom/copy_traits_sm90_im2col.hpp.
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    const size_t bytes = static_cast<size_t>(d.n_img) * d.H * d.W * d.C_in * 2;
+    if (drv <= 13010 && bytes < 131072) {
+      reinterpret_cast<uint64_t*>(&map_a)[1] &= ~(1ull << 21);
+    }
+  }
+  {
+    const cuuint64_t K_total = static_cast<cuuint64_t>(d.R) * d.S * d.C_in;
+    cuuint64_t dims[2] = {K_total, static_cast<cuuint64_t>(d.C_out)};
+    cuuint64_t strides[1] = {K_total * 2};
+    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(block_n)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims,
+                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  }
+
+  ConvParams p;
+  p.M_total = static_cast<int>(M_total);
+  p.P = P;
+  p.Q = Q;
+  p.C_out = d.C_out;
+  p.S = d.S;
+  p.stride = d.stride;
+  p.pad_h = d.pad_lo_h;
+  p.pad_w = d.pad_lo_w;
+  p.cblocks = d.C_in / kBlockK;
+  p.num_k_blocks = d.R * d.S * p.cblocks;
+  p.m_tiles = static_cast<int>((M_total + kBlockM - 1) / kBlockM);
+  p.n_tiles = d.C_out / block_n;
+  p.relu = d.relu;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+
+  switch (block_n) {
+    case 64:
+      return launch_conv<64>(map_a, map_b, p, stream, max_ctas);
+    case 128:
+      return launch_conv<128>(map_a, map_b, p, stream, max_ctas);
+    default:
+      return launch_conv<256>(map_a, map_b, p, stream, max_ctas);
+  }
+}
+
+}  // namespace mpx

@@ -1,0 +1,160 @@
+// Shared device/host helpers for the mpx kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace mpx {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, negative return codes; see include/mpx.h)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define MPX_OK 0
+#define MPX_ERR_INVALID -1
+#define MPX_ERR_CUDA -2
+#define MPX_ERR_UNSUPPORTED -3
+
+#define MPX_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      mpx::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,            \
+                     cudaGetErrorString(_e));                                         \
+      return MPX_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define MPX_REQUIRE(cond, ...)                                                        \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      mpx::set_error(__VA_ARGS__);                                                    \
+      return MPX_ERR_INVALID;                                                         \
+    }                                                                                 \
+  } while (0)
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-file declarations (conv_tc.cu, net.cu)
+// ---------------------------------------------------------------------------------------------
+struct ConvDesc {
+  int n_img, H, W, C_in;  // input NHWC
+  int C_out, R, S, stride;
+  int pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
+  int relu;
+};
+int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,
+                 const void* residual, void* out, int block_n_override, int max_ctas,
+                 cudaStream_t stream);
+int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride);
+int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream);
+int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const float* b, int out_dim,
+                   float* out, cudaStream_t stream);
+struct Net;
+int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* const* conv_b,
+               int n_convs, const float* head_w, const float* head_b, Net** out);
+size_t net_workspace_bytes(int n, int h, int w);
+int net_forward(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
+void net_destroy(Net* net);
+
+// raster.cu
+struct MeshDb {
+  int n_meshes;
+  int nv_max;
+  float* verts;             // [sum_nv,3]
+  float* normals;           // [sum_nv,3]
+  float* colors;            // [sum_nv,3]
+  int* faces;               // [sum_nf,3] local indices
+  long long* vert_offsets;  // [n+1]
+  long long* face_offsets;  // [n+1]
+  int4* vtx_cache;          // [slots, nv_max] {X, Y, 1/z bits, behind}
+  int slots;
+};
+struct RasterOut {
+  float* rgb;      // contract planes (fp32 NCHW), any may be null
+  float* normals;
+  float* depth;
+  __nv_bfloat16* x;  // fused network input (bf16 s2d NHWC), may be null
+  int c_pad, ch_offset, ch_per_view, views_per_sample;
+  const float* depth_norm_z;
+};
+int meshdb_create(int n_meshes, const float* verts, const float* normals, const float* colors,
+                  const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
+                  MeshDb** out);
+void meshdb_destroy(MeshDb* db);
+size_t raster_workspace_bytes(int h, int w);
+int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, const float* K, int n_views,
+                  int h, int w, unsigned flags, const RasterOut& out, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+
+// geom.cu
+int pose_init_autodepth(const float* points, int n_pts, const int* label_idx, const float* bboxes,
+                        const float* K, const float* R, int n, float* TCO, cudaStream_t stream);
+int normalize_T(const float* Tin, int n, float* Tout, cudaStream_t stream);
+int crop_geometry(const float* points, int n_pts, const int* label_idx, const float* TCO, const float* K,
+                  const float* tCR, int n, float lamb, int im_h, int im_w, int out_h, int out_w,
+                  float* boxes_rend, float* boxes_crop, float* K_crop, cudaStream_t stream);
+int multiview_cameras(const float* TCO, const float* tCR, int n, const float* h_offsets, int n_extra,
+                      float* TCV_O, cudaStream_t stream);
+int pose_update(const float* TCO, const float* K_crop, const float* pose9, const float* tCR, int n,
+                float* TCO_out, cudaStream_t stream);
+int topk_per_group(const float* logits, int n_groups, int m, int k, int* idx, cudaStream_t stream);
+
+// crop.cu
+struct CropOut {
+  float* nchw;       // [n, c, oh, ow] or null
+  __nv_bfloat16* x;  // fused network input or null
+  int c_pad;
+  const float* depth_norm_z;
+};
+int image_to_nhwc4(const float* in, int b, int c, int h, int w, float* out, cudaStream_t stream);
+int roi_align_launch(const float* images, int b, int h, int w, const int* im_idx, const float* boxes, int n,
+                     int c, int oh, int ow, const CropOut& out, cudaStream_t stream);
+
+}  // namespace mpx

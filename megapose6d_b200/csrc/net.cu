@@ -1,0 +1,229 @@
+// ResNet-34 execution plan around the tcgen05 convolution: max-pool, pooled linear tail, and the
+// fixed 36-convolution schedule of the reference backbone
+// (reference: src/megapose/models/torchvision_resnet.py:74-120 BasicBlock, :298-311 forward order;
+//  heads: src/megapose/models/pose_rigid.py:120-130, 314-334).
+#include <cuda.h>
+#include <vector>
+#include "mpx_common.cuh"
+
+namespace mpx {
+
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 / stride 2 / pad 1 max pool on bf16 NHWC; one thread = 8 channels (16 B) of one output pixel
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h,
+                                    int w, int c8, int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int ox = static_cast<int>(t % wo);
+    t /= wo;
+    const int oy = static_cast<int>(t % ho);
+    const int img = static_cast<int>(t / ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = oy * 2 - 1 + dy;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = ox * 2 - 1 + dx;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 v = __ldg(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c8 + cc);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(u[j]);
+          m[2 * j] = fmaxf(m[2 * j], f.x);
+          m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(m[0], m[1]);
+    o.y = pack_bf16x2(m[2], m[3]);
+    o.z = pack_bf16x2(m[4], m[5]);
+    o.w = pack_bf16x2(m[6], m[7]);
+    out[i] = o;
+  }
+}
+
+int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream) {
+  MPX_REQUIRE(c % 8 == 0, "maxpool: C=%d must be a multiple of 8", c);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
+  if (total == 0) return MPX_OK;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  maxpool3x3s2_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo);
+  MPX_CHECK_CUDA(cudaGetLastError());
+  return MPX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// global average pool + linear (fc and head folded into one [out_dim, C] matrix on the host)
+// one CTA (128 threads) per sample; warp-shuffle reductions for the dot products
+// ---------------------------------------------------------------------------------------------
+__global__ void avgpool_linear_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c,
+                                      const float* __restrict__ w, const float* __restrict__ b,
+                                      int out_dim, float* __restrict__ out) {
+  extern __shared__ float pooled[];  // [c]
+  const int img = blockIdx.x;
+  const __nv_bfloat16* xi = x + static_cast<size_t>(img) * hw * c;
+  const float inv = 1.f / static_cast<float>(hw);
+  for (int c0 = threadIdx.x * 4; c0 < c; c0 += blockDim.x * 4) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int p = 0; p < hw; ++p) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(xi + static_cast<size_t>(p) * c + c0));
+      const float2 a = unpack_bf16x2(v.x), d = unpack_bf16x2(v.y);
+      s0 += a.x;
+      s1 += a.y;
+      s2 += d.x;
+      s3 += d.y;
+    }
+    pooled[c0] = s0 * inv;
+    pooled[c0 + 1] = s1 * inv;
+    pooled[c0 + 2] = s2 * inv;
+    pooled[c0 + 3] = s3 * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int o = warp; o < out_dim; o += nwarps) {
+    float acc = 0.f;
+    for (int k = lane; k < c; k += 32) acc = fmaf(pooled[k], __ldg(w + static_cast<size_t>(o) * c + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<size_t>(img) * out_dim + o] = acc + __ldg(b + o);
+  }
+}
+
+int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const float* b, int out_dim,
+                   float* out, cudaStream_t stream) {
+  MPX_REQUIRE(c % 4 == 0 && c <= 4096, "avgpool_linear: C=%d unsupported", c);
+  if (n == 0) return MPX_OK;
+  avgpool_linear_kernel<<<n, 128, c * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), hw, c, w, b, out_dim, out);
+  MPX_CHECK_CUDA(cudaGetLastError());
+  return MPX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ResNet-34 plan
+// ---------------------------------------------------------------------------------------------
+struct Net {
+  int c_pad;
+  int out_dim;
+  std::vector<const void*> conv_w;
+  std::vector<const float*> conv_b;
+  const float* head_w;
+  const float* head_b;
+};
+
+static const int kLayerBlocks[4] = {3, 4, 6, 3};
+static const int kLayerWidth[4] = {64, 128, 256, 512};
+constexpr int kNumConvs = 36;  // stem + 2 per block (16 blocks) + 3 downsample
+
+int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* const* conv_b,
+               int n_convs, const float* head_w, const float* head_b, Net** out) {
+  MPX_REQUIRE(c_pad == 16 || c_pad == 32, "net: c_pad=%d must be 16 or 32", c_pad);
+  MPX_REQUIRE(n_convs == kNumConvs, "net: expected %d conv tensors, got %d", kNumConvs, n_convs);
+  MPX_REQUIRE(out_dim >= 1 && out_dim <= 512, "net: out_dim=%d unsupported", out_dim);
+  Net* net = new Net();
+  net->c_pad = c_pad;
+  net->out_dim = out_dim;
+  net->conv_w.assign(conv_w, conv_w + n_convs);
+  net->conv_b.assign(conv_b, conv_b + n_convs);
+  net->head_w = head_w;
+  net->head_b = head_b;
+  *out = net;
+  return MPX_OK;
+}
+
+void net_destroy(Net* net) { delete net; }
+
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t net_workspace_bytes(int n, int h, int w) {
+  const size_t hs = h / 2, ws = w / 2;
+  const size_t stem = align256(static_cast<size_t>(n) * hs * ws * 64 * 2);
+  const size_t hp = (hs + 2 - 3) / 2 + 1, wp = (ws + 2 - 3) / 2 + 1;
+  const size_t l1 = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
+  return stem + 3 * l1 + 1024;
+}
+
+int net_forward(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
+  MPX_REQUIRE(h % 2 == 0 && w % 2 == 0, "net: input %dx%d must be even", h, w);
+  MPX_REQUIRE(workspace_bytes >= net_workspace_bytes(n, h, w), "net: workspace too small");
+  MPX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "net: workspace must be 256-B aligned");
+  if (n == 0) return MPX_OK;
+  const int hs = h / 2, ws = w / 2;
+  const int hp = (hs + 2 - 3) / 2 + 1, wp = (ws + 2 - 3) / 2 + 1;
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  const size_t stem_bytes = align256(static_cast<size_t>(n) * hs * ws * 64 * 2);
+  const size_t l1_bytes = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
+  void* buf_stem = base;
+  void* bufs[3] = {base + stem_bytes, base + stem_bytes + l1_bytes, base + stem_bytes + 2 * l1_bytes};
+
+  int ci = 0;
+  int rc;
+  // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input
+  {
+    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1};
+    rc = conv_forward(d, x, net->conv_w[ci], net->conv_b[ci], nullptr, buf_stem, 0, 0, stream);
+    if (rc != MPX_OK) return rc;
+    ++ci;
+  }
+  rc = maxpool3x3s2(buf_stem, n, hs, ws, 64, bufs[0], stream);
+  if (rc != MPX_OK) return rc;
+
+  int cur = 0;  // index of the buffer holding the block input
+  int H = hp, W = wp, C = 64;
+  for (int layer = 0; layer < 4; ++layer) {
+    const int width = kLayerWidth[layer];
+    for (int blk = 0; blk < kLayerBlocks[layer]; ++blk) {
+      const int stride = (blk == 0 && layer > 0) ? 2 : 1;
+      const bool has_ds = (blk == 0 && layer > 0);
+      const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
+      const int Ho = conv_out_dim(H, 1, 1, 3, stride), Wo = conv_out_dim(W, 1, 1, 3, stride);
+      // conv1 + bn1 + relu
+      ConvDesc d1{n, H, W, C, width, 3, 3, stride, 1, 1, 1, 1, 1};
+      rc = conv_forward(d1, bufs[cur], net->conv_w[ci], net->conv_b[ci], nullptr, bufs[t1], 0, 0, stream);
+      if (rc != MPX_OK) return rc;
+      const int c1 = ci;
+      (void)c1;
+      ++ci;
+      const void* residual = bufs[cur];
+      int out_buf = t2;
+      if (has_ds) {
+        // downsample: 1x1/s2 conv + bn (no relu) -> residual; conv_w order: conv1, conv2, downsample
+        ConvDesc dd{n, H, W, C, width, 1, 1, stride, 0, 0, 0, 0, 0};
+        rc = conv_forward(dd, bufs[cur], net->conv_w[ci + 1], net->conv_b[ci + 1], nullptr, bufs[t2], 0, 0,
+                          stream);
+        if (rc != MPX_OK) return rc;
+        residual = bufs[t2];
+        out_buf = cur;  // block input is dead once conv1 and the downsample have consumed it
+      }
+      // conv2 + bn2 + residual + relu
+      ConvDesc d2{n, Ho, Wo, width, width, 3, 3, 1, 1, 1, 1, 1, 1};
+      rc = conv_forward(d2, bufs[t1], net->conv_w[ci], net->conv_b[ci], residual, bufs[out_buf], 0, 0,
+                        stream);
+      if (rc != MPX_OK) return rc;
+      ci += has_ds ? 2 : 1;
+      cur = out_buf;
+      H = Ho;
+      W = Wo;
+      C = width;
+    }
+  }
+  return avgpool_linear(bufs[cur], n, H * W, C, net->head_w, net->head_b, net->out_dim, out, stream);
+}
+
+}  // namespace mpx

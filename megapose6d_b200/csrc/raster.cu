@@ -1,0 +1,408 @@
+// Batched software rasteriser for sm_100a: one persistent CTA per view.
+//
+// Replaces the Panda3D/OpenGL path of the reference renderer
+// (reference: src/megapose/panda3d_renderer/panda3d_batch_renderer.py:217-282 render,
+//  :89-150 worker_loop; panda3d_scene_renderer.py:298-358 render_scene (pass 1 albedo under
+//  ambient light, pass 2 eye-normal texture); types.py:58-101 camera model, near/far 0.1/10;
+//  utils.py:44-68 depth linearisation and the 32^3 normal texture).
+//
+// Contract (restated in oracle/raster_ref.c, which this kernel must match bit for bit):
+//   * pinhole projection u = fx*X/Z + cx, v = fy*Y/Z + cy; pixel (i, j) is sampled at
+//     (u, v) = (j + 0.5, i + 0.5);
+//   * vertices snapped to 1/256 pixel; coverage by exact 64-bit integer edge functions, edges
+//     inclusive, two-sided; nearest depth wins, ties go to the lower triangle index;
+//   * triangles with a vertex in front of the near plane (z < 0.1) are dropped; fragments outside
+//     [0.1, 10] m are rejected;
+//   * 1/z is interpolated linearly in screen space, attributes perspective-correctly;
+//   * rgb = interpolated vertex albedo (ambient light 1.0); normals = frac-wrapped eye normal
+//     through the 32-level texture; depth = z in metres, 0 for background or d > 0.999;
+//   * all float arithmetic is written with explicit round-to-nearest intrinsics in a fixed order
+//     so that the CPU restatement reproduces it exactly.
+//
+// Per view: (A) clear a 64-bit visibility buffer (global scratch, L2 resident), (B) transform and
+// snap the vertices once, (C) one thread per triangle walks its bounding box and atomicMin's
+// (depth, triangle) keys -- large triangles are queued and rasterised by the whole CTA,
+// (D) resolve: one thread per pixel re-derives the winning triangle's barycentrics, shades and
+// writes the outputs.
+#include "mpx_common.cuh"
+
+namespace mpx {
+
+constexpr float kNear = 0.1f;
+constexpr float kFar = 10.0f;
+constexpr int kSubBits = 8;
+constexpr int kSub = 1 << kSubBits;       // 256 sub-pixel steps
+constexpr int kHalf = kSub / 2;
+constexpr float kClampUV = 1048576.0f;    // 2^20 pixels
+constexpr int kRasterThreads = 512;
+constexpr int kBigQueue = 2048;
+constexpr long long kBigArea = 1024;      // pixels; larger bounding boxes go to the CTA-wide path
+
+__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }
+
+// edge function of P against the directed edge a->b, exact in 64-bit
+__device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, int px, int py) {
+  return static_cast<long long>(bx - ax) * static_cast<long long>(py - ay) -
+         static_cast<long long>(by - ay) * static_cast<long long>(px - ax);
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+  int q = a / b;
+  if ((a % b != 0) && (a < 0)) --q;
+  return q;
+}
+
+// 32-level sawtooth of the reference's eye-normal texture with linear filtering and repeat wrap
+__device__ __forceinline__ float normal_texture(float s) {
+  const float u = __fmaf_rn(s, 32.0f, -0.5f);
+  const float fl = floorf(u);
+  const float f = __fsub_rn(u, fl);
+  int k0 = static_cast<int>(fl) & 31;
+  int k1 = (k0 + 1) & 31;
+  // texel value: uint8(k * 255 / 32) / 255
+  const float t0 = __fdiv_rn(static_cast<float>((k0 * 255) >> 5), 255.0f);
+  const float t1 = __fdiv_rn(static_cast<float>((k1 * 255) >> 5), 255.0f);
+  return __fmaf_rn(f, __fsub_rn(t1, t0), t0);
+}
+
+__device__ __forceinline__ float quant8(float v, bool on) {
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  if (!on) return v;
+  return __fdiv_rn(rintf(__fmul_rn(v, 255.0f)), 255.0f);
+}
+
+struct TriSetup {
+  int ax, ay, bx, by, cx, cy;
+  float iza, izb, izc;
+  long long area2;
+  bool flip;
+  bool ok;
+};
+
+__device__ __forceinline__ TriSetup load_tri(const int4* __restrict__ vtx, const int* __restrict__ faces,
+                                             int tri) {
+  TriSetup t;
+  const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1), ic = __ldg(faces + 3 * tri + 2);
+  const int4 a = __ldcg(vtx + ia), b = __ldcg(vtx + ib), c = __ldcg(vtx + ic);
+  t.ax = a.x; t.ay = a.y; t.bx = b.x; t.by = b.y; t.cx = c.x; t.cy = c.y;
+  t.iza = __int_as_float(a.z); t.izb = __int_as_float(b.z); t.izc = __int_as_float(c.z);
+  t.area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
+  t.flip = t.area2 < 0;
+  if (t.flip) t.area2 = -t.area2;
+  t.ok = (t.area2 != 0) && !(a.w | b.w | c.w);
+  return t;
+}
+
+// barycentrics + depth of pixel centre (px, py) (fixed point); returns false if outside
+__device__ __forceinline__ bool tri_sample(const TriSetup& t, int px, int py, float& l0, float& l1,
+                                           float& l2, float& iz, float& z) {
+  long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+  long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+  long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+  if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+  if ((w0 | w1 | w2) < 0) return false;
+  const float inv_area = static_cast<float>(t.area2);
+  l0 = __fdiv_rn(static_cast<float>(w0), inv_area);
+  l1 = __fdiv_rn(static_cast<float>(w1), inv_area);
+  l2 = __fdiv_rn(static_cast<float>(w2), inv_area);
+  iz = __fmaf_rn(l0, t.iza, __fmaf_rn(l1, t.izb, __fmul_rn(l2, t.izc)));
+  z = __fdiv_rn(1.0f, iz);
+  return (z >= kNear) && (z <= kFar);
+}
+
+__device__ __forceinline__ void raster_bbox(const TriSetup& t, int h, int w, int& j0, int& j1, int& i0,
+                                            int& i1) {
+  const int minx = min(t.ax, min(t.bx, t.cx)), maxx = max(t.ax, max(t.bx, t.cx));
+  const int miny = min(t.ay, min(t.by, t.cy)), maxy = max(t.ay, max(t.by, t.cy));
+  // pixel j has its centre at j*256 + 128
+  j0 = max(0, -floor_div(-(minx - kHalf), kSub));          // ceil((minx-128)/256)
+  j1 = min(w - 1, floor_div(maxx - kHalf, kSub));
+  i0 = max(0, -floor_div(-(miny - kHalf), kSub));
+  i1 = min(h - 1, floor_div(maxy - kHalf, kSub));
+}
+
+__global__ void __launch_bounds__(kRasterThreads, 2)
+raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
+              const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out,
+              unsigned long long* __restrict__ vis_all) {
+  __shared__ float sR[12];
+  __shared__ float sK[4];
+  __shared__ int s_valid;
+  __shared__ int s_big_count;
+  __shared__ int s_big[kBigQueue];
+
+  const int npix = h * w;
+  unsigned long long* vis = vis_all + static_cast<size_t>(blockIdx.x) * npix;
+  int4* vtx = db.vtx_cache + static_cast<size_t>(blockIdx.x) * db.nv_max;
+  const bool q8 = (flags & 1u) != 0;
+  const bool gl_axes = (flags & 2u) != 0;
+
+  for (int view = blockIdx.x; view < n_views; view += gridDim.x) {
+    __syncthreads();  // previous view fully resolved before scratch is reused
+    if (threadIdx.x == 0) {
+      bool ok = true;
+      const float* T = TCO + 16 * view;
+      const float* Kv = K + 9 * view;
+      for (int i = 0; i < 16; ++i) ok = ok && finite_f(T[i]);
+      for (int i = 0; i < 9; ++i) ok = ok && finite_f(Kv[i]);
+      const int lab = label_idx[view];
+      ok = ok && lab >= 0 && lab < db.n_meshes;
+      s_valid = ok ? 1 : 0;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) sR[r * 4 + c] = T[r * 4 + c];
+      sK[0] = Kv[0]; sK[1] = Kv[2]; sK[2] = Kv[4]; sK[3] = Kv[5];
+      s_big_count = 0;
+    }
+    __syncthreads();
+    const bool valid = s_valid != 0;
+    const int lab = valid ? label_idx[view] : 0;
+    const long long v_off = valid ? db.vert_offsets[lab] : 0;
+    const int nv = valid ? static_cast<int>(db.vert_offsets[lab + 1] - v_off) : 0;
+    const long long f_off = valid ? db.face_offsets[lab] : 0;
+    const int nf = valid ? static_cast<int>(db.face_offsets[lab + 1] - f_off) : 0;
+    const int* faces = db.faces + 3 * f_off;
+
+    // (A) clear visibility, (B) transform + snap vertices
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) vis[i] = ~0ull;
+    const float fx = sK[0], cx = sK[1], fy = sK[2], cy = sK[3];
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const float* p = db.verts + 3 * (v_off + i);
+      const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+      const float xc = __fmaf_rn(sR[0], px, __fmaf_rn(sR[1], py, __fmaf_rn(sR[2], pz, sR[3])));
+      const float yc = __fmaf_rn(sR[4], px, __fmaf_rn(sR[5], py, __fmaf_rn(sR[6], pz, sR[7])));
+      const float zc = __fmaf_rn(sR[8], px, __fmaf_rn(sR[9], py, __fmaf_rn(sR[10], pz, sR[11])));
+      int4 o;
+      o.w = !(zc >= kNear);
+      const float zs = o.w ? 1.0f : zc;
+      const float iz = __fdiv_rn(1.0f, zs);
+      float u = __fmaf_rn(fx, __fmul_rn(xc, iz), cx);
+      float v = __fmaf_rn(fy, __fmul_rn(yc, iz), cy);
+      u = fminf(fmaxf(u, -kClampUV), kClampUV);
+      v = fminf(fmaxf(v, -kClampUV), kClampUV);
+      if (!(u == u)) { u = 0.f; o.w = 1; }
+      if (!(v == v)) { v = 0.f; o.w = 1; }
+      o.x = __float2int_rn(__fmul_rn(u, static_cast<float>(kSub)));
+      o.y = __float2int_rn(__fmul_rn(v, static_cast<float>(kSub)));
+      o.z = __float_as_int(iz);
+      vtx[i] = o;
+    }
+    __syncthreads();
+
+    // (C) triangles
+    for (int tri = threadIdx.x; tri < nf; tri += blockDim.x) {
+      const TriSetup t = load_tri(vtx, faces, tri);
+      if (!t.ok) continue;
+      int j0, j1, i0, i1;
+      raster_bbox(t, h, w, j0, j1, i0, i1);
+      if (j0 > j1 || i0 > i1) continue;
+      const long long area = static_cast<long long>(j1 - j0 + 1) * (i1 - i0 + 1);
+      if (area > kBigArea) {
+        const int slot = atomicAdd(&s_big_count, 1);
+        if (slot < kBigQueue) {
+          s_big[slot] = tri;
+          continue;
+        }
+      }
+      for (int i = i0; i <= i1; ++i) {
+        const int py = i * kSub + kHalf;
+        for (int j = j0; j <= j1; ++j) {
+          float l0, l1, l2, iz, z;
+          if (!tri_sample(t, j * kSub + kHalf, py, l0, l1, l2, iz, z)) continue;
+          const unsigned long long key =
+              (static_cast<unsigned long long>(__float_as_uint(z)) << 32) | static_cast<unsigned>(tri);
+          atomicMin(vis + i * w + j, key);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int nbig = min(s_big_count, kBigQueue);
+      for (int b = 0; b < nbig; ++b) {
+        const int tri = s_big[b];
+        const TriSetup t = load_tri(vtx, faces, tri);
+        int j0, j1, i0, i1;
+        raster_bbox(t, h, w, j0, j1, i0, i1);
+        const int bw = j1 - j0 + 1;
+        const int cnt = bw * (i1 - i0 + 1);
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+          const int i = i0 + k / bw, j = j0 + k % bw;
+          float l0, l1, l2, iz, z;
+          if (!tri_sample(t, j * kSub + kHalf, i * kSub + kHalf, l0, l1, l2, iz, z)) continue;
+          const unsigned long long key =
+              (static_cast<unsigned long long>(__float_as_uint(z)) << 32) | static_cast<unsigned>(tri);
+          atomicMin(vis + i * w + j, key);
+        }
+      }
+    }
+    __syncthreads();
+
+    // (D) resolve + shade + write
+    const float* vcol = db.colors + 3 * v_off;
+    const float* vnrm = db.normals + 3 * v_off;
+    // d = a / z + b with a = 1 / (1/far - 1/near), b = -a / near (utils.py:44-55), as literals so
+    // that host and device agree on the rounding
+    const float dep_a = -0.10101010f;
+    const float dep_b = 1.01010101f;
+    const int sample = out.x ? view / out.views_per_sample : 0;
+    const int vslot = out.x ? view % out.views_per_sample : 0;
+    for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+      const int i = pix / w, j = pix - i * w;
+      const unsigned long long key = __ldcg(vis + pix);
+      float r = 0.f, g = 0.f, b = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dep = 0.f;
+      if (key != ~0ull) {
+        const int tri = static_cast<int>(key & 0xffffffffu);
+        const TriSetup t = load_tri(vtx, faces, tri);
+        float l0, l1, l2, iz, z;
+        tri_sample(t, j * kSub + kHalf, i * kSub + kHalf, l0, l1, l2, iz, z);
+        const float b0 = __fdiv_rn(__fmul_rn(l0, t.iza), iz);
+        const float b1 = __fdiv_rn(__fmul_rn(l1, t.izb), iz);
+        const float b2 = __fdiv_rn(__fmul_rn(l2, t.izc), iz);
+        const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1),
+                  ic = __ldg(faces + 3 * tri + 2);
+        float col[3], nrm[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          col[k] = __fmaf_rn(b0, __ldg(vcol + 3 * ia + k),
+                             __fmaf_rn(b1, __ldg(vcol + 3 * ib + k), __fmul_rn(b2, __ldg(vcol + 3 * ic + k))));
+          nrm[k] = __fmaf_rn(b0, __ldg(vnrm + 3 * ia + k),
+                             __fmaf_rn(b1, __ldg(vnrm + 3 * ib + k), __fmul_rn(b2, __ldg(vnrm + 3 * ic + k))));
+        }
+        r = quant8(col[0], q8);
+        g = quant8(col[1], q8);
+        b = quant8(col[2], q8);
+        // eye-space normal (OpenCV camera axes), normalised
+        float ex = __fmaf_rn(sR[0], nrm[0], __fmaf_rn(sR[1], nrm[1], __fmul_rn(sR[2], nrm[2])));
+        float ey = __fmaf_rn(sR[4], nrm[0], __fmaf_rn(sR[5], nrm[1], __fmul_rn(sR[6], nrm[2])));
+        float ez = __fmaf_rn(sR[8], nrm[0], __fmaf_rn(sR[9], nrm[1], __fmul_rn(sR[10], nrm[2])));
+        const float nn = __fsqrt_rn(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, __fmul_rn(ez, ez))));
+        if (nn > 0.f) {
+          ex = __fdiv_rn(ex, nn);
+          ey = __fdiv_rn(ey, nn);
+          ez = __fdiv_rn(ez, nn);
+        }
+        // Panda camera axes (x right, y forward, z up) or GL axes (x right, y up, z backward)
+        const float px_ = ex;
+        const float py_ = gl_axes ? -ey : ez;
+        const float pz_ = gl_axes ? -ez : -ey;
+        n0 = quant8(normal_texture(px_), q8);
+        n1 = quant8(normal_texture(py_), q8);
+        n2 = quant8(normal_texture(pz_), q8);
+        const float d = __fmaf_rn(dep_a, iz, dep_b);
+        dep = (d > 0.999f) ? 0.f : z;
+      }
+      if (out.rgb) {
+        float* o = out.rgb + (static_cast<size_t>(view) * 3) * npix + pix;
+        o[0] = r; o[npix] = g; o[2 * npix] = b;
+      }
+      if (out.normals) {
+        float* o = out.normals + (static_cast<size_t>(view) * 3) * npix + pix;
+        o[0] = n0; o[npix] = n1; o[2 * npix] = n2;
+      }
+      if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
+      if (out.x) {
+        const int hs = h >> 1, ws = w >> 1;
+        __nv_bfloat16* o = out.x +
+                           ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
+                           ((i & 1) * 2 + (j & 1)) * out.c_pad + out.ch_offset + vslot * out.ch_per_view;
+        o[0] = __float2bfloat16_rn(r);
+        o[1] = __float2bfloat16_rn(g);
+        o[2] = __float2bfloat16_rn(b);
+        o[3] = __float2bfloat16_rn(n0);
+        o[4] = __float2bfloat16_rn(n1);
+        o[5] = __float2bfloat16_rn(n2);
+        if (out.ch_per_view == 7) {
+          float dn = dep;
+          if (out.depth_norm_z) {
+            // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
+            dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
+          }
+          o[6] = __float2bfloat16_rn(dn);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+int meshdb_create(int n_meshes, const float* verts, const float* normals, const float* colors,
+                  const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
+                  MeshDb** out) {
+  MPX_REQUIRE(n_meshes > 0, "meshdb: need at least one mesh");
+  MeshDb* db = new MeshDb();
+  memset(db, 0, sizeof(MeshDb));
+  db->n_meshes = n_meshes;
+  const long long nv = vert_offsets[n_meshes], nf = face_offsets[n_meshes];
+  int nv_max = 0;
+  for (int i = 0; i < n_meshes; ++i) {
+    const long long c = vert_offsets[i + 1] - vert_offsets[i];
+    if (c > nv_max) nv_max = static_cast<int>(c);
+    const long long nfi = face_offsets[i + 1] - face_offsets[i];
+    for (long long f = 3 * face_offsets[i]; f < 3 * (face_offsets[i] + nfi); ++f) {
+      if (faces[f] < 0 || faces[f] >= c) {
+        delete db;
+        set_error("meshdb: mesh %d has a face index out of range", i);
+        return MPX_ERR_INVALID;
+      }
+    }
+  }
+  db->nv_max = nv_max > 0 ? nv_max : 1;
+  db->slots = 2 * sm_count();
+  MPX_CHECK_CUDA(cudaMalloc(&db->verts, sizeof(float) * 3 * (nv > 0 ? nv : 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->normals, sizeof(float) * 3 * (nv > 0 ? nv : 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->colors, sizeof(float) * 3 * (nv > 0 ? nv : 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->faces, sizeof(int) * 3 * (nf > 0 ? nf : 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->vert_offsets, sizeof(long long) * (n_meshes + 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->face_offsets, sizeof(long long) * (n_meshes + 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->vtx_cache, sizeof(int4) * static_cast<size_t>(db->slots) * db->nv_max));
+  MPX_CHECK_CUDA(cudaMemcpy(db->verts, verts, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->normals, normals, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->colors, colors, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->faces, faces, sizeof(int) * 3 * nf, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->vert_offsets, vert_offsets, sizeof(long long) * (n_meshes + 1),
+                            cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->face_offsets, face_offsets, sizeof(long long) * (n_meshes + 1),
+                            cudaMemcpyHostToDevice));
+  *out = db;
+  return MPX_OK;
+}
+
+void meshdb_destroy(MeshDb* db) {
+  if (!db) return;
+  cudaFree(db->verts);
+  cudaFree(db->normals);
+  cudaFree(db->colors);
+  cudaFree(db->faces);
+  cudaFree(db->vert_offsets);
+  cudaFree(db->face_offsets);
+  cudaFree(db->vtx_cache);
+  delete db;
+}
+
+size_t raster_workspace_bytes(int h, int w) {
+  return static_cast<size_t>(2 * sm_count()) * h * w * sizeof(unsigned long long);
+}
+
+int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, const float* K, int n_views,
+                  int h, int w, unsigned flags, const RasterOut& out, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream) {
+  MPX_REQUIRE(db != nullptr, "raster: null mesh database");
+  MPX_REQUIRE(h > 0 && w > 0 && h <= 4096 && w <= 4096, "raster: resolution %dx%d unsupported", h, w);
+  MPX_REQUIRE(workspace_bytes >= raster_workspace_bytes(h, w), "raster: workspace too small");
+  if (out.x) {
+    MPX_REQUIRE(h % 2 == 0 && w % 2 == 0, "raster: fused output needs even resolution");
+    MPX_REQUIRE(out.ch_per_view == 6 || out.ch_per_view == 7, "raster: ch_per_view must be 6 or 7");
+    MPX_REQUIRE(out.views_per_sample >= 1 &&
+                    out.ch_offset + out.views_per_sample * out.ch_per_view <= out.c_pad,
+                "raster: channels do not fit c_pad=%d", out.c_pad);
+  }
+  if (n_views == 0) return MPX_OK;
+  int grid = n_views < db->slots ? n_views : db->slots;
+  raster_kernel<<<grid, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out,
+                                                     reinterpret_cast<unsigned long long*>(workspace));
+  MPX_CHECK_CUDA(cudaGetLastError());
+  return MPX_OK;
+}
+
+}  // namespace mpx

@@ -1,0 +1,290 @@
+/*
+ * oracle/raster_ref.c -- CPU restatement of the renderer contract.  TEST INFRASTRUCTURE ONLY:
+ * nothing under megapose6d_b200/ may import, link or execute this file; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and only as
+ * the checker or the timed CPU baseline.
+ *
+ * What it restates: the reference renders through Panda3D/OpenGL
+ *   src/megapose/panda3d_renderer/panda3d_batch_renderer.py:89-150,217-282 (one view per
+ *     (label, TCO, K); non-finite pose or K => all-zero view)
+ *   src/megapose/panda3d_renderer/panda3d_scene_renderer.py:298-358 (pass 1: albedo under a single
+ *     ambient light of 1.0; pass 2: eye normal looked up in a 32^3 texture), :99-101 two-sided
+ *   src/megapose/panda3d_renderer/types.py:58-101 (pinhole lens from K, near 0.1, far 10)
+ *   src/megapose/panda3d_renderer/utils.py:44-68 (depth = a/(d-b), d > 0.999 => 0; texel
+ *     (x,y,z) = uint8((x,y,z)*255/32))
+ * Panda3D is a third-party engine that is neither in /root/reference nor installable here
+ * (conda/environment_full.yaml:40 `panda3d`, unpinned; docker builds github.com/ylabbe/panda3d@rebase),
+ * and the reference ships no rendering test or golden image.  PARITY UNPINNED: this file defines the
+ * geometric contract that the CUDA rasteriser implements bit for bit:
+ *   - pixel (i, j) sampled at (u, v) = (j + 0.5, i + 0.5), u = fx X/Z + cx, v = fy Y/Z + cy
+ *   - vertices snapped to 1/256 pixel, exact integer edge functions, inclusive edges, two-sided
+ *   - nearest z wins, ties -> lower triangle index; fragments outside [0.1, 10] m rejected;
+ *     triangles with a vertex at z < 0.1 are dropped (no near-plane clipping)
+ *   - 1/z linear in screen space, attributes perspective-correct
+ *   - single sample per pixel (the reference's 4x MSAA is not modelled)
+ * Every float operation is a single correctly-rounded IEEE operation in a fixed order (compile with
+ * -ffp-contract=off) so that the device kernel can reproduce the results exactly.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define K_NEAR 0.1f
+#define K_FAR 10.0f
+#define K_SUB 256
+#define K_HALF 128
+#define K_CLAMP 1048576.0f
+
+typedef struct {
+  int X, Y;
+  float iz;
+  int behind;
+} vtx_t;
+
+typedef struct {
+  int ax, ay, bx, by, cx, cy;
+  float iza, izb, izc;
+  int64_t area2;
+  int flip;
+  int ok;
+} tri_t;
+
+static int64_t edge_fn(int ax, int ay, int bx, int by, int px, int py) {
+  return (int64_t)(bx - ax) * (int64_t)(py - ay) - (int64_t)(by - ay) * (int64_t)(px - ax);
+}
+
+static int floor_div(int a, int b) {
+  int q = a / b;
+  if ((a % b != 0) && (a < 0)) --q;
+  return q;
+}
+
+static float normal_texture(float s) {
+  const float u = fmaf(s, 32.0f, -0.5f);
+  const float fl = floorf(u);
+  const float f = u - fl;
+  const int k0 = ((int)fl) & 31;
+  const int k1 = (k0 + 1) & 31;
+  const float t0 = (float)((k0 * 255) >> 5) / 255.0f;
+  const float t1 = (float)((k1 * 255) >> 5) / 255.0f;
+  return fmaf(f, t1 - t0, t0);
+}
+
+static float quant8(float v, int on) {
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  if (!on) return v;
+  return rintf(v * 255.0f) / 255.0f;
+}
+
+static tri_t load_tri(const vtx_t* vtx, const int32_t* faces, int tri) {
+  tri_t t;
+  const vtx_t a = vtx[faces[3 * tri]], b = vtx[faces[3 * tri + 1]], c = vtx[faces[3 * tri + 2]];
+  t.ax = a.X; t.ay = a.Y; t.bx = b.X; t.by = b.Y; t.cx = c.X; t.cy = c.Y;
+  t.iza = a.iz; t.izb = b.iz; t.izc = c.iz;
+  t.area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
+  t.flip = t.area2 < 0;
+  if (t.flip) t.area2 = -t.area2;
+  t.ok = (t.area2 != 0) && !(a.behind | b.behind | c.behind);
+  return t;
+}
+
+static int tri_sample(const tri_t* t, int px, int py, float* l0, float* l1, float* l2, float* iz, float* z) {
+  int64_t w0 = edge_fn(t->bx, t->by, t->cx, t->cy, px, py);
+  int64_t w1 = edge_fn(t->cx, t->cy, t->ax, t->ay, px, py);
+  int64_t w2 = edge_fn(t->ax, t->ay, t->bx, t->by, px, py);
+  if (t->flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+  if ((w0 | w1 | w2) < 0) return 0;
+  const float area = (float)t->area2;
+  *l0 = (float)w0 / area;
+  *l1 = (float)w1 / area;
+  *l2 = (float)w2 / area;
+  *iz = fmaf(*l0, t->iza, fmaf(*l1, t->izb, *l2 * t->izc));
+  *z = 1.0f / *iz;
+  return (*z >= K_NEAR) && (*z <= K_FAR);
+}
+
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/*
+ * Render one view.  verts/normals/colors: [nv,3]; faces: [nf,3]; TCO row-major 4x4; K row-major 3x3.
+ * flags: bit0 quantize8, bit1 GL eye axes.  Outputs (any may be NULL): rgb [3,h,w], nrm [3,h,w],
+ * depth [h,w], tri_id [h,w] (-1 = background).  Returns 0, or -1 on allocation failure.
+ */
+int raster_ref_render(const float* verts, const float* normals, const float* colors, int nv,
+                      const int32_t* faces, int nf, const float* TCO, const float* K, int h, int w,
+                      unsigned flags, float* rgb, float* nrm, float* depth, int32_t* tri_id) {
+  const int npix = h * w;
+  const int q8 = (flags & 1u) != 0, gl_axes = (flags & 2u) != 0;
+  int valid = 1;
+  for (int i = 0; i < 16; ++i) valid = valid && isfinite(TCO[i]);
+  for (int i = 0; i < 9; ++i) valid = valid && isfinite(K[i]);
+  if (rgb) memset(rgb, 0, sizeof(float) * 3 * npix);
+  if (nrm) memset(nrm, 0, sizeof(float) * 3 * npix);
+  if (depth) memset(depth, 0, sizeof(float) * npix);
+  if (tri_id) for (int i = 0; i < npix; ++i) tri_id[i] = -1;
+  if (!valid) return 0;
+
+  uint64_t* vis = (uint64_t*)malloc(sizeof(uint64_t) * npix);
+  vtx_t* vtx = (vtx_t*)malloc(sizeof(vtx_t) * (nv > 0 ? nv : 1));
+  if (!vis || !vtx) { free(vis); free(vtx); return -1; }
+  for (int i = 0; i < npix; ++i) vis[i] = ~(uint64_t)0;
+  const float* R = TCO;
+  const float fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+  for (int i = 0; i < nv; ++i) {
+    const float px = verts[3 * i], py = verts[3 * i + 1], pz = verts[3 * i + 2];
+    const float xc = fmaf(R[0], px, fmaf(R[1], py, fmaf(R[2], pz, R[3])));
+    const float yc = fmaf(R[4], px, fmaf(R[5], py, fmaf(R[6], pz, R[7])));
+    const float zc = fmaf(R[8], px, fmaf(R[9], py, fmaf(R[10], pz, R[11])));
+    vtx_t o;
+    o.behind = !(zc >= K_NEAR);
+    const float zs = o.behind ? 1.0f : zc;
+    const float iz = 1.0f / zs;
+    float u = fmaf(fx, xc * iz, cx);
+    float v = fmaf(fy, yc * iz, cy);
+    u = fminf(fmaxf(u, -K_CLAMP), K_CLAMP);
+    v = fminf(fmaxf(v, -K_CLAMP), K_CLAMP);
+    if (!(u == u)) { u = 0.f; o.behind = 1; }
+    if (!(v == v)) { v = 0.f; o.behind = 1; }
+    o.X = (int)lrintf(u * (float)K_SUB);
+    o.Y = (int)lrintf(v * (float)K_SUB);
+    o.iz = iz;
+    vtx[i] = o;
+  }
+  for (int tri = 0; tri < nf; ++tri) {
+    const tri_t t = load_tri(vtx, faces, tri);
+    if (!t.ok) continue;
+    const int minx = imin(t.ax, imin(t.bx, t.cx)), maxx = imax(t.ax, imax(t.bx, t.cx));
+    const int miny = imin(t.ay, imin(t.by, t.cy)), maxy = imax(t.ay, imax(t.by, t.cy));
+    const int j0 = imax(0, -floor_div(-(minx - K_HALF), K_SUB));
+    const int j1 = imin(w - 1, floor_div(maxx - K_HALF, K_SUB));
+    const int i0 = imax(0, -floor_div(-(miny - K_HALF), K_SUB));
+    const int i1 = imin(h - 1, floor_div(maxy - K_HALF, K_SUB));
+    for (int i = i0; i <= i1; ++i) {
+      for (int j = j0; j <= j1; ++j) {
+        float l0, l1, l2, iz, z;
+        if (!tri_sample(&t, j * K_SUB + K_HALF, i * K_SUB + K_HALF, &l0, &l1, &l2, &iz, &z)) continue;
+        uint32_t zb;
+        memcpy(&zb, &z, 4);
+        const uint64_t key = ((uint64_t)zb << 32) | (uint32_t)tri;
+        if (key < vis[i * w + j]) vis[i * w + j] = key;
+      }
+    }
+  }
+  const float dep_a = -0.10101010f;
+  const float dep_b = 1.01010101f;
+  for (int pix = 0; pix < npix; ++pix) {
+    const uint64_t key = vis[pix];
+    if (key == ~(uint64_t)0) continue;
+    const int i = pix / w, j = pix - i * w;
+    const int tri = (int)(key & 0xffffffffu);
+    const tri_t t = load_tri(vtx, faces, tri);
+    float l0, l1, l2, iz, z;
+    tri_sample(&t, j * K_SUB + K_HALF, i * K_SUB + K_HALF, &l0, &l1, &l2, &iz, &z);
+    const float b0 = (l0 * t.iza) / iz;
+    const float b1 = (l1 * t.izb) / iz;
+    const float b2 = (l2 * t.izc) / iz;
+    const int ia = faces[3 * tri], ib = faces[3 * tri + 1], ic = faces[3 * tri + 2];
+    float col[3], nn[3];
+    for (int k = 0; k < 3; ++k) {
+      col[k] = fmaf(b0, colors[3 * ia + k], fmaf(b1, colors[3 * ib + k], b2 * colors[3 * ic + k]));
+      nn[k] = fmaf(b0, normals[3 * ia + k], fmaf(b1, normals[3 * ib + k], b2 * normals[3 * ic + k]));
+    }
+    if (rgb) {
+      rgb[pix] = quant8(col[0], q8);
+      rgb[npix + pix] = quant8(col[1], q8);
+      rgb[2 * npix + pix] = quant8(col[2], q8);
+    }
+    if (nrm) {
+      float ex = fmaf(R[0], nn[0], fmaf(R[1], nn[1], R[2] * nn[2]));
+      float ey = fmaf(R[4], nn[0], fmaf(R[5], nn[1], R[6] * nn[2]));
+      float ez = fmaf(R[8], nn[0], fmaf(R[9], nn[1], R[10] * nn[2]));
+      const float len = sqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+      if (len > 0.f) { ex = ex / len; ey = ey / len; ez = ez / len; }
+      const float px_ = ex;
+      const float py_ = gl_axes ? -ey : ez;
+      const float pz_ = gl_axes ? -ez : -ey;
+      nrm[pix] = quant8(normal_texture(px_), q8);
+      nrm[npix + pix] = quant8(normal_texture(py_), q8);
+      nrm[2 * npix + pix] = quant8(normal_texture(pz_), q8);
+    }
+    if (depth) {
+      const float d = fmaf(dep_a, iz, dep_b);
+      depth[pix] = (d > 0.999f) ? 0.f : z;
+    }
+    if (tri_id) tri_id[pix] = tri;
+  }
+  free(vis);
+  free(vtx);
+  return 0;
+}
+
+/* Batched convenience: n views of (possibly different) meshes given by offsets, as the device API.
+ * Views are spread over n_threads POSIX threads (<= 0: one thread). */
+#include <pthread.h>
+
+typedef struct {
+  const float *verts, *normals, *colors;
+  const int64_t *vert_offsets, *face_offsets;
+  const int32_t *faces, *label_idx;
+  const float *TCO, *K;
+  int n_views, h, w;
+  unsigned flags;
+  float *rgb, *nrm, *depth;
+  int next;  /* work counter, protected by lock */
+  int status;
+  pthread_mutex_t lock;
+} batch_t;
+
+static void* batch_worker(void* arg) {
+  batch_t* b = (batch_t*)arg;
+  const size_t npix = (size_t)b->h * b->w;
+  for (;;) {
+    pthread_mutex_lock(&b->lock);
+    const int v = b->next++;
+    pthread_mutex_unlock(&b->lock);
+    if (v >= b->n_views) break;
+    const int lab = b->label_idx[v];
+    const int64_t vo = b->vert_offsets[lab], fo = b->face_offsets[lab];
+    const int rc = raster_ref_render(b->verts + 3 * vo, b->normals + 3 * vo, b->colors + 3 * vo,
+                                     (int)(b->vert_offsets[lab + 1] - vo), b->faces + 3 * fo,
+                                     (int)(b->face_offsets[lab + 1] - fo), b->TCO + 16 * v, b->K + 9 * v,
+                                     b->h, b->w, b->flags, b->rgb ? b->rgb + 3 * npix * v : NULL,
+                                     b->nrm ? b->nrm + 3 * npix * v : NULL,
+                                     b->depth ? b->depth + npix * v : NULL, NULL);
+    if (rc != 0) {
+      pthread_mutex_lock(&b->lock);
+      b->status = rc;
+      pthread_mutex_unlock(&b->lock);
+    }
+  }
+  return NULL;
+}
+
+int raster_ref_render_batch(int n_meshes, const float* verts, const float* normals, const float* colors,
+                            const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
+                            const int32_t* label_idx, const float* TCO, const float* K, int n_views, int h,
+                            int w, unsigned flags, float* rgb, float* nrm, float* depth, int n_threads) {
+  for (int v = 0; v < n_views; ++v)
+    if (label_idx[v] < 0 || label_idx[v] >= n_meshes) return -2;
+  batch_t b;
+  b.verts = verts; b.normals = normals; b.colors = colors;
+  b.vert_offsets = vert_offsets; b.face_offsets = face_offsets;
+  b.faces = faces; b.label_idx = label_idx; b.TCO = TCO; b.K = K;
+  b.n_views = n_views; b.h = h; b.w = w; b.flags = flags;
+  b.rgb = rgb; b.nrm = nrm; b.depth = depth;
+  b.next = 0; b.status = 0;
+  pthread_mutex_init(&b.lock, NULL);
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  if (n_threads > n_views) n_threads = n_views > 0 ? n_views : 1;
+  pthread_t th[256];
+  int started = 0;
+  for (int i = 0; i < n_threads - 1; ++i)
+    if (pthread_create(&th[started], NULL, batch_worker, &b) == 0) ++started;
+  batch_worker(&b);
+  for (int i = 0; i < started; ++i) pthread_join(th[i], NULL);
+  pthread_mutex_destroy(&b.lock);
+  return b.status;
+}

@@ -1,0 +1,156 @@
+"""oracle/resnet_ref.py -- torch fp32 restatement of the reference backbone + heads.
+
+TEST INFRASTRUCTURE ONLY (see oracle/lib3d_ref.py header for the import rule).
+
+Restates ResNet-34 as built by `resnet34(num_classes=512, n_input_channels=C)`
+(models/torchvision_resnet.py:181-316,345-353; BasicBlock :74-120) followed by the single linear
+head of PosePredictor (models/pose_rigid.py:120-130, 314-334), evaluated functionally from a
+reference-format state dict (keys `backbone.*`, `pose_fc.*` | `views_logits_head.*`).
+Validated against the reference's own nn.Module in tests/test_oracle_vs_reference.py.
+
+`forward_bf16_emulated` mirrors the engine's quantisation points (BN folded into bf16 weights, bf16
+activations between layers, fp32 accumulation) so that kernel tests can use a tight tolerance; the
+fp32 `forward` is the parity target with the tolerance stated in the tests.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+LAYERS = [3, 4, 6, 3]
+WIDTHS = [64, 128, 256, 512]
+BN_EPS = 1e-5
+
+
+def init_state_dict(n_inputs: int, head: str, head_dim: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded random weights in the reference checkpoint layout (kaiming fan_out convs as
+    torchvision_resnet.py:232-237, non-trivial BN statistics so that folding is exercised)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, k):
+        std = (2.0 / (co * k * k)) ** 0.5
+        sd[name + ".weight"] = torch.randn(co, ci, k, k, generator=g) * std
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1)
+
+    conv("backbone.conv1", 64, n_inputs, 7)
+    bn("backbone.bn1", 64)
+    inplanes = 64
+    for li, (nb, width) in enumerate(zip(LAYERS, WIDTHS)):
+        for b in range(nb):
+            p = f"backbone.layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            conv(p + ".conv1", width, inplanes, 3)
+            bn(p + ".bn1", width)
+            conv(p + ".conv2", width, width, 3)
+            bn(p + ".bn2", width)
+            if stride != 1 or inplanes != width:
+                conv(p + ".downsample.0", width, inplanes, 1)
+                bn(p + ".downsample.1", width)
+            inplanes = width
+    sd["backbone.fc.weight"] = torch.randn(512, 512, generator=g) * (1.0 / 512) ** 0.5
+    sd["backbone.fc.bias"] = 0.1 * torch.randn(512, generator=g)
+    sd[head + ".weight"] = torch.randn(head_dim, 512, generator=g) * (1.0 / 512) ** 0.5
+    sd[head + ".bias"] = 0.1 * torch.randn(head_dim, generator=g)
+    return sd
+
+
+def _bn(x, sd, name):
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
+                        sd[name + ".bias"], training=False, eps=BN_EPS)
+
+
+def head_name(sd) -> str:
+    return "pose_fc" if "pose_fc.weight" in sd else "views_logits_head"
+
+
+def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """fp32 forward: x [b,C,H,W] -> head output [b, 1|9]."""
+    x = F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3)
+    x = F.relu(_bn(x, sd, "backbone.bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, nb in enumerate(LAYERS):
+        for b in range(nb):
+            p = f"backbone.layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            identity = x
+            out = F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1)
+            out = F.relu(_bn(out, sd, p + ".bn1"))
+            out = F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1)
+            out = _bn(out, sd, p + ".bn2")
+            if (p + ".downsample.0.weight") in sd:
+                identity = _bn(F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride), sd, p + ".downsample.1")
+            x = F.relu(out + identity)
+    x = torch.flatten(F.adaptive_avg_pool2d(x, (1, 1)), 1)
+    x = F.linear(x, sd["backbone.fc.weight"], sd["backbone.fc.bias"])
+    h = head_name(sd)
+    return F.linear(x, sd[h + ".weight"], sd[h + ".bias"])
+
+
+def fold_bn(sd, conv: str, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps) (float64)."""
+    w = sd[conv + ".weight"].double()
+    scale = sd[bn + ".weight"].double() / torch.sqrt(sd[bn + ".running_var"].double() + BN_EPS)
+    return w * scale.view(-1, 1, 1, 1), sd[bn + ".bias"].double() - sd[bn + ".running_mean"].double() * scale
+
+
+def conv_plan(sd) -> List[Tuple[str, str]]:
+    """(conv, bn) names in the engine's execution order: stem, then per block conv1, conv2, [downsample]."""
+    plan = [("backbone.conv1", "backbone.bn1")]
+    for li, nb in enumerate(LAYERS):
+        for b in range(nb):
+            p = f"backbone.layer{li + 1}.{b}"
+            plan.append((p + ".conv1", p + ".bn1"))
+            plan.append((p + ".conv2", p + ".bn2"))
+            if (p + ".downsample.0.weight") in sd:
+                plan.append((p + ".downsample.0", p + ".downsample.1"))
+    return plan
+
+
+def _q(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).float()
+
+
+def forward_bf16_emulated(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """Same network with the engine's quantisation points (runs on x.device, fp32 math)."""
+    dev = x.device
+
+    def cw(conv, bn):
+        w, b = fold_bn(sd, conv, bn)
+        return _q(w.float()).to(dev), b.float().to(dev)
+
+    x = _q(x)
+    w, b = cw("backbone.conv1", "backbone.bn1")
+    x = _q(F.relu(F.conv2d(x, w, b, stride=2, padding=3)))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, nb in enumerate(LAYERS):
+        for bi in range(nb):
+            p = f"backbone.layer{li + 1}.{bi}"
+            stride = 2 if (bi == 0 and li > 0) else 1
+            identity = x
+            w, b = cw(p + ".conv1", p + ".bn1")
+            out = _q(F.relu(F.conv2d(x, w, b, stride=stride, padding=1)))
+            if (p + ".downsample.0.weight") in sd:
+                wd, bd = cw(p + ".downsample.0", p + ".downsample.1")
+                identity = _q(F.conv2d(x, wd, bd, stride=stride))
+            w, b = cw(p + ".conv2", p + ".bn2")
+            x = _q(F.relu(F.conv2d(out, w, b, stride=1, padding=1) + identity))
+    pooled = x.flatten(2).mean(dim=-1)
+    hw, hb = folded_head(sd)
+    return F.linear(pooled, hw.float().to(dev), hb.float().to(dev))
+
+
+def folded_head(sd) -> Tuple[torch.Tensor, torch.Tensor]:
+    """head o fc as one linear map (float64): W = Wh Wfc, b = Wh bfc + bh."""
+    h = head_name(sd)
+    Wh, bh = sd[h + ".weight"].double(), sd[h + ".bias"].double()
+    Wf, bf = sd["backbone.fc.weight"].double(), sd["backbone.fc.bias"].double()
+    return Wh @ Wf, Wh @ bf + bh
