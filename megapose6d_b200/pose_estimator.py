@@ -1,0 +1,300 @@
+"""Pipeline orchestrator: detections -> coarse scoring of the SO(3) grid -> top-K -> refiner -> scoring.
+
+Drop-in for the reference's PoseEstimator (src/megapose/inference/pose_estimator.py:52-667): same
+constructor, attributes, methods (`run_inference_pipeline`, `forward_coarse_model`, `forward_refiner`,
+`forward_scoring_model`, `filter_pose_estimates`, `forward_detection_model`, `run_depth_refiner`) and
+the same structure of the returned collections and `extra_data` dictionaries.
+
+Differences underneath: the B*M hypothesis table is built vectorised and scored in a few large fused
+launches instead of ceil(B*M / bsz_images) Python iterations; the frame is never replicated per
+hypothesis; pandas bookkeeping happens once per stage, after the GPU work; optionally the rows of each
+stage are sharded over the ranks of a torch.distributed group (see parallel.py).
+"""
+from __future__ import annotations
+
+import time
+from collections import defaultdict
+from typing import Any, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import lib3d, tensor_collection as tc
+from .parallel import HypothesisSharder
+from .so3 import load_SO3_grid
+from .tensor_collection import PandasTensorCollection
+from .types import DetectionsType, ObservationTensor, PoseEstimatesType, assert_detections_valid
+
+
+def add_instance_id(inputs):
+    """inference/utils.py:151-171: unique id per (batch_im_id, label) occurrence."""
+    if "instance_id" in inputs.infos:
+        return inputs
+    df = inputs.infos
+    df["instance_id"] = df.groupby(["batch_im_id", "label"]).cumcount().values
+    inputs.infos = df
+    return inputs
+
+
+def filter_detections(detections: DetectionsType, labels=None, one_instance_per_class: bool = False) -> DetectionsType:
+    """inference/utils.py:174-194."""
+    if labels is not None:
+        df = detections.infos
+        df = df[df.label.isin(labels)]
+        detections = detections[df.index.tolist()]
+    if one_instance_per_class:
+        df = detections.infos
+        df = df.sort_values("score", ascending=False).groupby(["batch_im_id", "label"]).head(1)
+        detections = detections[df.index.tolist()]
+    return detections
+
+
+class PoseEstimator(torch.nn.Module):
+    """Performs inference for pose estimation."""
+
+    def __init__(self, refiner_model: Optional[torch.nn.Module] = None, coarse_model: Optional[torch.nn.Module] = None,
+                 detector_model: Optional[torch.nn.Module] = None, depth_refiner: Optional[Any] = None,
+                 bsz_objects: int = 8, bsz_images: int = 256, SO3_grid_size: int = 576,
+                 sharder: Optional[HypothesisSharder] = None) -> None:
+        super().__init__()
+        self.coarse_model = coarse_model
+        self.refiner_model = refiner_model
+        self.detector_model = detector_model
+        self.depth_refiner = depth_refiner
+        self.bsz_objects = bsz_objects
+        self.bsz_images = bsz_images
+        self.sharder = sharder if sharder is not None else HypothesisSharder(enabled=False)
+        if SO3_grid_size is not None:
+            self.load_SO3_grid(SO3_grid_size)
+        if self.refiner_model is not None:
+            self.cfg = getattr(self.refiner_model, "cfg", None)
+            self.mesh_db = self.refiner_model.mesh_db
+        elif self.coarse_model is not None:
+            self.cfg = getattr(self.coarse_model, "cfg", None)
+            self.mesh_db = self.coarse_model.mesh_db
+        else:
+            raise ValueError("At least one of refiner_model or coarse_model must be specified.")
+        self.eval()
+        self.keep_all_outputs = False
+        self.keep_all_coarse_outputs = False
+        self.refiner_outputs = None
+        self.coarse_outputs = None
+        self.debug_dict: dict = dict()
+
+    def load_SO3_grid(self, grid_size: int) -> None:
+        self._SO3_grid = load_SO3_grid(grid_size).cuda()
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_refiner(self, observation: ObservationTensor, data_TCO_input: PoseEstimatesType, n_iterations: int = 5,
+                        keep_all_outputs: bool = False, cuda_timer: bool = False, **refiner_kwargs) -> Tuple[dict, dict]:
+        """pose_estimator.py:102-215 -> (preds{'iteration=n': collection}, extra_data)."""
+        start_time = time.time()
+        assert self.refiner_model is not None
+        model = self.refiner_model
+        B = data_TCO_input.poses.shape[0]
+        device = observation.images.device
+        df = data_TCO_input.infos.copy()
+        df["refiner_batch_idx"] = np.arange(B) // max(1, self.bsz_objects)
+        df["refiner_instance_idx"] = np.arange(B) % max(1, self.bsz_objects)
+        labels = df["label"].tolist()
+        batch_im_ids = torch.as_tensor(df["batch_im_id"].values, device=device)
+        K_all = observation.K[batch_im_ids]
+        TCO_all = data_TCO_input.poses.to(device)
+
+        s0, s1 = self.sharder.span(B)
+        chunk = max(1, model.max_batch // max(1, model.n_rendered_views))
+        model_time = 0.0
+        all_outputs = []
+        fields = ["poses", "poses_input", "K_crop", "K", "boxes_rend", "boxes_crop"]
+        local = {n: {f: [] for f in fields} for n in range(1, n_iterations + 1)}
+        for s in range(s0, s1, chunk):
+            e = min(s1, s + chunk)
+            t0 = time.time()
+            outputs_ = model(images=observation.images, K=K_all[s:e], TCO=TCO_all[s:e], n_iterations=n_iterations,
+                             labels=labels[s:e], batch_im_ids=batch_im_ids[s:e], cuda_timer=cuda_timer,
+                             **refiner_kwargs)
+            model_time += time.time() - t0
+            if keep_all_outputs:
+                all_outputs.append(outputs_)
+            for n in range(1, n_iterations + 1):
+                it = outputs_[f"iteration={n}"]
+                for f, v in zip(fields, (it.TCO_output, it.TCO_input, it.K_crop, it.K, it.boxes_rend, it.boxes_crop)):
+                    local[n][f].append(v)
+        preds = dict()
+        tails = dict(poses=(4, 4), poses_input=(4, 4), K_crop=(3, 3), K=(3, 3), boxes_rend=(4,), boxes_crop=(4,))
+        for n in range(1, n_iterations + 1):
+            tensors = dict()
+            for f in fields:
+                loc = torch.cat(local[n][f]) if local[n][f] else torch.empty((0,) + tails[f], device=device)
+                tensors[f] = self.sharder.gather_rows(loc, B)
+            preds[f"iteration={n}"] = PandasTensorCollection(df, **tensors)
+        extra_data = {"n_iterations": n_iterations, "outputs": all_outputs, "model_time": model_time,
+                      "time": time.time() - start_time}
+        return preds, extra_data
+
+    # ------------------------------------------------------------------------------------------
+    def _score(self, observation: ObservationTensor, df: pd.DataFrame, TCO: torch.Tensor, cuda_timer: bool,
+               return_debug_data: bool):
+        """Run the coarse model over all rows (sharded), returns (logits [n,1], scores [n,1], out dict)."""
+        device = observation.images.device
+        n = TCO.shape[0]
+        labels = df["label"].tolist()
+        batch_im_ids = torch.as_tensor(df["batch_im_id"].values, device=device)
+        K = observation.K[batch_im_ids]
+        s0, s1 = self.sharder.span(n)
+        out_ = self.coarse_model.forward_coarse(images=observation.images, K=K[s0:s1], labels=labels[s0:s1],
+                                                TCO_input=TCO[s0:s1], cuda_timer=cuda_timer,
+                                                return_debug_data=return_debug_data, batch_im_ids=batch_im_ids[s0:s1])
+        logits = self.sharder.gather_rows(out_["logits"], n)
+        return logits, torch.sigmoid(logits), out_
+
+    @torch.no_grad()
+    def forward_scoring_model(self, observation: ObservationTensor, data_TCO: PoseEstimatesType, cuda_timer: bool = False,
+                              return_debug_data: bool = False) -> Tuple[PoseEstimatesType, dict]:
+        """pose_estimator.py:218-322: adds pose_logit / pose_score to data_TCO.infos (in place)."""
+        start_time = time.time()
+        assert self.coarse_model is not None
+        df = data_TCO.infos
+        logits, scores, out_ = self._score(observation, df, data_TCO.poses.to(observation.images.device), cuda_timer,
+                                           return_debug_data)
+        debug_data = dict()
+        if return_debug_data:
+            debug_data = {"images_crop": out_["images_crop"], "renders": out_["renders"]}
+        df["pose_logit"] = logits.cpu().numpy()
+        df["pose_score"] = scores.cpu().numpy()
+        elapsed = time.time() - start_time
+        render_time, model_time = out_["render_time"], out_["model_time"]
+        extra_data = {"render_time": render_time, "model_time": model_time, "time": elapsed, "logits": logits,
+                      "scores": scores, "debug": debug_data,
+                      "n_batches": int(np.ceil(len(df) / max(1, self.bsz_images))),
+                      "timing_str": f"time: {elapsed:.2f}, model_time: {model_time:.2f}, render_time: {render_time:.2f}"}
+        data_TCO.infos = df
+        return data_TCO, extra_data
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_coarse_model(self, observation: ObservationTensor, detections: DetectionsType, cuda_timer: bool = False,
+                             return_debug_data: bool = False) -> Tuple[PoseEstimatesType, dict]:
+        """pose_estimator.py:325-483: every detection x every rotation of the SO(3) grid."""
+        start_time = time.time()
+        assert_detections_valid(detections)
+        coarse_model = self.coarse_model
+        device = observation.images.device
+        SO3_grid = self._SO3_grid
+        B, M = len(detections), SO3_grid.shape[0]
+        df = detections.infos
+        df_hypotheses = df.loc[df.index.repeat(M)].copy()
+        df_hypotheses["hypothesis_id"] = np.tile(np.arange(M), B)
+        df_hypotheses["bbox_id"] = np.repeat(df.index.values, M)
+
+        batch_im_ids = torch.as_tensor(df_hypotheses["batch_im_id"].values, device=device)
+        bbox_ids = torch.as_tensor(df_hypotheses["bbox_id"].values, device=device)
+        m_idx = torch.as_tensor(df_hypotheses["hypothesis_id"].values, device=device)
+        labels = df_hypotheses["label"].tolist()
+        K = observation.K[batch_im_ids]
+        bboxes = detections.bboxes.to(device)[bbox_ids]
+        label_idx = coarse_model.mesh_db.label_ids(labels, device)
+        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes.float(), coarse_model.mesh_db.points, label_idx, K,
+                                                         SO3_grid[m_idx])
+        logits, scores, out_ = self._score(observation, df_hypotheses, TCO, cuda_timer, return_debug_data)
+        logits = logits.reshape([B, M])
+        scores = scores.reshape([B, M])
+        debug_data = dict()
+        if return_debug_data:
+            H, W = out_["images_crop"].shape[2:]
+            debug_data = {"images_crop": out_["images_crop"].reshape([B, M, -1, H, W]),
+                          "renders": out_["renders"].reshape([B, M, -1, H, W])}
+        df_hypotheses["coarse_logit"] = logits.flatten().cpu().numpy()
+        df_hypotheses["coarse_score"] = scores.flatten().cpu().numpy()
+        elapsed = time.time() - start_time
+        render_time, model_time = out_["render_time"], out_["model_time"]
+        extra_data = {"render_time": render_time, "model_time": model_time, "time": elapsed, "logits": logits,
+                      "scores": scores, "TCO": TCO.reshape([B, M, 4, 4]), "debug": debug_data,
+                      "n_batches": int(np.ceil(B * M / max(1, self.bsz_images))),
+                      "timing_str": f"time: {elapsed:.2f}, model_time: {model_time:.2f}, render_time: {render_time:.2f}"}
+        data_TCO = PandasTensorCollection(df_hypotheses, poses=TCO, bboxes=bboxes)
+        return data_TCO, extra_data
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_detection_model(self, observation: ObservationTensor, *args: Any, **kwargs: Any) -> DetectionsType:
+        return self.detector_model.get_detections(observation, *args, **kwargs)
+
+    def run_depth_refiner(self, observation: ObservationTensor, predictions: PoseEstimatesType):
+        assert self.depth_refiner is not None, "You must specify a depth refiner"
+        return self.depth_refiner.refine_poses(predictions, depth=observation.depth, K=observation.K)
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run_inference_pipeline(self, observation: ObservationTensor, detections: Optional[DetectionsType] = None,
+                               run_detector: Optional[bool] = None, n_refiner_iterations: int = 5,
+                               n_pose_hypotheses: int = 1, keep_all_refiner_outputs: bool = False,
+                               detection_filter_kwargs: Optional[dict] = None, run_depth_refiner: bool = False,
+                               bsz_images: Optional[int] = None, bsz_objects: Optional[int] = None,
+                               cuda_timer: bool = False,
+                               coarse_estimates: Optional[PoseEstimatesType] = None) -> Tuple[PoseEstimatesType, dict]:
+        """pose_estimator.py:511-641."""
+        timing_str = ""
+        t_start = time.time()
+        if bsz_images is not None:
+            self.bsz_images = bsz_images
+        if bsz_objects is not None:
+            self.bsz_objects = bsz_objects
+        if coarse_estimates is None:
+            assert detections is not None or run_detector, "You must either pass in `detections` or set run_detector=True"
+            if detections is None and run_detector:
+                t0 = time.time()
+                detections = self.forward_detection_model(observation).cuda()
+                timing_str += f"detection={time.time() - t0:.2f}, "
+            assert detections is not None
+            detections = add_instance_id(detections)
+            if detection_filter_kwargs is not None:
+                detections = filter_detections(detections, **detection_filter_kwargs)
+            data_TCO_coarse, coarse_extra_data = self.forward_coarse_model(observation=observation, detections=detections,
+                                                                          cuda_timer=cuda_timer)
+            timing_str += f"coarse={coarse_extra_data['time']:.2f}, "
+            data_TCO_filtered = self.filter_pose_estimates(data_TCO_coarse, top_K=n_pose_hypotheses,
+                                                           filter_field="coarse_logit")
+        else:
+            data_TCO_coarse = coarse_estimates
+            coarse_extra_data = None
+            data_TCO_filtered = coarse_estimates
+
+        preds, refiner_extra_data = self.forward_refiner(observation, data_TCO_filtered, n_iterations=n_refiner_iterations,
+                                                         keep_all_outputs=keep_all_refiner_outputs, cuda_timer=cuda_timer)
+        data_TCO_refined = preds[f"iteration={n_refiner_iterations}"]
+        timing_str += f"refiner={refiner_extra_data['time']:.2f}, "
+        data_TCO_scored, scoring_extra_data = self.forward_scoring_model(observation, data_TCO_refined, cuda_timer=cuda_timer)
+        timing_str += f"scoring={scoring_extra_data['time']:.2f}, "
+        data_TCO_final_scored = self.filter_pose_estimates(data_TCO_scored, top_K=1, filter_field="pose_logit")
+        if run_depth_refiner:
+            t0 = time.time()
+            data_TCO_depth_refiner, _ = self.run_depth_refiner(observation, data_TCO_final_scored)
+            data_TCO_final = data_TCO_depth_refiner
+            timing_str += f"depth refiner={time.time() - t0:.2f}"
+        else:
+            data_TCO_depth_refiner = None
+            data_TCO_final = data_TCO_final_scored
+        elapsed = time.time() - t_start
+        timing_str = f"total={elapsed:.2f}, {timing_str}"
+        extra_data: dict = dict()
+        extra_data["coarse"] = {"preds": data_TCO_coarse, "data": coarse_extra_data}
+        extra_data["coarse_filter"] = {"preds": data_TCO_filtered}
+        extra_data["refiner_all_hypotheses"] = {"preds": preds, "data": refiner_extra_data}
+        extra_data["scoring"] = {"preds": data_TCO_scored, "data": scoring_extra_data}
+        extra_data["refiner"] = {"preds": data_TCO_final_scored, "data": refiner_extra_data}
+        extra_data["timing_str"] = timing_str
+        extra_data["time"] = elapsed
+        if run_depth_refiner:
+            extra_data["depth_refiner"] = {"preds": data_TCO_depth_refiner}
+        return data_TCO_final, extra_data
+
+    def filter_pose_estimates(self, data_TCO: PoseEstimatesType, top_K: int, filter_field: str,
+                              ascending: bool = False) -> PoseEstimatesType:
+        """pose_estimator.py:643-667: top-K rows per (batch_im_id, label, instance_id)."""
+        df = data_TCO.infos
+        group_cols = ["batch_im_id", "label", "instance_id"]
+        df = df.sort_values(filter_field, ascending=ascending, kind="stable").groupby(group_cols).head(top_K)
+        return data_TCO[df.index.tolist()]

@@ -1,0 +1,96 @@
+"""Procedurally generated objects and scenes (no dataset or checkpoint is available offline).
+
+Used by bench.py, __graft_entry__.smoke() and the tests for the synthetic configurations of
+BASELINE.json: bumpy UV spheres with per-vertex normals and colours, >= 2000
+vertices as the reference's point sampling requires (lib3d/mesh_ops.py:79).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from .meshes import TriMesh, compute_vertex_normals
+from .object_dataset import RigidObject, RigidObjectDataset
+
+
+def bumpy_sphere(n_seg: int = 100, n_lat: int = 51, radius: float = 0.05, bump: float = 0.25, seed: int = 0,
+                 squash: Tuple[float, float, float] = (1.0, 0.8, 0.6)) -> TriMesh:
+    """UV sphere with smooth radial bumps; 2*n_seg*(n_lat-1) triangles, n_seg*(n_lat-1)+2 vertices.
+
+    The default (100, 51) gives exactly 10 000 triangles / 5 002 vertices (BASELINE config 5).
+    """
+    rng = np.random.RandomState(seed)
+    th = np.linspace(0, np.pi, n_lat + 1)[1:-1]  # polar angles of the interior rings
+    ph = np.arange(n_seg) * (2 * np.pi / n_seg)
+    dirs = [np.array([0.0, 0.0, 1.0])]
+    for t in th:
+        for p in ph:
+            dirs.append(np.array([np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)]))
+    dirs.append(np.array([0.0, 0.0, -1.0]))
+    dirs = np.asarray(dirs)
+    # low-frequency bumps: a few random plane waves evaluated on the unit directions
+    r = np.ones(len(dirs))
+    for _ in range(6):
+        k = rng.randn(3) * 2.5
+        r += bump / 6 * np.sin(dirs @ k + rng.uniform(0, 2 * np.pi))
+    verts = dirs * r[:, None] * radius * np.asarray(squash)[None]
+    nring = len(th)
+    faces: List[List[int]] = []
+    for s in range(n_seg):
+        faces.append([0, 1 + s, 1 + (s + 1) % n_seg])
+    for ring in range(nring - 1):
+        a0 = 1 + ring * n_seg
+        b0 = a0 + n_seg
+        for s in range(n_seg):
+            s1 = (s + 1) % n_seg
+            faces.append([a0 + s, b0 + s, b0 + s1])
+            faces.append([a0 + s, b0 + s1, a0 + s1])
+    last = len(verts) - 1
+    a0 = 1 + (nring - 1) * n_seg
+    for s in range(n_seg):
+        faces.append([a0 + s, last, a0 + (s + 1) % n_seg])
+    faces_a = np.asarray(faces, dtype=np.int32)
+    # colours: smooth function of direction, quantised to uint8 levels like a vertex-colour PLY
+    col = 0.5 + 0.5 * np.stack([np.sin(3 * dirs[:, 0] + seed), np.sin(4 * dirs[:, 1] + 1.0), np.sin(5 * dirs[:, 2] + 2.0)], 1)
+    col = np.round(col * 255) / 255
+    return TriMesh(verts, faces_a, compute_vertex_normals(verts, faces_a), col)
+
+
+def make_object_dataset(n_objects: int = 1, seed: int = 0, n_seg: int = 100, n_lat: int = 51) -> RigidObjectDataset:
+    objs = []
+    for i in range(n_objects):
+        rng = np.random.RandomState(seed + 17 * i)
+        squash = tuple(0.6 + 0.4 * rng.rand(3))
+        mesh = bumpy_sphere(n_seg=n_seg, n_lat=n_lat, radius=0.04 + 0.03 * rng.rand(), seed=seed + i, squash=squash)
+        objs.append(RigidObject(label=f"obj_{i:06d}", mesh=mesh, mesh_units="m"))
+    return RigidObjectDataset(objs)
+
+
+def example_camera(h: int = 480, w: int = 640) -> np.ndarray:
+    """Intrinsics of the reference's barbecue-sauce example (README.md:226)."""
+    K = np.array([[605.9547119140625, 0.0, 319.029052734375], [0.0, 605.006591796875, 249.67617797851562], [0.0, 0.0, 1.0]])
+    if (h, w) != (480, 640):
+        K = K.copy()
+        K[0] *= w / 640.0
+        K[1] *= h / 480.0
+    return K
+
+
+def random_poses(n: int, seed: int = 0, z_range=(0.4, 1.2), xy_range=0.08) -> np.ndarray:
+    """Random object poses in front of the camera: [n,4,4] float64."""
+    rng = np.random.RandomState(seed)
+    q = rng.randn(n, 4)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    x, y, z, w = q.T
+    R = np.stack([
+        np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+        np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+        np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1),
+    ], -2)
+    T = np.tile(np.eye(4), (n, 1, 1))
+    T[:, :3, :3] = R
+    T[:, 0, 3] = rng.uniform(-xy_range, xy_range, n)
+    T[:, 1, 3] = rng.uniform(-xy_range, xy_range, n)
+    T[:, 2, 3] = rng.uniform(*z_range, n)
+    return T

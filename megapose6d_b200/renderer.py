@@ -1,0 +1,107 @@
+"""Batch renderer: the CUDA rasteriser behind the reference's renderer seam.
+
+Drop-in for Panda3dBatchRenderer (src/megapose/panda3d_renderer/panda3d_batch_renderer.py:153-340):
+same constructor keywords (worker/process arguments are accepted and ignored -- there are no worker
+processes), same `.render(labels, TCO, K, light_datas, resolution, render_depth, render_mask,
+render_normals) -> BatchRenderOutput(rgbs, normals, depths)` contract, `.stop()` is a no-op.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _abi
+from .meshes import BatchedMeshes, MeshDataBase
+from .object_dataset import RigidObjectDataset
+
+RASTER_QUANTIZE8 = 1
+RASTER_NORMALS_GL = 2
+
+
+@dataclass
+class Panda3dLightData:
+    """Light description of the reference API (panda3d_renderer/types.py:108-130); only ambient
+    white light (the zoo models' render_normals=True path) is rendered."""
+
+    light_type: str = "ambient"
+    color: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
+    positioning_function: Optional[object] = None
+
+
+@dataclass
+class BatchRenderOutput:
+    """rgbs [N,3,h,w] in [0,1]; normals [N,3,h,w] in [0,1]; depths [N,1,h,w] metres."""
+
+    rgbs: torch.Tensor
+    normals: Optional[torch.Tensor]
+    depths: Optional[torch.Tensor]
+
+
+class BatchRenderer:
+    def __init__(self, object_dataset: Optional[RigidObjectDataset] = None, n_workers: int = 0,
+                 preload_cache: bool = False, split_objects: bool = False,
+                 mesh_db: Optional[BatchedMeshes] = None, quantize8: bool = True, normals_gl_axes: bool = False):
+        if mesh_db is None:
+            assert object_dataset is not None
+            mesh_db = MeshDataBase.from_object_ds(object_dataset).batched()
+        self.mesh_db = mesh_db
+        self._object_dataset = object_dataset
+        self.flags = (RASTER_QUANTIZE8 if quantize8 else 0) | (RASTER_NORMALS_GL if normals_gl_axes else 0)
+        self._workspace: Optional[torch.Tensor] = None
+
+    def stop(self) -> None:  # the reference joins its worker processes here
+        pass
+
+    def workspace(self, h: int, w: int, device) -> torch.Tensor:
+        need = _abi.lib().mpx_raster_workspace_bytes(h, w)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != torch.device(device):
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._workspace
+
+    def _check_lights(self, light_datas) -> None:
+        if light_datas is None:
+            return
+        for lights in light_datas:
+            for light in lights:
+                if getattr(light, "light_type", "ambient") != "ambient":
+                    raise NotImplementedError("only ambient lighting (render_normals=True models) is implemented")
+
+    def render(self, labels: List[str], TCO: torch.Tensor, K: torch.Tensor, light_datas=None,
+               resolution: Tuple[int, int] = (240, 320), render_depth: bool = False, render_mask: bool = False,
+               render_normals: bool = False) -> BatchRenderOutput:
+        if render_mask:
+            raise NotImplementedError
+        self._check_lights(light_datas)
+        n = TCO.shape[0]
+        assert TCO.shape == (n, 4, 4) and K.shape == (n, 3, 3) and len(labels) == n
+        h, w = resolution
+        dev = TCO.device
+        TCO = TCO.detach().float().contiguous()
+        K = K.detach().float().contiguous()
+        label_idx = self.mesh_db.label_ids(labels, dev)
+        rgbs = torch.empty(n, 3, h, w, device=dev, dtype=torch.float32)
+        normals = torch.empty(n, 3, h, w, device=dev, dtype=torch.float32) if render_normals else None
+        depths = torch.empty(n, 1, h, w, device=dev, dtype=torch.float32) if render_depth else None
+        ws = self.workspace(h, w, dev)
+        _abi.check(_abi.lib().mpx_raster_render(self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K),
+                                                n, h, w, self.flags, _abi.ptr(rgbs), _abi.ptr(normals),
+                                                _abi.ptr(depths), _abi.ptr(ws), ws.numel(), _abi.stream_ptr()))
+        return BatchRenderOutput(rgbs=rgbs, normals=normals, depths=depths)
+
+    def render_fused(self, label_idx: torch.Tensor, TCO: torch.Tensor, K: torch.Tensor, views_per_sample: int,
+                     resolution: Tuple[int, int], x: torch.Tensor, c_pad: int, ch_offset: int, ch_per_view: int,
+                     depth_norm_z: Optional[torch.Tensor] = None) -> None:
+        """Render straight into the network input tensor `x` (see include/mpx.h)."""
+        n = TCO.shape[0]
+        h, w = resolution
+        ws = self.workspace(h, w, TCO.device)
+        _abi.check(_abi.lib().mpx_raster_render_fused(
+            self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K), n, views_per_sample, h, w, self.flags,
+            _abi.ptr(x), c_pad, ch_offset, ch_per_view, _abi.ptr(depth_norm_z), _abi.ptr(ws), ws.numel(),
+            _abi.stream_ptr()))
+
+
+# name used by the reference's callers
+Panda3dBatchRenderer = BatchRenderer

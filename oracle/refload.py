@@ -41,6 +41,9 @@ def _pkg(name: str) -> types.ModuleType:
     m = types.ModuleType(name)
     m.__path__ = []  # mark as package
     sys.modules[name] = m
+    parent, _, child = name.rpartition(".")
+    if parent in sys.modules:
+        setattr(sys.modules[parent], child, m)
     return m
 
 
