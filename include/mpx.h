@@ -30,6 +30,13 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------------ */
 int mpx_abi_version(void);
 const char* mpx_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (host-side counter) */
+long long mpx_launch_count(void);
+/* measurement aid for bench.py: when enabled every convolution launch is bracketed by CUDA events on
+ * its stream; mpx_profile_summary synchronises the device, returns the summed duration (ms), the
+ * algorithmic FLOPs (2*M*N*K per launch) and the launch count since enabling, and resets. */
+int mpx_profile_enable(int on);
+int mpx_profile_summary(double* conv_ms, double* conv_flops, long long* conv_launches);
 
 /* ---- mesh database ---------------------------------------------------------------------------
  * Replaces MeshDataBase / BatchedMeshes (lib3d/rigid_mesh_database.py:57-169) for the point sets
@@ -168,7 +175,7 @@ int mpx_avgpool_linear(const void* d_x, int n, int hw, int c, const float* d_w, 
                        int out_dim, float* d_out, void* stream);
 
 typedef struct mpx_net mpx_net;
-/* h_conv_w / h_conv_b: arrays of 37 DEVICE pointers in execution order (stem, then per BasicBlock
+/* h_conv_w / h_conv_b: arrays of 36 DEVICE pointers in execution order (stem, then per BasicBlock
  * conv1, conv2, [downsample]); c_pad as above; d_head_w [out_dim,512] fp32, d_head_b [out_dim]. */
 int mpx_net_create(int c_pad, int out_dim, const void* const* h_conv_w, const float* const* h_conv_b,
                    int n_convs, const float* d_head_w, const float* d_head_b, mpx_net** out);

@@ -56,14 +56,17 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_net_workspace_bytes.argtypes = [vp, c_int, c_int, c_int]
     lib.mpx_net_workspace_bytes.restype = c_size_t
     lib.mpx_net_forward.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]
+    lib.mpx_launch_count.restype = ctypes.c_longlong
+    lib.mpx_profile_enable.argtypes = [c_int]
+    lib.mpx_profile_summary.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                                        POINTER(ctypes.c_longlong)]
     for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is c_int or name.startswith("mpx_") and fn.restype not in (c_char_p, c_size_t):
-            fn.restype = c_int
+        getattr(lib, name)  # every declared symbol must be exported
 
 
 EXPORTS = [
-    "mpx_abi_version", "mpx_last_error", "mpx_meshdb_create", "mpx_meshdb_destroy",
+    "mpx_abi_version", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
+    "mpx_meshdb_create", "mpx_meshdb_destroy",
     "mpx_raster_workspace_bytes", "mpx_raster_render", "mpx_raster_render_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",

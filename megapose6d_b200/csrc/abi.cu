@@ -5,6 +5,7 @@
 #include "../../include/mpx.h"
 
 namespace mpx {
+long long g_launches = 0;
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,6 +23,18 @@ extern "C" {
 
 int mpx_abi_version(void) { return MPX_ABI_VERSION; }
 const char* mpx_last_error(void) { return g_err; }
+
+long long mpx_launch_count(void) { return g_launches; }
+int mpx_profile_enable(int on) {
+  conv_profile_enable(on);
+  return MPX_OK;
+}
+int mpx_profile_summary(double* conv_ms, double* conv_flops, long long* conv_launches) {
+  MPX_NOT_NULL(conv_ms);
+  MPX_NOT_NULL(conv_flops);
+  MPX_NOT_NULL(conv_launches);
+  return conv_profile_summary(conv_ms, conv_flops, conv_launches);
+}
 
 // ---- mesh database ----
 struct mpx_meshdb {

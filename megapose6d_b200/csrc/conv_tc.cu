@@ -18,6 +18,7 @@
 //   warps 4-7: epilogue (TMEM -> registers -> global), one TMEM lane quarter each
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue).
 #include <cuda.h>
+#include <vector>
 #include "mpx_common.cuh"
 
 namespace mpx {
@@ -125,6 +126,55 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;   // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
   return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optional per-launch timing (bench.py roofline): CUDA events around every conv launch
+// ---------------------------------------------------------------------------------------------
+struct ProfileSlot {
+  cudaEvent_t e0, e1;
+  double flops;
+};
+static bool g_profile = false;
+static std::vector<ProfileSlot> g_slots;
+static size_t g_slots_used = 0;
+
+static ProfileSlot* profile_begin(cudaStream_t stream) {
+  if (!g_profile) return nullptr;
+  if (g_slots_used == g_slots.size()) {
+    ProfileSlot s;
+    if (cudaEventCreate(&s.e0) != cudaSuccess || cudaEventCreate(&s.e1) != cudaSuccess) return nullptr;
+    s.flops = 0;
+    g_slots.push_back(s);
+  }
+  ProfileSlot* slot = &g_slots[g_slots_used++];
+  cudaEventRecord(slot->e0, stream);
+  return slot;
+}
+static void profile_end(ProfileSlot* slot, cudaStream_t stream, double flops) {
+  if (!slot) return;
+  slot->flops = flops;
+  cudaEventRecord(slot->e1, stream);
+}
+void conv_profile_enable(int on) {
+  g_profile = on != 0;
+  g_slots_used = 0;
+}
+// Synchronises the device; sums the recorded launches since conv_profile_enable(1) and resets.
+int conv_profile_summary(double* total_ms, double* total_flops, long long* launches) {
+  MPX_CHECK_CUDA(cudaDeviceSynchronize());
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < g_slots_used; ++i) {
+    float t = 0.f;
+    MPX_CHECK_CUDA(cudaEventElapsedTime(&t, g_slots[i].e0, g_slots[i].e1));
+    ms += t;
+    fl += g_slots[i].flops;
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *launches = static_cast<long long>(g_slots_used);
+  g_slots_used = 0;
+  return MPX_OK;
 }
 
 struct ConvParams {
@@ -410,8 +460,11 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvP
   int grid = p.m_tiles * p.n_tiles;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
+  ProfileSlot* slot = profile_begin(stream);
   conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(ma, mb, p);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+  profile_end(slot, stream, 2.0 * p.M_total * p.C_out * p.num_k_blocks * kBlockK);
   return MPX_OK;
 }
 

@@ -38,6 +38,7 @@ int image_to_nhwc4(const float* in, int b, int c, int h, int w, float* out, cuda
   image_to_nhwc4_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, b, c, h, w,
                                                                        reinterpret_cast<float4*>(out));
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 
@@ -136,6 +137,7 @@ int roi_align_launch(const float* images, int b, int h, int w, const int* im_idx
   roi_align_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(images), b, h, w, im_idx, boxes, n,
                                              c, oh, ow, out);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 

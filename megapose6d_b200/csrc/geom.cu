@@ -77,6 +77,7 @@ int pose_init_autodepth(const float* points, int n_pts, const int* label_idx, co
   MPX_REQUIRE(n_pts > 0, "pose_init: empty point set");
   pose_init_kernel<<<n, 256, 0, stream>>>(points, n_pts, label_idx, bboxes, K, R, TCO);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 
@@ -119,6 +120,7 @@ int normalize_T(const float* Tin, int n, float* Tout, cudaStream_t stream) {
   if (n == 0) return MPX_OK;
   normalize_T_kernel<<<(n + 127) / 128, 128, 0, stream>>>(Tin, n, Tout);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 
@@ -204,6 +206,7 @@ int crop_geometry(const float* points, int n_pts, const int* label_idx, const fl
   crop_geometry_kernel<<<n, 128, 0, stream>>>(points, n_pts, label_idx, TCO, K, tCR, lamb, im_h, im_w, out_h,
                                               out_w, boxes_rend, boxes_crop, K_crop);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 
@@ -302,6 +305,7 @@ int multiview_cameras(const float* TCO, const float* tCR, int n, const float* h_
   for (int i = 0; i < 3 * n_extra; ++i) offs.v[i] = h_offsets[i];
   multiview_kernel<<<(n + 63) / 64, 64, 0, stream>>>(TCO, tCR, n, offs, n_extra, TCV_O);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 
@@ -345,6 +349,7 @@ int pose_update(const float* TCO, const float* K_crop, const float* pose9, const
   if (n == 0) return MPX_OK;
   pose_update_kernel<<<(n + 127) / 128, 128, 0, stream>>>(TCO, K_crop, pose9, tCR, n, TCO_out);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 
@@ -407,6 +412,7 @@ int topk_per_group(const float* logits, int n_groups, int m, int k, int* idx, cu
   MPX_REQUIRE(m <= 12000, "topk: m=%d too large", m);
   topk_kernel<<<n_groups, 256, m * sizeof(float), stream>>>(logits, m, k, idx);
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 

@@ -82,6 +82,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // ---------------------------------------------------------------------------------------------
 // cross-file declarations (conv_tc.cu, net.cu)
 // ---------------------------------------------------------------------------------------------
+extern long long g_launches;  // kernels launched by this library (host-side counter)
+void conv_profile_enable(int on);
+int conv_profile_summary(double* total_ms, double* total_flops, long long* launches);
+
 struct ConvDesc {
   int n_img, H, W, C_in;  // input NHWC
   int C_out, R, S, stride;

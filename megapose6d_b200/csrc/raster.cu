@@ -402,6 +402,7 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
   raster_kernel<<<grid, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out,
                                                      reinterpret_cast<unsigned long long*>(workspace));
   MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
   return MPX_OK;
 }
 

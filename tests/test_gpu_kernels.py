@@ -1,0 +1,164 @@
+"""GPU parity tests of the individual kernels (called through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from megapose6d_b200 import _abi, lib3d, procedural
+from megapose6d_b200.meshes import MeshDataBase, TriMesh
+from megapose6d_b200.object_dataset import RigidObject, RigidObjectDataset
+from megapose6d_b200.renderer import BatchRenderer
+from oracle import lib3d_ref as L
+from oracle import pipeline_ref
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _poses(n, seed, **kw):
+    return torch.from_numpy(procedural.random_poses(n, seed, **kw)).float()
+
+
+@pytest.fixture(scope="module")
+def scene():
+    ds, images, K = helpers.make_scene(3, seed=1, with_depth=True)
+    db = MeshDataBase.from_object_ds(ds).batched().cuda()
+    return ds, images, K, db, helpers.ref_meshes_from_dataset(ds)
+
+
+def test_pose_init_and_normalize(scene):
+    ds, images, K, db, rm = scene
+    n = 64
+    g = torch.Generator().manual_seed(0)
+    labels = [ds[i % 3].label for i in range(n)]
+    R = L.compute_rotation_matrix_from_ortho6d(torch.randn(n, 6, generator=g))
+    bb = torch.tensor([[384.0, 234, 522, 455]]).repeat(n, 1) + 3 * torch.randn(n, 4, generator=g)
+    Kn = K.repeat(n, 1, 1)
+    want = L.TCO_init_from_boxes_autodepth_with_R(bb, rm.select_points(labels), Kn, R)
+    got = lib3d.TCO_init_from_boxes_autodepth_with_R(bb.cuda(), db.points, db.label_ids(labels, DEV), Kn.cuda(), R.cuda())
+    assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-6)
+    noisy = want + 0.01 * torch.randn(n, 4, 4, generator=g)
+    assert torch.allclose(lib3d.normalize_T(noisy.cuda()).cpu(), L.normalize_T(noisy), rtol=1e-5, atol=1e-6)
+    assert lib3d.normalize_T(torch.empty(0, 4, 4, device=DEV)).shape == (0, 4, 4)
+
+
+def test_crop_geometry(scene):
+    ds, images, K, db, rm = scene
+    n = 48
+    labels = [ds[i % 3].label for i in range(n)]
+    TCO = _poses(n, 3)
+    TCO[5, 2, 3] = 0.05  # partly behind the z_min clamp
+    Kn = K.repeat(n, 1, 1)
+    tCR = TCO[:, :3, 3] + 0.003
+    for npts in (2000, 200):
+        pts = rm.sample_points(labels, npts)
+        uv = L.project_points_robust(pts, Kn, TCO)
+        br = L.boxes_from_uv(uv)
+        bc, _ = L.deepim_crops_robust(torch.zeros(1, 3, 480, 640).expand(n, -1, -1, -1), br, Kn, TCO, tCR, pts, (240, 320), return_crops=False)
+        Kc = L.get_K_crop_resize(Kn, bc, (240, 320))
+        g_br, g_bc, g_Kc = lib3d.crop_geometry(db.point_subset(npts), db.label_ids(labels, DEV), TCO.cuda(), Kn.cuda(),
+                                                tCR.cuda(), (480, 640), (240, 320))
+        assert torch.allclose(g_br.cpu(), br, rtol=1e-5, atol=2e-3)
+        assert torch.allclose(g_bc.cpu(), bc, rtol=1e-5, atol=4e-3)
+        assert torch.allclose(g_Kc.cpu(), Kc, rtol=2e-5, atol=2e-3)
+
+
+def test_multiview_and_pose_update():
+    n = 33
+    TCO = _poses(n, 7)
+    tCR = TCO[:, :3, 3] + torch.tensor([0.002, -0.001, 0.004])
+    want = L.make_TCO_multiview(TCO, tCR, "TCO+front_3views", 4)
+    got = lib3d.make_TCO_multiview(TCO.cuda(), tCR.cuda(), "TCO+front_3views", 4).cpu()
+    assert got.shape == (n, 4, 4, 4)
+    assert torch.allclose(got, want, rtol=1e-5, atol=2e-6)
+    # non-finite pose -> identity fallback (multiview.py:44-46) must not crash
+    bad = TCO.clone()
+    bad[0, 0, 0] = float("nan")
+    lib3d.make_TCO_multiview(bad.cuda(), tCR.cuda(), "TCO+front_3views", 4)
+    torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(1)
+    out9 = torch.randn(n, 9, generator=g)
+    out9[:, 8] = 1.0 + 0.05 * out9[:, 8]
+    Kc = torch.tensor([[900.0, 0, 160], [0, 900, 120], [0, 0, 1]]).repeat(n, 1, 1)
+    assert torch.allclose(lib3d.update_pose(TCO.cuda(), Kc.cuda(), out9.cuda(), tCR.cuda()).cpu(),
+                          L.update_pose(TCO, Kc, out9, tCR), rtol=1e-5, atol=1e-6)
+
+
+def test_topk():
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(5, 576, generator=g)
+    logits[2, 10] = logits[2, 400] = 9.0  # tie -> lower index first
+    idx = lib3d.topk_per_group(logits.cuda(), 5).cpu()
+    want = torch.argsort(logits, dim=1, descending=True, stable=True)[:, :5]
+    assert torch.equal(idx.long(), want)
+    assert idx[2, 0] == 10 and idx[2, 1] == 400
+
+
+def test_roi_align_matches_torchvision(scene):
+    ds, images, K, db, rm = scene
+    boxes = torch.tensor([[100.0, 80, 420, 320], [-40, -30, 200, 150], [500, 380, 700, 530], [300, 200, 300.5, 200.2],
+                          [0, 0, 640, 480], [610.3, 440.7, 655.1, 490.2]])
+    n = boxes.shape[0]
+    nhwc4 = lib3d.image_to_nhwc4(images.cuda())
+    for c in (3, 4):
+        img = images[:, :c]
+        boxes5 = torch.cat((torch.zeros(n, 1), boxes), dim=1)
+        want = L.crop_images(img, boxes5, (240, 320))
+        got = lib3d.crop_images(nhwc4, boxes.cuda(), torch.zeros(n, dtype=torch.int32, device=DEV), c, (240, 320)).cpu()
+        assert torch.allclose(got, want, rtol=1e-5, atol=2e-6), (c, (got - want).abs().max())
+    # scalar restatement on a small case (independent of torchvision)
+    small = images[0, :3, :40, :48].contiguous()
+    got = lib3d.crop_images(lib3d.image_to_nhwc4(small.unsqueeze(0).cuda()), torch.tensor([[-3.0, 2.5, 30.2, 41.0]], device=DEV),
+                            None, 3, (6, 8)).cpu()[0]
+    want = torch.from_numpy(L.roi_align_scalar(small.numpy(), [-3.0, 2.5, 30.2, 41.0], 6, 8))
+    assert torch.allclose(got, want, rtol=1e-5, atol=2e-6)
+
+
+def _render_both(ds, rm, labels, TCO, K, res, depth=True):
+    r = BatchRenderer(object_dataset=ds)
+    out = r.render(labels, TCO.cuda(), K.cuda(), None, res, render_depth=depth, render_normals=True)
+    ref = pipeline_ref.RefRenderer(rm).render(labels, TCO, K, None, res, render_depth=depth, render_normals=True)
+    return out, ref
+
+
+def test_raster_bit_exact_vs_oracle(scene):
+    ds, images, K, db, rm = scene
+    n = 12
+    labels = [ds[i % 3].label for i in range(n)]
+    TCO = _poses(n, 21, z_range=(0.25, 0.9))
+    TCO[3, 2, 3] = 0.12   # very close: large triangles, near-plane drops
+    TCO[4, 0, 3] = 0.35   # mostly outside the frustum
+    Kc = torch.tensor([[1500.0, 0, 160], [0, 1500, 120], [0, 0, 1]]).repeat(n, 1, 1)
+    Kc[5] = torch.tensor([[300.0, 0, 150.3], [0, 310, 118.9], [0, 0, 1]])
+    out, ref = _render_both(ds, rm, labels, TCO, Kc, (240, 320))
+    for name, got, want in (("rgb", out.rgbs, ref["rgbs"]), ("normals", out.normals, ref["normals"]),
+                            ("depth", out.depths, ref["depths"])):
+        got = got.cpu()
+        mism = (got != want).flatten(1).any(dim=0).sum().item() if got.numel() else 0
+        assert torch.equal(got, want), f"{name}: {mism} differing pixel positions, max |d|={(got - want).abs().max()}"
+    assert (out.depths > 0).float().mean() > 0.05  # the views are not empty
+
+
+def test_raster_invalid_pose_and_big_triangles():
+    # a 12-triangle box: every triangle takes the CTA-wide path; plus a non-finite pose -> black view
+    v = np.array([[x, y, z] for x in (-.05, .05) for y in (-.04, .04) for z in (-.03, .03)], dtype=np.float64)
+    f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
+                  [1, 5, 7], [1, 7, 3]], dtype=np.int32)
+    col = np.random.RandomState(0).rand(8, 3).round(2)
+    ds = RigidObjectDataset([RigidObject("box", mesh=TriMesh(v, f, None, col))])
+    rm = helpers.ref_meshes_from_dataset(ds)
+    TCO = _poses(4, 2, z_range=(0.3, 0.5))
+    TCO[2, 1, 1] = float("inf")
+    Kc = torch.tensor([[600.0, 0, 160], [0, 600, 120], [0, 0, 1]]).repeat(4, 1, 1)
+    out, ref = _render_both(ds, rm, ["box"] * 4, TCO, Kc, (240, 320))
+    assert torch.equal(out.rgbs.cpu(), ref["rgbs"]) and torch.equal(out.depths.cpu(), ref["depths"])
+    assert torch.equal(out.normals.cpu(), ref["normals"])
+    assert out.rgbs[2].abs().sum() == 0 and out.depths[2].abs().sum() == 0
+    assert (out.depths[0] > 0).float().mean() > 0.02
+
+
+def test_raster_empty_batch():
+    ds = procedural.make_object_dataset(1)
+    r = BatchRenderer(object_dataset=ds)
+    out = r.render([], torch.empty(0, 4, 4, device=DEV), torch.empty(0, 3, 3, device=DEV), None, (240, 320), render_normals=True)
+    assert out.rgbs.shape == (0, 3, 240, 320)

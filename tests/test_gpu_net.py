@@ -1,0 +1,116 @@
+"""GPU parity of the tcgen05 convolution and of the whole ResNet-34 engine.
+
+Tolerances (stated, floating point):
+  * single conv vs fp32 torch conv on the same bf16-rounded operands: |err| <= 2^-7 * max|ref| + 1e-2
+    (one bf16 rounding of the output; accumulation is fp32 on both sides);
+  * full network vs the bf16-emulated oracle (same quantisation points): |err| <= 3% of max|ref| + 0.03;
+  * full network vs the fp32 oracle: |err| <= 8% of the output's standard deviation + 0.05 (36 layers of
+    bf16 activations; the reference itself was trained under fp16 autocast, train_megapose.py:299).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from megapose6d_b200 import _abi
+from megapose6d_b200.backbone import ResNet34Engine
+from oracle import resnet_ref
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_ref(x, w, bias, stride, pads, relu, residual):
+    xf = F.pad(x.float().permute(0, 3, 1, 2), (pads[1], pads[3], pads[0], pads[2]))
+    y = F.conv2d(xf, w.float().permute(0, 3, 1, 2), bias=bias, stride=stride).permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return torch.relu(y) if relu else y
+
+
+CASES = [
+    # name, n, h, w, cin, cout, r, s, stride, (pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w), relu, residual, block_n, max_ctas
+    ("gemm1x1", 1, 8, 16, 64, 64, 1, 1, 1, (0, 0, 0, 0), False, False, 0, 0),
+    ("c3x3_relu_res", 2, 12, 20, 64, 64, 3, 3, 1, (1, 1, 1, 1), True, True, 0, 0),
+    ("c3x3_s2", 2, 30, 40, 64, 128, 3, 3, 2, (1, 1, 1, 1), True, False, 0, 0),
+    ("odd_s2", 3, 15, 20, 128, 256, 3, 3, 2, (1, 1, 1, 1), True, False, 0, 0),
+    ("odd_1x1_s2", 3, 15, 20, 128, 256, 1, 1, 2, (0, 0, 0, 0), False, False, 0, 0),
+    ("stem4x4", 2, 24, 32, 64, 64, 4, 4, 1, (2, 2, 1, 1), True, False, 0, 0),
+    ("stem4x4_c128", 2, 24, 32, 128, 64, 4, 4, 1, (2, 2, 1, 1), True, False, 0, 0),
+    ("l4_bn256", 3, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 0, 0),
+    ("l4_bn128", 3, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 128, 0),
+    ("l3_bn64", 3, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 0),
+    ("persist_fewctas", 4, 60, 80, 64, 64, 3, 3, 1, (1, 1, 1, 1), True, True, 0, 7),
+    ("ragged_m", 1, 7, 9, 64, 64, 3, 3, 1, (1, 1, 1, 1), False, False, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_vs_torch(case):
+    torch.backends.cudnn.allow_tf32 = False
+    name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, max_ctas = case
+    g = torch.Generator(device="cuda").manual_seed(sum(map(ord, name)) % 1000)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    p = (h + pads[0] + pads[2] - r) // stride + 1
+    q = (w + pads[1] + pads[3] - s) // stride + 1
+    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
+                                          stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
+                                          _abi.ptr(out), block_n, max_ctas, _abi.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
+    err = (out.float() - ref).abs().max().item()
+    assert not torch.isnan(out.float()).any()
+    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-2, err
+
+
+def test_conv_rejects_bad_arguments():
+    x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(64, 48, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(64, device="cuda")
+    out = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+    rc = _abi.lib().mpx_conv2d_bf16(_abi.ptr(x), 1, 8, 8, 48, _abi.ptr(w), _abi.ptr(b), 64, 1, 1, 1, 0, 0, 0, 0, 0, None,
+                                    _abi.ptr(out), 0, 0, _abi.stream_ptr())
+    assert rc != 0 and b"multiple of 64" in _abi.lib().mpx_last_error()
+
+
+def test_maxpool_and_tail():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(3, 30, 40, 64, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.empty(3, 15, 20, 64, device="cuda", dtype=torch.bfloat16)
+    _abi.check(_abi.lib().mpx_maxpool3x3s2_bf16(_abi.ptr(x), 3, 30, 40, 64, _abi.ptr(out), _abi.stream_ptr()))
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), ref)
+    f = torch.randn(5, 80, 512, device="cuda", generator=g).to(torch.bfloat16)
+    W = torch.randn(9, 512, device="cuda", generator=g) * 0.05
+    b = torch.randn(9, device="cuda", generator=g)
+    o = torch.empty(5, 9, device="cuda")
+    _abi.check(_abi.lib().mpx_avgpool_linear(_abi.ptr(f), 5, 80, 512, _abi.ptr(W), _abi.ptr(b), 9, _abi.ptr(o), _abi.stream_ptr()))
+    ref = f.float().mean(dim=1) @ W.t() + b
+    assert torch.allclose(o, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cfg_name", ["coarse", "refiner", "refiner_rgbd"])
+def test_resnet34_engine_vs_oracle(cfg_name):
+    cfg = dict(coarse=helpers.COARSE_CFG, refiner=helpers.REFINER_CFG, refiner_rgbd=helpers.REFINER_RGBD_CFG)[cfg_name]
+    sd = helpers.make_state_dict(cfg, seed=2)
+    c = helpers.n_inputs(cfg)
+    head = resnet_ref.head_name(sd)
+    eng = ResNet34Engine(sd, n_inputs=c, head=head)
+    x = torch.rand(5, c, 240, 320, generator=torch.Generator().manual_seed(4))
+    got = eng(x.cuda()).cpu()
+    emu = resnet_ref.forward_bf16_emulated(sd, x.cuda()).cpu()
+    with torch.no_grad():
+        fp32 = resnet_ref.forward(sd, x)
+    e_emu = (got - emu).abs().max().item()
+    e_fp = (got - fp32).abs().max().item()
+    print(f"[{cfg_name}] max|engine-emulated|={e_emu:.4g} max|engine-fp32|={e_fp:.4g} ref max={fp32.abs().max():.4g} std={fp32.std():.4g}")
+    assert e_emu <= 0.03 * emu.abs().max().item() + 0.03
+    assert e_fp <= 0.08 * fp32.std().item() + 0.05
+    # small odd-sized input as well (stem / pooling edge handling): 64x96
+    x2 = torch.rand(3, c, 64, 96, generator=torch.Generator().manual_seed(5))
+    got2 = eng(x2.cuda()).cpu()
+    emu2 = resnet_ref.forward_bf16_emulated(sd, x2.cuda()).cpu()
+    assert (got2 - emu2).abs().max().item() <= 0.03 * emu2.abs().max().item() + 0.03

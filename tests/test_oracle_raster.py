@@ -1,0 +1,90 @@
+"""Properties of the CPU rasteriser (the contract the CUDA kernel is held to)."""
+import numpy as np
+import torch
+
+from megapose6d_b200 import procedural
+from megapose6d_b200.meshes import TriMesh, compute_vertex_normals
+from megapose6d_b200.object_dataset import RigidObject, RigidObjectDataset
+from oracle import pipeline_ref
+from tests import helpers
+
+
+def _sphere_ds(radius=0.05):
+    m = procedural.bumpy_sphere(n_seg=64, n_lat=33, radius=radius, bump=0.0, squash=(1, 1, 1))
+    return RigidObjectDataset([RigidObject("s", mesh=m)])
+
+
+def test_sphere_depth_silhouette_and_normals():
+    ds = _sphere_ds()
+    rm = helpers.ref_meshes_from_dataset(ds)
+    T = torch.eye(4).unsqueeze(0)
+    T[0, 2, 3] = 0.5
+    K = torch.tensor([[[800.0, 0, 160], [0, 800, 120], [0, 0, 1]]])
+    out = pipeline_ref.RefRenderer(rm, quantize8=False).render(["s"], T, K, None, (240, 320), render_depth=True, render_normals=True)
+    depth = out["depths"][0, 0]
+    mask = depth > 0
+    # silhouette radius of a sphere of radius r at distance d: f * r / sqrt(d^2 - r^2)
+    r_px = 800 * 0.05 / np.sqrt(0.25 - 0.0025)
+    area = np.pi * r_px ** 2
+    assert abs(mask.sum().item() - area) / area < 0.03
+    # the pixel next to the principal point sees the near pole: depth ~ d - r
+    assert abs(depth[119, 159].item() - 0.45) < 2e-4
+    # eye normals: analytic sphere normal at an oblique pixel, encoded with the 32-level wrapped texture
+    def enc(v):
+        u = v * 32 - 0.5
+        k0 = int(np.floor(u))
+        f = u - k0
+        t0, t1 = ((k0 % 32) * 255 // 32) / 255, (((k0 + 1) % 32) * 255 // 32) / 255
+        return t0 + f * (t1 - t0)
+
+    i, j = 105, 185
+    ray = np.array([(j + 0.5 - 160) / 800, (i + 0.5 - 120) / 800, 1.0])
+    ray /= np.linalg.norm(ray)
+    c = np.array([0, 0, 0.5])
+    b = ray @ c
+    t = b - np.sqrt(b * b - (c @ c - 0.05 ** 2))
+    n_cv = (t * ray - c) / 0.05                      # OpenCV camera axes
+    n_panda = np.array([n_cv[0], n_cv[2], -n_cv[1]])  # x right, y forward, z up
+    got = out["normals"][0, :, i, j].numpy()
+    assert abs(depth[i, j].item() - t * ray[2]) < 3e-4
+    assert np.allclose(got, [enc(v) for v in n_panda], atol=0.04), (got, n_panda)
+    # background is exactly zero everywhere
+    assert out["rgbs"][0][:, ~mask].abs().sum() == 0 and out["normals"][0][:, ~mask].abs().sum() == 0
+
+
+def test_invalid_pose_is_black_and_quantisation_levels():
+    ds = _sphere_ds()
+    rm = helpers.ref_meshes_from_dataset(ds)
+    T = torch.eye(4).unsqueeze(0).repeat(2, 1, 1)
+    T[:, 2, 3] = 0.4
+    T[1, 0, 0] = float("nan")
+    K = torch.tensor([[600.0, 0, 160], [0, 600, 120], [0, 0, 1]]).repeat(2, 1, 1)
+    out = pipeline_ref.RefRenderer(rm).render(["s", "s"], T, K, None, (240, 320), render_depth=True, render_normals=True)
+    assert out["rgbs"][1].abs().sum() == 0 and out["depths"][1].abs().sum() == 0 and out["normals"][1].abs().sum() == 0
+    v = out["rgbs"][0] * 255
+    assert torch.allclose(v, v.round(), atol=1e-4)  # k/255 levels (uint8 read-back of the reference)
+
+
+def test_nearest_surface_wins_and_order_independent():
+    # two parallel quads, the nearer one must win regardless of triangle order
+    def quad(z, col):
+        v = np.array([[-.05, -.05, z], [.05, -.05, z], [.05, .05, z], [-.05, .05, z]])
+        return v, np.array([[0, 1, 2], [0, 2, 3]]), np.tile(col, (4, 1))
+
+    v1, f1, c1 = quad(0.0, [1, 0, 0])
+    v2, f2, c2 = quad(0.02, [0, 1, 0])
+    T = torch.eye(4).unsqueeze(0)
+    T[0, 2, 3] = 0.5
+    K = torch.tensor([[[600.0, 0, 160], [0, 600, 120], [0, 0, 1]]])
+    outs = []
+    for order in (0, 1):
+        vs = np.concatenate([v1, v2]) if order == 0 else np.concatenate([v2, v1])
+        fs = np.concatenate([f1, f2 + 4]) if order == 0 else np.concatenate([f2, f1 + 4])
+        cs = np.concatenate([c1, c2]) if order == 0 else np.concatenate([c2, c1])
+        mesh = TriMesh(vs, fs.astype(np.int32), compute_vertex_normals(vs, fs), cs.astype(float))
+        rm = helpers.ref_meshes_from_dataset(RigidObjectDataset([RigidObject("q", mesh=mesh)]))
+        outs.append(pipeline_ref.RefRenderer(rm).render(["q"], T, K, None, (240, 320), render_depth=True, render_normals=True))
+    assert torch.equal(outs[0]["rgbs"], outs[1]["rgbs"]) and torch.equal(outs[0]["depths"], outs[1]["depths"])
+    centre = outs[0]["rgbs"][0, :, 120, 160]
+    assert centre[0] == 1 and centre[1] == 0  # the red quad (z = 0.5) hides the green one (z = 0.52)
+    assert abs(outs[0]["depths"][0, 0, 120, 160].item() - 0.5) < 1e-6

@@ -1,0 +1,76 @@
+"""Generate tests/golden/*.npz by running the REAL reference code (loaded by path, oracle/refload.py).
+
+Only runs where /root/reference exists.  The fixtures pin the oracle restatements on machines without the
+reference (tests/test_oracle_golden.py).  Inputs are seeded; outputs are the reference's own return values.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from megapose6d_b200 import procedural  # noqa: E402
+from oracle import refload, resnet_ref  # noqa: E402
+from tests import helpers  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+
+def lib3d_inputs():
+    g = torch.Generator().manual_seed(123)
+    n = 6
+    TCO = torch.from_numpy(procedural.random_poses(n, 42)).float()
+    K = torch.from_numpy(procedural.example_camera()).float().unsqueeze(0).repeat(n, 1, 1)
+    pts = torch.randn(n, 256, 3, generator=g) * 0.05
+    p9 = torch.randn(n, 9, generator=g)
+    p9[:, 8] = 1 + 0.1 * p9[:, 8]
+    bb = torch.tensor([[384.0, 234, 522, 455]]).repeat(n, 1) + 5 * torch.randn(n, 4, generator=g)
+    Tn = TCO + 0.01 * torch.randn(n, 4, 4, generator=g)
+    return dict(TCO=TCO, K=K, pts=pts, p9=p9, bb=bb, Tn=Tn)
+
+
+def main():
+    ref = refload.load()
+    OUT.mkdir(parents=True, exist_ok=True)
+    i = lib3d_inputs()
+    uv = ref.camera_geometry.project_points_robust(i["pts"], i["K"], i["TCO"])
+    boxes = ref.camera_geometry.boxes_from_uv(uv)
+    Kc = ref.camera_geometry.get_K_crop_resize(i["K"].clone(), boxes, (480, 640), (240, 320))
+    R6 = ref.rotations.compute_rotation_matrix_from_ortho6d(i["p9"][:, :6])
+    tCR = i["TCO"][:, :3, 3] + 0.01
+    upd = ref.cosypose_ops.pose_update_with_reference_point(i["TCO"], Kc, i["p9"][:, 6:], R6, tCR)
+    init = ref.cosypose_ops.TCO_init_from_boxes_autodepth_with_R(i["bb"], i["pts"], i["K"], R6)
+    center = ref.camera_geometry.project_points_robust(torch.zeros(6, 1, 3), i["K"], i["TCO"])
+    dboxes = ref.cropping.deepim_boxes(center, boxes, boxes, lamb=1.4, im_size=(480, 640))
+    np.savez(OUT / "lib3d.npz", **{k: v.numpy() for k, v in i.items()}, uv=uv.numpy(), boxes=boxes.numpy(), K_crop=Kc.numpy(),
+             R6=R6.numpy(), normT=ref.transform_ops.normalize_T(i["Tn"]).numpy(), update=upd.numpy(), init=init.numpy(),
+             deepim_boxes=dboxes.numpy(), sample_ids=np.random.RandomState(0).choice(5002, 2000, replace=False)[:64])
+
+    # crop (roi_align incl. depth masking) on a small synthetic RGB-D frame
+    rng = np.random.RandomState(7)
+    img = torch.from_numpy(rng.rand(1, 4, 60, 80).astype(np.float32))
+    img[:, 3, ::5, ::3] = 0
+    b5 = torch.tensor([[0, 10.3, 5.2, 60.7, 44.1], [0, -6.0, -4.0, 30.0, 20.0], [0, 50.0, 30.0, 95.0, 70.0]])
+    crops = ref.cropping.crop_images(img, b5, output_size=(12, 16), sampling_ratio=4)
+    np.savez(OUT / "crop.npz", img=img.numpy(), boxes5=b5.numpy(), crops=crops.numpy())
+
+    # backbone + head on a small input (coarse 9 channels / refiner 27 channels)
+    for name, cfg in (("coarse", helpers.COARSE_CFG), ("refiner", helpers.REFINER_CFG)):
+        sd = helpers.make_state_dict(cfg, seed=11)
+        c = helpers.n_inputs(cfg)
+        net = ref.torchvision_resnet.resnet34(num_classes=512, n_input_channels=c)
+        net.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")})
+        net.eval()
+        x = torch.rand(2, c, 64, 96, generator=torch.Generator().manual_seed(3))
+        head = resnet_ref.head_name(sd)
+        with torch.no_grad():
+            y = torch.nn.functional.linear(net(x), sd[head + ".weight"], sd[head + ".bias"])
+        np.savez(OUT / f"resnet_{name}.npz", y=y.numpy())
+    print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
+
+
+if __name__ == "__main__":
+    main()
