@@ -204,7 +204,7 @@ class RefPosePredictor:
             outputs[f"iteration={n + 1}"] = dict(TCO_input=TCO_input, TCO_output=TCO_output, TCV_O_input=TCV_O, tCR=tCR,
                                                  K=K, K_crop=K_crop, KV_crop=KV_crop, boxes_rend=boxes_rend,
                                                  boxes_crop=boxes_crop, network_output=out, renders=renders,
-                                                 images_crop=images_crop)
+                                                 images_crop=images_crop, x=x)
             TCO_input = TCO_output
         return outputs
 

@@ -95,6 +95,34 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, sd[h + ".weight"], sd[h + ".bias"])
 
 
+def pooled_features(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """fp32 backbone up to the global average pool: [b, 512] (the input of the folded fc o head map)."""
+    x = F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3)
+    x = F.relu(_bn(x, sd, "backbone.bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, nb in enumerate(LAYERS):
+        for b in range(nb):
+            p = f"backbone.layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            identity = x
+            out = F.relu(_bn(F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1), sd, p + ".bn1"))
+            out = _bn(F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1), sd, p + ".bn2")
+            if (p + ".downsample.0.weight") in sd:
+                identity = _bn(F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride), sd, p + ".downsample.1")
+            x = F.relu(out + identity)
+    return torch.flatten(F.adaptive_avg_pool2d(x, (1, 1)), 1)
+
+
+def bf16_forward_error_bound(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps: float = 0.01) -> torch.Tensor:
+    """Stated tolerance for a bf16-activation network against this fp32 oracle: eps times the absolute-value
+    condition bound of the folded head, sum_i |W_ji| |pooled_i| (+|b_j|), per output [b, out_dim].  bf16
+    activations carry ~2^-8 relative rounding per layer; outputs that are small only through cancellation of
+    large terms (random-weight networks) cannot be expected to agree more tightly than this."""
+    W, b = folded_head(sd)
+    pooled = pooled_features(sd, x).double()
+    return (eps * (pooled.abs() @ W.abs().t() + b.abs())).float()
+
+
 def fold_bn(sd, conv: str, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
     """w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps) (float64)."""
     w = sd[conv + ".weight"].double()

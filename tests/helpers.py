@@ -49,14 +49,46 @@ def n_inputs(cfg):
     return (3 + int(cfg["input_depth"])) + (6 + int(cfg["render_depth"])) * cfg["n_rendered_views"]
 
 
+def _calibration_batch(c, seed, n=4, h=240, w=320):
+    """Smooth images in [0,1]; half of them with the render channels masked to a blob on black, like real inputs."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.rand(n, c, h // 8, w // 8, generator=g)
+    x = torch.nn.functional.interpolate(x, size=(h, w), mode="bilinear", align_corners=False)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+    blob = ((xx ** 2 + yy ** 2) < 0.4).float()
+    x[n // 2:, 3:] *= blob
+    return x.clamp(0, 1)
+
+
+_SD_CACHE = {}
+
+
 def make_state_dict(cfg, seed=0):
+    """Seeded random weights in the checkpoint layout with a conditioned head: the head is made orthogonal to the
+    dominant feature direction of a calibration batch and scaled so that coarse logits are O(1) and pose updates are
+    small (R ~ I, v_z ~ 1) -- random heads otherwise produce |logit| ~ 300 and 20x depth jumps."""
+    key = (tuple(sorted(cfg.items())), seed)
+    if key in _SD_CACHE:
+        return dict(_SD_CACHE[key])
     head = "pose_fc" if cfg["predict_pose_update"] else "views_logits_head"
     dim = 9 if cfg["predict_pose_update"] else cfg["n_rendered_views"]
-    sd = resnet_ref.init_state_dict(n_inputs(cfg), head, dim, seed=seed)
+    c = n_inputs(cfg)
+    sd = resnet_ref.init_state_dict(c, head, dim, seed=seed)
+    with torch.no_grad():
+        pooled = resnet_ref.pooled_features(sd, _calibration_batch(c, seed))
+        feats = torch.nn.functional.linear(pooled, sd["backbone.fc.weight"], sd["backbone.fc.bias"])
+    v = torch.linalg.svd(feats, full_matrices=False)[2][0]
+    W = sd[head + ".weight"]
+    W = W - (W @ v).unsqueeze(1) * v.unsqueeze(0)
+    raw = feats @ W.t()
+    W = W * ((0.02 if cfg["predict_pose_update"] else 1.5) / (raw - raw.mean(0)).std().clamp_min(1e-12))
+    sd[head + ".weight"] = W
+    offset = (feats @ W.t()).mean(0)
     if cfg["predict_pose_update"]:
-        # keep random-weight pose updates small and well-conditioned: R ~ I, vz ~ 1
-        sd["pose_fc.weight"] = sd["pose_fc.weight"] * 0.05
-        sd["pose_fc.bias"] = torch.tensor([1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]) + 0.02 * sd["pose_fc.bias"]
+        sd[head + ".bias"] = torch.tensor([1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]) - offset
+    else:
+        sd[head + ".bias"] = -offset
+    _SD_CACHE[key] = dict(sd)
     return sd
 
 

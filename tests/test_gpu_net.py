@@ -3,9 +3,10 @@
 Tolerances (stated, floating point):
   * single conv vs fp32 torch conv on the same bf16-rounded operands: |err| <= 2^-7 * max|ref| + 1e-2
     (one bf16 rounding of the output; accumulation is fp32 on both sides);
-  * full network vs the bf16-emulated oracle (same quantisation points): |err| <= 3% of max|ref| + 0.03;
-  * full network vs the fp32 oracle: |err| <= 8% of the output's standard deviation + 0.05 (36 layers of
-    bf16 activations; the reference itself was trained under fp16 autocast, train_megapose.py:299).
+  * full network vs the fp32 oracle: |err_j| <= 2^-8 * sum_i |W_ji| |pooled_i| (one bf16 ulp of the folded head's
+    absolute-value condition bound, oracle/resnet_ref.py:bf16_forward_error_bound); vs the bf16-emulated oracle
+    (same quantisation points, only the accumulation order differs): a quarter of that.  The reference itself was
+    trained under fp16 autocast (train_megapose.py:299).
 """
 import pytest
 import torch
@@ -99,18 +100,22 @@ def test_resnet34_engine_vs_oracle(cfg_name):
     c = helpers.n_inputs(cfg)
     head = resnet_ref.head_name(sd)
     eng = ResNet34Engine(sd, n_inputs=c, head=head)
-    x = torch.rand(5, c, 240, 320, generator=torch.Generator().manual_seed(4))
+    x = helpers._calibration_batch(c, 40, n=5)
     got = eng(x.cuda()).cpu()
     emu = resnet_ref.forward_bf16_emulated(sd, x.cuda()).cpu()
     with torch.no_grad():
         fp32 = resnet_ref.forward(sd, x)
-    e_emu = (got - emu).abs().max().item()
-    e_fp = (got - fp32).abs().max().item()
-    print(f"[{cfg_name}] max|engine-emulated|={e_emu:.4g} max|engine-fp32|={e_fp:.4g} ref max={fp32.abs().max():.4g} std={fp32.std():.4g}")
-    assert e_emu <= 0.03 * emu.abs().max().item() + 0.03
-    assert e_fp <= 0.08 * fp32.std().item() + 0.05
-    # small odd-sized input as well (stem / pooling edge handling): 64x96
-    x2 = torch.rand(3, c, 64, 96, generator=torch.Generator().manual_seed(5))
+        bound = resnet_ref.bf16_forward_error_bound(sd, x, eps=2 ** -8)
+    e_emu = (got - emu).abs()
+    e_fp = (got - fp32).abs()
+    print(f"[{cfg_name}] max|engine-emulated|={e_emu.max():.4g} max|engine-fp32|={e_fp.max():.4g} "
+          f"bound(2^-8)={bound.min():.4g}..{bound.max():.4g} out std={fp32.std():.4g}")
+    assert (e_emu <= 0.25 * bound + 1e-3).all()   # same quantisation points: only accumulation order differs
+    assert (e_fp <= bound + 1e-3).all()           # stated bf16-vs-fp32 tolerance (resnet_ref.bf16_forward_error_bound)
+    # small input as well (stem / pooling edge handling): 64x96
+    x2 = helpers._calibration_batch(c, 41, n=3, h=64, w=96)
     got2 = eng(x2.cuda()).cpu()
     emu2 = resnet_ref.forward_bf16_emulated(sd, x2.cuda()).cpu()
-    assert (got2 - emu2).abs().max().item() <= 0.03 * emu2.abs().max().item() + 0.03
+    with torch.no_grad():
+        bound2 = resnet_ref.bf16_forward_error_bound(sd, x2, eps=2 ** -8)
+    assert ((got2 - emu2).abs() <= 0.25 * bound2 + 1e-3).all()
