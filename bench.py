@@ -77,7 +77,8 @@ def cpu_sample_rate(scene, n_coarse: int):
     from tests import helpers
 
     ds, images, K, det_df, bboxes, sds = scene
-    cores = os.cpu_count() or 1
+    # torch's CPU convolutions stop scaling (and regress) past a few dozen threads at these batch sizes
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     meshes = helpers.ref_meshes_from_dataset(ds)
     rr = pipeline_ref.RefRenderer(meshes, n_threads=cores)

@@ -166,6 +166,11 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
                     int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                     void* d_out, int block_n, int max_ctas, void* stream);
 
+/* bring-up probe (tools/gpu_probe_rowshift.py): D[128,64] = A[r0:r0+128, :64] * B[64,64]^T with the UMMA
+ * A descriptor started r0 rows into a TMA-written 128B-swizzled tile; d_a [144,64] bf16, d_b [64,64] bf16 */
+int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out,
+                            void* stream);
+
 /* 3x3/s2/p1 max pool, bf16 NHWC (torchvision_resnet.py:302) */
 int mpx_maxpool3x3s2_bf16(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream);
 

@@ -259,6 +259,13 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
                       static_cast<cudaStream_t>(stream));
 }
 
+int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out, void* stream) {
+  MPX_NOT_NULL(d_a);
+  MPX_NOT_NULL(d_b);
+  MPX_NOT_NULL(d_out);
+  return umma_rowshift_probe(d_a, d_b, r0, base_offset, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int mpx_maxpool3x3s2_bf16(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream) {
   MPX_NOT_NULL(d_x);
   MPX_NOT_NULL(d_out);

@@ -565,4 +565,107 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bring-up probe: D[128,64] = A[r0 : r0+128, 0:64] * B[64,64]^T with the A descriptor started r0 rows
+// into a 128B-swizzled tile that TMA wrote at a 1024-byte aligned address.  Answers whether a
+// row-shifted start address (plus optional base_offset) addresses the swizzled rows correctly, the
+// precondition for reusing one shared-memory halo tile across the filter taps.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_rowshift_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                           int r0, int base_off, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;                 // 144 rows x 128 B
+  uint8_t* smem_b = smem + 144 * 128 + 1024 - (144 * 128) % 1024;  // next 1024-aligned address
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + 64 * 128);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"(64)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], 144 * 128 + 64 * 128);
+    tma_load_2d(smem_a, &map_a, &bars[0], 0, 0);
+    tma_load_2d(smem_b, &map_b, &bars[0], 0, 0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(64 >> 3) << 17) |
+                               (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint64_t da = make_sw128_desc(smem_u32(smem_a) + static_cast<uint32_t>(r0) * 128u) |
+                        (static_cast<uint64_t>(base_off & 7) << 49);
+    const uint64_t db = make_sw128_desc(smem_u32(smem_b));
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      tc_mma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                  k > 0 ? 1u : 0u);
+    tc_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+#pragma unroll 1
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t v[32];
+    tc_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c), v);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[row * 64 + c + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+  }
+}
+
+// a: [144, 64] bf16 row-major, b: [64, 64] bf16 row-major (K contiguous), out: [128, 64] fp32
+int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, float* out, cudaStream_t stream) {
+  MPX_REQUIRE(r0 >= 0 && r0 <= 16, "probe: r0 out of range");
+  int rc = load_driver_entry_points();
+  if (rc != MPX_OK) return rc;
+  CUtensorMap map_a, map_b;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {64, 144};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 144};
+    CUresult r = g_encode_tiled(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPX_REQUIRE(r == CUDA_SUCCESS, "probe: encode A failed (%d)", static_cast<int>(r));
+  }
+  {
+    cuuint64_t dims[2] = {64, 64};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 64};
+    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPX_REQUIRE(r == CUDA_SUCCESS, "probe: encode B failed (%d)", static_cast<int>(r));
+  }
+  const int smem_bytes = 1024 + 144 * 128 + 1024 + 64 * 128 + 64;
+  MPX_CHECK_CUDA(cudaFuncSetAttribute(umma_rowshift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_bytes));
+  umma_rowshift_probe_kernel<<<1, 128, smem_bytes, stream>>>(map_a, map_b, r0, base_off, out);
+  MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+  return MPX_OK;
+}
+
 }  // namespace mpx

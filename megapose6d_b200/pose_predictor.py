@@ -127,6 +127,7 @@ class PosePredictor(nn.Module):
         self.keep_images = False  # materialise fp32 images_crop / renders in the outputs
         self.max_batch = 1152     # hypotheses per fused launch (memory: ~9 MB each at 240x320)
         self._nhwc4_cache: Optional[Tuple[Any, torch.Tensor]] = None
+        self._x_cache: Dict[Tuple[int, int, int], torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -252,7 +253,13 @@ class PosePredictor(nn.Module):
             KV_crop = K_crop.unsqueeze(1)
         depth_z = tCR[:, 2].contiguous() if (self.input_depth or self.render_depth) else None
 
-        x = self.backbone.alloc_input(n, h, w)
+        # persistent network input per batch size: the pad channels are zeroed once, every real channel of every
+        # pixel is rewritten by the crop and raster kernels on each call (background pixels included)
+        x = self._x_cache.get((n, h, w))
+        if x is None:
+            if len(self._x_cache) >= 8:
+                self._x_cache.clear()
+            x = self._x_cache[(n, h, w)] = self.backbone.alloc_input(n, h, w)
         from . import _abi  # local import keeps the module import light
 
         nhwc4 = self._nhwc4(images)
