@@ -87,6 +87,16 @@ int mpx_raster_render_fused(const mpx_meshdb* db, const int32_t* d_label_idx, co
                             const float* d_depth_norm_z, void* d_workspace, size_t workspace_bytes,
                             void* stream);
 
+/* single-view samples (coarse / scoring model, models/pose_rigid.py:634-708): crop + render in one pass.
+ * Sample i renders (d_label_idx[i], d_TCO[i], d_K[i] = its crop intrinsics) and crops the observation
+ * d_img_nhwc4[d_im_idx[i]] with d_boxes_crop[i] (roi_align as in mpx_roi_align); each pixel's complete channel
+ * vector [crop rgb(d) | render rgb, normals(, depth) | zero pad] is stored once.  c_in = 3|4, ch_per_view = 6|7. */
+int mpx_render_crop_fused(const mpx_meshdb* db, const int32_t* d_label_idx, const float* d_TCO,
+                          const float* d_K, int n, int h, int w, uint32_t flags, const float* d_img_nhwc4,
+                          int b, int im_h, int im_w, const int32_t* d_im_idx, const float* d_boxes_crop,
+                          int c_in, void* d_x, int c_pad, int ch_per_view, const float* d_depth_norm_z,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- hypothesis geometry -----------------------------------------------------------------------
  * mpx_pose_init_autodepth: TCO_init_from_boxes_autodepth_with_R (lib3d/cosypose_ops.py:169-218).
  *   d_points [n_labels, n_pts, 3]; d_label_idx, d_bboxes [n,4], d_K [n,9], d_R [n,9] -> d_TCO [n,16]

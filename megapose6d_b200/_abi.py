@@ -34,6 +34,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_raster_render.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_uint32, vp, vp, vp, vp, c_size_t, vp]
     lib.mpx_raster_render_fused.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_uint32, vp, c_int,
                                             c_int, c_int, vp, vp, c_size_t, vp]
+    lib.mpx_render_crop_fused.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_uint32, vp, c_int, c_int, c_int, vp,
+                                          vp, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]
+    lib.mpx_debug_umma_rowshift.argtypes = [vp, vp, c_int, c_int, vp, vp]
     lib.mpx_pose_init_autodepth.argtypes = [vp, c_int, vp, vp, vp, vp, c_int, vp, vp]
     lib.mpx_normalize_T.argtypes = [vp, c_int, vp, vp]
     lib.mpx_crop_geometry.argtypes = [vp, c_int, vp, vp, vp, vp, c_int, c_float, c_int, c_int, c_int, c_int,
@@ -67,7 +70,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 EXPORTS = [
     "mpx_abi_version", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
     "mpx_meshdb_create", "mpx_meshdb_destroy",
-    "mpx_raster_workspace_bytes", "mpx_raster_render", "mpx_raster_render_fused",
+    "mpx_raster_workspace_bytes", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",
     "mpx_net_input_bytes", "mpx_conv2d_bf16", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2_bf16", "mpx_avgpool_linear",

@@ -117,6 +117,42 @@ int mpx_raster_render_fused(const mpx_meshdb* db, const int32_t* d_label_idx, co
                        static_cast<cudaStream_t>(stream));
 }
 
+int mpx_render_crop_fused(const mpx_meshdb* db, const int32_t* d_label_idx, const float* d_TCO, const float* d_K,
+                          int n, int h, int w, uint32_t flags, const float* d_img_nhwc4, int b, int im_h, int im_w,
+                          const int32_t* d_im_idx, const float* d_boxes_crop, int c_in, void* d_x, int c_pad,
+                          int ch_per_view, const float* d_depth_norm_z, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+  MPX_NOT_NULL(db);
+  MPX_NOT_NULL(d_x);
+  MPX_REQUIRE(n >= 0, "mpx_render_crop_fused: n < 0");
+  if (n > 0) {
+    MPX_NOT_NULL(d_label_idx);
+    MPX_NOT_NULL(d_TCO);
+    MPX_NOT_NULL(d_K);
+    MPX_NOT_NULL(d_img_nhwc4);
+    MPX_NOT_NULL(d_boxes_crop);
+    MPX_NOT_NULL(d_workspace);
+  }
+  MPX_REQUIRE(b > 0 && im_h > 0 && im_w > 0, "mpx_render_crop_fused: empty observation");
+  RasterOut out;
+  memset(&out, 0, sizeof(out));
+  out.x = reinterpret_cast<__nv_bfloat16*>(d_x);
+  out.c_pad = c_pad;
+  out.ch_offset = c_in;
+  out.ch_per_view = ch_per_view;
+  out.views_per_sample = 1;
+  out.depth_norm_z = d_depth_norm_z;
+  out.crop_images = reinterpret_cast<const float4*>(d_img_nhwc4);
+  out.crop_b = b;
+  out.crop_h = im_h;
+  out.crop_w = im_w;
+  out.crop_c = c_in;
+  out.crop_im_idx = d_im_idx;
+  out.crop_boxes = d_boxes_crop;
+  return raster_launch(db->db, d_label_idx, d_TCO, d_K, n, h, w, flags, out, d_workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
 // ---- geometry ----
 int mpx_pose_init_autodepth(const float* d_points, int n_pts, const int32_t* d_label_idx, const float* d_bboxes,
                             const float* d_K, const float* d_R, int n, float* d_TCO, void* stream) {

@@ -6,8 +6,9 @@
 // The reference first materialises observation.images[batch_im_ids] (one full-resolution copy per
 // hypothesis, inference/pose_estimator.py:389); here the crop kernel indexes the frame through
 // d_im_idx instead, and the frame is packed once to NHWC4 so that each bilinear tap is one 16-byte
-// load that hits L2.
-#include "mpx_common.cuh"
+// load that hits L2.  For single-view samples (coarse / scoring) the crop is computed inside the
+// rasteriser's resolve pass instead (raster.cu) so that whole pixel vectors are written once.
+#include "crop_device.cuh"
 
 namespace mpx {
 
@@ -42,47 +43,12 @@ int image_to_nhwc4(const float* in, int b, int c, int h, int w, float* out, cuda
   return MPX_OK;
 }
 
-// one bilinear sample, torchvision semantics; returns rgb(d) and the depth validity
-__device__ __forceinline__ void bilinear4(const float4* __restrict__ img, int h, int w, float y, float x,
-                                          float4& acc, float& vacc) {
-  if (y < -1.0f || y > static_cast<float>(h) || x < -1.0f || x > static_cast<float>(w)) return;
-  if (y <= 0.f) y = 0.f;
-  if (x <= 0.f) x = 0.f;
-  int y_low = static_cast<int>(y), x_low = static_cast<int>(x);
-  int y_high, x_high;
-  if (y_low >= h - 1) {
-    y_high = y_low = h - 1;
-    y = static_cast<float>(y_low);
-  } else {
-    y_high = y_low + 1;
-  }
-  if (x_low >= w - 1) {
-    x_high = x_low = w - 1;
-    x = static_cast<float>(x_low);
-  } else {
-    x_high = x_low + 1;
-  }
-  const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
-  const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-  const float4 v1 = __ldg(img + y_low * w + x_low), v2 = __ldg(img + y_low * w + x_high);
-  const float4 v3 = __ldg(img + y_high * w + x_low), v4 = __ldg(img + y_high * w + x_high);
-  acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-  acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-  acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-  acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
-  vacc += w1 * (v1.w > 0.f ? 1.f : 0.f) + w2 * (v2.w > 0.f ? 1.f : 0.f) + w3 * (v3.w > 0.f ? 1.f : 0.f) +
-          w4 * (v4.w > 0.f ? 1.f : 0.f);
-}
-
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const float4* __restrict__ images, int b, int h, int w, const int* __restrict__ im_idx,
                  const float* __restrict__ boxes, int n, int c, int oh, int ow, CropOut out) {
   const int roi = blockIdx.x;
   const int npix = oh * ow;
-  const float* bx = boxes + 4 * roi;
-  const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
-  const float roi_w = fmaxf(x2 - x1, 1.f), roi_h = fmaxf(y2 - y1, 1.f);
-  const float bin_w = roi_w / static_cast<float>(ow), bin_h = roi_h / static_cast<float>(oh);
+  const RoiParams rp = make_roi(boxes + 4 * roi, oh, ow);
   int im = im_idx ? im_idx[roi] : roi;
   const bool im_ok = im >= 0 && im < b;
   const float4* img = images + static_cast<size_t>(im_ok ? im : 0) * h * w;
@@ -90,18 +56,7 @@ roi_align_kernel(const float4* __restrict__ images, int b, int h, int w, const i
     const int ph = pix / ow, pw = pix - ph * ow;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float vacc = 0.f;
-    if (im_ok) {
-#pragma unroll
-      for (int iy = 0; iy < 4; ++iy) {
-        const float y = y1 + ph * bin_h + (iy + 0.5f) * bin_h / 4.f;
-#pragma unroll
-        for (int ix = 0; ix < 4; ++ix) {
-          const float x = x1 + pw * bin_w + (ix + 0.5f) * bin_w / 4.f;
-          bilinear4(img, h, w, y, x, acc, vacc);
-        }
-      }
-    }
-    acc.x /= 16.f; acc.y /= 16.f; acc.z /= 16.f; acc.w /= 16.f; vacc /= 16.f;
+    if (im_ok) roi_align_pixel(img, h, w, rp, ph, pw, acc, vacc);
     if (c == 4 && vacc < 0.99f) acc.w = 0.f;
     if (out.nchw) {
       float* o = out.nchw + static_cast<size_t>(roi) * c * npix + pix;

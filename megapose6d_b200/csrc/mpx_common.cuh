@@ -128,6 +128,12 @@ struct RasterOut {
   __nv_bfloat16* x;  // fused network input (bf16 s2d NHWC), may be null
   int c_pad, ch_offset, ch_per_view, views_per_sample;
   const float* depth_norm_z;
+  // optional: observation crop computed in the resolve pass (views_per_sample == 1), so that each
+  // pixel's whole channel vector (crop | render | zero pad) is written with 16-byte stores
+  const float4* crop_images;  // [crop_b, crop_h, crop_w] NHWC4, nullptr = no fused crop
+  int crop_b, crop_h, crop_w, crop_c;
+  const int* crop_im_idx;     // [n_samples] or nullptr
+  const float* crop_boxes;    // [n_samples, 4]
 };
 int meshdb_create(int n_meshes, const float* verts, const float* normals, const float* colors,
                   const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,

@@ -10,33 +10,47 @@
 //   * pinhole projection u = fx*X/Z + cx, v = fy*Y/Z + cy; pixel (i, j) is sampled at
 //     (u, v) = (j + 0.5, i + 0.5);
 //   * vertices snapped to 1/256 pixel; coverage by exact 64-bit integer edge functions, edges
-//     inclusive, two-sided; nearest depth wins, ties go to the lower triangle index;
-//   * triangles with a vertex in front of the near plane (z < 0.1) are dropped; fragments outside
-//     [0.1, 10] m are rejected;
-//   * 1/z is interpolated linearly in screen space, attributes perspective-correctly;
+//     inclusive, two-sided; the fragment with the largest interpolated 1/z wins, ties go to the lower
+//     triangle index;
+//   * triangles with a vertex in front of the near plane (z < 0.1) are dropped; fragments with 1/z
+//     outside [1/10, 1/0.1] are rejected;
+//   * barycentrics l_k = w_k * (1/area) from the integer edge values, 1/z interpolated linearly in
+//     screen space, attributes perspective-correctly (b_k = l_k/z_k * z);
 //   * rgb = interpolated vertex albedo (ambient light 1.0); normals = frac-wrapped eye normal
-//     through the 32-level texture; depth = z in metres, 0 for background or d > 0.999;
-//   * all float arithmetic is written with explicit round-to-nearest intrinsics in a fixed order
-//     so that the CPU restatement reproduces it exactly.
+//     through the 32-level texture; depth = z = 1/(1/z) in metres, 0 for background or d > 0.999;
+//   * every float operation is a single correctly-rounded IEEE operation in a fixed order
+//     (reciprocals are 1/x, quantisation levels come from a k/255 table) so that the CPU restatement
+//     reproduces it exactly.
 //
 // Per view: (A) clear a 64-bit visibility buffer (global scratch, L2 resident), (B) transform and
-// snap the vertices once, (C) one thread per triangle walks its bounding box and atomicMin's
-// (depth, triangle) keys -- large triangles are queued and rasterised by the whole CTA,
-// (D) resolve: one thread per pixel re-derives the winning triangle's barycentrics, shades and
-// writes the outputs.
-#include "mpx_common.cuh"
+// snap the vertices once, (C) one thread per triangle walks its bounding box with incremental edge
+// functions and atomicMin's (~1/z bits, triangle) keys -- large triangles are queued and rasterised by
+// the whole CTA, (D) resolve: one thread per pixel re-derives the winning triangle's barycentrics,
+// shades and writes the outputs.  In the fused single-view mode the resolve pass also computes the
+// observation crop of its pixel (roi_align) and stores the complete channel vector of the network
+// input with 16-byte stores.
+#include "crop_device.cuh"
 
 namespace mpx {
 
 constexpr float kNear = 0.1f;
-constexpr float kFar = 10.0f;
+constexpr float kIzMax = 10.0f;  // 1 / near
+constexpr float kIzMin = 0.1f;   // 1 / far
 constexpr int kSubBits = 8;
-constexpr int kSub = 1 << kSubBits;       // 256 sub-pixel steps
+constexpr int kSub = 1 << kSubBits;  // 256 sub-pixel steps
 constexpr int kHalf = kSub / 2;
-constexpr float kClampUV = 1048576.0f;    // 2^20 pixels
+constexpr float kClampUV = 1048576.0f;  // 2^20 pixels
 constexpr int kRasterThreads = 512;
 constexpr int kBigQueue = 2048;
-constexpr long long kBigArea = 1024;      // pixels; larger bounding boxes go to the CTA-wide path
+constexpr long long kBigArea = 1024;  // pixels; larger bounding boxes go to the CTA-wide path
+
+// k / 255 (uint8 read-back levels of the reference) and the 32 texel values uint8(k*255/32) / 255
+struct QuantTables {
+  float q8[256];
+  float tex[32];
+};
+__constant__ QuantTables c_tables;
+static bool g_tables_ready = false;
 
 __device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }
 
@@ -57,24 +71,23 @@ __device__ __forceinline__ float normal_texture(float s) {
   const float u = __fmaf_rn(s, 32.0f, -0.5f);
   const float fl = floorf(u);
   const float f = __fsub_rn(u, fl);
-  int k0 = static_cast<int>(fl) & 31;
-  int k1 = (k0 + 1) & 31;
-  // texel value: uint8(k * 255 / 32) / 255
-  const float t0 = __fdiv_rn(static_cast<float>((k0 * 255) >> 5), 255.0f);
-  const float t1 = __fdiv_rn(static_cast<float>((k1 * 255) >> 5), 255.0f);
+  const int k0 = static_cast<int>(fl) & 31;
+  const int k1 = (k0 + 1) & 31;
+  const float t0 = c_tables.tex[k0];
+  const float t1 = c_tables.tex[k1];
   return __fmaf_rn(f, __fsub_rn(t1, t0), t0);
 }
 
 __device__ __forceinline__ float quant8(float v, bool on) {
   v = fminf(fmaxf(v, 0.0f), 1.0f);
   if (!on) return v;
-  return __fdiv_rn(rintf(__fmul_rn(v, 255.0f)), 255.0f);
+  return c_tables.q8[__float2int_rn(__fmul_rn(v, 255.0f))];
 }
 
 struct TriSetup {
   int ax, ay, bx, by, cx, cy;
   float iza, izb, izc;
-  long long area2;
+  float inv_area;
   bool flip;
   bool ok;
 };
@@ -86,28 +99,21 @@ __device__ __forceinline__ TriSetup load_tri(const int4* __restrict__ vtx, const
   const int4 a = __ldcg(vtx + ia), b = __ldcg(vtx + ib), c = __ldcg(vtx + ic);
   t.ax = a.x; t.ay = a.y; t.bx = b.x; t.by = b.y; t.cx = c.x; t.cy = c.y;
   t.iza = __int_as_float(a.z); t.izb = __int_as_float(b.z); t.izc = __int_as_float(c.z);
-  t.area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
-  t.flip = t.area2 < 0;
-  if (t.flip) t.area2 = -t.area2;
-  t.ok = (t.area2 != 0) && !(a.w | b.w | c.w);
+  long long area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
+  t.flip = area2 < 0;
+  if (t.flip) area2 = -area2;
+  t.ok = (area2 != 0) && !(a.w | b.w | c.w);
+  t.inv_area = t.ok ? __frcp_rn(static_cast<float>(area2)) : 0.f;
   return t;
 }
 
-// barycentrics + depth of pixel centre (px, py) (fixed point); returns false if outside
-__device__ __forceinline__ bool tri_sample(const TriSetup& t, int px, int py, float& l0, float& l1,
-                                           float& l2, float& iz, float& z) {
-  long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
-  long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
-  long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
-  if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
-  if ((w0 | w1 | w2) < 0) return false;
-  const float inv_area = static_cast<float>(t.area2);
-  l0 = __fdiv_rn(static_cast<float>(w0), inv_area);
-  l1 = __fdiv_rn(static_cast<float>(w1), inv_area);
-  l2 = __fdiv_rn(static_cast<float>(w2), inv_area);
-  iz = __fmaf_rn(l0, t.iza, __fmaf_rn(l1, t.izb, __fmul_rn(l2, t.izc)));
-  z = __fdiv_rn(1.0f, iz);
-  return (z >= kNear) && (z <= kFar);
+// interpolated 1/z of a covered sample from its (orientation-corrected) edge values
+__device__ __forceinline__ float sample_iz(const TriSetup& t, long long w0, long long w1, long long w2, float& l0,
+                                           float& l1, float& l2) {
+  l0 = __fmul_rn(static_cast<float>(w0), t.inv_area);
+  l1 = __fmul_rn(static_cast<float>(w1), t.inv_area);
+  l2 = __fmul_rn(static_cast<float>(w2), t.inv_area);
+  return __fmaf_rn(l0, t.iza, __fmaf_rn(l1, t.izb, __fmul_rn(l2, t.izc)));
 }
 
 __device__ __forceinline__ void raster_bbox(const TriSetup& t, int h, int w, int& j0, int& j1, int& i0,
@@ -115,16 +121,27 @@ __device__ __forceinline__ void raster_bbox(const TriSetup& t, int h, int w, int
   const int minx = min(t.ax, min(t.bx, t.cx)), maxx = max(t.ax, max(t.bx, t.cx));
   const int miny = min(t.ay, min(t.by, t.cy)), maxy = max(t.ay, max(t.by, t.cy));
   // pixel j has its centre at j*256 + 128
-  j0 = max(0, -floor_div(-(minx - kHalf), kSub));          // ceil((minx-128)/256)
+  j0 = max(0, -floor_div(-(minx - kHalf), kSub));  // ceil((minx-128)/256)
   j1 = min(w - 1, floor_div(maxx - kHalf, kSub));
   i0 = max(0, -floor_div(-(miny - kHalf), kSub));
   i1 = min(h - 1, floor_div(maxy - kHalf, kSub));
 }
 
+__device__ __forceinline__ void emit_fragment(const TriSetup& t, long long w0, long long w1, long long w2, int tri,
+                                              unsigned long long* __restrict__ cell) {
+  if ((w0 | w1 | w2) < 0) return;
+  float l0, l1, l2;
+  const float iz = sample_iz(t, w0, w1, w2, l0, l1, l2);
+  if (!(iz >= kIzMin && iz <= kIzMax)) return;
+  const unsigned long long key =
+      (static_cast<unsigned long long>(~__float_as_uint(iz)) << 32) | static_cast<unsigned>(tri);
+  if (key < __ldcg(cell)) atomicMin(cell, key);
+}
+
 __global__ void __launch_bounds__(kRasterThreads, 2)
 raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
               const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out,
-              unsigned long long* __restrict__ vis_all) {
+              unsigned long long* __restrict__ vis_all, int strips) {
   __shared__ float sR[12];
   __shared__ float sK[4];
   __shared__ int s_valid;
@@ -137,8 +154,14 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
   const bool q8 = (flags & 1u) != 0;
   const bool gl_axes = (flags & 2u) != 0;
 
-  for (int view = blockIdx.x; view < n_views; view += gridDim.x) {
-    __syncthreads();  // previous view fully resolved before scratch is reused
+  // work item = (view, horizontal strip of rows); strips > 1 only when there are fewer views than CTA slots
+  // (refiner: a handful of views would otherwise run on a handful of SMs)
+  const int rows_per_strip = (h + strips - 1) / strips;
+  for (int item = blockIdx.x; item < n_views * strips; item += gridDim.x) {
+    const int view = item / strips;
+    const int row_lo = (item - view * strips) * rows_per_strip;
+    const int row_hi = min(h, row_lo + rows_per_strip) - 1;  // inclusive
+    __syncthreads();  // previous item fully resolved before scratch is reused
     if (threadIdx.x == 0) {
       bool ok = true;
       const float* T = TCO + 16 * view;
@@ -163,7 +186,7 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     const int* faces = db.faces + 3 * f_off;
 
     // (A) clear visibility, (B) transform + snap vertices
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) vis[i] = ~0ull;
+    for (int i = row_lo * w + threadIdx.x; i < (row_hi + 1) * w; i += blockDim.x) vis[i] = ~0ull;
     const float fx = sK[0], cx = sK[1], fy = sK[2], cy = sK[3];
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
       const float* p = db.verts + 3 * (v_off + i);
@@ -174,7 +197,7 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
       int4 o;
       o.w = !(zc >= kNear);
       const float zs = o.w ? 1.0f : zc;
-      const float iz = __fdiv_rn(1.0f, zs);
+      const float iz = __frcp_rn(zs);
       float u = __fmaf_rn(fx, __fmul_rn(xc, iz), cx);
       float v = __fmaf_rn(fy, __fmul_rn(yc, iz), cy);
       u = fminf(fmaxf(u, -kClampUV), kClampUV);
@@ -194,6 +217,8 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
       if (!t.ok) continue;
       int j0, j1, i0, i1;
       raster_bbox(t, h, w, j0, j1, i0, i1);
+      i0 = max(i0, row_lo);
+      i1 = min(i1, row_hi);
       if (j0 > j1 || i0 > i1) continue;
       const long long area = static_cast<long long>(j1 - j0 + 1) * (i1 - i0 + 1);
       if (area > kBigArea) {
@@ -203,15 +228,22 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
           continue;
         }
       }
+      // incremental edge functions (exact integers): d/dx = -(by-ay)*256, d/dy = (bx-ax)*256
+      const int px0 = j0 * kSub + kHalf, py0 = i0 * kSub + kHalf;
+      const long long sgn = t.flip ? -1 : 1;
+      long long r0 = sgn * edge_fn(t.bx, t.by, t.cx, t.cy, px0, py0);
+      long long r1 = sgn * edge_fn(t.cx, t.cy, t.ax, t.ay, px0, py0);
+      long long r2 = sgn * edge_fn(t.ax, t.ay, t.bx, t.by, px0, py0);
+      const long long dx0 = -sgn * static_cast<long long>(t.cy - t.by) * kSub, dy0 = sgn * static_cast<long long>(t.cx - t.bx) * kSub;
+      const long long dx1 = -sgn * static_cast<long long>(t.ay - t.cy) * kSub, dy1 = sgn * static_cast<long long>(t.ax - t.cx) * kSub;
+      const long long dx2 = -sgn * static_cast<long long>(t.by - t.ay) * kSub, dy2 = sgn * static_cast<long long>(t.bx - t.ax) * kSub;
       for (int i = i0; i <= i1; ++i) {
-        const int py = i * kSub + kHalf;
+        long long w0 = r0, w1 = r1, w2 = r2;
         for (int j = j0; j <= j1; ++j) {
-          float l0, l1, l2, iz, z;
-          if (!tri_sample(t, j * kSub + kHalf, py, l0, l1, l2, iz, z)) continue;
-          const unsigned long long key =
-              (static_cast<unsigned long long>(__float_as_uint(z)) << 32) | static_cast<unsigned>(tri);
-          atomicMin(vis + i * w + j, key);
+          emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
+          w0 += dx0; w1 += dx1; w2 += dx2;
         }
+        r0 += dy0; r1 += dy1; r2 += dy2;
       }
     }
     __syncthreads();
@@ -222,15 +254,18 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
         const TriSetup t = load_tri(vtx, faces, tri);
         int j0, j1, i0, i1;
         raster_bbox(t, h, w, j0, j1, i0, i1);
+        i0 = max(i0, row_lo);
+        i1 = min(i1, row_hi);
         const int bw = j1 - j0 + 1;
         const int cnt = bw * (i1 - i0 + 1);
         for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
           const int i = i0 + k / bw, j = j0 + k % bw;
-          float l0, l1, l2, iz, z;
-          if (!tri_sample(t, j * kSub + kHalf, i * kSub + kHalf, l0, l1, l2, iz, z)) continue;
-          const unsigned long long key =
-              (static_cast<unsigned long long>(__float_as_uint(z)) << 32) | static_cast<unsigned>(tri);
-          atomicMin(vis + i * w + j, key);
+          const int px = j * kSub + kHalf, py = i * kSub + kHalf;
+          long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+          long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+          long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+          if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+          emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
         }
       }
     }
@@ -245,18 +280,32 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     const float dep_b = 1.01010101f;
     const int sample = out.x ? view / out.views_per_sample : 0;
     const int vslot = out.x ? view % out.views_per_sample : 0;
-    for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+    const bool fuse_crop = out.x != nullptr && out.crop_images != nullptr;
+    RoiParams roi;
+    const float4* crop_img = nullptr;
+    if (fuse_crop) {
+      roi = make_roi(out.crop_boxes + 4 * sample, h, w);
+      const int im = out.crop_im_idx ? out.crop_im_idx[sample] : sample;
+      if (im >= 0 && im < out.crop_b) crop_img = out.crop_images + static_cast<size_t>(im) * out.crop_h * out.crop_w;
+    }
+    for (int pix = row_lo * w + threadIdx.x; pix < (row_hi + 1) * w; pix += blockDim.x) {
       const int i = pix / w, j = pix - i * w;
       const unsigned long long key = __ldcg(vis + pix);
       float r = 0.f, g = 0.f, b = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dep = 0.f;
       if (key != ~0ull) {
         const int tri = static_cast<int>(key & 0xffffffffu);
         const TriSetup t = load_tri(vtx, faces, tri);
-        float l0, l1, l2, iz, z;
-        tri_sample(t, j * kSub + kHalf, i * kSub + kHalf, l0, l1, l2, iz, z);
-        const float b0 = __fdiv_rn(__fmul_rn(l0, t.iza), iz);
-        const float b1 = __fdiv_rn(__fmul_rn(l1, t.izb), iz);
-        const float b2 = __fdiv_rn(__fmul_rn(l2, t.izc), iz);
+        const int px = j * kSub + kHalf, py = i * kSub + kHalf;
+        long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+        long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+        long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+        if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+        float l0, l1, l2;
+        const float iz = sample_iz(t, w0, w1, w2, l0, l1, l2);
+        const float z = __frcp_rn(iz);
+        const float b0 = __fmul_rn(__fmul_rn(l0, t.iza), z);
+        const float b1 = __fmul_rn(__fmul_rn(l1, t.izb), z);
+        const float b2 = __fmul_rn(__fmul_rn(l2, t.izc), z);
         const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1),
                   ic = __ldg(faces + 3 * tri + 2);
         float col[3], nrm[3];
@@ -276,9 +325,10 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
         float ez = __fmaf_rn(sR[8], nrm[0], __fmaf_rn(sR[9], nrm[1], __fmul_rn(sR[10], nrm[2])));
         const float nn = __fsqrt_rn(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, __fmul_rn(ez, ez))));
         if (nn > 0.f) {
-          ex = __fdiv_rn(ex, nn);
-          ey = __fdiv_rn(ey, nn);
-          ez = __fdiv_rn(ez, nn);
+          const float inv = __frcp_rn(nn);
+          ex = __fmul_rn(ex, inv);
+          ey = __fmul_rn(ey, inv);
+          ez = __fmul_rn(ez, inv);
         }
         // Panda camera axes (x right, y forward, z up) or GL axes (x right, y up, z backward)
         const float px_ = ex;
@@ -301,22 +351,49 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
       if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
       if (out.x) {
         const int hs = h >> 1, ws = w >> 1;
-        __nv_bfloat16* o = out.x +
-                           ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
-                           ((i & 1) * 2 + (j & 1)) * out.c_pad + out.ch_offset + vslot * out.ch_per_view;
-        o[0] = __float2bfloat16_rn(r);
-        o[1] = __float2bfloat16_rn(g);
-        o[2] = __float2bfloat16_rn(b);
-        o[3] = __float2bfloat16_rn(n0);
-        o[4] = __float2bfloat16_rn(n1);
-        o[5] = __float2bfloat16_rn(n2);
-        if (out.ch_per_view == 7) {
-          float dn = dep;
-          if (out.depth_norm_z) {
-            // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
-            dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
+        __nv_bfloat16* base = out.x +
+                              ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
+                              ((i & 1) * 2 + (j & 1)) * out.c_pad;
+        float dn = dep;
+        if (out.ch_per_view == 7 && out.depth_norm_z) {
+          // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
+          dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
+        }
+        if (fuse_crop) {
+          // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          float vacc = 0.f;
+          if (crop_img) roi_align_pixel(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
+          float ch[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) ch[k] = 0.f;
+          int c = 0;
+          ch[c++] = acc.x; ch[c++] = acc.y; ch[c++] = acc.z;
+          if (out.crop_c == 4) {
+            float d4 = (vacc < 0.99f) ? 0.f : acc.w;
+            if (out.depth_norm_z) d4 = fminf(fmaxf(d4 / __ldg(out.depth_norm_z + sample), 0.f), 2.f) - 1.f;
+            ch[c++] = d4;
           }
-          o[6] = __float2bfloat16_rn(dn);
+          ch[c++] = r; ch[c++] = g; ch[c++] = b; ch[c++] = n0; ch[c++] = n1; ch[c++] = n2;
+          if (out.ch_per_view == 7) ch[c++] = dn;
+          uint4* o4 = reinterpret_cast<uint4*>(base);
+          uint4 v0, v1;
+          v0.x = pack_bf16x2(ch[0], ch[1]); v0.y = pack_bf16x2(ch[2], ch[3]);
+          v0.z = pack_bf16x2(ch[4], ch[5]); v0.w = pack_bf16x2(ch[6], ch[7]);
+          v1.x = pack_bf16x2(ch[8], ch[9]); v1.y = pack_bf16x2(ch[10], ch[11]);
+          v1.z = pack_bf16x2(ch[12], ch[13]); v1.w = pack_bf16x2(ch[14], ch[15]);
+          o4[0] = v0;
+          o4[1] = v1;
+          for (int k = 2; k < out.c_pad / 8; ++k) o4[k] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          __nv_bfloat16* o = base + out.ch_offset + vslot * out.ch_per_view;
+          o[0] = __float2bfloat16_rn(r);
+          o[1] = __float2bfloat16_rn(g);
+          o[2] = __float2bfloat16_rn(b);
+          o[3] = __float2bfloat16_rn(n0);
+          o[4] = __float2bfloat16_rn(n1);
+          o[5] = __float2bfloat16_rn(n2);
+          if (out.ch_per_view == 7) o[6] = __float2bfloat16_rn(dn);
         }
       }
     }
@@ -326,10 +403,22 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
+static int upload_tables() {
+  if (g_tables_ready) return MPX_OK;
+  QuantTables t;
+  for (int k = 0; k < 256; ++k) t.q8[k] = static_cast<float>(k) / 255.0f;
+  for (int k = 0; k < 32; ++k) t.tex[k] = static_cast<float>((k * 255) >> 5) / 255.0f;
+  MPX_CHECK_CUDA(cudaMemcpyToSymbol(c_tables, &t, sizeof(t)));
+  g_tables_ready = true;
+  return MPX_OK;
+}
+
 int meshdb_create(int n_meshes, const float* verts, const float* normals, const float* colors,
                   const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
                   MeshDb** out) {
   MPX_REQUIRE(n_meshes > 0, "meshdb: need at least one mesh");
+  int rc = upload_tables();
+  if (rc != MPX_OK) return rc;
   MeshDb* db = new MeshDb();
   memset(db, 0, sizeof(MeshDb));
   db->n_meshes = n_meshes;
@@ -396,11 +485,26 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
     MPX_REQUIRE(out.views_per_sample >= 1 &&
                     out.ch_offset + out.views_per_sample * out.ch_per_view <= out.c_pad,
                 "raster: channels do not fit c_pad=%d", out.c_pad);
+    if (out.crop_images) {
+      MPX_REQUIRE(out.views_per_sample == 1, "raster: the fused crop needs one view per sample");
+      MPX_REQUIRE(out.crop_c == out.ch_offset && (out.crop_c == 3 || out.crop_c == 4),
+                  "raster: fused crop channels (%d) must equal ch_offset (%d)", out.crop_c, out.ch_offset);
+      MPX_REQUIRE(out.crop_c + out.ch_per_view <= 16 && (out.c_pad == 16 || out.c_pad == 32),
+                  "raster: fused crop layout unsupported");
+      MPX_REQUIRE((reinterpret_cast<uintptr_t>(out.x) & 15) == 0, "raster: x must be 16-byte aligned");
+    }
   }
   if (n_views == 0) return MPX_OK;
-  int grid = n_views < db->slots ? n_views : db->slots;
+  int strips = 1;
+  if (n_views < db->slots) {
+    strips = db->slots / n_views;
+    if (strips > 16) strips = 16;
+    if (strips > h) strips = h;
+  }
+  const long long items = static_cast<long long>(n_views) * strips;
+  const int grid = items < db->slots ? static_cast<int>(items) : db->slots;
   raster_kernel<<<grid, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out,
-                                                     reinterpret_cast<unsigned long long*>(workspace));
+                                                     reinterpret_cast<unsigned long long*>(workspace), strips);
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;

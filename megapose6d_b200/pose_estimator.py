@@ -294,7 +294,25 @@ class PoseEstimator(torch.nn.Module):
     def filter_pose_estimates(self, data_TCO: PoseEstimatesType, top_K: int, filter_field: str,
                               ascending: bool = False) -> PoseEstimatesType:
         """pose_estimator.py:643-667: top-K rows per (batch_im_id, label, instance_id)."""
+        # same selection and row order as `df.sort_values(field).groupby(cols).head(top_K)` of the reference, computed on
+        # numpy arrays (sorting a 10^4-row DataFrame costs milliseconds, this costs microseconds)
         df = data_TCO.infos
-        group_cols = ["batch_im_id", "label", "instance_id"]
-        df = df.sort_values(filter_field, ascending=ascending, kind="stable").groupby(group_cols).head(top_K)
-        return data_TCO[df.index.tolist()]
+        n = len(df)
+        if n == 0:
+            return data_TCO[[]]
+        vals = df[filter_field].to_numpy(dtype=np.float64)
+        order = np.argsort(vals if ascending else -vals, kind="stable")
+        keys = (df["batch_im_id"].to_numpy(), df["label"].to_numpy(), df["instance_id"].to_numpy())
+        codes = np.zeros(n, dtype=np.int64)
+        for k in keys:
+            _, inv = np.unique(k, return_inverse=True)
+            codes = codes * (int(inv.max()) + 1) + inv
+        sorted_codes = codes[order]
+        # rank of each row inside its group, in sorted order
+        by_group = np.argsort(sorted_codes, kind="stable")
+        grp_sorted = sorted_codes[by_group]
+        starts = np.r_[0, np.flatnonzero(np.diff(grp_sorted)) + 1]
+        rank = np.empty(n, dtype=np.int64)
+        rank[by_group] = np.arange(n) - np.repeat(starts, np.diff(np.r_[starts, n]))
+        keep = order[rank < top_K]
+        return data_TCO[keep.tolist()]

@@ -265,13 +265,21 @@ class PosePredictor(nn.Module):
         nhwc4 = self._nhwc4(images)
         t_r = _Timer(cuda_timer)
         t_r.start()
-        _abi.check(_abi.lib().mpx_roi_align_fused(
-            _abi.ptr(nhwc4), nhwc4.shape[0], nhwc4.shape[1], nhwc4.shape[2], _abi.ptr(im_idx), _abi.ptr(boxes_crop), n,
-            c_in, h, w, _abi.ptr(x), self.backbone.c_pad, _abi.ptr(depth_z if self.input_depth else None),
-            _abi.stream_ptr()))
-        self.renderer.render_fused(lab_mv, TCV_O.reshape(-1, 4, 4).contiguous(), KV_crop.reshape(-1, 3, 3).contiguous(),
-                                   n_views, self.render_size, x, self.backbone.c_pad, c_in,
-                                   self._n_single_render_channels, depth_z if self.render_depth else None)
+        if n_views == 1:
+            # one kernel: the rasteriser's resolve pass also crops the observation and stores whole pixel vectors
+            self.renderer.render_crop_fused(lab_mv, TCV_O.reshape(-1, 4, 4).contiguous(),
+                                            KV_crop.reshape(-1, 3, 3).contiguous(), self.render_size, nhwc4, im_idx,
+                                            boxes_crop, c_in, x, self.backbone.c_pad, self._n_single_render_channels,
+                                            depth_z)
+        else:
+            _abi.check(_abi.lib().mpx_roi_align_fused(
+                _abi.ptr(nhwc4), nhwc4.shape[0], nhwc4.shape[1], nhwc4.shape[2], _abi.ptr(im_idx), _abi.ptr(boxes_crop),
+                n, c_in, h, w, _abi.ptr(x), self.backbone.c_pad, _abi.ptr(depth_z if self.input_depth else None),
+                _abi.stream_ptr()))
+            self.renderer.render_fused(lab_mv, TCV_O.reshape(-1, 4, 4).contiguous(),
+                                       KV_crop.reshape(-1, 3, 3).contiguous(), n_views, self.render_size, x,
+                                       self.backbone.c_pad, c_in, self._n_single_render_channels,
+                                       depth_z if self.render_depth else None)
         timing["render"] += t_r.stop()
         t_m = _Timer(cuda_timer)
         t_m.start()

@@ -103,5 +103,20 @@ class BatchRenderer:
             _abi.stream_ptr()))
 
 
+    def render_crop_fused(self, label_idx: torch.Tensor, TCO: torch.Tensor, K_crop: torch.Tensor,
+                          resolution: Tuple[int, int], images_nhwc4: torch.Tensor, im_idx: torch.Tensor,
+                          boxes_crop: torch.Tensor, c_in: int, x: torch.Tensor, c_pad: int, ch_per_view: int,
+                          depth_norm_z: Optional[torch.Tensor] = None) -> None:
+        """Single-view samples: render + observation crop in one pass, whole pixel vectors written once."""
+        n = TCO.shape[0]
+        h, w = resolution
+        ws = self.workspace(h, w, TCO.device)
+        _abi.check(_abi.lib().mpx_render_crop_fused(
+            self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K_crop), n, h, w, self.flags,
+            _abi.ptr(images_nhwc4), images_nhwc4.shape[0], images_nhwc4.shape[1], images_nhwc4.shape[2], _abi.ptr(im_idx),
+            _abi.ptr(boxes_crop), c_in, _abi.ptr(x), c_pad, ch_per_view, _abi.ptr(depth_norm_z), _abi.ptr(ws), ws.numel(),
+            _abi.stream_ptr()))
+
+
 # name used by the reference's callers
 Panda3dBatchRenderer = BatchRenderer

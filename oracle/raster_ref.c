@@ -18,9 +18,10 @@
  * geometric contract that the CUDA rasteriser implements bit for bit:
  *   - pixel (i, j) sampled at (u, v) = (j + 0.5, i + 0.5), u = fx X/Z + cx, v = fy Y/Z + cy
  *   - vertices snapped to 1/256 pixel, exact integer edge functions, inclusive edges, two-sided
- *   - nearest z wins, ties -> lower triangle index; fragments outside [0.1, 10] m rejected;
- *     triangles with a vertex at z < 0.1 are dropped (no near-plane clipping)
- *   - 1/z linear in screen space, attributes perspective-correct
+ *   - barycentrics l_k = w_k * (1/area); the fragment with the largest interpolated 1/z wins, ties -> lower
+ *     triangle index; fragments with 1/z outside [1/10, 1/0.1] rejected; triangles with a vertex at z < 0.1
+ *     are dropped (no near-plane clipping)
+ *   - 1/z linear in screen space, attributes perspective-correct (b_k = l_k/z_k * z, z = 1/(1/z))
  *   - single sample per pixel (the reference's 4x MSAA is not modelled)
  * Every float operation is a single correctly-rounded IEEE operation in a fixed order (compile with
  * -ffp-contract=off) so that the device kernel can reproduce the results exactly.
@@ -31,7 +32,8 @@
 #include <string.h>
 
 #define K_NEAR 0.1f
-#define K_FAR 10.0f
+#define K_IZ_MAX 10.0f /* 1 / near */
+#define K_IZ_MIN 0.1f  /* 1 / far */
 #define K_SUB 256
 #define K_HALF 128
 #define K_CLAMP 1048576.0f
@@ -45,7 +47,7 @@ typedef struct {
 typedef struct {
   int ax, ay, bx, by, cx, cy;
   float iza, izb, izc;
-  int64_t area2;
+  float inv_area;
   int flip;
   int ok;
 } tri_t;
@@ -66,7 +68,7 @@ static float normal_texture(float s) {
   const float f = u - fl;
   const int k0 = ((int)fl) & 31;
   const int k1 = (k0 + 1) & 31;
-  const float t0 = (float)((k0 * 255) >> 5) / 255.0f;
+  const float t0 = (float)((k0 * 255) >> 5) / 255.0f; /* texel uint8(k*255/32) read back as /255 */
   const float t1 = (float)((k1 * 255) >> 5) / 255.0f;
   return fmaf(f, t1 - t0, t0);
 }
@@ -74,7 +76,7 @@ static float normal_texture(float s) {
 static float quant8(float v, int on) {
   v = fminf(fmaxf(v, 0.0f), 1.0f);
   if (!on) return v;
-  return rintf(v * 255.0f) / 255.0f;
+  return (float)lrintf(v * 255.0f) / 255.0f; /* uint8 level k, read back as k / 255 */
 }
 
 static tri_t load_tri(const vtx_t* vtx, const int32_t* faces, int tri) {
@@ -82,26 +84,26 @@ static tri_t load_tri(const vtx_t* vtx, const int32_t* faces, int tri) {
   const vtx_t a = vtx[faces[3 * tri]], b = vtx[faces[3 * tri + 1]], c = vtx[faces[3 * tri + 2]];
   t.ax = a.X; t.ay = a.Y; t.bx = b.X; t.by = b.Y; t.cx = c.X; t.cy = c.Y;
   t.iza = a.iz; t.izb = b.iz; t.izc = c.iz;
-  t.area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
-  t.flip = t.area2 < 0;
-  if (t.flip) t.area2 = -t.area2;
-  t.ok = (t.area2 != 0) && !(a.behind | b.behind | c.behind);
+  int64_t area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
+  t.flip = area2 < 0;
+  if (t.flip) area2 = -area2;
+  t.ok = (area2 != 0) && !(a.behind | b.behind | c.behind);
+  t.inv_area = t.ok ? 1.0f / (float)area2 : 0.f;
   return t;
 }
 
-static int tri_sample(const tri_t* t, int px, int py, float* l0, float* l1, float* l2, float* iz, float* z) {
+/* returns 1 and the barycentrics / interpolated 1/z if pixel centre (px, py) is covered and inside the depth range */
+static int tri_sample(const tri_t* t, int px, int py, float* l0, float* l1, float* l2, float* iz) {
   int64_t w0 = edge_fn(t->bx, t->by, t->cx, t->cy, px, py);
   int64_t w1 = edge_fn(t->cx, t->cy, t->ax, t->ay, px, py);
   int64_t w2 = edge_fn(t->ax, t->ay, t->bx, t->by, px, py);
   if (t->flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
   if ((w0 | w1 | w2) < 0) return 0;
-  const float area = (float)t->area2;
-  *l0 = (float)w0 / area;
-  *l1 = (float)w1 / area;
-  *l2 = (float)w2 / area;
+  *l0 = (float)w0 * t->inv_area;
+  *l1 = (float)w1 * t->inv_area;
+  *l2 = (float)w2 * t->inv_area;
   *iz = fmaf(*l0, t->iza, fmaf(*l1, t->izb, *l2 * t->izc));
-  *z = 1.0f / *iz;
-  return (*z >= K_NEAR) && (*z <= K_FAR);
+  return (*iz >= K_IZ_MIN) && (*iz <= K_IZ_MAX);
 }
 
 static int imin(int a, int b) { return a < b ? a : b; }
@@ -163,11 +165,11 @@ int raster_ref_render(const float* verts, const float* normals, const float* col
     const int i1 = imin(h - 1, floor_div(maxy - K_HALF, K_SUB));
     for (int i = i0; i <= i1; ++i) {
       for (int j = j0; j <= j1; ++j) {
-        float l0, l1, l2, iz, z;
-        if (!tri_sample(&t, j * K_SUB + K_HALF, i * K_SUB + K_HALF, &l0, &l1, &l2, &iz, &z)) continue;
+        float l0, l1, l2, iz;
+        if (!tri_sample(&t, j * K_SUB + K_HALF, i * K_SUB + K_HALF, &l0, &l1, &l2, &iz)) continue;
         uint32_t zb;
-        memcpy(&zb, &z, 4);
-        const uint64_t key = ((uint64_t)zb << 32) | (uint32_t)tri;
+        memcpy(&zb, &iz, 4);
+        const uint64_t key = ((uint64_t)(~zb) << 32) | (uint32_t)tri;
         if (key < vis[i * w + j]) vis[i * w + j] = key;
       }
     }
@@ -180,11 +182,12 @@ int raster_ref_render(const float* verts, const float* normals, const float* col
     const int i = pix / w, j = pix - i * w;
     const int tri = (int)(key & 0xffffffffu);
     const tri_t t = load_tri(vtx, faces, tri);
-    float l0, l1, l2, iz, z;
-    tri_sample(&t, j * K_SUB + K_HALF, i * K_SUB + K_HALF, &l0, &l1, &l2, &iz, &z);
-    const float b0 = (l0 * t.iza) / iz;
-    const float b1 = (l1 * t.izb) / iz;
-    const float b2 = (l2 * t.izc) / iz;
+    float l0, l1, l2, iz;
+    tri_sample(&t, j * K_SUB + K_HALF, i * K_SUB + K_HALF, &l0, &l1, &l2, &iz);
+    const float z = 1.0f / iz;
+    const float b0 = (l0 * t.iza) * z;
+    const float b1 = (l1 * t.izb) * z;
+    const float b2 = (l2 * t.izc) * z;
     const int ia = faces[3 * tri], ib = faces[3 * tri + 1], ic = faces[3 * tri + 2];
     float col[3], nn[3];
     for (int k = 0; k < 3; ++k) {
@@ -201,7 +204,10 @@ int raster_ref_render(const float* verts, const float* normals, const float* col
       float ey = fmaf(R[4], nn[0], fmaf(R[5], nn[1], R[6] * nn[2]));
       float ez = fmaf(R[8], nn[0], fmaf(R[9], nn[1], R[10] * nn[2]));
       const float len = sqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
-      if (len > 0.f) { ex = ex / len; ey = ey / len; ez = ez / len; }
+      if (len > 0.f) {
+        const float inv = 1.0f / len;
+        ex = ex * inv; ey = ey * inv; ez = ez * inv;
+      }
       const float px_ = ex;
       const float py_ = gl_axes ? -ey : ez;
       const float pz_ = gl_axes ? -ez : -ey;

@@ -164,3 +164,40 @@ def test_raster_empty_batch():
     r = BatchRenderer(object_dataset=ds)
     out = r.render([], torch.empty(0, 4, 4, device=DEV), torch.empty(0, 3, 3, device=DEV), None, (240, 320), render_normals=True)
     assert out.rgbs.shape == (0, 3, 240, 320)
+
+
+def test_raster_many_views_persistent_loop(scene):
+    """More views than resident CTAs: one view per CTA, persistent loop over the rest (no row strips)."""
+    ds, images, K, db, rm = scene
+    n = 2 * 148 * 2 + 37
+    labels = [ds[i % 3].label for i in range(n)]
+    TCO = _poses(n, 77, z_range=(0.3, 0.9))
+    Kc = torch.tensor([[400.0, 0, 40], [0, 400, 32], [0, 0, 1]]).repeat(n, 1, 1)
+    out, ref = _render_both(ds, rm, labels, TCO, Kc, (64, 80))
+    assert torch.equal(out.rgbs.cpu(), ref["rgbs"]) and torch.equal(out.normals.cpu(), ref["normals"])
+    assert torch.equal(out.depths.cpu(), ref["depths"])
+
+
+def test_fused_crop_render_matches_separate_kernels(scene):
+    """mpx_render_crop_fused writes the same bf16 network input as roi_align_fused + raster_render_fused."""
+    from megapose6d_b200 import _abi
+
+    ds, images, K, db, rm = scene
+    r = BatchRenderer(object_dataset=ds)
+    n, h, w, c_pad = 5, 240, 320, 16
+    labels = [ds[i % 3].label for i in range(n)]
+    lab = r.mesh_db.label_ids(labels, DEV)
+    TCO = _poses(n, 5, z_range=(0.4, 0.8)).cuda()
+    Kc = torch.tensor([[1200.0, 0, 160], [0, 1200, 120], [0, 0, 1]]).repeat(n, 1, 1).cuda()
+    boxes = torch.tensor([[100.0, 80, 420, 320], [-40, -30, 200, 150], [500, 380, 700, 530], [0, 0, 640, 480],
+                          [250, 150, 390, 255]]).cuda()
+    im_idx = torch.zeros(n, dtype=torch.int32, device=DEV)
+    nhwc4 = lib3d.image_to_nhwc4(images[:, :3].contiguous().cuda())
+    xa = torch.zeros(n, h // 2, w // 2, 4 * c_pad, device=DEV, dtype=torch.bfloat16)
+    xb = torch.full_like(xa, 7.0)  # the fused kernel must overwrite every channel, pad included
+    _abi.check(_abi.lib().mpx_roi_align_fused(_abi.ptr(nhwc4), 1, 480, 640, _abi.ptr(im_idx), _abi.ptr(boxes), n, 3, h, w,
+                                              _abi.ptr(xa), c_pad, None, _abi.stream_ptr()))
+    r.render_fused(lab, TCO, Kc, 1, (h, w), xa, c_pad, 3, 6)
+    r.render_crop_fused(lab, TCO, Kc, (h, w), nhwc4, im_idx, boxes, 3, xb, c_pad, 6)
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb)
