@@ -176,6 +176,10 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
                     int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                     void* d_out, int block_n, int max_ctas, void* stream);
 
+/* kernel selection for block_n == 0 (auto): 1 (default) = the shared-memory window kernel serves the 64->64
+ * channel stride-1 convolutions (stem, layer1) and the TMA-im2col kernel everything else; 0 = im2col kernel only */
+int mpx_conv_set_mode(int mode);
+
 /* bring-up probe (tools/gpu_probe_rowshift.py): D[128,64] = A[r0:r0+128, :64] * B[64,64]^T with the UMMA
  * A descriptor started r0 rows into a TMA-written 128B-swizzled tile; d_a [144,64] bf16, d_b [64,64] bf16 */
 int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out,
@@ -195,6 +199,9 @@ typedef struct mpx_net mpx_net;
 int mpx_net_create(int c_pad, int out_dim, const void* const* h_conv_w, const float* const* h_conv_b,
                    int n_convs, const float* d_head_w, const float* d_head_b, mpx_net** out);
 int mpx_net_destroy(mpx_net* net);
+/* mpx_net_forward replays a cached CUDA graph per (buffers, shape) after the first call; 0 disables that
+ * (every launch is then issued eagerly on the caller's stream). Default: enabled. */
+int mpx_net_set_graphs(int on);
 size_t mpx_net_workspace_bytes(const mpx_net* net, int n, int h, int w);
 /* d_x: network input tensor (see above) for n samples of size h x w; d_out [n, out_dim] fp32 */
 int mpx_net_forward(const mpx_net* net, const void* d_x, int n, int h, int w, float* d_out,

@@ -73,8 +73,8 @@ EXPORTS = [
     "mpx_raster_workspace_bytes", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",
-    "mpx_net_input_bytes", "mpx_conv2d_bf16", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2_bf16", "mpx_avgpool_linear",
-    "mpx_net_create", "mpx_net_destroy", "mpx_net_workspace_bytes", "mpx_net_forward",
+    "mpx_net_input_bytes", "mpx_conv2d_bf16", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2_bf16", "mpx_avgpool_linear",
+    "mpx_net_create", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_workspace_bytes", "mpx_net_forward",
 ]
 
 

@@ -105,6 +105,7 @@ class ResNet34Engine:
                                              _abi.ptr(self.head_b), ctypes.byref(handle)))
         self._handle = handle
         self._workspace: Optional[torch.Tensor] = None
+        self._out_cache: Dict[int, torch.Tensor] = {}
 
     def __del__(self):
         try:
@@ -133,10 +134,13 @@ class ResNet34Engine:
         need = _abi.lib().mpx_net_workspace_bytes(self._handle, n, h, w)
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        out = torch.empty(n, self.out_dim, device=self.device, dtype=torch.float32)
+        # persistent output buffer per batch size: (x, out, workspace, shape) identify the cached CUDA graph
+        out = self._out_cache.get(n)
+        if out is None:
+            out = self._out_cache[n] = torch.empty(n, self.out_dim, device=self.device, dtype=torch.float32)
         _abi.check(_abi.lib().mpx_net_forward(self._handle, _abi.ptr(x), n, h, w, _abi.ptr(out),
                                               _abi.ptr(self._workspace), self._workspace.numel(), _abi.stream_ptr()))
-        return out
+        return out.clone()
 
     def __call__(self, x_nchw: torch.Tensor) -> torch.Tensor:
         n, c, h, w = x_nchw.shape

@@ -338,6 +338,16 @@ int mpx_net_create(int c_pad, int out_dim, const void* const* h_conv_w, const fl
   return MPX_OK;
 }
 
+int mpx_conv_set_mode(int mode) {
+  conv_set_mode(mode);
+  return MPX_OK;
+}
+
+int mpx_net_set_graphs(int on) {
+  net_set_graphs(on);
+  return MPX_OK;
+}
+
 int mpx_net_destroy(mpx_net* net) {
   if (net) {
     net_destroy(net->net);

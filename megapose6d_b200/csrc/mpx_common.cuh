@@ -84,6 +84,9 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // ---------------------------------------------------------------------------------------------
 extern long long g_launches;  // kernels launched by this library (host-side counter)
 void conv_profile_enable(int on);
+bool conv_profile_enabled();
+void net_set_graphs(int on);
+void conv_set_mode(int mode);
 int conv_profile_summary(double* total_ms, double* total_flops, long long* launches);
 
 struct ConvDesc {

@@ -119,6 +119,17 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
 // ---------------------------------------------------------------------------------------------
 // ResNet-34 plan
 // ---------------------------------------------------------------------------------------------
+// One captured CUDA graph per (buffers, shape): the 38 launches of a forward pass become one graph launch.  For the
+// refiner (a handful of samples) the forward pass is launch-latency bound, not throughput bound.
+struct GraphEntry {
+  const void* x;
+  float* out;
+  void* ws;
+  int n, h, w;
+  int warm;  // direct runs seen (the first call of a shape runs eagerly: one-time attribute / driver set-up)
+  cudaGraphExec_t exec;
+};
+
 struct Net {
   int c_pad;
   int out_dim;
@@ -126,7 +137,13 @@ struct Net {
   std::vector<const float*> conv_b;
   const float* head_w;
   const float* head_b;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t side = nullptr;  // capture / replay stream (the caller's stream may be the legacy default stream)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
+
+static bool g_use_graphs = true;
+void net_set_graphs(int on) { g_use_graphs = on != 0; }
 
 static const int kLayerBlocks[4] = {3, 4, 6, 3};
 static const int kLayerWidth[4] = {64, 128, 256, 512};
@@ -148,7 +165,15 @@ int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* c
   return MPX_OK;
 }
 
-void net_destroy(Net* net) { delete net; }
+void net_destroy(Net* net) {
+  if (!net) return;
+  for (auto& g : net->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (net->ev_in) cudaEventDestroy(net->ev_in);
+  if (net->ev_out) cudaEventDestroy(net->ev_out);
+  if (net->side) cudaStreamDestroy(net->side);
+  delete net;
+}
 
 static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
@@ -160,8 +185,71 @@ size_t net_workspace_bytes(int n, int h, int w) {
   return stem + 3 * l1 + 1024;
 }
 
-int net_forward(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
+static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream);
+
+int net_forward(const Net* cnet, const void* x, int n, int h, int w, float* out, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream) {
+  Net* net = const_cast<Net*>(cnet);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  if (!g_use_graphs || conv_profile_enabled() || n == 0 || cap != cudaStreamCaptureStatusNone)
+    return net_forward_direct(net, x, n, h, w, out, workspace, workspace_bytes, stream);
+  GraphEntry* e = nullptr;
+  for (auto& g : net->graphs)
+    if (g.x == x && g.out == out && g.ws == workspace && g.n == n && g.h == h && g.w == w) e = &g;
+  if (!e) {
+    if (net->graphs.size() >= 32) {
+      for (auto& g : net->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      net->graphs.clear();
+    }
+    net->graphs.push_back(GraphEntry{x, out, workspace, n, h, w, 0, nullptr});
+    e = &net->graphs.back();
+  }
+  if (e->exec == nullptr) {
+    if (e->warm == 0) {  // first sight of this shape: run eagerly
+      e->warm = 1;
+      return net_forward_direct(net, x, n, h, w, out, workspace, workspace_bytes, stream);
+    }
+    if (!net->side) {
+      MPX_CHECK_CUDA(cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking));
+      MPX_CHECK_CUDA(cudaEventCreateWithFlags(&net->ev_in, cudaEventDisableTiming));
+      MPX_CHECK_CUDA(cudaEventCreateWithFlags(&net->ev_out, cudaEventDisableTiming));
+    }
+    cudaGraph_t graph = nullptr;
+    MPX_CHECK_CUDA(cudaStreamBeginCapture(net->side, cudaStreamCaptureModeThreadLocal));
+    const long long launches_before = g_launches;
+    int rc = net_forward_direct(net, x, n, h, w, out, workspace, workspace_bytes, net->side);
+    cudaError_t ce = cudaStreamEndCapture(net->side, &graph);
+    e->warm = static_cast<int>(g_launches - launches_before);  // launches per replay
+    g_launches = launches_before;
+    if (rc != MPX_OK || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g_use_graphs = false;  // fall back to eager launches for the rest of the process
+      return net_forward_direct(net, x, n, h, w, out, workspace, workspace_bytes, stream);
+    }
+    ce = cudaGraphInstantiate(&e->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      e->exec = nullptr;
+      cudaGetLastError();
+      g_use_graphs = false;
+      return net_forward_direct(net, x, n, h, w, out, workspace, workspace_bytes, stream);
+    }
+  }
+  MPX_CHECK_CUDA(cudaEventRecord(net->ev_in, stream));
+  MPX_CHECK_CUDA(cudaStreamWaitEvent(net->side, net->ev_in, 0));
+  MPX_CHECK_CUDA(cudaGraphLaunch(e->exec, net->side));
+  MPX_CHECK_CUDA(cudaEventRecord(net->ev_out, net->side));
+  MPX_CHECK_CUDA(cudaStreamWaitEvent(stream, net->ev_out, 0));
+  g_launches += e->warm;
+  return MPX_OK;
+}
+
+static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream) {
   MPX_REQUIRE(h % 2 == 0 && w % 2 == 0, "net: input %dx%d must be even", h, w);
   MPX_REQUIRE(workspace_bytes >= net_workspace_bytes(n, h, w), "net: workspace too small");
   MPX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "net: workspace must be 256-B aligned");

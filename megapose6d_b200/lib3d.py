@@ -110,11 +110,13 @@ def topk_per_group(logits: torch.Tensor, k: int) -> torch.Tensor:
     return idx
 
 
-def image_to_nhwc4(images: torch.Tensor) -> torch.Tensor:
+def image_to_nhwc4(images: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[B, 3|4, H, W] float32 -> [B, H, W, 4] float32 (depth or 0 in channel 3)."""
     images = _f32(images)
     b, c, h, w = images.shape
-    out = torch.empty(b, h, w, 4, device=images.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(b, h, w, 4, device=images.device, dtype=torch.float32)
+    assert out.shape == (b, h, w, 4) and out.dtype == torch.float32 and out.is_contiguous()
     _abi.check(_abi.lib().mpx_image_to_nhwc4(_abi.ptr(images), b, c, h, w, _abi.ptr(out), _abi.stream_ptr()))
     return out
 

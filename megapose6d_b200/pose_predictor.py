@@ -126,7 +126,10 @@ class PosePredictor(nn.Module):
         self.debug = False
         self.keep_images = False  # materialise fp32 images_crop / renders in the outputs
         self.max_batch = 1152     # hypotheses per fused launch (memory: ~9 MB each at 240x320)
-        self._nhwc4_cache: Optional[Tuple[Any, torch.Tensor]] = None
+        self._nhwc4_bufs: Dict[Tuple[int, ...], torch.Tensor] = {}
+        self._graphs: Dict[Any, Dict[str, Any]] = {}
+        self.use_cuda_graphs = True   # replay the refinement loop as one CUDA graph for small batches
+        self.graph_max_batch = 64
         self._x_cache: Dict[Tuple[int, int, int], torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------
@@ -140,11 +143,20 @@ class PosePredictor(nn.Module):
     def input_depth_dims(self) -> List[int]:
         return self._input_depth_dims
 
-    def _nhwc4(self, images: torch.Tensor) -> torch.Tensor:
-        key = (images.data_ptr(), tuple(images.shape), images._version)
-        if self._nhwc4_cache is None or self._nhwc4_cache[0] != key:
-            self._nhwc4_cache = (key, lib3d.image_to_nhwc4(images))
-        return self._nhwc4_cache[1]
+    def _nhwc4(self, images: torch.Tensor, refresh: bool = False) -> torch.Tensor:
+        """NHWC4 copy of the frame(s) in a persistent buffer per shape (stable address for the captured graphs).
+        Every public entry point refreshes it once (`refresh=True`); the inner steps only look it up."""
+        key = tuple(images.shape)
+        buf = self._nhwc4_bufs.get(key)
+        if buf is None:
+            if len(self._nhwc4_bufs) >= 4:
+                self._nhwc4_bufs.clear()
+            b, _, h, w = images.shape
+            buf = self._nhwc4_bufs[key] = torch.empty(b, h, w, 4, device=images.device, dtype=torch.float32)
+            refresh = True
+        if refresh:
+            lib3d.image_to_nhwc4(images, out=buf)
+        return buf
 
     def _label_idx(self, labels: List[str], device) -> torch.Tensor:
         return self.mesh_db.label_ids(labels, device)
@@ -160,7 +172,7 @@ class PosePredictor(nn.Module):
         label_idx = self._label_idx(labels, TCO.device)
         boxes_rend, boxes_crop, K_crop = lib3d.crop_geometry(
             self.mesh_db.point_subset(2000), label_idx, TCO, K, tCR, images.shape[-2:], self.render_size)
-        crops = lib3d.crop_images(self._nhwc4(images), boxes_crop, None, images.shape[1], self.render_size)
+        crops = lib3d.crop_images(self._nhwc4(images, refresh=True), boxes_crop, None, images.shape[1], self.render_size)
         return crops, K_crop, boxes_rend, boxes_crop
 
     def compute_crops_multiview(self, images: torch.Tensor, K: torch.Tensor, TCV_O: torch.Tensor,
@@ -313,9 +325,36 @@ class PosePredictor(nn.Module):
         K = K.float().contiguous()
         label_idx = self._label_idx(labels, dev)
         timing: Dict[str, float] = defaultdict(float)
+        TCO0 = TCO.float().contiguous()
+        self._nhwc4(images, refresh=True)
+        eager = self.keep_images or self.debug or cuda_timer or not self.use_cuda_graphs or bsz > self.graph_max_batch
+        if eager:
+            iters = self._iterate(images, im_idx, K, label_idx, TCO0, n_iterations, timing, cuda_timer)
+        else:
+            iters = self._iterate_graphed(images, im_idx, K, label_idx, TCO0, n_iterations, timing)
         outputs: Dict[str, PosePredictorOutput] = dict()
-        TCO_input = TCO.float()
-        for n in range(n_iterations):
+        for n, it in enumerate(iters):
+            images_crop = renders = None
+            if self.keep_images or self.debug:
+                images_crop, renders = self._materialize(images, im_idx, it["boxes_crop"], labels, it["TCV_O"],
+                                                         it["KV_crop"], it["tCR"])
+            if self.predict_pose_update:
+                network_outputs = {"pose": it["out"]}
+                renderings_logits = torch.empty(bsz, self.n_rendered_views, dtype=TCO0.dtype, device=dev)
+            else:
+                network_outputs = {"renderings_logits": it["out"]}
+                renderings_logits = it["out"]
+            outputs[f"iteration={n + 1}"] = PosePredictorOutput(
+                renders=renders, images_crop=images_crop, TCO_input=it["TCO_input"], TCO_output=it["TCO_output"],
+                TCV_O_input=it["TCV_O"], tCR=it["tCR"], labels=labels, K=K, K_crop=it["K_crop"], KV_crop=it["KV_crop"],
+                network_outputs=network_outputs, boxes_rend=it["boxes_rend"], boxes_crop=it["boxes_crop"],
+                renderings_logits=renderings_logits, timing_dict=timing)
+        return outputs
+
+    def _iterate(self, images, im_idx, K, label_idx, TCO_input, n_iterations, timing, cuda_timer=False):
+        """The refinement loop on tensors only (pose_rigid.py:523-603); returns one dict of tensors per iteration."""
+        iters = []
+        for _ in range(n_iterations):
             TCO_input = lib3d.normalize_T(TCO_input)
             tCR = TCO_input[:, :3, 3].contiguous()  # tOR = 0 (pose_rigid.py:527-529)
             TCV_O = lib3d.make_TCO_multiview(TCO_input, tCR, multiview_type=self.multiview_type,
@@ -323,24 +362,51 @@ class PosePredictor(nn.Module):
                                              remove_TCO_rendering=self.remove_TCO_rendering)
             step = self._step(images, im_idx, K, label_idx, TCO_input, tCR, TCV_O, timing, cuda_timer)
             if self.predict_pose_update:
-                network_outputs = {"pose": step["out"]}
                 TCO_output = self.update_pose(TCO_input, step["K_crop"], step["out"], tCR)
-                renderings_logits = torch.empty(bsz, self.n_rendered_views, dtype=TCO_input.dtype, device=dev)
             else:
-                network_outputs = {"renderings_logits": step["out"]}
                 TCO_output = TCO_input.detach().clone()
-                renderings_logits = step["out"]
-            images_crop = renders = None
-            if self.keep_images or self.debug:
-                images_crop, renders = self._materialize(images, im_idx, step["boxes_crop"], labels, TCV_O,
-                                                         step["KV_crop"], tCR)
-            outputs[f"iteration={n + 1}"] = PosePredictorOutput(
-                renders=renders, images_crop=images_crop, TCO_input=TCO_input, TCO_output=TCO_output,
-                TCV_O_input=TCV_O, tCR=tCR, labels=labels, K=K, K_crop=step["K_crop"], KV_crop=step["KV_crop"],
-                network_outputs=network_outputs, boxes_rend=step["boxes_rend"], boxes_crop=step["boxes_crop"],
-                renderings_logits=renderings_logits, timing_dict=timing)
+            iters.append(dict(TCO_input=TCO_input, TCO_output=TCO_output, tCR=tCR, TCV_O=TCV_O, out=step["out"],
+                              K_crop=step["K_crop"], KV_crop=step["KV_crop"], boxes_rend=step["boxes_rend"],
+                              boxes_crop=step["boxes_crop"]))
             TCO_input = TCO_output
-        return outputs
+        return iters
+
+    def _iterate_graphed(self, images, im_idx, K, label_idx, TCO0, n_iterations, timing):
+        """Replay the whole refinement loop as one CUDA graph: with a handful of hypotheses the loop is bound by the
+        ~60 launches per iteration, not by the GPU work.  One graph per (batch size, iterations, frame buffer)."""
+        bsz = TCO0.shape[0]
+        # the graph reads the frame from the persistent NHWC4 buffer of this shape (refreshed by forward())
+        key = (bsz, n_iterations, tuple(images.shape), self._nhwc4(images).data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            # first sight: run eagerly (allocates the persistent buffers, one-time CUDA set-up); capture next time
+            static = dict(im_idx=im_idx.clone(), K=K.clone(), label_idx=label_idx.clone(), TCO=TCO0.clone())
+            if len(self._graphs) >= 16:
+                self._graphs.clear()
+            self._graphs[key] = dict(graph=None, static=static)
+            return self._iterate(images, im_idx, K, label_idx, TCO0, n_iterations, timing)
+        if entry["graph"] is None:
+            static = entry["static"]
+            for name, src in (("im_idx", im_idx), ("K", K), ("label_idx", label_idx), ("TCO", TCO0)):
+                static[name].copy_(src)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    iters = self._iterate(images, static["im_idx"], static["K"], static["label_idx"], static["TCO"],
+                                          n_iterations, defaultdict(float))
+            except Exception:  # noqa: BLE001 -- capture not possible here: stay eager for this predictor
+                self.use_cuda_graphs = False
+                torch.cuda.synchronize()
+                return self._iterate(images, im_idx, K, label_idx, TCO0, n_iterations, timing)
+            entry["graph"], entry["iters"] = graph, iters
+        static = entry["static"]
+        for name, src in (("im_idx", im_idx), ("K", K), ("label_idx", label_idx), ("TCO", TCO0)):
+            static[name].copy_(src)
+        t0 = time.time()
+        entry["graph"].replay()
+        timing["model"] += time.time() - t0
+        return [{k: v.clone() for k, v in it.items()} for it in entry["iters"]]
 
     # ------------------------------------------------------------------------------------------
     # reference API: coarse / scoring forward
@@ -372,6 +438,7 @@ class PosePredictor(nn.Module):
         K = K.float().contiguous()
         label_idx = self._label_idx(labels, dev)
         TCO_n = lib3d.normalize_T(TCO_input.float())
+        self._nhwc4(images, refresh=True)
         timing: Dict[str, float] = defaultdict(float)
         logits_chunks, extra = [], defaultdict(list)
         for s in range(0, bsz, self.max_batch):
