@@ -496,6 +496,11 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvP
 
 static int conv_window_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
                            void* out, int max_ctas, cudaStream_t stream);
+static int conv_mode();
+struct ConvParams;
+template <int BLOCK_N>
+static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream,
+                        int max_ctas);
 
 int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride) {
   return (in + pad_lo + pad_hi - k) / stride + 1;
@@ -528,6 +533,7 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   if (block_n <= 0) block_n = d.C_out >= 256 ? 256 : d.C_out;
   MPX_REQUIRE((block_n == 64 || block_n == 128 || block_n == 256) && d.C_out % block_n == 0,
               "conv: BLOCK_N=%d invalid for C_out=%d", block_n, d.C_out);
+  const bool use_pair = (conv_mode() & 2) != 0 && block_n_override == 0 && block_n >= 128;
 
   // --- activation map (im2col). Dims are innermost-first: {C, W, H, N}.
   CUtensorMap map_a, map_b;
@@ -561,7 +567,8 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
     const cuuint64_t K_total = static_cast<cuuint64_t>(d.R) * d.S * d.C_in;
     cuuint64_t dims[2] = {K_total, static_cast<cuuint64_t>(d.C_out)};
     cuuint64_t strides[1] = {K_total * 2};
-    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(block_n)};
+    // the CTA-pair kernel loads half of the weight tile per CTA
+    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(use_pair ? block_n / 2 : block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims,
                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -588,6 +595,10 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
 
+  if (use_pair) {
+    if (block_n == 128) return launch_conv2<128>(map_a, map_b, p, stream, max_ctas);
+    return launch_conv2<256>(map_a, map_b, p, stream, max_ctas);
+  }
   switch (block_n) {
     case 64:
       return launch_conv<64>(map_a, map_b, p, stream, max_ctas);
@@ -737,17 +748,23 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int wi = 0; wi < p.n_windows; ++wi) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + static_cast<size_t>(stage) * p.win_bytes);
-          for (int t = 0; t < p.taps_per_win; ++t) {
-            const int r = t / p.S, s = t - r * p.S;
-            const uint64_t da = make_sw128_desc(a_base + static_cast<uint32_t>(r * p.Wp + s) * 128u);
-            const uint64_t db = make_sw128_desc(smem_u32(smem_b + (wi * p.taps_per_win + t) * kWinBTile));
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              tc_mma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                          first ? 0u : 1u);
+          // descriptors advance by plain 64-bit adds on the (address >> 4) field: one 128-byte row = 8, one weight
+          // tile = 512; the issuing thread's instruction count per MMA bounds the rate of these short (N = 64) MMAs
+          const uint64_t da_win = make_sw128_desc(smem_u32(smem_a + static_cast<size_t>(stage) * p.win_bytes));
+          uint64_t db = make_sw128_desc(smem_u32(smem_b + wi * p.taps_per_win * kWinBTile));
+          uint64_t da_row = da_win;
+          for (int r = 0; r < p.rg; ++r) {
+            uint64_t da = da_row;
+            for (int s = 0; s < p.S; ++s) {
+              tc_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
+              da += 8;
+              db += kWinBTile / 16;
             }
+            da_row += static_cast<uint64_t>(p.Wp) * 8;
           }
           tc_commit(&empty_bar[stage]);
           if (++stage == stages) {
@@ -798,13 +815,16 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-static int g_conv_mode = 1;  // 1: use the window kernel where it applies, 0: always the im2col kernel
+// bit 0: shared-memory window kernel for the 64 -> 64 stride-1 layers; bit 1: CTA-pair (cta_group::2) kernel for
+// C_out >= 128; 0 = single-CTA im2col kernel everywhere
+static int g_conv_mode = 1;
+static int conv_mode() { return g_conv_mode; }
 void conv_set_mode(int mode) { g_conv_mode = mode; }
 
 // Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the window kernel.
 static int conv_window_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
                            void* out, int max_ctas, cudaStream_t stream) {
-  if (g_conv_mode == 0) return MPX_ERR_UNSUPPORTED;
+  if ((g_conv_mode & 1) == 0) return MPX_ERR_UNSUPPORTED;
   if (d.stride != 1 || d.C_in != 64 || d.C_out != 64) return MPX_ERR_UNSUPPORTED;
   if (d.R > 4 || d.S > 4 || d.R * d.S > 16) return MPX_ERR_UNSUPPORTED;
   const int P = conv_out_dim(d.H, d.pad_lo_h, d.pad_hi_h, d.R, 1), Q = conv_out_dim(d.W, d.pad_lo_w, d.pad_hi_w, d.S, 1);
@@ -897,6 +917,266 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 64.0 * n_taps * 64.0);
+  return MPX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant of the im2col kernel (tcgen05.mma.cta_group::2): two CTAs of a cluster compute one 256 x BLOCK_N
+// tile; each loads its own 128 activation rows and HALF of the weight tile, the leader issues the MMAs that read
+// both CTAs' shared memory and write both CTAs' TMEM.  Per CTA and K-block the shared-memory fill drops from
+// 16 KB + BLOCK_N*128 B to 16 KB + BLOCK_N*64 B -- the wide layers (C_out >= 128) are L2->SM bandwidth bound.
+// Barrier protocol (DeepGEMM / CUTLASS sm100 2-SM pattern):
+//   full[s]       lives in the leader; the leader arms expect_tx for both CTAs' bytes, the peer arrives remotely;
+//                 both CTAs' TMA loads complete_tx on the leader's barrier (peer bit of the address cleared)
+//   empty[s]      per CTA; the leader's tcgen05.commit multicasts the arrive to both
+//   tmem_full[a]  per CTA, multicast commit; tmem_empty[a] in the leader, 4 warps of each CTA arrive (peer remotely)
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+constexpr uint64_t kTmaCacheHintNormal = 0x1000000000000000ull;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta_rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(kTmaCacheHintNormal)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c, int w,
+                                                    int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+      "l"(kTmaCacheHintNormal)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+template <int BLOCK_N>
+struct Conv2Cfg {
+  static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 2048;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const ConvParams p) {
+  using Cfg = Conv2Cfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kATileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* bias_s = reinterpret_cast<float*>(bars + 32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const int m_pair_tiles = (p.m_tiles + 1) >> 1;  // 256-row tiles
+  const int total_tiles = m_pair_tiles * p.n_tiles;
+  for (int i = threadIdx.x; i < p.C_out; i += blockDim.x) bias_s[i] = p.bias[i];
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);   // leader's expect_tx arrive + peer's remote arrive
+      mbar_init(&empty_bar[i], 1);  // multicast commit from the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int pq = p.P * p.Q;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m_pair = tile / p.n_tiles;
+        const int n_tile = tile - m_pair * p.n_tiles;
+        const long long m0 = static_cast<long long>(m_pair) * 256 + static_cast<long long>(rank) * kBlockM;
+        const int img = static_cast<int>(m0 / pq);
+        const int rem = static_cast<int>(m0 - static_cast<long long>(img) * pq);
+        const int p0 = rem / p.Q;
+        const int q0 = rem - p0 * p.Q;
+        const int base_w = q0 * p.stride - p.pad_w;
+        const int base_h = p0 * p.stride - p.pad_h;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2u * Cfg::kStageBytes);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          const int r = tap / p.S;
+          const int s = tap - r * p.S;
+          tma2_load_im2col_4d(smem_a + stage * kATileBytes, &map_a, &full_bar[stage], cb * kBlockK, base_w, base_h, img,
+                              static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+          tma2_load_2d(smem_b + stage * Cfg::kBHalfBytes, &map_b, &full_bar[stage], kb * kBlockK,
+                       n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tap;
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+                                 (static_cast<uint32_t>(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * kATileBytes));
+          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * Cfg::kBHalfBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            tc2_mma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc2_commit_mc(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc2_commit_mc(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    int local = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++local) {
+      const int m_pair = tile / p.n_tiles;
+      const int n_tile = tile - m_pair * p.n_tiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const long long m = static_cast<long long>(m_pair) * 256 + static_cast<long long>(rank) * kBlockM + row;
+      const bool valid = m < p.M_total;
+      const int n0 = n_tile * BLOCK_N;
+      const size_t off = static_cast<size_t>(valid ? m : 0) * p.C_out + n0;
+      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      uint4 res_cur[4];
+      if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      epilogue_row<BLOCK_N>(taddr, valid, p.out + off, res_row, bias_s + n0, p.relu, res_cur);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(&tmem_empty[acc], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's shared memory / TMEM must stay alive until the leader's MMAs have retired
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+template <int BLOCK_N>
+static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream,
+                        int max_ctas) {
+  using Cfg = Conv2Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MPX_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  int cap = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
+  if (cap < 1) cap = 1;
+  const int pairs = pair_tiles < cap ? pair_tiles : cap;
+  ProfileSlot* slot = profile_begin(stream);
+  conv_igemm2_kernel<BLOCK_N><<<2 * pairs, 256, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+  profile_end(slot, stream, 2.0 * p.M_total * p.C_out * p.num_k_blocks * kBlockK);
   return MPX_OK;
 }
 

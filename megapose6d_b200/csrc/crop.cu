@@ -56,7 +56,10 @@ roi_align_kernel(const float4* __restrict__ images, int b, int h, int w, const i
     const int ph = pix / ow, pw = pix - ph * ow;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float vacc = 0.f;
-    if (im_ok) roi_align_pixel(img, h, w, rp, ph, pw, acc, vacc);
+    if (im_ok) {
+      if (c == 4) roi_align_pixel<true>(img, h, w, rp, ph, pw, acc, vacc);
+      else roi_align_pixel<false>(img, h, w, rp, ph, pw, acc, vacc);
+    }
     if (c == 4 && vacc < 0.99f) acc.w = 0.f;
     if (out.nchw) {
       float* o = out.nchw + static_cast<size_t>(roi) * c * npix + pix;

@@ -363,7 +363,10 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
           // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           float vacc = 0.f;
-          if (crop_img) roi_align_pixel(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
+          if (crop_img) {
+            if (out.crop_c == 4) roi_align_pixel<true>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
+            else roi_align_pixel<false>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
+          }
           float ch[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) ch[k] = 0.f;

@@ -95,11 +95,9 @@ class PoseEstimator(torch.nn.Module):
         model = self.refiner_model
         B = data_TCO_input.poses.shape[0]
         device = observation.images.device
-        df = data_TCO_input.infos.copy()
-        df["refiner_batch_idx"] = np.arange(B) // max(1, self.bsz_objects)
-        df["refiner_instance_idx"] = np.arange(B) % max(1, self.bsz_objects)
-        labels = df["label"].tolist()
-        batch_im_ids = torch.as_tensor(df["batch_im_id"].values, device=device)
+        infos_in = data_TCO_input.infos
+        labels = infos_in["label"].tolist()
+        batch_im_ids = torch.as_tensor(infos_in["batch_im_id"].to_numpy(), device=device)
         K_all = observation.K[batch_im_ids]
         TCO_all = data_TCO_input.poses.to(device)
 
@@ -109,7 +107,7 @@ class PoseEstimator(torch.nn.Module):
         all_outputs = []
         fields = ["poses", "poses_input", "K_crop", "K", "boxes_rend", "boxes_crop"]
         local = {n: {f: [] for f in fields} for n in range(1, n_iterations + 1)}
-        for s in range(s0, s1, chunk):
+        for s in range(s0, s1, chunk):  # GPU work is enqueued first ...
             e = min(s1, s + chunk)
             t0 = time.time()
             outputs_ = model(images=observation.images, K=K_all[s:e], TCO=TCO_all[s:e], n_iterations=n_iterations,
@@ -122,6 +120,10 @@ class PoseEstimator(torch.nn.Module):
                 it = outputs_[f"iteration={n}"]
                 for f, v in zip(fields, (it.TCO_output, it.TCO_input, it.K_crop, it.K, it.boxes_rend, it.boxes_crop)):
                     local[n][f].append(v)
+        # ... and the DataFrame bookkeeping runs on the host while the device computes
+        df = infos_in.copy()
+        df["refiner_batch_idx"] = np.arange(B) // max(1, self.bsz_objects)
+        df["refiner_instance_idx"] = np.arange(B) % max(1, self.bsz_objects)
         preds = dict()
         tails = dict(poses=(4, 4), poses_input=(4, 4), K_crop=(3, 3), K=(3, 3), boxes_rend=(4,), boxes_crop=(4,))
         for n in range(1, n_iterations + 1):
@@ -135,20 +137,17 @@ class PoseEstimator(torch.nn.Module):
         return preds, extra_data
 
     # ------------------------------------------------------------------------------------------
-    def _score(self, observation: ObservationTensor, df: pd.DataFrame, TCO: torch.Tensor, cuda_timer: bool,
-               return_debug_data: bool):
-        """Run the coarse model over all rows (sharded), returns (logits [n,1], scores [n,1], out dict)."""
-        device = observation.images.device
+    def _score(self, observation: ObservationTensor, labels, batch_im_ids: torch.Tensor, TCO: torch.Tensor,
+               cuda_timer: bool, return_debug_data: bool, label_idx: Optional[torch.Tensor] = None):
+        """Enqueue the coarse model over all rows (sharded); returns (logits [n,1] on device, out dict)."""
         n = TCO.shape[0]
-        labels = df["label"].tolist()
-        batch_im_ids = torch.as_tensor(df["batch_im_id"].values, device=device)
         K = observation.K[batch_im_ids]
         s0, s1 = self.sharder.span(n)
         out_ = self.coarse_model.forward_coarse(images=observation.images, K=K[s0:s1], labels=labels[s0:s1],
                                                 TCO_input=TCO[s0:s1], cuda_timer=cuda_timer,
-                                                return_debug_data=return_debug_data, batch_im_ids=batch_im_ids[s0:s1])
-        logits = self.sharder.gather_rows(out_["logits"], n)
-        return logits, torch.sigmoid(logits), out_
+                                                return_debug_data=return_debug_data, batch_im_ids=batch_im_ids[s0:s1],
+                                                label_idx=None if label_idx is None else label_idx[s0:s1])
+        return self.sharder.gather_rows(out_["logits"], n), out_
 
     @torch.no_grad()
     def forward_scoring_model(self, observation: ObservationTensor, data_TCO: PoseEstimatesType, cuda_timer: bool = False,
@@ -156,14 +155,18 @@ class PoseEstimator(torch.nn.Module):
         """pose_estimator.py:218-322: adds pose_logit / pose_score to data_TCO.infos (in place)."""
         start_time = time.time()
         assert self.coarse_model is not None
+        device = observation.images.device
         df = data_TCO.infos
-        logits, scores, out_ = self._score(observation, df, data_TCO.poses.to(observation.images.device), cuda_timer,
-                                           return_debug_data)
+        batch_im_ids = torch.as_tensor(df["batch_im_id"].to_numpy(), device=device)
+        logits, out_ = self._score(observation, df["label"].tolist(), batch_im_ids, data_TCO.poses.to(device), cuda_timer,
+                                   return_debug_data)
+        scores = torch.sigmoid(logits)
         debug_data = dict()
         if return_debug_data:
             debug_data = {"images_crop": out_["images_crop"], "renders": out_["renders"]}
-        df["pose_logit"] = logits.cpu().numpy()
-        df["pose_score"] = scores.cpu().numpy()
+        both = torch.cat((logits.reshape(-1, 1), scores.reshape(-1, 1)), dim=1).cpu().numpy()  # one D2H read
+        df["pose_logit"] = both[:, 0]
+        df["pose_score"] = both[:, 1]
         elapsed = time.time() - start_time
         render_time, model_time = out_["render_time"], out_["model_time"]
         extra_data = {"render_time": render_time, "model_time": model_time, "time": elapsed, "logits": logits,
@@ -185,20 +188,28 @@ class PoseEstimator(torch.nn.Module):
         SO3_grid = self._SO3_grid
         B, M = len(detections), SO3_grid.shape[0]
         df = detections.infos
+        # device-side row tables straight from the B detections (row = detection * M + hypothesis) ...
+        det_labels = df["label"].tolist()
+        bim = torch.as_tensor(df["batch_im_id"].to_numpy(), device=device)
+        batch_im_ids = bim.repeat_interleave(M)
+        bbox_ids = torch.arange(B, device=device).repeat_interleave(M)
+        m_idx = torch.arange(M, device=device).repeat(B)
+        K = observation.K[batch_im_ids]
+        bboxes = detections.bboxes.to(device)[bbox_ids]
+        label_idx = coarse_model.mesh_db.label_ids(det_labels, device).repeat_interleave(M)
+        labels = [l for l in det_labels for _ in range(M)]
+        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes.float(), coarse_model.mesh_db.points, label_idx, K,
+                                                         SO3_grid[m_idx])
+        logits, out_ = self._score(observation, labels, batch_im_ids, TCO, cuda_timer, return_debug_data, label_idx)
+        scores = torch.sigmoid(logits)
+        both = torch.cat((logits.reshape(-1, 1), scores.reshape(-1, 1)), dim=1)
+        # ... the B*M-row DataFrame is built on the host while the device scores the hypotheses
         df_hypotheses = df.loc[df.index.repeat(M)].copy()
         df_hypotheses["hypothesis_id"] = np.tile(np.arange(M), B)
         df_hypotheses["bbox_id"] = np.repeat(df.index.values, M)
-
-        batch_im_ids = torch.as_tensor(df_hypotheses["batch_im_id"].values, device=device)
-        bbox_ids = torch.as_tensor(df_hypotheses["bbox_id"].values, device=device)
-        m_idx = torch.as_tensor(df_hypotheses["hypothesis_id"].values, device=device)
-        labels = df_hypotheses["label"].tolist()
-        K = observation.K[batch_im_ids]
-        bboxes = detections.bboxes.to(device)[bbox_ids]
-        label_idx = coarse_model.mesh_db.label_ids(labels, device)
-        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes.float(), coarse_model.mesh_db.points, label_idx, K,
-                                                         SO3_grid[m_idx])
-        logits, scores, out_ = self._score(observation, df_hypotheses, TCO, cuda_timer, return_debug_data)
+        both = both.cpu().numpy()  # the stage's only synchronisation
+        df_hypotheses["coarse_logit"] = both[:, 0]
+        df_hypotheses["coarse_score"] = both[:, 1]
         logits = logits.reshape([B, M])
         scores = scores.reshape([B, M])
         debug_data = dict()
@@ -206,8 +217,6 @@ class PoseEstimator(torch.nn.Module):
             H, W = out_["images_crop"].shape[2:]
             debug_data = {"images_crop": out_["images_crop"].reshape([B, M, -1, H, W]),
                           "renders": out_["renders"].reshape([B, M, -1, H, W])}
-        df_hypotheses["coarse_logit"] = logits.flatten().cpu().numpy()
-        df_hypotheses["coarse_score"] = scores.flatten().cpu().numpy()
         elapsed = time.time() - start_time
         render_time, model_time = out_["render_time"], out_["model_time"]
         extra_data = {"render_time": render_time, "model_time": model_time, "time": elapsed, "logits": logits,

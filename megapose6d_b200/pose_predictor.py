@@ -250,7 +250,8 @@ class PosePredictor(nn.Module):
         c_in = 4 if self.input_depth else 3
         boxes_rend, boxes_crop, K_crop = lib3d.crop_geometry(self.mesh_db.point_subset(2000), label_idx, TCO_input, K,
                                                              tCR, im_size, self.render_size)
-        if n_views > 1 or self.remove_TCO_rendering:
+        # coarse / scoring models render the single view with the crop intrinsics themselves (pose_rigid.py:684-693)
+        if (n_views > 1 or self.remove_TCO_rendering) and self.predict_pose_update:
             lab_mv = label_idx.repeat_interleave(n_views)
             K_mv = K.unsqueeze(1).expand(n, n_views, 3, 3).reshape(-1, 3, 3).contiguous()
             # tOR = 0  =>  the reference point seen from each view is that view's translation
@@ -424,7 +425,8 @@ class PosePredictor(nn.Module):
     @torch.no_grad()
     def forward_coarse(self, images: torch.Tensor, K: torch.Tensor, labels: List[str], TCO_input: torch.Tensor,
                        cuda_timer: bool = False, return_debug_data: bool = False,
-                       batch_im_ids: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+                       batch_im_ids: Optional[torch.Tensor] = None,
+                       label_idx: Optional[torch.Tensor] = None) -> Dict[str, Any]:
         """pose_rigid.py:634-708 -> dict(logits [B,1], scores [B,1], time, render_time, model_time)."""
         assert self.predict_rendered_views_logits, "Method only valid if coarse classification model"
         bsz = TCO_input.shape[0]
@@ -436,10 +438,20 @@ class PosePredictor(nn.Module):
         else:
             im_idx = batch_im_ids.to(device=dev, dtype=torch.int32).contiguous()
         K = K.float().contiguous()
-        label_idx = self._label_idx(labels, dev)
-        TCO_n = lib3d.normalize_T(TCO_input.float())
+        if label_idx is None:
+            label_idx = self._label_idx(labels, dev)
+        else:
+            label_idx = label_idx.to(device=dev, dtype=torch.int32).contiguous()
         self._nhwc4(images, refresh=True)
         timing: Dict[str, float] = defaultdict(float)
+        if (0 < bsz <= self.graph_max_batch and self.use_cuda_graphs and not (return_debug_data or cuda_timer or self.debug)
+                and self.n_rendered_views == 1 and not self.predict_pose_update):
+            # a handful of rows (the scoring pass): one graph replay instead of ~45 launches
+            it = self._iterate_graphed(images, im_idx, K, label_idx, TCO_input.float().contiguous(), 1, timing)[0]
+            logits = it["out"]
+            return {"logits": logits, "scores": torch.sigmoid(logits), "time": timing["model"],
+                    "render_time": timing["render"], "model_time": timing["model"]}
+        TCO_n = lib3d.normalize_T(TCO_input.float())
         logits_chunks, extra = [], defaultdict(list)
         for s in range(0, bsz, self.max_batch):
             e = min(bsz, s + self.max_batch)

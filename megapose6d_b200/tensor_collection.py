@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import Dict, Iterable
 
+import numpy as np
 import pandas as pd
 import torch
 
@@ -94,6 +95,16 @@ class PandasTensorCollection(TensorCollection):
         self.infos = infos.reset_index(drop=True)
         self.meta: dict = dict()
 
+    @classmethod
+    def _wrap(cls, infos: pd.DataFrame, tensors: Dict[str, torch.Tensor]) -> "PandasTensorCollection":
+        """Constructor for a freshly made `infos` frame: re-labels its index in place instead of copying it."""
+        out = cls.__new__(cls)
+        TensorCollection.__init__(out, **tensors)
+        infos.index = pd.RangeIndex(len(infos))
+        out.infos = infos
+        out.meta = dict()
+        return out
+
     def __len__(self) -> int:
         return len(self.infos)
 
@@ -102,9 +113,11 @@ class PandasTensorCollection(TensorCollection):
             row_ids = ids.cpu().numpy()
         else:
             row_ids = ids
-        infos = self.infos.iloc[row_ids].reset_index(drop=True)
+        infos = self.infos.iloc[row_ids]
+        if infos is self.infos or not isinstance(infos, pd.DataFrame):
+            infos = self.infos.iloc[list(np.atleast_1d(row_ids))]
         tensors = {k: v[ids] for k, v in self._tensors.items()}
-        return PandasTensorCollection(infos, **tensors)
+        return PandasTensorCollection._wrap(infos, tensors)
 
     def merge_df(self, df: pd.DataFrame, *args, **kwargs) -> "PandasTensorCollection":
         infos = self.infos.merge(df, how="left", *args, **kwargs)
