@@ -533,7 +533,10 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   if (block_n <= 0) block_n = d.C_out >= 256 ? 256 : d.C_out;
   MPX_REQUIRE((block_n == 64 || block_n == 128 || block_n == 256) && d.C_out % block_n == 0,
               "conv: BLOCK_N=%d invalid for C_out=%d", block_n, d.C_out);
-  const bool use_pair = (conv_mode() & 2) != 0 && block_n_override == 0 && block_n >= 128;
+  // measured on B200 (tools/gpu_probe_pair.py): the pair kernel wins for BLOCK_N = 256 (layer3 1184 -> 1314, layer4 1382 ->
+  // 1488 TFLOP/s) and is on par or slightly behind for 128, so it serves the 256-wide tiles only (bit 2 forces 128 too)
+  const bool use_pair = (conv_mode() & 2) != 0 && block_n_override == 0 &&
+                        (block_n == 256 || (block_n == 128 && (conv_mode() & 4) != 0));
 
   // --- activation map (im2col). Dims are innermost-first: {C, W, H, N}.
   CUtensorMap map_a, map_b;
@@ -817,7 +820,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // bit 0: shared-memory window kernel for the 64 -> 64 stride-1 layers; bit 1: CTA-pair (cta_group::2) kernel for
 // C_out >= 128; 0 = single-CTA im2col kernel everywhere
-static int g_conv_mode = 1;
+static int g_conv_mode = 3;
 static int conv_mode() { return g_conv_mode; }
 void conv_set_mode(int mode) { g_conv_mode = mode; }
 

@@ -119,3 +119,96 @@ def test_resnet34_engine_vs_oracle(cfg_name):
     with torch.no_grad():
         bound2 = resnet_ref.bf16_forward_error_bound(sd, x2, eps=2 ** -8)
     assert ((got2 - emu2).abs() <= 0.25 * bound2 + 1e-3).all()
+
+
+WINDOW_CASES = [
+    # the 64 -> 64 stride-1 "same" convolutions are served by the shared-memory window kernel (mode bit 0)
+    ("win_3x3", 3, 60, 80, 3, 3, (1, 1, 1, 1), True, True),
+    ("win_3x3_tiny", 5, 7, 9, 3, 3, (1, 1, 1, 1), False, False),
+    ("win_stem", 2, 120, 160, 4, 4, (2, 2, 1, 1), True, False),
+    ("win_stem_small", 2, 24, 32, 4, 4, (2, 2, 1, 1), True, False),
+]
+
+
+@pytest.mark.parametrize("case", WINDOW_CASES, ids=[c[0] for c in WINDOW_CASES])
+def test_window_and_im2col_kernels_agree(case):
+    """Both kernels accumulate the same products in fp32 (possibly in a different order): outputs agree to one bf16 ulp,
+    and each is within the stated tolerance of the fp32 reference."""
+    name, n, h, w, r, s, pads, relu, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(64, r, s, 64, device="cuda", generator=g) / (r * s * 64) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(64, device="cuda", generator=g)
+    res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    outs = []
+    try:
+        for mode in (1, 0):
+            _abi.lib().mpx_conv_set_mode(mode)
+            out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, s, 1,
+                                                  pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(out), 0, 0,
+                                                  _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out.float())
+    finally:
+        _abi.lib().mpx_conv_set_mode(3)
+    ref = _conv_ref(x, wt, bias, 1, pads, relu, res)
+    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
+    assert (outs[0] - outs[1]).abs().max() <= tol
+
+
+def test_graph_replay_equals_eager_launches():
+    cfg = helpers.COARSE_CFG
+    sd = helpers.make_state_dict(cfg, seed=2)
+    eng = ResNet34Engine(sd, n_inputs=9, head="views_logits_head")
+    x = eng.pack_input(helpers._calibration_batch(9, 3, n=3).cuda())
+    try:
+        _abi.lib().mpx_net_set_graphs(0)
+        eager = eng.forward(x, 240, 320)
+        _abi.lib().mpx_net_set_graphs(1)
+        outs = [eng.forward(x, 240, 320) for _ in range(3)]  # eager warm-up, capture, replay
+    finally:
+        _abi.lib().mpx_net_set_graphs(1)
+    for o in outs:
+        assert torch.equal(o, eager)
+
+
+PAIR_CASES = [
+    ("pair_l3", 5, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), True, True),
+    ("pair_l4_two_ntiles", 3, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True),
+    ("pair_s2", 3, 30, 40, 128, 256, 3, 3, 2, (1, 1, 1, 1), True, False),
+    ("pair_ds_1x1", 3, 30, 40, 128, 256, 1, 1, 2, (0, 0, 0, 0), False, False),
+    ("pair_single_tile", 1, 8, 10, 256, 256, 3, 3, 1, (1, 1, 1, 1), False, False),
+    ("pair_forced_128", 4, 30, 40, 128, 128, 3, 3, 1, (1, 1, 1, 1), True, True),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_cta_pair_kernel_vs_torch_and_single_cta(case):
+    """tcgen05.mma.cta_group::2 kernel (mode bit 1; bit 2 also routes 128-wide tiles through it) vs fp32 torch and vs
+    the single-CTA kernel."""
+    name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    p = (h + pads[0] + pads[2] - r) // stride + 1
+    q = (w + pads[1] + pads[3] - s) // stride + 1
+    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    outs = []
+    try:
+        for mode in (7, 1):
+            _abi.lib().mpx_conv_set_mode(mode)
+            out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
+                                                  stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
+                                                  _abi.ptr(out), 0, 0, _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out.float())
+    finally:
+        _abi.lib().mpx_conv_set_mode(3)
+    ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
+    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
+    assert torch.equal(outs[0], outs[1])  # same products, same K order, fp32 accumulation in TMEM

@@ -160,3 +160,27 @@ def test_pipeline_matches_oracle(setup):
     for _, row in final.infos.iterrows():
         grp = scored[(scored["label"] == row["label"]) & (scored["instance_id"] == row["instance_id"])]
         assert row["pose_logit"] == grp["pose_logit"].max()
+
+
+def test_refiner_graph_replay_equals_eager(setup):
+    est = load_model.load_named_model("megapose-1.0-RGB", setup["ds"], models_root=setup["root"])
+    model = est.refiner_model
+    n = 3
+    labels = [setup["ds"][i % 2].label for i in range(n)]
+    images = setup["images"][:, :3].contiguous().cuda()
+    Kn = setup["K"].repeat(n, 1, 1).cuda()
+    ims = torch.zeros(n, dtype=torch.long)
+    runs = []
+    for seed in (21, 22):
+        TCO = torch.from_numpy(procedural.random_poses(n, seed, z_range=(0.4, 0.8))).float().cuda()
+        model.use_cuda_graphs = False
+        eager = model(images=images, K=Kn, labels=labels, TCO=TCO, n_iterations=3, batch_im_ids=ims)
+        model.use_cuda_graphs = True
+        for _ in range(3):  # eager first sight, capture, replay
+            graphed = model(images=images, K=Kn, labels=labels, TCO=TCO, n_iterations=3, batch_im_ids=ims)
+        runs.append((eager, graphed))
+    for eager, graphed in runs:
+        for it in ("iteration=1", "iteration=2", "iteration=3"):
+            assert torch.equal(eager[it].TCO_output, graphed[it].TCO_output)
+            assert torch.equal(eager[it].K_crop, graphed[it].K_crop)
+            assert torch.equal(eager[it].network_outputs["pose"], graphed[it].network_outputs["pose"])
