@@ -1,0 +1,87 @@
+"""Two-rank NCCL run of the hypothesis-sharded pipeline: every rank must end with the single-rank result.
+Skipped unless two CUDA devices are visible (the single-GPU `-m gpu` run covers the sharder with world size 1;
+tests/test_parallel_gloo.py covers the collective logic on CPU)."""
+import os
+import socket
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _scene():
+    from megapose6d_b200 import procedural
+    from tests import helpers
+
+    ds, images, K = helpers.make_scene(2, seed=6)
+    TCO_gt = torch.from_numpy(procedural.random_poses(2, 11)).float()
+    TCO_gt[:, 2, 3] = torch.tensor([0.55, 0.7])
+    bboxes = torch.stack([helpers.detection_for_pose(K[0], TCO_gt[i], torch.from_numpy(ds[i].mesh.vertices).float()) for i in range(2)])
+    det_df = pd.DataFrame(dict(label=[o.label for o in ds.list_objects], batch_im_id=0, instance_id=np.arange(2)))
+    sds = {"coarse-rgb-906902141": helpers.make_state_dict(helpers.COARSE_CFG, 5),
+           "refiner-rgb-653307694": helpers.make_state_dict(helpers.REFINER_CFG, 6)}
+    return ds, images, K, det_df, bboxes, sds
+
+
+def _run(rank, world, port, root, q):
+    from megapose6d_b200 import load_model
+    from megapose6d_b200.parallel import HypothesisSharder
+    from megapose6d_b200.tensor_collection import PandasTensorCollection
+    from megapose6d_b200.types import ObservationTensor
+
+    torch.cuda.set_device(rank if world > 1 else 0)
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ds, images, K, det_df, bboxes, sds = _scene()
+    est = load_model.load_named_model("megapose-1.0-RGB-multi-hypothesis", ds, models_root=Path(root))
+    est.load_SO3_grid(72)
+    est.sharder = HypothesisSharder(enabled=world > 1)
+    obs = ObservationTensor(images.clone(), K.clone()).cuda()
+    det = PandasTensorCollection(det_df.copy(), bboxes=bboxes.cuda())
+    final, extra = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=2, n_pose_hypotheses=2)
+    out = dict(poses=final.poses.cpu(), hyp=final.infos["hypothesis_id"].tolist(),
+               coarse=torch.as_tensor(extra["coarse"]["preds"].infos["coarse_logit"].values))
+    if q is not None:
+        q.put((rank, out))
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def test_two_rank_pipeline_equals_single_rank():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from megapose6d_b200 import load_model
+
+    with tempfile.TemporaryDirectory() as root:
+        _, _, _, _, _, sds = _scene()
+        for run_id, sd in sds.items():
+            load_model.write_run(root, run_id, sd)
+        single = _run(0, 1, 0, root, None)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_run, args=(r, 2, port, root, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        results = dict(q.get(timeout=600) for _ in procs)
+        for p in procs:
+            p.join(timeout=120)
+    for r in (0, 1):
+        assert torch.equal(results[r]["coarse"], single["coarse"])
+        assert results[r]["hyp"] == single["hyp"]
+        assert torch.equal(results[r]["poses"], single["poses"])
