@@ -530,7 +530,13 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   MPX_REQUIRE(M_total > 0 && M_total < (1LL << 31), "conv: M=%lld out of range", M_total);
 
   int block_n = block_n_override;
-  if (block_n <= 0) block_n = d.C_out >= 256 ? 256 : d.C_out;
+  if (block_n <= 0) {
+    // wide tiles amortise the activation loads; with only a handful of output tiles (refiner: one sample) the
+    // conv is bound by the serial K loop of a single tile instead, so narrower tiles spread it over more SMs
+    const long long m_tiles_est = (M_total + kBlockM - 1) / kBlockM;
+    block_n = d.C_out >= 256 ? 256 : d.C_out;
+    while (block_n > 64 && m_tiles_est * (d.C_out / block_n) < 32) block_n /= 2;
+  }
   MPX_REQUIRE((block_n == 64 || block_n == 128 || block_n == 256) && d.C_out % block_n == 0,
               "conv: BLOCK_N=%d invalid for C_out=%d", block_n, d.C_out);
   // measured on B200 (tools/gpu_probe_pair.py): the pair kernel wins for BLOCK_N = 256 (layer3 1184 -> 1314, layer4 1382 ->

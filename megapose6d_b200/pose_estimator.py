@@ -76,6 +76,7 @@ class PoseEstimator(torch.nn.Module):
         else:
             raise ValueError("At least one of refiner_model or coarse_model must be specified.")
         self.eval()
+        self.fused_pipeline = True  # run_inference_pipeline enqueues all stages without intermediate host syncs
         self.keep_all_outputs = False
         self.keep_all_coarse_outputs = False
         self.refiner_outputs = None
@@ -251,6 +252,13 @@ class PoseEstimator(torch.nn.Module):
             self.bsz_images = bsz_images
         if bsz_objects is not None:
             self.bsz_objects = bsz_objects
+        if (self.fused_pipeline and coarse_estimates is None and detections is not None and not run_depth_refiner
+                and not cuda_timer and not keep_all_refiner_outputs and self.refiner_model is not None
+                and self.coarse_model is not None and len(detections) > 0 and n_refiner_iterations >= 1):
+            out = self._run_pipeline_fused(observation, detections, n_refiner_iterations, n_pose_hypotheses,
+                                           detection_filter_kwargs, t_start)
+            if out is not None:
+                return out
         if coarse_estimates is None:
             assert detections is not None or run_detector, "You must either pass in `detections` or set run_detector=True"
             if detections is None and run_detector:
@@ -299,6 +307,113 @@ class PoseEstimator(torch.nn.Module):
         if run_depth_refiner:
             extra_data["depth_refiner"] = {"preds": data_TCO_depth_refiner}
         return data_TCO_final, extra_data
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _run_pipeline_fused(self, observation: ObservationTensor, detections: DetectionsType, n_refiner_iterations: int,
+                            n_pose_hypotheses: int, detection_filter_kwargs: Optional[dict], t_start: float):
+        """The same pipeline with every stage enqueued back to back: the top-K selection between the stages runs on the
+        device (mpx_topk_per_group + a stable sort), so the host never waits for the coarse logits before it can launch
+        the refiner.  All DataFrame bookkeeping happens while the device works; one synchronisation at the end.
+        Returns None (caller falls back to the staged path) when two detections share a (batch_im_id, label,
+        instance_id) key, because then the reference's groupby merges their hypotheses."""
+        coarse_model, refiner = self.coarse_model, self.refiner_model
+        device = observation.images.device
+        detections = add_instance_id(detections)
+        if detection_filter_kwargs is not None:
+            detections = filter_detections(detections, **detection_filter_kwargs)
+        assert_detections_valid(detections)
+        df = detections.infos
+        B, M = len(df), self._SO3_grid.shape[0]
+        if B == 0 or df.duplicated(["batch_im_id", "label", "instance_id"]).any():
+            return None
+        Kh = min(n_pose_hypotheses, M)
+        t0 = time.time()
+        # ---- coarse: B*M rows, row = detection * M + hypothesis
+        det_labels = df["label"].tolist()
+        bim = torch.as_tensor(df["batch_im_id"].to_numpy(), device=device)
+        batch_im_ids = bim.repeat_interleave(M)
+        bbox_ids = torch.arange(B, device=device).repeat_interleave(M)
+        m_idx = torch.arange(M, device=device).repeat(B)
+        K_rows = observation.K[batch_im_ids]
+        bboxes = detections.bboxes.to(device)[bbox_ids]
+        det_label_idx = coarse_model.mesh_db.label_ids(det_labels, device)
+        label_idx = det_label_idx.repeat_interleave(M)
+        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes.float(), coarse_model.mesh_db.points, label_idx, K_rows,
+                                                         self._SO3_grid[m_idx])
+        labels_rows = [l for l in det_labels for _ in range(M)]
+        logits, out_c = self._score(observation, labels_rows, batch_im_ids, TCO, False, False, label_idx)
+        scores = torch.sigmoid(logits)
+        # ---- top-K per detection on the device, rows ordered by descending logit like sort_values().groupby().head()
+        top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()                       # [B, Kh]
+        rows = (top + torch.arange(B, device=device).unsqueeze(1) * M).flatten()
+        order = torch.sort(logits.flatten()[rows], descending=True, stable=True).indices
+        rows = rows[order]
+        n_sel = rows.shape[0]
+        TCO_sel, bim_sel, lab_sel, K_sel = TCO[rows], batch_im_ids[rows], label_idx[rows], K_rows[rows]
+        # ---- refiner on the selected rows (sharded), then scoring, all enqueued without a host round trip
+        s0, s1 = self.sharder.span(n_sel)
+        iters = refiner.refine_tensors(observation.images, bim_sel[s0:s1], K_sel[s0:s1], lab_sel[s0:s1], TCO_sel[s0:s1],
+                                       n_refiner_iterations)
+        fields = dict(poses="TCO_output", poses_input="TCO_input", K_crop="K_crop", boxes_rend="boxes_rend",
+                      boxes_crop="boxes_crop")
+        tails = dict(poses=(4, 4), poses_input=(4, 4), K_crop=(3, 3), boxes_rend=(4,), boxes_crop=(4,))
+        refined = []
+        for n in range(n_refiner_iterations):
+            tensors = dict()
+            for f, src in fields.items():
+                loc = iters[n][src] if iters else torch.empty((0,) + tails[f], device=device)
+                tensors[f] = self.sharder.gather_rows(loc, n_sel)
+            tensors["K"] = K_sel
+            refined.append(tensors)
+        TCO_ref = refined[-1]["poses"] if n_refiner_iterations > 0 else TCO_sel
+        t_ref = time.time()
+        labels_sel_placeholder = [""] * n_sel
+        pose_logits, out_s = self._score(observation, labels_sel_placeholder, bim_sel, TCO_ref, False, False, lab_sel)
+        pose_scores = torch.sigmoid(pose_logits)
+        packed = torch.cat((pose_logits.reshape(-1), pose_scores.reshape(-1), rows.to(pose_logits.dtype)))
+        # ---- host bookkeeping while the device works
+        df_hyp = df.loc[df.index.repeat(M)].copy()
+        df_hyp["hypothesis_id"] = np.tile(np.arange(M), B)
+        df_hyp["bbox_id"] = np.repeat(df.index.values, M)
+        coarse_np = torch.cat((logits.reshape(-1, 1), scores.reshape(-1, 1)), dim=1).cpu().numpy()  # first sync point
+        df_hyp["coarse_logit"] = coarse_np[:, 0]
+        df_hyp["coarse_score"] = coarse_np[:, 1]
+        data_TCO_coarse = PandasTensorCollection(df_hyp, poses=TCO, bboxes=bboxes)
+        t_coarse = time.time() - t0
+        coarse_extra = {"render_time": out_c["render_time"], "model_time": out_c["model_time"], "time": t_coarse,
+                        "logits": logits.reshape(B, M), "scores": scores.reshape(B, M), "TCO": TCO.reshape(B, M, 4, 4),
+                        "debug": dict(), "n_batches": int(np.ceil(B * M / max(1, self.bsz_images))),
+                        "timing_str": f"time: {t_coarse:.2f}, model_time: {out_c['model_time']:.2f}, "
+                                      f"render_time: {out_c['render_time']:.2f}"}
+        packed_np = packed.cpu().numpy()                                                   # final sync point
+        rows_np = packed_np[2 * n_sel:].astype(np.int64)
+        df_sel = data_TCO_coarse.infos.iloc[rows_np].copy()
+        data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=TCO_sel, bboxes=bboxes[rows]))
+        df_ref = data_TCO_filtered.infos.copy()
+        df_ref["refiner_batch_idx"] = np.arange(n_sel) // max(1, self.bsz_objects)
+        df_ref["refiner_instance_idx"] = np.arange(n_sel) % max(1, self.bsz_objects)
+        preds = {f"iteration={n + 1}": PandasTensorCollection(df_ref, **refined[n]) for n in range(n_refiner_iterations)}
+        refiner_extra = {"n_iterations": n_refiner_iterations, "outputs": [], "model_time": t_ref - t0 - t_coarse,
+                         "time": max(0.0, t_ref - t0)}
+        data_TCO_scored = preds[f"iteration={n_refiner_iterations}"]
+        data_TCO_scored.infos["pose_logit"] = packed_np[:n_sel]
+        data_TCO_scored.infos["pose_score"] = packed_np[n_sel:2 * n_sel]
+        scoring_extra = {"render_time": out_s["render_time"], "model_time": out_s["model_time"], "time": time.time() - t_ref,
+                         "logits": pose_logits, "scores": pose_scores, "debug": dict(),
+                         "n_batches": int(np.ceil(n_sel / max(1, self.bsz_images))), "timing_str": ""}
+        final = self.filter_pose_estimates(data_TCO_scored, top_K=1, filter_field="pose_logit")
+        elapsed = time.time() - t_start
+        extra_data: dict = dict()
+        extra_data["coarse"] = {"preds": data_TCO_coarse, "data": coarse_extra}
+        extra_data["coarse_filter"] = {"preds": data_TCO_filtered}
+        extra_data["refiner_all_hypotheses"] = {"preds": preds, "data": refiner_extra}
+        extra_data["scoring"] = {"preds": data_TCO_scored, "data": scoring_extra}
+        extra_data["refiner"] = {"preds": final, "data": refiner_extra}
+        extra_data["timing_str"] = (f"total={elapsed:.2f}, coarse={t_coarse:.2f}, refiner={refiner_extra['time']:.2f}, "
+                                    f"scoring={scoring_extra['time']:.2f}, ")
+        extra_data["time"] = elapsed
+        return final, extra_data
 
     def filter_pose_estimates(self, data_TCO: PoseEstimatesType, top_K: int, filter_field: str,
                               ascending: bool = False) -> PoseEstimatesType:

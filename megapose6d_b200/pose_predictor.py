@@ -352,6 +352,22 @@ class PosePredictor(nn.Module):
                 renderings_logits=renderings_logits, timing_dict=timing)
         return outputs
 
+    @torch.no_grad()
+    def refine_tensors(self, images: torch.Tensor, im_idx: torch.Tensor, K: torch.Tensor, label_idx: torch.Tensor,
+                       TCO: torch.Tensor, n_iterations: int) -> List[Dict[str, torch.Tensor]]:
+        """`forward` on device tensors only (no label strings, no output dataclasses): used by the pipeline's
+        sync-free path.  Returns one dict per iteration (TCO_input, TCO_output, K_crop, boxes_rend, boxes_crop, ...)."""
+        if TCO.shape[0] == 0:
+            return []
+        self._nhwc4(images, refresh=True)
+        timing: Dict[str, float] = defaultdict(float)
+        im_idx = im_idx.to(torch.int32).contiguous()
+        K, TCO = K.float().contiguous(), TCO.float().contiguous()
+        label_idx = label_idx.to(torch.int32).contiguous()
+        if self.use_cuda_graphs and TCO.shape[0] <= self.graph_max_batch and not (self.keep_images or self.debug):
+            return self._iterate_graphed(images, im_idx, K, label_idx, TCO, n_iterations, timing)
+        return self._iterate(images, im_idx, K, label_idx, TCO, n_iterations, timing)
+
     def _iterate(self, images, im_idx, K, label_idx, TCO_input, n_iterations, timing, cuda_timer=False):
         """The refinement loop on tensors only (pose_rigid.py:523-603); returns one dict of tensors per iteration."""
         iters = []

@@ -184,3 +184,65 @@ def test_refiner_graph_replay_equals_eager(setup):
             assert torch.equal(eager[it].TCO_output, graphed[it].TCO_output)
             assert torch.equal(eager[it].K_crop, graphed[it].K_crop)
             assert torch.equal(eager[it].network_outputs["pose"], graphed[it].network_outputs["pose"])
+
+
+def test_rgbd_multi_object_pipeline_runs_and_scores_match_oracle(setup):
+    """BASELINE config 3 in miniature: RGB-D refiner, several detections (two instances of one object), K=1."""
+    ds, images, K = setup["ds"], setup["images"], setup["K"]
+    est = load_model.load_named_model("megapose-1.0-RGBD", ds, models_root=setup["root"])
+    est.load_SO3_grid(72)
+    labels = [ds[0].label, ds[1].label, ds[0].label]
+    TCO_gt = torch.from_numpy(procedural.random_poses(3, 13)).float()
+    TCO_gt[:, 2, 3] = torch.tensor([0.5, 0.65, 0.8])
+    bboxes = torch.stack([helpers.detection_for_pose(K[0], TCO_gt[i], torch.from_numpy(ds.get_object_by_label(labels[i]).mesh.vertices).float())
+                          for i in range(3)])
+    det_df = pd.DataFrame(dict(label=labels, batch_im_id=0))  # no instance_id: the pipeline assigns it
+    obs = ObservationTensor(images.clone(), K.clone()).cuda()
+    final, extra = est.run_inference_pipeline(obs, detections=PandasTensorCollection(det_df.copy(), bboxes=bboxes.cuda()),
+                                              n_refiner_iterations=2, n_pose_hypotheses=1)
+    assert len(final) == 3 and sorted(final.infos["instance_id"].tolist()) == [0, 0, 1]
+    assert torch.isfinite(final.poses).all()
+    # scoring pass vs the oracle's coarse model evaluated on the engine's refined poses
+    oc = _oracle(setup, "coarse-rgb-906902141", helpers.COARSE_CFG)
+    scored = extra["scoring"]["preds"]
+    lab = scored.infos["label"].tolist()
+    n = len(lab)
+    ref = oc.forward_coarse(images[:, :3].repeat(n, 1, 1, 1), K.repeat(n, 1, 1), lab, scored.poses.cpu())
+    bound = resnet_ref.bf16_forward_error_bound(setup["sds"]["coarse-rgb-906902141"], ref["x"], eps=EPS)
+    got = torch.as_tensor(scored.infos["pose_logit"].values).float().view(-1, 1)
+    assert ((got - ref["logits"]).abs() <= bound + 1e-3).all()
+
+
+def test_fused_pipeline_equals_staged_pipeline(setup):
+    """The sync-free path (device-side top-K, everything enqueued back to back) returns the same collections as the staged
+    path that mirrors the reference stage by stage."""
+    ds, images, K = setup["ds"], setup["images"][:, :3].contiguous(), setup["K"]
+    est = load_model.load_named_model("megapose-1.0-RGB-multi-hypothesis", ds, models_root=setup["root"])
+    est.load_SO3_grid(72)
+    labels = [ds[0].label, ds[1].label, ds[0].label]
+    TCO_gt = torch.from_numpy(procedural.random_poses(3, 17)).float()
+    TCO_gt[:, 2, 3] = torch.tensor([0.5, 0.65, 0.8])
+    bboxes = torch.stack([helpers.detection_for_pose(K[0], TCO_gt[i], torch.from_numpy(ds.get_object_by_label(labels[i]).mesh.vertices).float())
+                          for i in range(3)])
+    det_df = pd.DataFrame(dict(label=labels, batch_im_id=0))
+    outs = []
+    for fused in (True, False):
+        est.fused_pipeline = fused
+        obs = ObservationTensor(images.clone(), K.clone()).cuda()
+        det = PandasTensorCollection(det_df.copy(), bboxes=bboxes.cuda())
+        outs.append(est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=2, n_pose_hypotheses=3))
+    (fa, ea), (fb, eb) = outs
+    assert set(ea.keys()) == set(eb.keys())
+    for key in ("coarse", "coarse_filter", "scoring", "refiner"):
+        a, b = ea[key]["preds"], eb[key]["preds"]
+        cols = [c for c in b.infos.columns]
+        assert list(a.infos.columns) == cols or set(a.infos.columns) == set(cols)
+        pd.testing.assert_frame_equal(a.infos[cols].reset_index(drop=True), b.infos[cols].reset_index(drop=True), check_dtype=False)
+        for t in b.tensors:
+            assert torch.equal(getattr(a, t), getattr(b, t)), (key, t)
+    for it in ("iteration=1", "iteration=2"):
+        a, b = ea["refiner_all_hypotheses"]["preds"][it], eb["refiner_all_hypotheses"]["preds"][it]
+        for t in b.tensors:
+            assert torch.equal(getattr(a, t), getattr(b, t)), (it, t)
+    assert torch.equal(fa.poses, fb.poses)
+    pd.testing.assert_frame_equal(fa.infos[fb.infos.columns], fb.infos, check_dtype=False)
