@@ -68,6 +68,11 @@ int mpx_meshdb_destroy(mpx_meshdb* db);
 
 size_t mpx_raster_workspace_bytes(int h, int w);
 
+/* kernel selection, default 1: bit 0 = batches of at most SMs/8 views (refiner iterations, final scoring) spread
+ * the triangles of each view over many CTAs (coverage kernel + resolve kernel) instead of one CTA per
+ * (view, row strip); 0 = always the one-kernel path.  Both produce identical pixels. */
+int mpx_raster_set_mode(int mode);
+
 /* contract output: float32 NCHW planes; any of d_rgb [N,3,h,w], d_normals [N,3,h,w],
  * d_depth [N,1,h,w] may be NULL. */
 int mpx_raster_render(const mpx_meshdb* db, const int32_t* d_label_idx, const float* d_TCO,
@@ -176,8 +181,20 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
                     int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                     void* d_out, int block_n, int max_ctas, void* stream);
 
-/* kernel selection for block_n == 0 (auto): 1 (default) = the shared-memory window kernel serves the 64->64
- * channel stride-1 convolutions (stem, layer1) and the TMA-im2col kernel everything else; 0 = im2col kernel only */
+/* the same convolution with its K loop split over `splits` CTAs per output tile (0 = heuristic) — the form the
+ * network uses for small batches (refiner iterations: a handful of output tiles, up to 72 serial k-blocks).
+ * Each k-split stores its fp32 partial tile into its own slab of d_scratch (4 KiB of tickets, then
+ * splits * n*P*Q*c_out*4 bytes; 256-B aligned); the last CTA to arrive sums the slabs in split order, so results are
+ * deterministic.  A scratch too small for `splits` slabs reduces the split count.  block_n must be explicit. */
+int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
+                           const float* d_bias, int c_out, int r, int s, int stride, int pad_lo_h,
+                           int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
+                           void* d_out, int block_n, int splits, void* d_scratch, size_t scratch_bytes,
+                           void* stream);
+
+/* kernel selection bits for block_n == 0 (auto), default 11: 1 = the shared-memory window kernel serves the
+ * 64->64 channel stride-1 convolutions (stem, layer1); 2 = the CTA-pair kernel serves 256-wide tiles; 4 = and
+ * 128-wide tiles; 8 = mpx_net_forward uses split-K for batches <= 64.  0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 
 /* bring-up probe (tools/gpu_probe_rowshift.py): D[128,64] = A[r0:r0+128, :64] * B[64,64]^T with the UMMA

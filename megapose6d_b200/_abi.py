@@ -5,6 +5,7 @@ The product path has no CPU fallback: if the library is missing or a call fails,
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 from typing import Optional
@@ -52,6 +53,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_net_input_bytes.restype = c_size_t
     lib.mpx_conv2d_bf16.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp]
+    lib.mpx_conv2d_bf16_splitk.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp, c_size_t, vp]
     lib.mpx_maxpool3x3s2_bf16.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
     lib.mpx_avgpool_linear.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp, vp]
     lib.mpx_net_create.argtypes = [c_int, c_int, POINTER(vp), POINTER(vp), c_int, vp, vp, POINTER(vp)]
@@ -65,15 +68,20 @@ def _declare(lib: ctypes.CDLL) -> None:
                                         POINTER(ctypes.c_longlong)]
     for name in EXPORTS:
         getattr(lib, name)  # every declared symbol must be exported
+    # diagnostic overrides of the kernel-selection bits (see include/mpx.h)
+    if os.environ.get("MPX_CONV_MODE"):
+        lib.mpx_conv_set_mode(int(os.environ["MPX_CONV_MODE"]))
+    if os.environ.get("MPX_RASTER_MODE"):
+        lib.mpx_raster_set_mode(int(os.environ["MPX_RASTER_MODE"]))
 
 
 EXPORTS = [
     "mpx_abi_version", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
     "mpx_meshdb_create", "mpx_meshdb_destroy",
-    "mpx_raster_workspace_bytes", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
+    "mpx_raster_workspace_bytes", "mpx_raster_set_mode", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",
-    "mpx_net_input_bytes", "mpx_conv2d_bf16", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2_bf16", "mpx_avgpool_linear",
+    "mpx_net_input_bytes", "mpx_conv2d_bf16", "mpx_conv2d_bf16_splitk", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2_bf16", "mpx_avgpool_linear",
     "mpx_net_create", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_workspace_bytes", "mpx_net_forward",
 ]
 

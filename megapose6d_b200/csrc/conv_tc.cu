@@ -195,6 +195,66 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bf
   }
 }
 
+// split-K: store this CTA's fp32 partial row into its own slab of the scratch (L2 resident)
+template <int NCOLS>
+__device__ __forceinline__ void splitk_store_row(uint32_t taddr, bool valid, float* part_row) {
+#pragma unroll 1
+  for (int c = 0; c < NCOLS; c += 32) {
+    uint32_t v[32];
+    tc_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+    tc_wait_ld();
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        __stcg(reinterpret_cast<float4*>(part_row + c + 4 * i),
+               make_float4(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]),
+                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+    }
+  }
+}
+
+// split-K: the last arriver sums the slabs in split order (deterministic), applies bias / residual / ReLU
+template <int NCOLS>
+__device__ __forceinline__ void splitk_finalize_row(const float* part_row, size_t slab, int splits,
+                                                    __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
+                                                    const float* bias_s, int relu) {
+#pragma unroll 1
+  for (int c = 0; c < NCOLS; c += 8) {
+    float4 a0 = __ldcg(reinterpret_cast<const float4*>(part_row + c));
+    float4 a1 = __ldcg(reinterpret_cast<const float4*>(part_row + c + 4));
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 t0 = __ldcg(reinterpret_cast<const float4*>(part_row + sp * slab + c));
+      const float4 t1 = __ldcg(reinterpret_cast<const float4*>(part_row + sp * slab + c + 4));
+      a0.x += t0.x; a0.y += t0.y; a0.z += t0.z; a0.w += t0.w;
+      a1.x += t1.x; a1.y += t1.y; a1.z += t1.z; a1.w += t1.w;
+    }
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 4);
+    float f[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
+                  a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+    if (res_row != nullptr) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_row + c));
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(rr[j]);
+        f[2 * j] += t.x;
+        f[2 * j + 1] += t.y;
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out_row + c) = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // optional per-launch timing (bench.py roofline): CUDA events around every conv launch
 // ---------------------------------------------------------------------------------------------
@@ -259,6 +319,13 @@ struct ConvParams {
   const float* bias;                // [C_out] folded BN shift
   const __nv_bfloat16* residual;    // [M_total, C_out] or nullptr
   __nv_bfloat16* out;               // [M_total, C_out]
+  // split-K (small batches: a handful of output tiles with a long serial K loop): `splits` CTAs share one output tile,
+  // each accumulates a contiguous range of k-blocks and stores its fp32 partial tile into its own slab of `partial`;
+  // the last CTA to arrive per (tile, row quarter) sums the slabs in split order (deterministic), applies
+  // bias/residual/ReLU, stores bf16 and resets the ticket
+  int splits;
+  float* partial;      // [splits, M_total, C_out] fp32
+  unsigned* counters;  // [m_tiles * n_tiles * 4], zero on entry, left zero
 };
 
 constexpr int kBlockM = 128;
@@ -296,7 +363,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;  // work items: (tile, k-split)
   for (int i = threadIdx.x; i < p.C_out; i += blockDim.x) bias_s[i] = p.bias[i];
 
   if (warp == 0 && lane == 0) {
@@ -332,7 +399,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const int pq = p.P * p.Q;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / p.splits;
+        const int split = item - tile * p.splits;
+        const int kb_begin = split * p.num_k_blocks / p.splits;
+        const int kb_end = (split + 1) * p.num_k_blocks / p.splits;
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
         const int m0 = m_tile * kBlockM;
@@ -342,8 +413,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int q0 = rem - p0 * p.Q;
         const int base_w = q0 * p.stride - p.pad_w;
         const int base_h = p0 * p.stride - p.pad_h;
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int r = tap / p.S;
@@ -375,13 +446,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++local) {
+        const int split = item % p.splits;
+        const int kb_begin = split * p.num_k_blocks / p.splits;
+        const int kb_end = (split + 1) * p.num_k_blocks / p.splits;
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * kATileBytes));
@@ -390,7 +464,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
             tc_mma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
@@ -406,7 +480,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int q4 = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q4 * 32 + lane;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++local) {
+      const int tile = item / p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const int acc = local & 1;
@@ -416,16 +491,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int n0 = n_tile * BLOCK_N;
       const size_t off = static_cast<size_t>(valid ? m : 0) * p.C_out + n0;
       const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
-      uint4 res_cur[4];
-      if (valid && res_row) load_res_chunk(res_row, 0, res_cur);  // in flight while the MMAs finish
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-      epilogue_row<BLOCK_N>(taddr, valid, p.out + off, res_row, bias_s + n0, p.relu, res_cur);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (p.splits == 1) {
+        uint4 res_cur[4];
+        if (valid && res_row) load_res_chunk(res_row, 0, res_cur);  // in flight while the MMAs finish
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        epilogue_row<BLOCK_N>(taddr, valid, p.out + off, res_row, bias_s + n0, p.relu, res_cur);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      } else {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const int split = item - tile * p.splits;
+        const size_t slab = static_cast<size_t>(p.M_total) * p.C_out;
+        splitk_store_row<BLOCK_N>(taddr, valid, p.partial + split * slab + off);
+        tc_fence_before();
+        __threadfence();  // partial sums visible before the ticket is taken
+        __syncwarp();
+        unsigned ticket = 0;
+        if (lane == 0) {
+          mbar_arrive(&tmem_empty[acc]);
+          ticket = atomicAdd(p.counters + tile * 4 + q4, 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == static_cast<unsigned>(p.splits - 1)) {  // every other split of this row quarter has landed
+          __threadfence();
+          if (valid)
+            splitk_finalize_row<BLOCK_N>(p.partial + off, slab, p.splits, p.out + off, res_row, bias_s + n0, p.relu);
+          if (lane == 0) p.counters[tile * 4 + q4] = 0u;
+        }
+      }
     }
   }
 
@@ -483,7 +581,7 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvP
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  int grid = p.m_tiles * p.n_tiles;
+  int grid = p.m_tiles * p.n_tiles * p.splits;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
   ProfileSlot* slot = profile_begin(stream);
@@ -510,7 +608,7 @@ int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride) {
 // residual/out: [n_img, P, Q, C_out] bf16.
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,
                  const void* residual, void* out, int block_n_override, int max_ctas,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const SplitKScratch* sk) {
   MPX_REQUIRE(d.C_in % 64 == 0 && d.C_in >= 64, "conv: C_in=%d must be a multiple of 64", d.C_in);
   MPX_REQUIRE(d.C_out % 64 == 0 && d.C_out <= 512, "conv: C_out=%d must be a multiple of 64, at most 512", d.C_out);
   MPX_REQUIRE(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
@@ -603,6 +701,29 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.splits = 1;
+  p.partial = nullptr;
+  p.counters = nullptr;
+  if (sk != nullptr && sk->partial != nullptr && !use_pair) {
+    // Few output tiles and a long K loop (deep layers at batch 1: one 80-row tile, 72 k-blocks): split K over idle SMs.
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int sms = max_ctas > 0 ? max_ctas : sm_count();
+    int splits = sk->force_splits > 0 ? sk->force_splits : 1;
+    if (sk->force_splits == 0 && tiles * 2 <= sms && p.num_k_blocks >= 8) {
+      splits = p.num_k_blocks / 4;
+      if (splits > sms / tiles) splits = sms / tiles;
+      if (splits > 16) splits = 16;
+    }
+    if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+    const size_t slab_bytes = static_cast<size_t>(M_total) * d.C_out * sizeof(float);
+    if (static_cast<size_t>(splits) * slab_bytes > sk->partial_bytes)
+      splits = static_cast<int>(sk->partial_bytes / slab_bytes);
+    if (splits > 1 && static_cast<size_t>(tiles) * 4 <= sk->n_counters) {
+      p.splits = splits;
+      p.partial = sk->partial;
+      p.counters = sk->counters;
+    }
+  }
 
   if (use_pair) {
     if (block_n == 128) return launch_conv2<128>(map_a, map_b, p, stream, max_ctas);
@@ -826,8 +947,9 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // bit 0: shared-memory window kernel for the 64 -> 64 stride-1 layers; bit 1: CTA-pair (cta_group::2) kernel for
 // C_out >= 128; 0 = single-CTA im2col kernel everywhere
-static int g_conv_mode = 3;
+static int g_conv_mode = 11;
 static int conv_mode() { return g_conv_mode; }
+int conv_get_mode() { return g_conv_mode; }
 void conv_set_mode(int mode) { g_conv_mode = mode; }
 
 // Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the window kernel.

@@ -52,11 +52,17 @@ roi_align_kernel(const float4* __restrict__ images, int b, int h, int w, const i
   int im = im_idx ? im_idx[roi] : roi;
   const bool im_ok = im >= 0 && im < b;
   const float4* img = images + static_cast<size_t>(im_ok ? im : 0) * h * w;
+  __shared__ AxisW s_axis[kAxisTableMax];
+  bool collapsed = false;  // block-uniform
+  if (im_ok && oh + ow <= kAxisTableMax) collapsed = build_axis_tables(rp, oh, ow, h, w, s_axis, s_axis + oh);
   for (int pix = blockIdx.y * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.y * blockDim.x) {
     const int ph = pix / ow, pw = pix - ph * ow;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float vacc = 0.f;
-    if (im_ok) {
+    if (collapsed) {
+      if (c == 4) roi_align_pixel_collapsed<true>(img, w, s_axis[ph], s_axis[oh + pw], acc, vacc);
+      else roi_align_pixel_collapsed<false>(img, w, s_axis[ph], s_axis[oh + pw], acc, vacc);
+    } else if (im_ok) {
       if (c == 4) roi_align_pixel<true>(img, h, w, rp, ph, pw, acc, vacc);
       else roi_align_pixel<false>(img, h, w, rp, ph, pw, acc, vacc);
     }

@@ -93,4 +93,89 @@ __device__ __forceinline__ void roi_align_pixel(const float4* __restrict__ img, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Collapsed form.  The bilinear weight of a sample factors into a row weight and a column weight, so the average
+// of the 4x4 samples of one output pixel is  sum_a sum_b Wy[a] * Wx[b] * img[y0 + a][x0 + b]  with
+// Wy[a] = (1/4) * sum over the 4 sample rows of their weight on image row y0 + a (same for columns).  When the four
+// sample coordinates of an output row / column touch at most four consecutive image rows / columns (bin < 2.67 px:
+// every crop that is not a strong minification) the 64 taps of the plain form become <= 16, usually 4-9.
+// Sample coordinates, floor / clamp decisions and the validity rule are those of torchvision (axis_tap); only the
+// order of the fp32 additions differs (tests: 2e-5).  AxisW entries live in shared memory, one per output row and
+// one per output column of a crop, built once per crop.
+// ---------------------------------------------------------------------------------------------
+struct AxisW {
+  int base;    // first image row / column touched
+  float w[4];  // collapsed weights on base .. base+3 (1/4 folded in); zero weight = not touched
+};
+
+// returns false when the four samples span more than four image rows / columns
+__device__ __forceinline__ bool axis_collapse(float start, float bin, int p, int size, AxisW& e) {
+  AxisTap t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = axis_tap(start + p * bin + (k + 0.5f) * bin / 4.f, size);
+  e.base = t[0].lo;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!t[k].ok) continue;
+    const int a = t[k].lo - e.base, b = t[k].hi - e.base;
+    w0 += (a == 0 ? t[k].h : 0.f) + (b == 0 ? t[k].l : 0.f);
+    w1 += (a == 1 ? t[k].h : 0.f) + (b == 1 ? t[k].l : 0.f);
+    w2 += (a == 2 ? t[k].h : 0.f) + (b == 2 ? t[k].l : 0.f);
+    w3 += (a == 3 ? t[k].h : 0.f) + (b == 3 ? t[k].l : 0.f);
+  }
+  e.w[0] = 0.25f * w0;
+  e.w[1] = 0.25f * w1;
+  e.w[2] = 0.25f * w2;
+  e.w[3] = 0.25f * w3;
+  return t[3].hi - e.base <= 3;
+}
+
+// Fills ay[0..oh) and ax[0..ow) (shared memory) with all threads of the CTA; returns (to every thread, via
+// __syncthreads_and) whether the collapsed form is valid for this crop.  Contains a barrier.
+__device__ __forceinline__ bool build_axis_tables(const RoiParams& r, int oh, int ow, int h, int w, AxisW* ay,
+                                                  AxisW* ax) {
+  bool ok = true;
+  for (int p = threadIdx.x; p < oh + ow; p += blockDim.x) {
+    AxisW e;
+    if (p < oh) {
+      ok = axis_collapse(r.y1, r.bin_h, p, h, e) && ok;
+      ay[p] = e;
+    } else {
+      ok = axis_collapse(r.x1, r.bin_w, p - oh, w, e) && ok;
+      ax[p - oh] = e;
+    }
+  }
+  return __syncthreads_and(ok ? 1 : 0) != 0;
+}
+
+template <bool WITH_DEPTH>
+__device__ __forceinline__ void roi_align_pixel_collapsed(const float4* __restrict__ img, int w, const AxisW& ey,
+                                                          const AxisW& ex, float4& acc, float& vacc) {
+  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  vacc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float wy = ey.w[a];
+    if (wy == 0.f) continue;
+    const float4* row = img + static_cast<size_t>(ey.base + a) * w + ex.base;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float wx = ex.w[b];
+      if (wx == 0.f) continue;
+      const float4 v = __ldg(row + b);
+      const float wgt = wy * wx;
+      acc.x += wgt * v.x;
+      acc.y += wgt * v.y;
+      acc.z += wgt * v.z;
+      if (WITH_DEPTH) {
+        acc.w += wgt * v.w;
+        vacc += v.w > 0.f ? wgt : 0.f;
+      }
+    }
+  }
+}
+
+constexpr int kAxisTableMax = 1024;  // oh + ow entries of shared memory (20 KB) per CTA
+
 }  // namespace mpx

@@ -87,6 +87,7 @@ void conv_profile_enable(int on);
 bool conv_profile_enabled();
 void net_set_graphs(int on);
 void conv_set_mode(int mode);
+int conv_get_mode();
 int conv_profile_summary(double* total_ms, double* total_flops, long long* launches);
 
 struct ConvDesc {
@@ -95,9 +96,21 @@ struct ConvDesc {
   int pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
   int relu;
 };
+// Scratch of the split-K path (conv_tc.cu): one fp32 slab per k-split and per-(tile, row quarter) tickets.  The tickets
+// must be zero when a convolution starts; every convolution leaves them zero again.  The slabs need no initialisation.
+struct SplitKScratch {
+  float* partial;
+  size_t partial_bytes;
+  unsigned* counters;
+  size_t n_counters;
+  int force_splits;  // 0 = heuristic, > 0 = exactly this many k-splits (tests)
+};
+constexpr size_t kSplitKPartialBytes = 8u << 20;
+constexpr size_t kSplitKCounters = 1024;
+constexpr size_t kSplitKScratchBytes = kSplitKPartialBytes + kSplitKCounters * sizeof(unsigned);
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,
                  const void* residual, void* out, int block_n_override, int max_ctas,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const SplitKScratch* sk = nullptr);
 int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride);
 int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, float* out, cudaStream_t stream);
 int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream);
@@ -143,6 +156,7 @@ int meshdb_create(int n_meshes, const float* verts, const float* normals, const 
                   MeshDb** out);
 void meshdb_destroy(MeshDb* db);
 size_t raster_workspace_bytes(int h, int w);
+void raster_set_scatter(int on);
 int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, const float* K, int n_views,
                   int h, int w, unsigned flags, const RasterOut& out, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream);

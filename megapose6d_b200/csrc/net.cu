@@ -71,32 +71,47 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
 
 // ---------------------------------------------------------------------------------------------
 // global average pool + linear (fc and head folded into one [out_dim, C] matrix on the host)
-// one CTA (128 threads) per sample; warp-shuffle reductions for the dot products
+// one CTA (512 threads) per sample: the pixels are split over G = 512 / (C/4) thread groups (each thread sums
+// 4 channels over every G-th pixel, fixed order), the groups are combined through shared memory, then one warp per
+// output does the dot product with warp-shuffle reductions.  With one sample per launch (refiner) the old
+// one-thread-per-4-channels loop over all pixels was a 27 us latency chain.
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool_linear_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c,
-                                      const float* __restrict__ w, const float* __restrict__ b,
-                                      int out_dim, float* __restrict__ out) {
-  extern __shared__ float pooled[];  // [c]
+constexpr int kPoolThreads = 512;
+__global__ void __launch_bounds__(kPoolThreads)
+avgpool_linear_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c, const float* __restrict__ w,
+                      const float* __restrict__ b, int out_dim, float* __restrict__ out) {
+  extern __shared__ float smem_pool[];  // [G][c] partial sums, then [c] pooled
   const int img = blockIdx.x;
   const __nv_bfloat16* xi = x + static_cast<size_t>(img) * hw * c;
-  const float inv = 1.f / static_cast<float>(hw);
-  for (int c0 = threadIdx.x * 4; c0 < c; c0 += blockDim.x * 4) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int p = 0; p < hw; ++p) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(xi + static_cast<size_t>(p) * c + c0));
-      const float2 a = unpack_bf16x2(v.x), d = unpack_bf16x2(v.y);
-      s0 += a.x;
-      s1 += a.y;
-      s2 += d.x;
-      s3 += d.y;
+  const int nq = c >> 2;
+  const int G = nq >= kPoolThreads ? 1 : kPoolThreads / nq;
+  float* part = smem_pool;
+  float* pooled = smem_pool + static_cast<size_t>(G) * c;
+  const int g = threadIdx.x / nq;
+  if (g < G) {
+    for (int q = threadIdx.x - g * nq; q < nq; q += kPoolThreads) {  // one pass unless C > 2048
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+      for (int p = g; p < hw; p += G) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(xi + static_cast<size_t>(p) * c + 4 * q));
+        const float2 a = unpack_bf16x2(v.x), d = unpack_bf16x2(v.y);
+        s0 += a.x;
+        s1 += a.y;
+        s2 += d.x;
+        s3 += d.y;
+      }
+      *reinterpret_cast<float4*>(part + static_cast<size_t>(g) * c + 4 * q) = make_float4(s0, s1, s2, s3);
     }
-    pooled[c0] = s0 * inv;
-    pooled[c0 + 1] = s1 * inv;
-    pooled[c0 + 2] = s2 * inv;
-    pooled[c0 + 3] = s3 * inv;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float inv = 1.f / static_cast<float>(hw);
+  for (int k = threadIdx.x; k < c; k += kPoolThreads) {
+    float s = 0.f;
+    for (int gg = 0; gg < G; ++gg) s += part[static_cast<size_t>(gg) * c + k];
+    pooled[k] = s * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kPoolThreads >> 5;
   for (int o = warp; o < out_dim; o += nwarps) {
     float acc = 0.f;
     for (int k = lane; k < c; k += 32) acc = fmaf(pooled[k], __ldg(w + static_cast<size_t>(o) * c + k), acc);
@@ -109,8 +124,12 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
                    float* out, cudaStream_t stream) {
   MPX_REQUIRE(c % 4 == 0 && c <= 4096, "avgpool_linear: C=%d unsupported", c);
   if (n == 0) return MPX_OK;
-  avgpool_linear_kernel<<<n, 128, c * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), hw, c, w, b, out_dim, out);
+  const int nq = c / 4;
+  const int G = nq >= kPoolThreads ? 1 : kPoolThreads / nq;
+  const size_t smem = static_cast<size_t>(G + 1) * c * sizeof(float);
+  MPX_REQUIRE(smem <= 48 * 1024, "avgpool_linear: C=%d needs %zu bytes of shared memory", c, smem);
+  avgpool_linear_kernel<<<n, kPoolThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), hw, c, w, b,
+                                                           out_dim, out);
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;
@@ -182,7 +201,7 @@ size_t net_workspace_bytes(int n, int h, int w) {
   const size_t stem = align256(static_cast<size_t>(n) * hs * ws * 64 * 2);
   const size_t hp = (hs + 2 - 3) / 2 + 1, wp = (ws + 2 - 3) / 2 + 1;
   const size_t l1 = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
-  return stem + 3 * l1 + 1024;
+  return stem + 3 * l1 + 1024 + kSplitKScratchBytes;
 }
 
 static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
@@ -261,6 +280,20 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   const size_t l1_bytes = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
   void* buf_stem = base;
   void* bufs[3] = {base + stem_bytes, base + stem_bytes + l1_bytes, base + stem_bytes + 2 * l1_bytes};
+  // split-K scratch for the small-batch forwards (refiner iterations, final scoring): tickets zeroed once per forward
+  // (every convolution leaves them zero again), slabs behind them
+  SplitKScratch sk_store{};
+  const SplitKScratch* sk = nullptr;
+  if ((conv_get_mode() & 8) != 0 && n <= 64) {
+    uint8_t* scratch = base + stem_bytes + 3 * l1_bytes + 1024;
+    MPX_CHECK_CUDA(cudaMemsetAsync(scratch, 0, kSplitKCounters * sizeof(unsigned), stream));
+    sk_store.counters = reinterpret_cast<unsigned*>(scratch);
+    sk_store.partial = reinterpret_cast<float*>(scratch + kSplitKCounters * sizeof(unsigned));
+    sk_store.partial_bytes = kSplitKPartialBytes;
+    sk_store.n_counters = kSplitKCounters;
+    sk_store.force_splits = 0;
+    sk = &sk_store;
+  }
 
   int ci = 0;
   int rc;
@@ -285,7 +318,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
       const int Ho = conv_out_dim(H, 1, 1, 3, stride), Wo = conv_out_dim(W, 1, 1, 3, stride);
       // conv1 + bn1 + relu
       ConvDesc d1{n, H, W, C, width, 3, 3, stride, 1, 1, 1, 1, 1};
-      rc = conv_forward(d1, bufs[cur], net->conv_w[ci], net->conv_b[ci], nullptr, bufs[t1], 0, 0, stream);
+      rc = conv_forward(d1, bufs[cur], net->conv_w[ci], net->conv_b[ci], nullptr, bufs[t1], 0, 0, stream, sk);
       if (rc != MPX_OK) return rc;
       const int c1 = ci;
       (void)c1;
@@ -296,7 +329,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
         // downsample: 1x1/s2 conv + bn (no relu) -> residual; conv_w order: conv1, conv2, downsample
         ConvDesc dd{n, H, W, C, width, 1, 1, stride, 0, 0, 0, 0, 0};
         rc = conv_forward(dd, bufs[cur], net->conv_w[ci + 1], net->conv_b[ci + 1], nullptr, bufs[t2], 0, 0,
-                          stream);
+                          stream, sk);
         if (rc != MPX_OK) return rc;
         residual = bufs[t2];
         out_buf = cur;  // block input is dead once conv1 and the downsample have consumed it
@@ -304,7 +337,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
       // conv2 + bn2 + residual + relu
       ConvDesc d2{n, Ho, Wo, width, width, 3, 3, 1, 1, 1, 1, 1, 1};
       rc = conv_forward(d2, bufs[t1], net->conv_w[ci], net->conv_b[ci], residual, bufs[out_buf], 0, 0,
-                        stream);
+                        stream, sk);
       if (rc != MPX_OK) return rc;
       ci += has_ds ? 2 : 1;
       cur = out_buf;

@@ -51,6 +51,8 @@ struct QuantTables {
 };
 __constant__ QuantTables c_tables;
 static bool g_tables_ready = false;
+static bool g_scatter = true;  // small-batch scatter path (raster_set_scatter)
+void raster_set_scatter(int on) { g_scatter = on != 0; }
 
 __device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }
 
@@ -92,11 +94,50 @@ struct TriSetup {
   bool ok;
 };
 
-__device__ __forceinline__ TriSetup load_tri(const int4* __restrict__ vtx, const int* __restrict__ faces,
-                                             int tri) {
+// camera transform, projection and 1/256-pixel snapping of one model vertex: {X, Y, 1/z bits, behind-near-plane}
+__device__ __forceinline__ int4 snap_vertex(const float* __restrict__ p, const float* sR, float fx, float cx, float fy,
+                                            float cy) {
+  const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+  const float xc = __fmaf_rn(sR[0], px, __fmaf_rn(sR[1], py, __fmaf_rn(sR[2], pz, sR[3])));
+  const float yc = __fmaf_rn(sR[4], px, __fmaf_rn(sR[5], py, __fmaf_rn(sR[6], pz, sR[7])));
+  const float zc = __fmaf_rn(sR[8], px, __fmaf_rn(sR[9], py, __fmaf_rn(sR[10], pz, sR[11])));
+  int4 o;
+  o.w = !(zc >= kNear);
+  const float zs = o.w ? 1.0f : zc;
+  const float iz = __frcp_rn(zs);
+  float u = __fmaf_rn(fx, __fmul_rn(xc, iz), cx);
+  float v = __fmaf_rn(fy, __fmul_rn(yc, iz), cy);
+  u = fminf(fmaxf(u, -kClampUV), kClampUV);
+  v = fminf(fmaxf(v, -kClampUV), kClampUV);
+  if (!(u == u)) { u = 0.f; o.w = 1; }
+  if (!(v == v)) { v = 0.f; o.w = 1; }
+  o.x = __float2int_rn(__fmul_rn(u, static_cast<float>(kSub)));
+  o.y = __float2int_rn(__fmul_rn(v, static_cast<float>(kSub)));
+  o.z = __float_as_int(iz);
+  return o;
+}
+
+// Where a triangle's snapped vertices come from: the per-CTA cache filled in phase (B) of raster_kernel, or (scatter
+// path for a handful of views) recomputed from the model vertices -- same arithmetic, same result.
+struct VtxSrc {
+  const int4* cache;   // CACHED
+  const float* verts;  // !CACHED: model vertices of this mesh
+  const float* sR;     // pose rows (shared memory)
+  float fx, cx, fy, cy;
+};
+
+template <bool CACHED>
+__device__ __forceinline__ TriSetup load_tri(const VtxSrc& src, const int* __restrict__ faces, int tri) {
   TriSetup t;
   const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1), ic = __ldg(faces + 3 * tri + 2);
-  const int4 a = __ldcg(vtx + ia), b = __ldcg(vtx + ib), c = __ldcg(vtx + ic);
+  int4 a, b, c;
+  if (CACHED) {
+    a = __ldcg(src.cache + ia); b = __ldcg(src.cache + ib); c = __ldcg(src.cache + ic);
+  } else {
+    a = snap_vertex(src.verts + 3 * ia, src.sR, src.fx, src.cx, src.fy, src.cy);
+    b = snap_vertex(src.verts + 3 * ib, src.sR, src.fx, src.cx, src.fy, src.cy);
+    c = snap_vertex(src.verts + 3 * ic, src.sR, src.fx, src.cx, src.fy, src.cy);
+  }
   t.ax = a.x; t.ay = a.y; t.bx = b.x; t.by = b.y; t.cx = c.x; t.cy = c.y;
   t.iza = __int_as_float(a.z); t.izb = __int_as_float(b.z); t.izc = __int_as_float(c.z);
   long long area2 = edge_fn(t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
@@ -138,6 +179,236 @@ __device__ __forceinline__ void emit_fragment(const TriSetup& t, long long w0, l
   if (key < __ldcg(cell)) atomicMin(cell, key);
 }
 
+// (C) coverage of one triangle restricted to rows [row_lo, row_hi]; bounding boxes above kBigArea pixels are queued
+// for the CTA-wide path
+template <bool CACHED>
+__device__ __forceinline__ void cover_triangle(const VtxSrc& src, const int* __restrict__ faces, int tri, int row_lo,
+                                               int row_hi, int h, int w, unsigned long long* __restrict__ vis,
+                                               int* s_big_count, int* s_big) {
+  const TriSetup t = load_tri<CACHED>(src, faces, tri);
+  if (!t.ok) return;
+  int j0, j1, i0, i1;
+  raster_bbox(t, h, w, j0, j1, i0, i1);
+  i0 = max(i0, row_lo);
+  i1 = min(i1, row_hi);
+  if (j0 > j1 || i0 > i1) return;
+  const long long area = static_cast<long long>(j1 - j0 + 1) * (i1 - i0 + 1);
+  if (area > kBigArea) {
+    const int slot = atomicAdd(s_big_count, 1);
+    if (slot < kBigQueue) {
+      s_big[slot] = tri;
+      return;
+    }
+  }
+  // incremental edge functions (exact integers): d/dx = -(by-ay)*256, d/dy = (bx-ax)*256
+  const int px0 = j0 * kSub + kHalf, py0 = i0 * kSub + kHalf;
+  const long long sgn = t.flip ? -1 : 1;
+  long long r0 = sgn * edge_fn(t.bx, t.by, t.cx, t.cy, px0, py0);
+  long long r1 = sgn * edge_fn(t.cx, t.cy, t.ax, t.ay, px0, py0);
+  long long r2 = sgn * edge_fn(t.ax, t.ay, t.bx, t.by, px0, py0);
+  const long long dx0 = -sgn * static_cast<long long>(t.cy - t.by) * kSub, dy0 = sgn * static_cast<long long>(t.cx - t.bx) * kSub;
+  const long long dx1 = -sgn * static_cast<long long>(t.ay - t.cy) * kSub, dy1 = sgn * static_cast<long long>(t.ax - t.cx) * kSub;
+  const long long dx2 = -sgn * static_cast<long long>(t.by - t.ay) * kSub, dy2 = sgn * static_cast<long long>(t.bx - t.ax) * kSub;
+  for (int i = i0; i <= i1; ++i) {
+    long long w0 = r0, w1 = r1, w2 = r2;
+    for (int j = j0; j <= j1; ++j) {
+      emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
+      w0 += dx0; w1 += dx1; w2 += dx2;
+    }
+    r0 += dy0; r1 += dy1; r2 += dy2;
+  }
+}
+
+// queued large triangles: the whole CTA shares each bounding box
+template <bool CACHED>
+__device__ __forceinline__ void cover_big_triangles(const VtxSrc& src, const int* __restrict__ faces, int nbig,
+                                                    const int* s_big, int row_lo, int row_hi, int h, int w,
+                                                    unsigned long long* __restrict__ vis) {
+  for (int b = 0; b < nbig; ++b) {
+    const int tri = s_big[b];
+    const TriSetup t = load_tri<CACHED>(src, faces, tri);
+    int j0, j1, i0, i1;
+    raster_bbox(t, h, w, j0, j1, i0, i1);
+    i0 = max(i0, row_lo);
+    i1 = min(i1, row_hi);
+    const int bw = j1 - j0 + 1;
+    const int cnt = bw * (i1 - i0 + 1);
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const int i = i0 + k / bw, j = j0 + k % bw;
+      const int px = j * kSub + kHalf, py = i * kSub + kHalf;
+      long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+      long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+      long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+      if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+      emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
+    }
+  }
+}
+
+// pose / intrinsics of one view into shared memory (thread 0); returns nothing, *s_valid = 0 for non-finite input or an
+// unknown label (such views render black)
+__device__ __forceinline__ void load_view(const MeshDb& db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
+                                          const float* __restrict__ K, int view, float* sR, float* sK, int* s_valid) {
+  bool ok = true;
+  const float* T = TCO + 16 * view;
+  const float* Kv = K + 9 * view;
+  for (int i = 0; i < 16; ++i) ok = ok && finite_f(T[i]);
+  for (int i = 0; i < 9; ++i) ok = ok && finite_f(Kv[i]);
+  const int lab = label_idx[view];
+  ok = ok && lab >= 0 && lab < db.n_meshes;
+  *s_valid = ok ? 1 : 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) sR[r * 4 + c] = T[r * 4 + c];
+  sK[0] = Kv[0]; sK[1] = Kv[2]; sK[2] = Kv[4]; sK[3] = Kv[5];
+}
+
+// (D) resolve + shade + write for rows [row_lo, row_hi] of one view.  Called by every thread of the CTA (contains
+// barriers when the crop is fused).
+template <bool CACHED>
+__device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __restrict__ faces,
+                                             const float* __restrict__ colors, const float* __restrict__ normals,
+                                             const unsigned long long* __restrict__ vis, int view, int row_lo, int row_hi,
+                                             int h, int w, bool q8, bool gl_axes, const RasterOut& out, AxisW* s_axis) {
+  const int npix = h * w;
+  const float* sR = src.sR;
+  // (D) resolve + shade + write
+  const float* vcol = colors;
+  const float* vnrm = normals;
+  // d = a / z + b with a = 1 / (1/far - 1/near), b = -a / near (utils.py:44-55), as literals so
+  // that host and device agree on the rounding
+  const float dep_a = -0.10101010f;
+  const float dep_b = 1.01010101f;
+  const int sample = out.x ? view / out.views_per_sample : 0;
+  const int vslot = out.x ? view % out.views_per_sample : 0;
+  const bool fuse_crop = out.x != nullptr && out.crop_images != nullptr;
+  RoiParams roi;
+  const float4* crop_img = nullptr;
+  bool crop_collapsed = false;
+  if (fuse_crop) {
+    roi = make_roi(out.crop_boxes + 4 * sample, h, w);
+    const int im = out.crop_im_idx ? out.crop_im_idx[sample] : sample;
+    if (im >= 0 && im < out.crop_b) crop_img = out.crop_images + static_cast<size_t>(im) * out.crop_h * out.crop_w;
+    // block-uniform: every thread sees the same sample / image
+    if (crop_img != nullptr && h + w <= kAxisTableMax)
+      crop_collapsed = build_axis_tables(roi, h, w, out.crop_h, out.crop_w, s_axis, s_axis + h);
+  }
+  for (int pix = row_lo * w + threadIdx.x; pix < (row_hi + 1) * w; pix += blockDim.x) {
+    const int i = pix / w, j = pix - i * w;
+    const unsigned long long key = __ldcg(vis + pix);
+    float r = 0.f, g = 0.f, b = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dep = 0.f;
+    if (key != ~0ull) {
+      const int tri = static_cast<int>(key & 0xffffffffu);
+      const TriSetup t = load_tri<CACHED>(src, faces, tri);
+      const int px = j * kSub + kHalf, py = i * kSub + kHalf;
+      long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+      long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+      long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+      if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+      float l0, l1, l2;
+      const float iz = sample_iz(t, w0, w1, w2, l0, l1, l2);
+      const float z = __frcp_rn(iz);
+      const float b0 = __fmul_rn(__fmul_rn(l0, t.iza), z);
+      const float b1 = __fmul_rn(__fmul_rn(l1, t.izb), z);
+      const float b2 = __fmul_rn(__fmul_rn(l2, t.izc), z);
+      const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1),
+                ic = __ldg(faces + 3 * tri + 2);
+      float col[3], nrm[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        col[k] = __fmaf_rn(b0, __ldg(vcol + 3 * ia + k),
+                           __fmaf_rn(b1, __ldg(vcol + 3 * ib + k), __fmul_rn(b2, __ldg(vcol + 3 * ic + k))));
+        nrm[k] = __fmaf_rn(b0, __ldg(vnrm + 3 * ia + k),
+                           __fmaf_rn(b1, __ldg(vnrm + 3 * ib + k), __fmul_rn(b2, __ldg(vnrm + 3 * ic + k))));
+      }
+      r = quant8(col[0], q8);
+      g = quant8(col[1], q8);
+      b = quant8(col[2], q8);
+      // eye-space normal (OpenCV camera axes), normalised
+      float ex = __fmaf_rn(sR[0], nrm[0], __fmaf_rn(sR[1], nrm[1], __fmul_rn(sR[2], nrm[2])));
+      float ey = __fmaf_rn(sR[4], nrm[0], __fmaf_rn(sR[5], nrm[1], __fmul_rn(sR[6], nrm[2])));
+      float ez = __fmaf_rn(sR[8], nrm[0], __fmaf_rn(sR[9], nrm[1], __fmul_rn(sR[10], nrm[2])));
+      const float nn = __fsqrt_rn(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, __fmul_rn(ez, ez))));
+      if (nn > 0.f) {
+        const float inv = __frcp_rn(nn);
+        ex = __fmul_rn(ex, inv);
+        ey = __fmul_rn(ey, inv);
+        ez = __fmul_rn(ez, inv);
+      }
+      // Panda camera axes (x right, y forward, z up) or GL axes (x right, y up, z backward)
+      const float px_ = ex;
+      const float py_ = gl_axes ? -ey : ez;
+      const float pz_ = gl_axes ? -ez : -ey;
+      n0 = quant8(normal_texture(px_), q8);
+      n1 = quant8(normal_texture(py_), q8);
+      n2 = quant8(normal_texture(pz_), q8);
+      const float d = __fmaf_rn(dep_a, iz, dep_b);
+      dep = (d > 0.999f) ? 0.f : z;
+    }
+    if (out.rgb) {
+      float* o = out.rgb + (static_cast<size_t>(view) * 3) * npix + pix;
+      o[0] = r; o[npix] = g; o[2 * npix] = b;
+    }
+    if (out.normals) {
+      float* o = out.normals + (static_cast<size_t>(view) * 3) * npix + pix;
+      o[0] = n0; o[npix] = n1; o[2 * npix] = n2;
+    }
+    if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
+    if (out.x) {
+      const int hs = h >> 1, ws = w >> 1;
+      __nv_bfloat16* base = out.x +
+                            ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
+                            ((i & 1) * 2 + (j & 1)) * out.c_pad;
+      float dn = dep;
+      if (out.ch_per_view == 7 && out.depth_norm_z) {
+        // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
+        dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
+      }
+      if (fuse_crop) {
+        // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float vacc = 0.f;
+        if (crop_collapsed) {
+          if (out.crop_c == 4) roi_align_pixel_collapsed<true>(crop_img, out.crop_w, s_axis[i], s_axis[h + j], acc, vacc);
+          else roi_align_pixel_collapsed<false>(crop_img, out.crop_w, s_axis[i], s_axis[h + j], acc, vacc);
+        } else if (crop_img) {
+          if (out.crop_c == 4) roi_align_pixel<true>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
+          else roi_align_pixel<false>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
+        }
+        float ch[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ch[k] = 0.f;
+        int c = 0;
+        ch[c++] = acc.x; ch[c++] = acc.y; ch[c++] = acc.z;
+        if (out.crop_c == 4) {
+          float d4 = (vacc < 0.99f) ? 0.f : acc.w;
+          if (out.depth_norm_z) d4 = fminf(fmaxf(d4 / __ldg(out.depth_norm_z + sample), 0.f), 2.f) - 1.f;
+          ch[c++] = d4;
+        }
+        ch[c++] = r; ch[c++] = g; ch[c++] = b; ch[c++] = n0; ch[c++] = n1; ch[c++] = n2;
+        if (out.ch_per_view == 7) ch[c++] = dn;
+        uint4* o4 = reinterpret_cast<uint4*>(base);
+        uint4 v0, v1;
+        v0.x = pack_bf16x2(ch[0], ch[1]); v0.y = pack_bf16x2(ch[2], ch[3]);
+        v0.z = pack_bf16x2(ch[4], ch[5]); v0.w = pack_bf16x2(ch[6], ch[7]);
+        v1.x = pack_bf16x2(ch[8], ch[9]); v1.y = pack_bf16x2(ch[10], ch[11]);
+        v1.z = pack_bf16x2(ch[12], ch[13]); v1.w = pack_bf16x2(ch[14], ch[15]);
+        o4[0] = v0;
+        o4[1] = v1;
+        for (int k = 2; k < out.c_pad / 8; ++k) o4[k] = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        __nv_bfloat16* o = base + out.ch_offset + vslot * out.ch_per_view;
+        o[0] = __float2bfloat16_rn(r);
+        o[1] = __float2bfloat16_rn(g);
+        o[2] = __float2bfloat16_rn(b);
+        o[3] = __float2bfloat16_rn(n0);
+        o[4] = __float2bfloat16_rn(n1);
+        o[5] = __float2bfloat16_rn(n2);
+        if (out.ch_per_view == 7) o[6] = __float2bfloat16_rn(dn);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kRasterThreads, 2)
 raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
               const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out,
@@ -147,6 +418,7 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
   __shared__ int s_valid;
   __shared__ int s_big_count;
   __shared__ int s_big[kBigQueue];
+  __shared__ AxisW s_axis[kAxisTableMax];  // fused crop: collapsed roi_align weights, rows then columns
 
   const int npix = h * w;
   unsigned long long* vis = vis_all + static_cast<size_t>(blockIdx.x) * npix;
@@ -155,7 +427,6 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
   const bool gl_axes = (flags & 2u) != 0;
 
   // work item = (view, horizontal strip of rows); strips > 1 only when there are fewer views than CTA slots
-  // (refiner: a handful of views would otherwise run on a handful of SMs)
   const int rows_per_strip = (h + strips - 1) / strips;
   for (int item = blockIdx.x; item < n_views * strips; item += gridDim.x) {
     const int view = item / strips;
@@ -163,17 +434,7 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     const int row_hi = min(h, row_lo + rows_per_strip) - 1;  // inclusive
     __syncthreads();  // previous item fully resolved before scratch is reused
     if (threadIdx.x == 0) {
-      bool ok = true;
-      const float* T = TCO + 16 * view;
-      const float* Kv = K + 9 * view;
-      for (int i = 0; i < 16; ++i) ok = ok && finite_f(T[i]);
-      for (int i = 0; i < 9; ++i) ok = ok && finite_f(Kv[i]);
-      const int lab = label_idx[view];
-      ok = ok && lab >= 0 && lab < db.n_meshes;
-      s_valid = ok ? 1 : 0;
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 4; ++c) sR[r * 4 + c] = T[r * 4 + c];
-      sK[0] = Kv[0]; sK[1] = Kv[2]; sK[2] = Kv[4]; sK[3] = Kv[5];
+      load_view(db, label_idx, TCO, K, view, sR, sK, &s_valid);
       s_big_count = 0;
     }
     __syncthreads();
@@ -188,219 +449,96 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     // (A) clear visibility, (B) transform + snap vertices
     for (int i = row_lo * w + threadIdx.x; i < (row_hi + 1) * w; i += blockDim.x) vis[i] = ~0ull;
     const float fx = sK[0], cx = sK[1], fy = sK[2], cy = sK[3];
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-      const float* p = db.verts + 3 * (v_off + i);
-      const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
-      const float xc = __fmaf_rn(sR[0], px, __fmaf_rn(sR[1], py, __fmaf_rn(sR[2], pz, sR[3])));
-      const float yc = __fmaf_rn(sR[4], px, __fmaf_rn(sR[5], py, __fmaf_rn(sR[6], pz, sR[7])));
-      const float zc = __fmaf_rn(sR[8], px, __fmaf_rn(sR[9], py, __fmaf_rn(sR[10], pz, sR[11])));
-      int4 o;
-      o.w = !(zc >= kNear);
-      const float zs = o.w ? 1.0f : zc;
-      const float iz = __frcp_rn(zs);
-      float u = __fmaf_rn(fx, __fmul_rn(xc, iz), cx);
-      float v = __fmaf_rn(fy, __fmul_rn(yc, iz), cy);
-      u = fminf(fmaxf(u, -kClampUV), kClampUV);
-      v = fminf(fmaxf(v, -kClampUV), kClampUV);
-      if (!(u == u)) { u = 0.f; o.w = 1; }
-      if (!(v == v)) { v = 0.f; o.w = 1; }
-      o.x = __float2int_rn(__fmul_rn(u, static_cast<float>(kSub)));
-      o.y = __float2int_rn(__fmul_rn(v, static_cast<float>(kSub)));
-      o.z = __float_as_int(iz);
-      vtx[i] = o;
-    }
+    for (int i = threadIdx.x; i < nv; i += blockDim.x)
+      vtx[i] = snap_vertex(db.verts + 3 * (v_off + i), sR, fx, cx, fy, cy);
     __syncthreads();
+    VtxSrc src;
+    src.cache = vtx;
+    src.verts = nullptr;
+    src.sR = sR;
+    src.fx = fx; src.cx = cx; src.fy = fy; src.cy = cy;
 
     // (C) triangles
-    for (int tri = threadIdx.x; tri < nf; tri += blockDim.x) {
-      const TriSetup t = load_tri(vtx, faces, tri);
-      if (!t.ok) continue;
-      int j0, j1, i0, i1;
-      raster_bbox(t, h, w, j0, j1, i0, i1);
-      i0 = max(i0, row_lo);
-      i1 = min(i1, row_hi);
-      if (j0 > j1 || i0 > i1) continue;
-      const long long area = static_cast<long long>(j1 - j0 + 1) * (i1 - i0 + 1);
-      if (area > kBigArea) {
-        const int slot = atomicAdd(&s_big_count, 1);
-        if (slot < kBigQueue) {
-          s_big[slot] = tri;
-          continue;
-        }
-      }
-      // incremental edge functions (exact integers): d/dx = -(by-ay)*256, d/dy = (bx-ax)*256
-      const int px0 = j0 * kSub + kHalf, py0 = i0 * kSub + kHalf;
-      const long long sgn = t.flip ? -1 : 1;
-      long long r0 = sgn * edge_fn(t.bx, t.by, t.cx, t.cy, px0, py0);
-      long long r1 = sgn * edge_fn(t.cx, t.cy, t.ax, t.ay, px0, py0);
-      long long r2 = sgn * edge_fn(t.ax, t.ay, t.bx, t.by, px0, py0);
-      const long long dx0 = -sgn * static_cast<long long>(t.cy - t.by) * kSub, dy0 = sgn * static_cast<long long>(t.cx - t.bx) * kSub;
-      const long long dx1 = -sgn * static_cast<long long>(t.ay - t.cy) * kSub, dy1 = sgn * static_cast<long long>(t.ax - t.cx) * kSub;
-      const long long dx2 = -sgn * static_cast<long long>(t.by - t.ay) * kSub, dy2 = sgn * static_cast<long long>(t.bx - t.ax) * kSub;
-      for (int i = i0; i <= i1; ++i) {
-        long long w0 = r0, w1 = r1, w2 = r2;
-        for (int j = j0; j <= j1; ++j) {
-          emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
-          w0 += dx0; w1 += dx1; w2 += dx2;
-        }
-        r0 += dy0; r1 += dy1; r2 += dy2;
-      }
-    }
+    for (int tri = threadIdx.x; tri < nf; tri += blockDim.x)
+      cover_triangle<true>(src, faces, tri, row_lo, row_hi, h, w, vis, &s_big_count, s_big);
     __syncthreads();
-    {
-      const int nbig = min(s_big_count, kBigQueue);
-      for (int b = 0; b < nbig; ++b) {
-        const int tri = s_big[b];
-        const TriSetup t = load_tri(vtx, faces, tri);
-        int j0, j1, i0, i1;
-        raster_bbox(t, h, w, j0, j1, i0, i1);
-        i0 = max(i0, row_lo);
-        i1 = min(i1, row_hi);
-        const int bw = j1 - j0 + 1;
-        const int cnt = bw * (i1 - i0 + 1);
-        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-          const int i = i0 + k / bw, j = j0 + k % bw;
-          const int px = j * kSub + kHalf, py = i * kSub + kHalf;
-          long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
-          long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
-          long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
-          if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
-          emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
-        }
-      }
-    }
+    cover_big_triangles<true>(src, faces, min(s_big_count, kBigQueue), s_big, row_lo, row_hi, h, w, vis);
     __syncthreads();
 
-    // (D) resolve + shade + write
-    const float* vcol = db.colors + 3 * v_off;
-    const float* vnrm = db.normals + 3 * v_off;
-    // d = a / z + b with a = 1 / (1/far - 1/near), b = -a / near (utils.py:44-55), as literals so
-    // that host and device agree on the rounding
-    const float dep_a = -0.10101010f;
-    const float dep_b = 1.01010101f;
-    const int sample = out.x ? view / out.views_per_sample : 0;
-    const int vslot = out.x ? view % out.views_per_sample : 0;
-    const bool fuse_crop = out.x != nullptr && out.crop_images != nullptr;
-    RoiParams roi;
-    const float4* crop_img = nullptr;
-    if (fuse_crop) {
-      roi = make_roi(out.crop_boxes + 4 * sample, h, w);
-      const int im = out.crop_im_idx ? out.crop_im_idx[sample] : sample;
-      if (im >= 0 && im < out.crop_b) crop_img = out.crop_images + static_cast<size_t>(im) * out.crop_h * out.crop_w;
-    }
-    for (int pix = row_lo * w + threadIdx.x; pix < (row_hi + 1) * w; pix += blockDim.x) {
-      const int i = pix / w, j = pix - i * w;
-      const unsigned long long key = __ldcg(vis + pix);
-      float r = 0.f, g = 0.f, b = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dep = 0.f;
-      if (key != ~0ull) {
-        const int tri = static_cast<int>(key & 0xffffffffu);
-        const TriSetup t = load_tri(vtx, faces, tri);
-        const int px = j * kSub + kHalf, py = i * kSub + kHalf;
-        long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
-        long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
-        long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
-        if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
-        float l0, l1, l2;
-        const float iz = sample_iz(t, w0, w1, w2, l0, l1, l2);
-        const float z = __frcp_rn(iz);
-        const float b0 = __fmul_rn(__fmul_rn(l0, t.iza), z);
-        const float b1 = __fmul_rn(__fmul_rn(l1, t.izb), z);
-        const float b2 = __fmul_rn(__fmul_rn(l2, t.izc), z);
-        const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1),
-                  ic = __ldg(faces + 3 * tri + 2);
-        float col[3], nrm[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          col[k] = __fmaf_rn(b0, __ldg(vcol + 3 * ia + k),
-                             __fmaf_rn(b1, __ldg(vcol + 3 * ib + k), __fmul_rn(b2, __ldg(vcol + 3 * ic + k))));
-          nrm[k] = __fmaf_rn(b0, __ldg(vnrm + 3 * ia + k),
-                             __fmaf_rn(b1, __ldg(vnrm + 3 * ib + k), __fmul_rn(b2, __ldg(vnrm + 3 * ic + k))));
-        }
-        r = quant8(col[0], q8);
-        g = quant8(col[1], q8);
-        b = quant8(col[2], q8);
-        // eye-space normal (OpenCV camera axes), normalised
-        float ex = __fmaf_rn(sR[0], nrm[0], __fmaf_rn(sR[1], nrm[1], __fmul_rn(sR[2], nrm[2])));
-        float ey = __fmaf_rn(sR[4], nrm[0], __fmaf_rn(sR[5], nrm[1], __fmul_rn(sR[6], nrm[2])));
-        float ez = __fmaf_rn(sR[8], nrm[0], __fmaf_rn(sR[9], nrm[1], __fmul_rn(sR[10], nrm[2])));
-        const float nn = __fsqrt_rn(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, __fmul_rn(ez, ez))));
-        if (nn > 0.f) {
-          const float inv = __frcp_rn(nn);
-          ex = __fmul_rn(ex, inv);
-          ey = __fmul_rn(ey, inv);
-          ez = __fmul_rn(ez, inv);
-        }
-        // Panda camera axes (x right, y forward, z up) or GL axes (x right, y up, z backward)
-        const float px_ = ex;
-        const float py_ = gl_axes ? -ey : ez;
-        const float pz_ = gl_axes ? -ez : -ey;
-        n0 = quant8(normal_texture(px_), q8);
-        n1 = quant8(normal_texture(py_), q8);
-        n2 = quant8(normal_texture(pz_), q8);
-        const float d = __fmaf_rn(dep_a, iz, dep_b);
-        dep = (d > 0.999f) ? 0.f : z;
-      }
-      if (out.rgb) {
-        float* o = out.rgb + (static_cast<size_t>(view) * 3) * npix + pix;
-        o[0] = r; o[npix] = g; o[2 * npix] = b;
-      }
-      if (out.normals) {
-        float* o = out.normals + (static_cast<size_t>(view) * 3) * npix + pix;
-        o[0] = n0; o[npix] = n1; o[2 * npix] = n2;
-      }
-      if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
-      if (out.x) {
-        const int hs = h >> 1, ws = w >> 1;
-        __nv_bfloat16* base = out.x +
-                              ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
-                              ((i & 1) * 2 + (j & 1)) * out.c_pad;
-        float dn = dep;
-        if (out.ch_per_view == 7 && out.depth_norm_z) {
-          // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
-          dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
-        }
-        if (fuse_crop) {
-          // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float vacc = 0.f;
-          if (crop_img) {
-            if (out.crop_c == 4) roi_align_pixel<true>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
-            else roi_align_pixel<false>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
-          }
-          float ch[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) ch[k] = 0.f;
-          int c = 0;
-          ch[c++] = acc.x; ch[c++] = acc.y; ch[c++] = acc.z;
-          if (out.crop_c == 4) {
-            float d4 = (vacc < 0.99f) ? 0.f : acc.w;
-            if (out.depth_norm_z) d4 = fminf(fmaxf(d4 / __ldg(out.depth_norm_z + sample), 0.f), 2.f) - 1.f;
-            ch[c++] = d4;
-          }
-          ch[c++] = r; ch[c++] = g; ch[c++] = b; ch[c++] = n0; ch[c++] = n1; ch[c++] = n2;
-          if (out.ch_per_view == 7) ch[c++] = dn;
-          uint4* o4 = reinterpret_cast<uint4*>(base);
-          uint4 v0, v1;
-          v0.x = pack_bf16x2(ch[0], ch[1]); v0.y = pack_bf16x2(ch[2], ch[3]);
-          v0.z = pack_bf16x2(ch[4], ch[5]); v0.w = pack_bf16x2(ch[6], ch[7]);
-          v1.x = pack_bf16x2(ch[8], ch[9]); v1.y = pack_bf16x2(ch[10], ch[11]);
-          v1.z = pack_bf16x2(ch[12], ch[13]); v1.w = pack_bf16x2(ch[14], ch[15]);
-          o4[0] = v0;
-          o4[1] = v1;
-          for (int k = 2; k < out.c_pad / 8; ++k) o4[k] = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          __nv_bfloat16* o = base + out.ch_offset + vslot * out.ch_per_view;
-          o[0] = __float2bfloat16_rn(r);
-          o[1] = __float2bfloat16_rn(g);
-          o[2] = __float2bfloat16_rn(b);
-          o[3] = __float2bfloat16_rn(n0);
-          o[4] = __float2bfloat16_rn(n1);
-          o[5] = __float2bfloat16_rn(n2);
-          if (out.ch_per_view == 7) o[6] = __float2bfloat16_rn(dn);
-        }
-      }
-    }
+    resolve_rows<true>(src, faces, db.colors + 3 * v_off, db.normals + 3 * v_off, vis, view, row_lo, row_hi, h, w, q8,
+                       gl_axes, out, s_axis);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scatter path for a handful of views (refiner iterations, final scoring): with one CTA per (view, strip) every CTA
+// still transforms all vertices and sets up all triangles -- a ~180 us latency chain for 4 views.  Here the
+// TRIANGLES of a view are spread over `parts` CTAs that share the view's visibility buffer through global atomics
+// (each thread sets up about one triangle, recomputing its three vertices), and a second kernel resolves the
+// pixels, again recomputing the winning triangle's vertices.  Same arithmetic per vertex / triangle / fragment and
+// an order-independent atomicMin: results are identical to raster_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCoverThreads = 256;
+__global__ void __launch_bounds__(kCoverThreads)
+raster_cover_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
+                    const float* __restrict__ K, int n_views, int h, int w, unsigned long long* __restrict__ vis_all,
+                    int parts) {
+  __shared__ float sR[12];
+  __shared__ float sK[4];
+  __shared__ int s_valid;
+  __shared__ int s_big_count;
+  __shared__ int s_big[kBigQueue];
+  const int view = blockIdx.x / parts, part = blockIdx.x - view * parts;
+  if (threadIdx.x == 0) {
+    load_view(db, label_idx, TCO, K, view, sR, sK, &s_valid);
+    s_big_count = 0;
+  }
+  __syncthreads();
+  if (s_valid == 0) return;
+  const int lab = label_idx[view];
+  const long long v_off = db.vert_offsets[lab];
+  const long long f_off = db.face_offsets[lab];
+  const int nf = static_cast<int>(db.face_offsets[lab + 1] - f_off);
+  const int* faces = db.faces + 3 * f_off;
+  unsigned long long* vis = vis_all + static_cast<size_t>(view) * h * w;
+  VtxSrc src;
+  src.cache = nullptr;
+  src.verts = db.verts + 3 * v_off;
+  src.sR = sR;
+  src.fx = sK[0]; src.cx = sK[1]; src.fy = sK[2]; src.cy = sK[3];
+  for (int tri = part * kCoverThreads + threadIdx.x; tri < nf; tri += parts * kCoverThreads)
+    cover_triangle<false>(src, faces, tri, 0, h - 1, h, w, vis, &s_big_count, s_big);
+  __syncthreads();
+  cover_big_triangles<false>(src, faces, min(s_big_count, kBigQueue), s_big, 0, h - 1, h, w, vis);
+}
+
+__global__ void __launch_bounds__(kRasterThreads, 2)
+raster_resolve_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
+                      const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out,
+                      const unsigned long long* __restrict__ vis_all, int strips) {
+  __shared__ float sR[12];
+  __shared__ float sK[4];
+  __shared__ int s_valid;
+  __shared__ AxisW s_axis[kAxisTableMax];
+  const int view = blockIdx.x / strips, strip = blockIdx.x - view * strips;
+  const int rows_per_strip = (h + strips - 1) / strips;
+  const int row_lo = strip * rows_per_strip;
+  const int row_hi = min(h, row_lo + rows_per_strip) - 1;
+  if (threadIdx.x == 0) load_view(db, label_idx, TCO, K, view, sR, sK, &s_valid);
+  __syncthreads();
+  const bool valid = s_valid != 0;
+  const int lab = valid ? label_idx[view] : 0;
+  const long long v_off = db.vert_offsets[lab];
+  const long long f_off = db.face_offsets[lab];
+  VtxSrc src;
+  src.cache = nullptr;
+  src.verts = db.verts + 3 * v_off;
+  src.sR = sR;
+  src.fx = sK[0]; src.cx = sK[1]; src.fy = sK[2]; src.cy = sK[3];
+  // an invalid view has an untouched (all ~0) visibility buffer: every pixel resolves to background
+  resolve_rows<false>(src, db.faces + 3 * f_off, db.colors + 3 * v_off, db.normals + 3 * v_off,
+                      vis_all + static_cast<size_t>(view) * h * w, view, row_lo, row_hi, h, w, (flags & 1u) != 0,
+                      (flags & 2u) != 0, out, s_axis);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -498,6 +636,25 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
     }
   }
   if (n_views == 0) return MPX_OK;
+  if (g_scatter && n_views * 8 <= sm_count()) {
+    // a handful of views: triangles of a view spread over `parts` CTAs, then a resolve kernel over row strips
+    unsigned long long* vis = reinterpret_cast<unsigned long long*>(workspace);
+    MPX_CHECK_CUDA(cudaMemsetAsync(vis, 0xFF, static_cast<size_t>(n_views) * h * w * sizeof(unsigned long long), stream));
+    int parts = sm_count() / n_views;
+    if (parts > 40) parts = 40;  // 10k triangles / (40 * 256 threads) = one triangle per thread
+    raster_cover_kernel<<<n_views * parts, kCoverThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, vis,
+                                                                       parts);
+    MPX_CHECK_CUDA(cudaGetLastError());
+    int strips = 2 * sm_count() / n_views;
+    if (strips > h) strips = h;
+    const int rows = (h + strips - 1) / strips;
+    strips = (h + rows - 1) / rows;  // no empty strips
+    raster_resolve_kernel<<<n_views * strips, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w,
+                                                                          flags, out, vis, strips);
+    MPX_CHECK_CUDA(cudaGetLastError());
+    g_launches += 2;
+    return MPX_OK;
+  }
   int strips = 1;
   if (n_views < db->slots) {
     strips = db->slots / n_views;

@@ -97,7 +97,9 @@ def test_topk():
 def test_roi_align_matches_torchvision(scene):
     ds, images, K, db, rm = scene
     boxes = torch.tensor([[100.0, 80, 420, 320], [-40, -30, 200, 150], [500, 380, 700, 530], [300, 200, 300.5, 200.2],
-                          [0, 0, 640, 480], [610.3, 440.7, 655.1, 490.2]])
+                          [0, 0, 640, 480], [610.3, 440.7, 655.1, 490.2],
+                          # minification: bins of 2.8 / 3.3 px and one mixed case take the uncollapsed path
+                          [-100, -100, 800, 700], [10, -200, 630, 700], [-0.4, 0.3, 820.2, 615.9]])
     n = boxes.shape[0]
     nhwc4 = lib3d.image_to_nhwc4(images.cuda())
     for c in (3, 4):
@@ -123,7 +125,17 @@ def _render_both(ds, rm, labels, TCO, K, res, depth=True):
     return out, ref
 
 
-def test_raster_bit_exact_vs_oracle(scene):
+@pytest.fixture(params=[1, 0], ids=["scatter", "strips"])
+def raster_mode(request):
+    """Small batches have two implementations (include/mpx.h mpx_raster_set_mode): triangles scattered over many CTAs
+    + resolve kernel (default), or one CTA per (view, row strip).  Both must match the oracle bit for bit."""
+    from megapose6d_b200 import _abi
+    _abi.lib().mpx_raster_set_mode(request.param)
+    yield request.param
+    _abi.lib().mpx_raster_set_mode(1)
+
+
+def test_raster_bit_exact_vs_oracle(scene, raster_mode):
     ds, images, K, db, rm = scene
     n = 12
     labels = [ds[i % 3].label for i in range(n)]
@@ -141,7 +153,7 @@ def test_raster_bit_exact_vs_oracle(scene):
     assert (out.depths > 0).float().mean() > 0.05  # the views are not empty
 
 
-def test_raster_invalid_pose_and_big_triangles():
+def test_raster_invalid_pose_and_big_triangles(raster_mode):
     # a 12-triangle box: every triangle takes the CTA-wide path; plus a non-finite pose -> black view
     v = np.array([[x, y, z] for x in (-.05, .05) for y in (-.04, .04) for z in (-.03, .03)], dtype=np.float64)
     f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
@@ -178,7 +190,7 @@ def test_raster_many_views_persistent_loop(scene):
     assert torch.equal(out.depths.cpu(), ref["depths"])
 
 
-def test_fused_crop_render_matches_separate_kernels(scene):
+def test_fused_crop_render_matches_separate_kernels(scene, raster_mode):
     """mpx_render_crop_fused writes the same bf16 network input as roi_align_fused + raster_render_fused."""
     from megapose6d_b200 import _abi
 

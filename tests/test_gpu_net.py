@@ -67,6 +67,58 @@ def test_conv_vs_torch(case):
     assert err <= 2 ** -7 * ref.abs().max().item() + 1e-2, err
 
 
+DEFAULT_CONV_MODE = 11  # window | pair(256) | split-K in the network
+
+
+SPLITK_CASES = [
+    # name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, splits
+    ("layer4_b1", 1, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 16),
+    ("layer4_b1_heur", 1, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 0),
+    ("layer3_s2", 1, 30, 40, 128, 256, 3, 3, 2, (1, 1, 1, 1), True, False, 64, 5),
+    ("layer3_ds_1x1", 2, 30, 40, 128, 256, 1, 1, 2, (0, 0, 0, 0), False, False, 128, 2),
+    ("layer2_b2", 2, 30, 40, 128, 128, 3, 3, 1, (1, 1, 1, 1), True, True, 128, 3),
+    ("uneven_split", 1, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), False, True, 256, 7),
+    ("splits_gt_ctas", 3, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 24),
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES, ids=[c[0] for c in SPLITK_CASES])
+def test_conv_splitk_matches_unsplit_and_reference(case):
+    name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, splits = case
+    g = torch.Generator(device="cuda").manual_seed(sum(map(ord, name)) % 1000)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    p = (h + pads[0] + pads[2] - r) // stride + 1
+    q = (w + pads[1] + pads[3] - s) // stride + 1
+    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    scratch = torch.full((4096 + max(splits, 16) * n * p * q * cout * 4,), 0xAB, device="cuda", dtype=torch.uint8)
+    assert scratch.data_ptr() % 256 == 0
+    lib = _abi.lib()
+    outs = []
+    for rep in range(2):  # the second call finds the slabs as the first left them
+        out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        _abi.check(lib.mpx_conv2d_bf16_splitk(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r,
+                                              s, stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
+                                              _abi.ptr(out), block_n, splits, _abi.ptr(scratch), scratch.numel(),
+                                              _abi.stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append(out.float())
+        assert int(scratch[:4096].max()) == 0, "split-K tickets must be left zeroed"
+    unsplit = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _abi.check(lib.mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s, stride,
+                                   pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(unsplit), block_n, 0,
+                                   _abi.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
+    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    assert not torch.isnan(outs[0]).any()
+    assert (outs[0] - ref).abs().max() <= tol
+    # fp32 partial sums are combined in a different (fixed) order than the unsplit K loop: one bf16 rounding at most
+    assert (outs[0] - unsplit.float()).abs().max() <= 2 ** -7 * ref.abs().max().item()
+    assert torch.equal(outs[0], outs[1])  # slabs are summed in split order: deterministic
+
+
 def test_conv_rejects_bad_arguments():
     x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
     w = torch.zeros(64, 48, device="cuda", dtype=torch.bfloat16)
@@ -151,11 +203,41 @@ def test_window_and_im2col_kernels_agree(case):
             torch.cuda.synchronize()
             outs.append(out.float())
     finally:
-        _abi.lib().mpx_conv_set_mode(3)
+        _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, 1, pads, relu, res)
     tol = 2 ** -7 * ref.abs().max().item() + 1e-2
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
     assert (outs[0] - outs[1]).abs().max() <= tol
+
+
+@pytest.mark.parametrize("cfg_name,n", [("refiner", 1), ("coarse", 2), ("refiner", 5)])
+def test_small_batch_splitk_network_matches_unsplit(cfg_name, n):
+    """Small batches run layers 2-4 with split-K (mode bit 3).  Same logits as the unsplit network up to fp32
+    summation order, stable over repeated calls (the scratch is left zeroed) and under graph replay."""
+    cfg = helpers.REFINER_CFG if cfg_name == "refiner" else helpers.COARSE_CFG
+    c = helpers.n_inputs(cfg)
+    head = "pose_fc" if cfg["predict_pose_update"] else "views_logits_head"
+    sd = helpers.make_state_dict(cfg, seed=3)
+    eng = ResNet34Engine(sd, n_inputs=c, head=head)
+    x = eng.pack_input(helpers._calibration_batch(c, 5, n=n).cuda())
+    lib = _abi.lib()
+    try:
+        lib.mpx_net_set_graphs(0)
+        lib.mpx_conv_set_mode(3)
+        unsplit = eng.forward(x, 240, 320)
+        lib.mpx_conv_set_mode(DEFAULT_CONV_MODE)
+        split = [eng.forward(x, 240, 320) for _ in range(3)]
+        lib.mpx_net_set_graphs(1)
+        graphed = [eng.forward(x, 240, 320) for _ in range(4)]
+    finally:
+        lib.mpx_net_set_graphs(1)
+        lib.mpx_conv_set_mode(DEFAULT_CONV_MODE)
+    with torch.no_grad():
+        bound = resnet_ref.bf16_forward_error_bound(sd, helpers._calibration_batch(c, 5, n=n), eps=2 ** -8).cuda()
+    for o in split + graphed:
+        assert torch.isfinite(o).all()
+        assert ((o - unsplit).abs() <= 0.1 * bound + 1e-6).all(), ((o - unsplit).abs().max(), bound.min())
+        assert torch.equal(o, split[0])  # deterministic
 
 
 def test_graph_replay_equals_eager_launches():
@@ -207,7 +289,7 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
             torch.cuda.synchronize()
             outs.append(out.float())
     finally:
-        _abi.lib().mpx_conv_set_mode(3)
+        _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
     tol = 2 ** -7 * ref.abs().max().item() + 1e-2
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
