@@ -30,6 +30,10 @@ sys.path.insert(0, str(ROOT))
 
 M_GRID = 576
 GFLOP_PER_HYP = 12.213  # coarse 12.068 + (5 * 14.236 + 12.068) / 576, 240x320, FLOP = 2*MAC
+GFLOP_COARSE_PER_HYP = 12.068
+# bf16 bytes the 36 convolutions of one coarse forward move at least once per hypothesis (each conv: input read +
+# output write + residual read; weights excluded): stem 2 x 2.46 MB, layer1 6 convs of 60x80x64, ... = 28.26 MB
+ALGO_CONV_BYTES_PER_HYP = 28.26e6
 N_REFINER_ITERS = 5
 
 
@@ -288,8 +292,18 @@ def run_mpx_arm(args):
         else:
             peak, peak_src = 1400.0, "fallback sustained figure of B200_PROFILING.md (of fallback)"
         conv_ms_per_step = conv_ms.value / prof_steps
-        algo_tflop_per_step = GFLOP_PER_HYP * M_GRID / 1000.0  # this rank's unit: one object x 576
+        # The event-timed launches are the 36 convolutions of the 576-hypothesis coarse forward (the refiner iterations and
+        # the final scoring replay CUDA graphs, whose kernels are not individually timed): algorithmic work of exactly
+        # those launches = 576 x 12.068 GFLOP (coarse model, FLOP = 2*MAC)
+        launches_per_step = conv_n.value / prof_steps
+        gflop_per_hyp = GFLOP_COARSE_PER_HYP if abs(launches_per_step - 36.0) < 0.5 else GFLOP_PER_HYP
+        algo_tflop_per_step = gflop_per_hyp * M_GRID / 1000.0  # this rank's unit: one object x 576
         achieved = algo_tflop_per_step / (conv_ms_per_step / 1000.0)
+        traffic = None
+        tpath = Path(__file__).resolve().parent / "profiles" / "conv_traffic.json"
+        if tpath.exists():  # dram__bytes_read.sum + dram__bytes_write.sum of the same 36 launches, one ncu pass (see file)
+            tj = json.loads(tpath.read_text())
+            traffic = float(tj["dram_read_bytes"]) + float(tj["dram_write_bytes"])
         line = {
             "metric": "pose hypotheses/sec through render+coarse+5x refine", "value": value, "unit": "hypotheses/s",
             "impl": "mpx", "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -300,8 +314,13 @@ def run_mpx_arm(args):
                     "d2h_bytes_per_step": int(n_gpus * 16 * 4 + n_gpus * 4 * 2 + M_GRID * n_gpus * 4 * 2)},
             "gpu_launches": int(launches.item()),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05, all 36 convs x 3 forwards of the step)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "tensor",
+                         "kernel": "tcgen05 implicit-GEMM convolutions (conv_window / conv_igemm / conv_igemm2): the 36 "
+                                   "launches of the 576-hypothesis coarse forward, summed",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_unit": "bytes of DRAM traffic of the same 36 launches (ncu), vs "
+                                         "algorithmic_activation_bytes",
+                         "algorithmic_activation_bytes": ALGO_CONV_BYTES_PER_HYP * M_GRID,
                          "peak_source": peak_src, "algorithmic_tflop_per_step": algo_tflop_per_step,
                          "executed_tflop_per_step": conv_fl.value / prof_steps / 1e12,
                          "conv_ms_per_step": conv_ms_per_step, "conv_launches_per_step": conv_n.value / prof_steps,

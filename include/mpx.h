@@ -181,16 +181,14 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
                     int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                     void* d_out, int block_n, int max_ctas, void* stream);
 
-/* the same convolution with its K loop split over `splits` CTAs per output tile (0 = heuristic) — the form the
- * network uses for small batches (refiner iterations: a handful of output tiles, up to 72 serial k-blocks).
- * Each k-split stores its fp32 partial tile into its own slab of d_scratch (4 KiB of tickets, then
- * splits * n*P*Q*c_out*4 bytes; 256-B aligned); the last CTA to arrive sums the slabs in split order, so results are
- * deterministic.  A scratch too small for `splits` slabs reduces the split count.  block_n must be explicit. */
+/* the same convolution with its K loop split over the `splits` (0 = heuristic, 1, 2, 4, 8) CTAs of a thread-block
+ * cluster per output tile -- the form the network uses for small batches (refiner iterations: a handful of output
+ * tiles, up to 72 serial k-blocks).  The partial tiles are reduced through distributed shared memory in rank order
+ * (deterministic).  block_n must be explicit. */
 int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
                            const float* d_bias, int c_out, int r, int s, int stride, int pad_lo_h,
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
-                           void* d_out, int block_n, int splits, void* d_scratch, size_t scratch_bytes,
-                           void* stream);
+                           void* d_out, int block_n, int splits, void* stream);
 
 /* kernel selection bits for block_n == 0 (auto), default 11: 1 = the shared-memory window kernel serves the
  * 64->64 channel stride-1 convolutions (stem, layer1); 2 = the CTA-pair kernel serves 256-wide tiles; 4 = and

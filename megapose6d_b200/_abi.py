@@ -54,7 +54,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_conv2d_bf16.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp]
     lib.mpx_conv2d_bf16_splitk.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
-                                           c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp, c_size_t, vp]
+                                           c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp]
     lib.mpx_maxpool3x3s2_bf16.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
     lib.mpx_avgpool_linear.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp, vp]
     lib.mpx_net_create.argtypes = [c_int, c_int, POINTER(vp), POINTER(vp), c_int, vp, vp, POINTER(vp)]

@@ -303,32 +303,22 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
 int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w, const float* d_bias,
                            int c_out, int r, int s, int stride, int pad_lo_h, int pad_lo_w, int pad_hi_h,
                            int pad_hi_w, int relu, const void* d_residual, void* d_out, int block_n, int splits,
-                           void* d_scratch, size_t scratch_bytes, void* stream) {
+                           void* stream) {
   MPX_NOT_NULL(d_x);
   MPX_NOT_NULL(d_w);
   MPX_NOT_NULL(d_bias);
   MPX_NOT_NULL(d_out);
-  MPX_NOT_NULL(d_scratch);
   MPX_REQUIRE(n > 0 && h > 0 && w > 0, "mpx_conv2d_bf16_splitk: empty input");
-  MPX_REQUIRE(splits >= 0 && splits <= 64, "mpx_conv2d_bf16_splitk: splits=%d out of range", splits);
+  MPX_REQUIRE(splits == 0 || splits == 1 || splits == 2 || splits == 4 || splits == 8,
+              "mpx_conv2d_bf16_splitk: splits=%d must be 0 (heuristic), 1, 2, 4 or 8", splits);
   MPX_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "mpx_conv2d_bf16_splitk: block_n must be 64|128|256");
   MPX_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(d_residual) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(d_scratch) & 255) == 0,
-              "mpx_conv2d_bf16_splitk: pointers must be 16-byte aligned (scratch: 256)");
-  const size_t counter_bytes = kSplitKCounters * sizeof(unsigned);
-  MPX_REQUIRE(scratch_bytes > counter_bytes + 256, "mpx_conv2d_bf16_splitk: scratch too small");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MPX_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, counter_bytes, st));
-  SplitKScratch sk;
-  sk.counters = reinterpret_cast<unsigned*>(d_scratch);
-  sk.n_counters = kSplitKCounters;
-  sk.partial = reinterpret_cast<float*>(static_cast<uint8_t*>(d_scratch) + counter_bytes);
-  sk.partial_bytes = scratch_bytes - counter_bytes;
-  sk.force_splits = splits;
+                  (reinterpret_cast<uintptr_t>(d_residual) & 15) == 0,
+              "mpx_conv2d_bf16_splitk: pointers must be 16-byte aligned");
   ConvDesc d{n, h, w, c_in, c_out, r, s, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w, relu};
-  return conv_forward(d, d_x, d_w, d_bias, d_residual, d_out, block_n, 0, st, &sk);
+  return conv_forward(d, d_x, d_w, d_bias, d_residual, d_out, block_n, 0, static_cast<cudaStream_t>(stream),
+                      splits == 0 ? -1 : splits);
 }
 
 int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out, void* stream) {

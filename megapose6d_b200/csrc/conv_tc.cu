@@ -195,63 +195,93 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bf
   }
 }
 
-// split-K: store this CTA's fp32 partial row into its own slab of the scratch (L2 resident)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-K over a thread-block cluster (small batches: a handful of output tiles, up to 72 serial k-blocks whose TMA
+// issue rate bounds a single CTA).  The S CTAs of a cluster compute the same output tile over disjoint k-ranges; each
+// parks its fp32 accumulator tile in its own shared memory (the drained pipeline stages), the cluster synchronises,
+// and CTA `rank` finishes rows [rank*128/S, (rank+1)*128/S): it sums the S partial rows through distributed shared
+// memory in rank order (deterministic), applies bias / residual / ReLU and stores bf16.  No global scratch, no
+// second kernel; the reduction costs two cluster barriers and one round of DSMEM reads.
+// ---------------------------------------------------------------------------------------------
 template <int NCOLS>
-__device__ __forceinline__ void splitk_store_row(uint32_t taddr, bool valid, float* part_row) {
+struct SplitKTile {
+  static constexpr int kPitch = NCOLS * 4 + 16;  // bytes per row; +16 keeps the row-owner 16-byte stores conflict-free
+  static constexpr int kBytes = 128 * kPitch;
+};
+
+// this thread's accumulator row -> own shared memory
+template <int NCOLS>
+__device__ __forceinline__ void splitk_park_row(uint32_t taddr, uint32_t tile_smem, int row) {
+  const uint32_t base = tile_smem + static_cast<uint32_t>(row * SplitKTile<NCOLS>::kPitch);
 #pragma unroll 1
   for (int c = 0; c < NCOLS; c += 32) {
     uint32_t v[32];
     tc_ld_32x32(taddr + static_cast<uint32_t>(c), v);
     tc_wait_ld();
-    if (valid) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        __stcg(reinterpret_cast<float4*>(part_row + c + 4 * i),
-               make_float4(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]),
-                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
-    }
+    for (int i = 0; i < 8; ++i)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + static_cast<uint32_t>((c + 4 * i) * 4)),
+                   "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
+                   : "memory");
   }
 }
 
-// split-K: the last arriver sums the slabs in split order (deterministic), applies bias / residual / ReLU
+// rows [rank*128/S, (rank+1)*128/S) of the tile: sum over the cluster, epilogue, store.  All threads of the CTA.
 template <int NCOLS>
-__device__ __forceinline__ void splitk_finalize_row(const float* part_row, size_t slab, int splits,
-                                                    __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
-                                                    const float* bias_s, int relu) {
-#pragma unroll 1
-  for (int c = 0; c < NCOLS; c += 8) {
-    float4 a0 = __ldcg(reinterpret_cast<const float4*>(part_row + c));
-    float4 a1 = __ldcg(reinterpret_cast<const float4*>(part_row + c + 4));
-    for (int sp = 1; sp < splits; ++sp) {
-      const float4 t0 = __ldcg(reinterpret_cast<const float4*>(part_row + sp * slab + c));
-      const float4 t1 = __ldcg(reinterpret_cast<const float4*>(part_row + sp * slab + c + 4));
-      a0.x += t0.x; a0.y += t0.y; a0.z += t0.z; a0.w += t0.w;
-      a1.x += t1.x; a1.y += t1.y; a1.z += t1.z; a1.w += t1.w;
-    }
-    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 4);
-    float f[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
-                  a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-    if (res_row != nullptr) {
-      const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_row + c));
-      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+__device__ __forceinline__ void splitk_reduce_slice(uint32_t tile_smem, int splits, int rank, long long m0,
+                                                    int M_total, int C_out, int n0, __nv_bfloat16* __restrict__ out,
+                                                    const __nv_bfloat16* __restrict__ residual, const float* bias_s,
+                                                    int relu) {
+  constexpr int kVecPerRow = NCOLS / 4;
+  const int rows_per = 128 / splits;
+  for (int u = threadIdx.x; u < rows_per * kVecPerRow; u += blockDim.x) {
+    const int r = rank * rows_per + u / kVecPerRow;
+    const int c = (u % kVecPerRow) * 4;
+    const long long m = m0 + r;
+    if (m >= M_total) continue;
+    const uint32_t local = tile_smem + static_cast<uint32_t>(r * SplitKTile<NCOLS>::kPitch + c * 4);
+    float4 part[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16x2(rr[j]);
-        f[2 * j] += t.x;
-        f[2 * j + 1] += t.y;
+    for (int sp = 0; sp < 8; ++sp) {
+      if (sp < splits) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(sp));
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(part[sp].x), "=f"(part[sp].y), "=f"(part[sp].z), "=f"(part[sp].w)
+                     : "r"(remote)
+                     : "memory");
       }
+    }
+    float4 a = part[0];
+#pragma unroll
+    for (int sp = 1; sp < 8; ++sp)
+      if (sp < splits) { a.x += part[sp].x; a.y += part[sp].y; a.z += part[sp].z; a.w += part[sp].w; }
+    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c);
+    float f[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
+    const size_t off = static_cast<size_t>(m) * C_out + n0 + c;
+    if (residual != nullptr) {
+      const uint2 rr = __ldg(reinterpret_cast<const uint2*>(residual + off));
+      const float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y);
+      f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
     }
     if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      for (int j = 0; j < 4; ++j) f[j] = fmaxf(f[j], 0.f);
     }
-    uint4 o;
+    uint2 o;
     o.x = pack_bf16x2(f[0], f[1]);
     o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out_row + c) = o;
+    *reinterpret_cast<uint2*>(out + off) = o;
   }
 }
 
@@ -319,13 +349,9 @@ struct ConvParams {
   const float* bias;                // [C_out] folded BN shift
   const __nv_bfloat16* residual;    // [M_total, C_out] or nullptr
   __nv_bfloat16* out;               // [M_total, C_out]
-  // split-K (small batches: a handful of output tiles with a long serial K loop): `splits` CTAs share one output tile,
-  // each accumulates a contiguous range of k-blocks and stores its fp32 partial tile into its own slab of `partial`;
-  // the last CTA to arrive per (tile, row quarter) sums the slabs in split order (deterministic), applies
-  // bias/residual/ReLU, stores bf16 and resets the ticket
+  // split-K: the `splits` (1, 2, 4 or 8) CTAs of a cluster share one output tile, each accumulating a contiguous
+  // range of k-blocks; reduction through distributed shared memory (see SplitKTile)
   int splits;
-  float* partial;      // [splits, M_total, C_out] fp32
-  unsigned* counters;  // [m_tiles * n_tiles * 4], zero on entry, left zero
 };
 
 constexpr int kBlockM = 128;
@@ -503,32 +529,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       } else {
+        // one item per CTA: park the fp32 accumulator row in the (drained) pipeline stage memory
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const int split = item - tile * p.splits;
-        const size_t slab = static_cast<size_t>(p.M_total) * p.C_out;
-        splitk_store_row<BLOCK_N>(taddr, valid, p.partial + split * slab + off);
+        splitk_park_row<BLOCK_N>(taddr, smem_u32(smem), row);
         tc_fence_before();
-        __threadfence();  // partial sums visible before the ticket is taken
-        __syncwarp();
-        unsigned ticket = 0;
-        if (lane == 0) {
-          mbar_arrive(&tmem_empty[acc]);
-          ticket = atomicAdd(p.counters + tile * 4 + q4, 1u);
-        }
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket == static_cast<unsigned>(p.splits - 1)) {  // every other split of this row quarter has landed
-          __threadfence();
-          if (valid)
-            splitk_finalize_row<BLOCK_N>(p.partial + off, slab, p.splits, p.out + off, res_row, bias_s + n0, p.relu);
-          if (lane == 0) p.counters[tile * 4 + q4] = 0u;
-        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.splits > 1) {
+    cluster_sync_all();  // every CTA of the cluster has parked its partial tile
+    const int item = blockIdx.x;
+    const int tile = item / p.splits;
+    const int m_tile = tile / p.n_tiles;
+    const int n_tile = tile - m_tile * p.n_tiles;
+    const int n0 = n_tile * BLOCK_N;
+    splitk_reduce_slice<BLOCK_N>(smem_u32(smem), p.splits, static_cast<int>(cluster_ctarank()),
+                                 static_cast<long long>(m_tile) * kBlockM, p.M_total, p.C_out, n0, p.out, p.residual,
+                                 bias_s + n0, p.relu);
+    cluster_sync_all();  // peers may still be reading this CTA's shared memory
+  }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -583,9 +606,26 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvP
   }
   int grid = p.m_tiles * p.n_tiles * p.splits;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
-  if (grid > cap) grid = cap;
   ProfileSlot* slot = profile_begin(stream);
-  conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  if (p.splits > 1) {
+    // one work item per CTA, the k-splits of a tile form a cluster
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.splits;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MPX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N>, ma, mb, p));
+  } else {
+    if (grid > cap) grid = cap;
+    conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  }
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * p.M_total * p.C_out * p.num_k_blocks * kBlockK);
@@ -608,7 +648,7 @@ int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride) {
 // residual/out: [n_img, P, Q, C_out] bf16.
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,
                  const void* residual, void* out, int block_n_override, int max_ctas,
-                 cudaStream_t stream, const SplitKScratch* sk) {
+                 cudaStream_t stream, int splitk) {
   MPX_REQUIRE(d.C_in % 64 == 0 && d.C_in >= 64, "conv: C_in=%d must be a multiple of 64", d.C_in);
   MPX_REQUIRE(d.C_out % 64 == 0 && d.C_out <= 512, "conv: C_out=%d must be a multiple of 64, at most 512", d.C_out);
   MPX_REQUIRE(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
@@ -702,27 +742,18 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.splits = 1;
-  p.partial = nullptr;
-  p.counters = nullptr;
-  if (sk != nullptr && sk->partial != nullptr && !use_pair) {
-    // Few output tiles and a long K loop (deep layers at batch 1: one 80-row tile, 72 k-blocks): split K over idle SMs.
+  if (splitk != 0 && !use_pair) {
+    // Few output tiles and a long K loop (deep layers at batch 1: one 80-row tile, 72 k-blocks): split K over a cluster.
     const int tiles = p.m_tiles * p.n_tiles;
     const int sms = max_ctas > 0 ? max_ctas : sm_count();
-    int splits = sk->force_splits > 0 ? sk->force_splits : 1;
-    if (sk->force_splits == 0 && tiles * 2 <= sms && p.num_k_blocks >= 8) {
-      splits = p.num_k_blocks / 4;
-      if (splits > sms / tiles) splits = sms / tiles;
-      if (splits > 16) splits = 16;
+    int want = splitk > 0 ? splitk : 1;
+    if (splitk < 0 && tiles * 2 <= sms && p.num_k_blocks >= 8) {
+      want = p.num_k_blocks / 4;
+      if (want > sms / tiles) want = sms / tiles;
     }
-    if (splits > p.num_k_blocks) splits = p.num_k_blocks;
-    const size_t slab_bytes = static_cast<size_t>(M_total) * d.C_out * sizeof(float);
-    if (static_cast<size_t>(splits) * slab_bytes > sk->partial_bytes)
-      splits = static_cast<int>(sk->partial_bytes / slab_bytes);
-    if (splits > 1 && static_cast<size_t>(tiles) * 4 <= sk->n_counters) {
-      p.splits = splits;
-      p.partial = sk->partial;
-      p.counters = sk->counters;
-    }
+    int splits = 1;
+    while (splits * 2 <= want && splits * 2 <= 8 && splits * 2 <= p.num_k_blocks) splits *= 2;
+    p.splits = splits;
   }
 
   if (use_pair) {
@@ -771,6 +802,7 @@ struct WinParams {
   long long q_base;    // first padded-linear index that can be a valid output
   int m_tiles;
   int relu;
+  unsigned long long kskip;  // bit (tap * 4 + k): the 16-channel K step k of that tap has all-zero weights, no MMA issued
   const float* bias;
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
@@ -779,7 +811,12 @@ struct WinParams {
 constexpr int kWinN = 64;          // C_out
 constexpr int kWinBTile = 64 * 128;  // one tap's weights: 64 rows x 64 channels bf16
 
-__global__ void __launch_bounds__(256, 1)
+// Epilogue organisation: one epilogue warp per scheduler cannot hide its own latencies (tcgen05.ld, the dependent
+// fp32 math, the stores): ~2 us per 128 x 64 tile against 0.6 us of MMAs.  EPI_SETS groups of four warps therefore take
+// tiles round-robin (set = tile % EPI_SETS) over kWinAccBufs TMEM accumulators, so several tiles are drained at once.
+constexpr int kWinAccBufs = 4;
+template <int EPI_SETS>
+__global__ void __launch_bounds__(128 + 128 * EPI_SETS, 1)
 conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const WinParams p, int stages, int n_taps) {
   extern __shared__ uint8_t smem_raw[];
@@ -790,10 +827,10 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + static_cast<size_t>(stages) * p.win_bytes);
   uint64_t* full_bar = bars;             // [stages]
   uint64_t* empty_bar = bars + 8;        // [stages]
-  uint64_t* tmem_full = bars + 16;       // [2]
-  uint64_t* tmem_empty = bars + 18;      // [2]
-  uint64_t* b_full = bars + 20;          // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* tmem_full = bars + 16;       // [kWinAccBufs]
+  uint64_t* tmem_empty = bars + 20;      // [kWinAccBufs]
+  uint64_t* b_full = bars + 24;          // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 25);
   float* bias_s = reinterpret_cast<float*>(bars + 32);  // [64]
 
   const int warp = threadIdx.x >> 5;
@@ -809,7 +846,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kWinAccBufs; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
@@ -819,7 +856,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_ptr_smem)),
-                 "r"(2 * kWinN)
+                 "r"(kWinAccBufs * kWinN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -869,8 +906,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
+        const int acc = local % kWinAccBufs;
+        const uint32_t acc_phase = (local / kWinAccBufs) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kWinN);
@@ -883,14 +920,26 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint64_t da_win = make_sw128_desc(smem_u32(smem_a + static_cast<size_t>(stage) * p.win_bytes));
           uint64_t db = make_sw128_desc(smem_u32(smem_b + wi * p.taps_per_win * kWinBTile));
           uint64_t da_row = da_win;
+          unsigned long long skip = p.kskip >> (wi * p.taps_per_win * 4);
           for (int r = 0; r < p.rg; ++r) {
             uint64_t da = da_row;
             for (int s = 0; s < p.S; ++s) {
-              tc_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
-              first = 0;
+              const unsigned m = static_cast<unsigned>(skip) & 0xFu;
+              skip >>= 4;
+              if (m == 0) {
+                tc_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+                tc_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+                tc_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
+                tc_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+                first = 0;
+              } else {  // structurally zero K steps (the 7x7 stem inside its 8x8 space-to-depth footprint)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if ((m >> k) & 1u) continue;
+                  tc_mma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+              }
               da += 8;
               db += kWinBTile / 16;
             }
@@ -908,11 +957,13 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q4 = warp & 3;
+    const int set = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
     int local = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++local) {
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      if (local % EPI_SETS != set) continue;
+      const int acc = local % kWinAccBufs;
+      const uint32_t acc_phase = (local / kWinAccBufs) & 1;
       const long long q = p.q_base + static_cast<long long>(tile) * kBlockM + row;
       bool valid = q < p.M_pad;
       size_t off = 0;
@@ -924,12 +975,12 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         valid = (y >= 0) && (y < p.H) && (x >= 0) && (x < p.W);
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kWinN : 0;
       }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
       const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);  // in flight while the MMAs finish
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
       epilogue_row<kWinN>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
       tc_fence_before();
       __syncwarp();
@@ -941,7 +992,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kWinN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kWinAccBufs * kWinN)
+                 : "memory");
   }
 }
 
@@ -971,7 +1023,10 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
   p.S = d.S;
   const int n_taps = d.R * d.S;
   const int b_bytes = n_taps * kWinBTile;
-  const int smem_limit = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers + bias*/;
+  // two epilogue warp sets hide the residual read of conv2 (0.352 -> 0.291 ms at batch 576, tools/gpu_probe_epilogue.py);
+  // mode bit 4 (16) selects a single set
+  const int epi_sets = (g_conv_mode & 16) != 0 ? 1 : 2;
+  const int smem_limit = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, bias*/;
   // choose the number of filter rows per window: largest row group whose windows fit at least twice
   int rg = d.R, stages = 0;
   for (; rg >= 1; --rg) {
@@ -1000,6 +1055,7 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
   if (m_tiles <= 0 || m_tiles >= (1LL << 31)) return MPX_ERR_UNSUPPORTED;
   p.m_tiles = static_cast<int>(m_tiles);
   p.relu = d.relu;
+  p.kskip = n_taps <= 16 ? d.kskip : 0ull;
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -1035,16 +1091,23 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
   }
   const int smem_bytes = 1024 + b_bytes + stages * p.win_bytes + 1024;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    MPX_CHECK_CUDA(cudaFuncSetAttribute(conv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_bytes = 227 * 1024;
-  }
   int grid = p.m_tiles;
   const int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
   ProfileSlot* slot = profile_begin(stream);
-  conv_window_kernel<<<grid, 256, smem_bytes, stream>>>(map_a, map_b, p, stages, n_taps);
+  rc = MPX_OK;
+#define MPX_WIN_LAUNCH(E)                                                                                        \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      MPX_CHECK_CUDA(cudaFuncSetAttribute(conv_window_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                          227 * 1024));                                                          \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    conv_window_kernel<E><<<grid, 128 + 128 * E, smem_bytes, stream>>>(map_a, map_b, p, stages, n_taps);           \
+  } while (0)
+  if (epi_sets == 1) MPX_WIN_LAUNCH(1);
+  else MPX_WIN_LAUNCH(2);
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 64.0 * n_taps * 64.0);
@@ -1065,15 +1128,6 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 constexpr uint64_t kTmaCacheHintNormal = 0x1000000000000000ull;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta_rank));

@@ -95,22 +95,14 @@ struct ConvDesc {
   int C_out, R, S, stride;
   int pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
   int relu;
+  // optional (window kernel, <= 16 taps): bit (tap * 4 + k) set = the weights of 16-channel K step k of filter tap
+  // `tap` are all zero, the step is not executed.  0 = execute everything.
+  unsigned long long kskip;
 };
-// Scratch of the split-K path (conv_tc.cu): one fp32 slab per k-split and per-(tile, row quarter) tickets.  The tickets
-// must be zero when a convolution starts; every convolution leaves them zero again.  The slabs need no initialisation.
-struct SplitKScratch {
-  float* partial;
-  size_t partial_bytes;
-  unsigned* counters;
-  size_t n_counters;
-  int force_splits;  // 0 = heuristic, > 0 = exactly this many k-splits (tests)
-};
-constexpr size_t kSplitKPartialBytes = 8u << 20;
-constexpr size_t kSplitKCounters = 1024;
-constexpr size_t kSplitKScratchBytes = kSplitKPartialBytes + kSplitKCounters * sizeof(unsigned);
+// splitk: 0 = never, -1 = heuristic (few output tiles, long K loop), 1|2|4|8 = that many k-splits (cluster size)
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,
                  const void* residual, void* out, int block_n_override, int max_ctas,
-                 cudaStream_t stream, const SplitKScratch* sk = nullptr);
+                 cudaStream_t stream, int splitk = 0);
 int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride);
 int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, float* out, cudaStream_t stream);
 int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream);

@@ -156,6 +156,7 @@ struct Net {
   std::vector<const float*> conv_b;
   const float* head_w;
   const float* head_b;
+  unsigned long long stem_kskip = 0;  // structurally zero K steps of the space-to-depth stem (ConvDesc::kskip)
   std::vector<GraphEntry> graphs;
   cudaStream_t side = nullptr;  // capture / replay stream (the caller's stream may be the legacy default stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -180,6 +181,24 @@ int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* c
   net->conv_b.assign(conv_b, conv_b + n_convs);
   net->head_w = head_w;
   net->head_b = head_b;
+  if (c_pad == 16) {
+    // 7x7/s2 stem as 4x4 taps x (2x2 sub-pixels x 16 channels): the taps of the first row / column only use the
+    // second sub-pixel row / column -- 15 of the 64 (tap, sub-pixel) K steps carry no weights at all.  Read them off
+    // the packed weights so that any stem matrix (not only a 7x7-derived one) is handled correctly.
+    const size_t k_total = 16 * 64, n_el = 64 * k_total;
+    std::vector<uint16_t> hw(n_el);
+    MPX_CHECK_CUDA(cudaMemcpy(hw.data(), conv_w[0], n_el * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    unsigned long long skip = 0;
+    for (int tap = 0; tap < 16; ++tap)
+      for (int k = 0; k < 4; ++k) {
+        bool zero = true;
+        for (int co = 0; co < 64 && zero; ++co)
+          for (int c = 0; c < 16; ++c)
+            if ((hw[co * k_total + tap * 64 + k * 16 + c] & 0x7fffu) != 0) { zero = false; break; }
+        if (zero) skip |= 1ull << (tap * 4 + k);
+      }
+    net->stem_kskip = skip;
+  }
   *out = net;
   return MPX_OK;
 }
@@ -201,7 +220,7 @@ size_t net_workspace_bytes(int n, int h, int w) {
   const size_t stem = align256(static_cast<size_t>(n) * hs * ws * 64 * 2);
   const size_t hp = (hs + 2 - 3) / 2 + 1, wp = (ws + 2 - 3) / 2 + 1;
   const size_t l1 = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
-  return stem + 3 * l1 + 1024 + kSplitKScratchBytes;
+  return stem + 3 * l1 + 1024;
 }
 
 static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
@@ -280,26 +299,14 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   const size_t l1_bytes = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
   void* buf_stem = base;
   void* bufs[3] = {base + stem_bytes, base + stem_bytes + l1_bytes, base + stem_bytes + 2 * l1_bytes};
-  // split-K scratch for the small-batch forwards (refiner iterations, final scoring): tickets zeroed once per forward
-  // (every convolution leaves them zero again), slabs behind them
-  SplitKScratch sk_store{};
-  const SplitKScratch* sk = nullptr;
-  if ((conv_get_mode() & 8) != 0 && n <= 64) {
-    uint8_t* scratch = base + stem_bytes + 3 * l1_bytes + 1024;
-    MPX_CHECK_CUDA(cudaMemsetAsync(scratch, 0, kSplitKCounters * sizeof(unsigned), stream));
-    sk_store.counters = reinterpret_cast<unsigned*>(scratch);
-    sk_store.partial = reinterpret_cast<float*>(scratch + kSplitKCounters * sizeof(unsigned));
-    sk_store.partial_bytes = kSplitKPartialBytes;
-    sk_store.n_counters = kSplitKCounters;
-    sk_store.force_splits = 0;
-    sk = &sk_store;
-  }
+  // small batches (refiner iterations, final scoring): layers 2-4 split their K loop over a cluster
+  const int sk = ((conv_get_mode() & 8) != 0 && n <= 64) ? -1 : 0;
 
   int ci = 0;
   int rc;
   // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input
   {
-    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1};
+    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, net->stem_kskip};
     rc = conv_forward(d, x, net->conv_w[ci], net->conv_b[ci], nullptr, buf_stem, 0, 0, stream);
     if (rc != MPX_OK) return rc;
     ++ci;

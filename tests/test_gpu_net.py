@@ -18,6 +18,7 @@ from oracle import resnet_ref
 from tests import helpers
 
 pytestmark = pytest.mark.gpu
+DEFAULT_CONV_MODE = 11  # window | pair(256) | split-K in the network
 
 
 def _conv_ref(x, w, bias, stride, pads, relu, residual):
@@ -67,23 +68,22 @@ def test_conv_vs_torch(case):
     assert err <= 2 ** -7 * ref.abs().max().item() + 1e-2, err
 
 
-DEFAULT_CONV_MODE = 11  # window | pair(256) | split-K in the network
-
-
 SPLITK_CASES = [
-    # name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, splits
-    ("layer4_b1", 1, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 16),
+    # name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, splits (0 = heuristic)
+    ("layer4_b1", 1, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 8),
     ("layer4_b1_heur", 1, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 0),
-    ("layer3_s2", 1, 30, 40, 128, 256, 3, 3, 2, (1, 1, 1, 1), True, False, 64, 5),
+    ("layer3_s2", 1, 30, 40, 128, 256, 3, 3, 2, (1, 1, 1, 1), True, False, 64, 4),
     ("layer3_ds_1x1", 2, 30, 40, 128, 256, 1, 1, 2, (0, 0, 0, 0), False, False, 128, 2),
-    ("layer2_b2", 2, 30, 40, 128, 128, 3, 3, 1, (1, 1, 1, 1), True, True, 128, 3),
-    ("uneven_split", 1, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), False, True, 256, 7),
-    ("splits_gt_ctas", 3, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 24),
+    ("layer2_b2", 2, 30, 40, 128, 128, 3, 3, 1, (1, 1, 1, 1), True, True, 128, 4),
+    ("wide_tile", 1, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), False, True, 256, 8),
+    ("many_tiles", 3, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 8),
+    ("single_split", 1, 8, 10, 256, 256, 3, 3, 1, (1, 1, 1, 1), True, True, 64, 1),
 ]
 
 
 @pytest.mark.parametrize("case", SPLITK_CASES, ids=[c[0] for c in SPLITK_CASES])
 def test_conv_splitk_matches_unsplit_and_reference(case):
+    """K loop split over a thread-block cluster, partial tiles reduced through distributed shared memory."""
     name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, splits = case
     g = torch.Generator(device="cuda").manual_seed(sum(map(ord, name)) % 1000)
     x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
@@ -92,19 +92,15 @@ def test_conv_splitk_matches_unsplit_and_reference(case):
     p = (h + pads[0] + pads[2] - r) // stride + 1
     q = (w + pads[1] + pads[3] - s) // stride + 1
     res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
-    scratch = torch.full((4096 + max(splits, 16) * n * p * q * cout * 4,), 0xAB, device="cuda", dtype=torch.uint8)
-    assert scratch.data_ptr() % 256 == 0
     lib = _abi.lib()
     outs = []
-    for rep in range(2):  # the second call finds the slabs as the first left them
+    for rep in range(2):
         out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
         _abi.check(lib.mpx_conv2d_bf16_splitk(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r,
                                               s, stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
-                                              _abi.ptr(out), block_n, splits, _abi.ptr(scratch), scratch.numel(),
-                                              _abi.stream_ptr()))
+                                              _abi.ptr(out), block_n, splits, _abi.stream_ptr()))
         torch.cuda.synchronize()
         outs.append(out.float())
-        assert int(scratch[:4096].max()) == 0, "split-K tickets must be left zeroed"
     unsplit = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     _abi.check(lib.mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s, stride,
                                    pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(unsplit), block_n, 0,
@@ -116,7 +112,17 @@ def test_conv_splitk_matches_unsplit_and_reference(case):
     assert (outs[0] - ref).abs().max() <= tol
     # fp32 partial sums are combined in a different (fixed) order than the unsplit K loop: one bf16 rounding at most
     assert (outs[0] - unsplit.float()).abs().max() <= 2 ** -7 * ref.abs().max().item()
-    assert torch.equal(outs[0], outs[1])  # slabs are summed in split order: deterministic
+    assert torch.equal(outs[0], outs[1])  # partial tiles are summed in rank order: deterministic
+
+
+def test_conv_splitk_rejects_bad_split_count():
+    x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(64, device="cuda")
+    out = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+    rc = _abi.lib().mpx_conv2d_bf16_splitk(_abi.ptr(x), 1, 8, 8, 64, _abi.ptr(w), _abi.ptr(b), 64, 1, 1, 1, 0, 0, 0, 0, 0, None,
+                                           _abi.ptr(out), 64, 3, _abi.stream_ptr())
+    assert rc != 0 and b"splits" in _abi.lib().mpx_last_error()
 
 
 def test_conv_rejects_bad_arguments():
