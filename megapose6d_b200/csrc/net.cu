@@ -3,6 +3,7 @@
 // (reference: src/megapose/models/torchvision_resnet.py:74-120 BasicBlock, :298-311 forward order;
 //  heads: src/megapose/models/pose_rigid.py:120-130, 314-334).
 #include <cuda.h>
+#include <cstdlib>
 #include <vector>
 #include "mpx_common.cuh"
 
@@ -197,7 +198,8 @@ int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* c
             if ((hw[co * k_total + tap * 64 + k * 16 + c] & 0x7fffu) != 0) { zero = false; break; }
         if (zero) skip |= 1ull << (tap * 4 + k);
       }
-    net->stem_kskip = skip;
+    const char* env = getenv("MPX_STEM_KSKIP");  // diagnostic: MPX_STEM_KSKIP=0 executes every K step
+    net->stem_kskip = (env && env[0] == '0') ? 0ull : skip;
   }
   *out = net;
   return MPX_OK;

@@ -85,6 +85,7 @@ class PoseEstimator(torch.nn.Module):
 
     def load_SO3_grid(self, grid_size: int) -> None:
         self._SO3_grid = load_SO3_grid(grid_size).cuda()
+        self.__dict__.pop("_rows_cache", None)
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -309,12 +310,42 @@ class PoseEstimator(torch.nn.Module):
         return data_TCO_final, extra_data
 
     # ------------------------------------------------------------------------------------------
+    def _pipeline_rows(self, df: pd.DataFrame, device) -> dict:
+        """Index tensors of the coarse stage (row = detection * M + hypothesis): functions of the detections' image ids
+        and labels only, cached so that a stream of frames with the same detections does not rebuild them."""
+        M = self._SO3_grid.shape[0]
+        labels = tuple(df["label"].tolist())
+        key = (tuple(df["batch_im_id"].tolist()), labels, M, str(device))
+        cache = self.__dict__.setdefault("_rows_cache", {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 8:
+                cache.clear()
+            B = len(df)
+            bim = torch.as_tensor(np.ascontiguousarray(df["batch_im_id"].to_numpy()), device=device)
+            det_label_idx = self.coarse_model.mesh_db.label_ids(list(labels), device)
+            ent = cache[key] = dict(
+                batch_im_ids=bim.repeat_interleave(M), bbox_ids=torch.arange(B, device=device).repeat_interleave(M),
+                label_idx=det_label_idx.repeat_interleave(M), R=self._SO3_grid.repeat(B, 1, 1).contiguous(),
+                group_base=(torch.arange(B, device=device) * M).unsqueeze(1),
+                labels_rows=[l for l in labels for _ in range(M)])
+        return ent
+
+    def _pinned(self, name: str, n: int) -> torch.Tensor:
+        bufs = self.__dict__.setdefault("_pinned_bufs", {})
+        buf = bufs.get(name)
+        if buf is None or buf.numel() < n:
+            buf = bufs[name] = torch.empty(max(n, 1024), dtype=torch.float64, pin_memory=True)
+        return buf[:n]
+
     @torch.no_grad()
     def _run_pipeline_fused(self, observation: ObservationTensor, detections: DetectionsType, n_refiner_iterations: int,
                             n_pose_hypotheses: int, detection_filter_kwargs: Optional[dict], t_start: float):
-        """The same pipeline with every stage enqueued back to back: the top-K selection between the stages runs on the
-        device (mpx_topk_per_group + a stable sort), so the host never waits for the coarse logits before it can launch
-        the refiner.  All DataFrame bookkeeping happens while the device works; one synchronisation at the end.
+        """The same pipeline with every stage enqueued back to back.  The top-K selection between the stages and the
+        final best-hypothesis selection run on the device (mpx_topk_per_group + stable sorts), so the host never waits
+        for logits before it can launch the next stage.  The coarse logits come back on a side stream as soon as the
+        coarse stage is done; all DataFrame bookkeeping of the reference's outputs is done while the refiner and the
+        scoring pass run; after the last synchronisation only two columns are filled in.
         Returns None (caller falls back to the staged path) when two detections share a (batch_im_id, label,
         instance_id) key, because then the reference's groupby merges their hypotheses."""
         coarse_model, refiner = self.coarse_model, self.refiner_model
@@ -328,29 +359,38 @@ class PoseEstimator(torch.nn.Module):
         if B == 0 or df.duplicated(["batch_im_id", "label", "instance_id"]).any():
             return None
         Kh = min(n_pose_hypotheses, M)
+        n_sel = B * Kh
         t0 = time.time()
+        main = torch.cuda.current_stream(device)
+        side = self.__dict__.get("_copy_stream")
+        if side is None:
+            side = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=device)
         # ---- coarse: B*M rows, row = detection * M + hypothesis
-        det_labels = df["label"].tolist()
-        bim = torch.as_tensor(df["batch_im_id"].to_numpy(), device=device)
-        batch_im_ids = bim.repeat_interleave(M)
-        bbox_ids = torch.arange(B, device=device).repeat_interleave(M)
-        m_idx = torch.arange(M, device=device).repeat(B)
+        rows_c = self._pipeline_rows(df, device)
+        batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
         K_rows = observation.K[batch_im_ids]
-        bboxes = detections.bboxes.to(device)[bbox_ids]
-        det_label_idx = coarse_model.mesh_db.label_ids(det_labels, device)
-        label_idx = det_label_idx.repeat_interleave(M)
+        bboxes = detections.bboxes.to(device)[rows_c["bbox_ids"]]
         TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes.float(), coarse_model.mesh_db.points, label_idx, K_rows,
-                                                         self._SO3_grid[m_idx])
-        labels_rows = [l for l in det_labels for _ in range(M)]
-        logits, out_c = self._score(observation, labels_rows, batch_im_ids, TCO, False, False, label_idx)
+                                                         rows_c["R"])
+        logits, out_c = self._score(observation, rows_c["labels_rows"], batch_im_ids, TCO, False, False, label_idx)
         scores = torch.sigmoid(logits)
         # ---- top-K per detection on the device, rows ordered by descending logit like sort_values().groupby().head()
+        flat = logits.flatten()
         top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()                       # [B, Kh]
-        rows = (top + torch.arange(B, device=device).unsqueeze(1) * M).flatten()
-        order = torch.sort(logits.flatten()[rows], descending=True, stable=True).indices
-        rows = rows[order]
-        n_sel = rows.shape[0]
+        rows = (top + rows_c["group_base"]).flatten()
+        rows = rows[torch.sort(flat[rows], descending=True, stable=True).indices]
+        packed_c = torch.cat((flat.double(), scores.flatten().double(), rows.double()))
+        pin_c = self._pinned("coarse", packed_c.numel())
+        ev_c = torch.cuda.Event()
+        ev_c.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_c)
+            pin_c.copy_(packed_c, non_blocking=True)
+            ev_c_done = torch.cuda.Event()
+            ev_c_done.record(side)
+        packed_c.record_stream(side)
         TCO_sel, bim_sel, lab_sel, K_sel = TCO[rows], batch_im_ids[rows], label_idx[rows], K_rows[rows]
+        bboxes_sel = bboxes[rows]
         # ---- refiner on the selected rows (sharded), then scoring, all enqueued without a host round trip
         s0, s1 = self.sharder.span(n_sel)
         iters = refiner.refine_tensors(observation.images, bim_sel[s0:s1], K_sel[s0:s1], lab_sel[s0:s1], TCO_sel[s0:s1],
@@ -368,41 +408,64 @@ class PoseEstimator(torch.nn.Module):
             refined.append(tensors)
         TCO_ref = refined[-1]["poses"] if n_refiner_iterations > 0 else TCO_sel
         t_ref = time.time()
-        labels_sel_placeholder = [""] * n_sel
-        pose_logits, out_s = self._score(observation, labels_sel_placeholder, bim_sel, TCO_ref, False, False, lab_sel)
+        pose_logits, out_s = self._score(observation, [""] * n_sel, bim_sel, TCO_ref, False, False, lab_sel)
         pose_scores = torch.sigmoid(pose_logits)
-        packed = torch.cat((pose_logits.reshape(-1), pose_scores.reshape(-1), rows.to(pose_logits.dtype)))
+        # ---- best hypothesis per detection, ordered like sort_values(pose_logit, descending).groupby().head(1)
+        pl = pose_logits.flatten()
+        grp = torch.div(rows, M, rounding_mode="floor")
+        order = torch.sort(pl, descending=True, stable=True).indices           # all rows by descending pose logit
+        g_sorted = grp[order]
+        pos = torch.arange(n_sel, device=device)
+        first = torch.full((B,), n_sel, device=device, dtype=torch.long).scatter_reduce_(0, g_sorted, pos, "amin")
+        keep = order[torch.sort(first).values]                                 # [B] rows of the scored collection
+        final_tensors = {k: v[keep] for k, v in refined[-1].items()} if n_refiner_iterations > 0 else None
+        packed_f = torch.cat((pl.double(), pose_scores.flatten().double(), keep.double()))
+        pin_f = self._pinned("final", packed_f.numel())
+        pin_f.copy_(packed_f, non_blocking=True)
+        ev_f_done = torch.cuda.Event()
+        ev_f_done.record(main)
+
         # ---- host bookkeeping while the device works
         df_hyp = df.loc[df.index.repeat(M)].copy()
+        df_hyp.index = pd.RangeIndex(B * M)
         df_hyp["hypothesis_id"] = np.tile(np.arange(M), B)
         df_hyp["bbox_id"] = np.repeat(df.index.values, M)
-        coarse_np = torch.cat((logits.reshape(-1, 1), scores.reshape(-1, 1)), dim=1).cpu().numpy()  # first sync point
-        df_hyp["coarse_logit"] = coarse_np[:, 0]
-        df_hyp["coarse_score"] = coarse_np[:, 1]
-        data_TCO_coarse = PandasTensorCollection(df_hyp, poses=TCO, bboxes=bboxes)
+        ev_c_done.synchronize()                                                # coarse stage done (refiner still running)
+        coarse_np = pin_c.numpy()
+        nBM = B * M
+        df_hyp["coarse_logit"] = coarse_np[:nBM].astype(np.float32)
+        df_hyp["coarse_score"] = coarse_np[nBM:2 * nBM].astype(np.float32)
+        rows_np = coarse_np[2 * nBM:].astype(np.int64)
+        data_TCO_coarse = PandasTensorCollection._wrap(df_hyp, dict(poses=TCO, bboxes=bboxes))
         t_coarse = time.time() - t0
         coarse_extra = {"render_time": out_c["render_time"], "model_time": out_c["model_time"], "time": t_coarse,
                         "logits": logits.reshape(B, M), "scores": scores.reshape(B, M), "TCO": TCO.reshape(B, M, 4, 4),
                         "debug": dict(), "n_batches": int(np.ceil(B * M / max(1, self.bsz_images))),
                         "timing_str": f"time: {t_coarse:.2f}, model_time: {out_c['model_time']:.2f}, "
                                       f"render_time: {out_c['render_time']:.2f}"}
-        packed_np = packed.cpu().numpy()                                                   # final sync point
-        rows_np = packed_np[2 * n_sel:].astype(np.int64)
-        df_sel = data_TCO_coarse.infos.iloc[rows_np].copy()
-        data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=TCO_sel, bboxes=bboxes[rows]))
-        df_ref = data_TCO_filtered.infos.copy()
+        df_sel = df_hyp.iloc[rows_np].copy()
+        df_sel.index = pd.RangeIndex(n_sel)
+        data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=TCO_sel, bboxes=bboxes_sel))
+        df_ref = df_sel.copy()
         df_ref["refiner_batch_idx"] = np.arange(n_sel) // max(1, self.bsz_objects)
         df_ref["refiner_instance_idx"] = np.arange(n_sel) % max(1, self.bsz_objects)
-        preds = {f"iteration={n + 1}": PandasTensorCollection(df_ref, **refined[n]) for n in range(n_refiner_iterations)}
-        refiner_extra = {"n_iterations": n_refiner_iterations, "outputs": [], "model_time": t_ref - t0 - t_coarse,
+        preds = {f"iteration={n + 1}": PandasTensorCollection._wrap(df_ref.copy(), refined[n])
+                 for n in range(n_refiner_iterations)}
+        refiner_extra = {"n_iterations": n_refiner_iterations, "outputs": [], "model_time": max(0.0, t_ref - t0 - t_coarse),
                          "time": max(0.0, t_ref - t0)}
         data_TCO_scored = preds[f"iteration={n_refiner_iterations}"]
-        data_TCO_scored.infos["pose_logit"] = packed_np[:n_sel]
-        data_TCO_scored.infos["pose_score"] = packed_np[n_sel:2 * n_sel]
+        infos_scored = data_TCO_scored.infos
+        ev_f_done.synchronize()                                                # everything done
+        final_np = pin_f.numpy()
+        infos_scored["pose_logit"] = final_np[:n_sel].astype(np.float32)
+        infos_scored["pose_score"] = final_np[n_sel:2 * n_sel].astype(np.float32)
+        keep_np = final_np[2 * n_sel:].astype(np.int64)
+        df_final = infos_scored.iloc[keep_np].copy()
+        df_final.index = pd.RangeIndex(len(keep_np))
+        final = PandasTensorCollection._wrap(df_final, final_tensors)
         scoring_extra = {"render_time": out_s["render_time"], "model_time": out_s["model_time"], "time": time.time() - t_ref,
                          "logits": pose_logits, "scores": pose_scores, "debug": dict(),
                          "n_batches": int(np.ceil(n_sel / max(1, self.bsz_images))), "timing_str": ""}
-        final = self.filter_pose_estimates(data_TCO_scored, top_K=1, filter_field="pose_logit")
         elapsed = time.time() - t_start
         extra_data: dict = dict()
         extra_data["coarse"] = {"preds": data_TCO_coarse, "data": coarse_extra}
