@@ -95,9 +95,6 @@ struct ConvDesc {
   int C_out, R, S, stride;
   int pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
   int relu;
-  // optional (window kernel, <= 16 taps): bit (tap * 4 + k) set = the weights of 16-channel K step k of filter tap
-  // `tap` are all zero, the step is not executed.  0 = execute everything.
-  unsigned long long kskip;
 };
 // splitk: 0 = never, -1 = heuristic (few output tiles, long K loop), 1|2|4|8 = that many k-splits (cluster size)
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,

@@ -157,7 +157,6 @@ struct Net {
   std::vector<const float*> conv_b;
   const float* head_w;
   const float* head_b;
-  unsigned long long stem_kskip = 0;  // structurally zero K steps of the space-to-depth stem (ConvDesc::kskip)
   std::vector<GraphEntry> graphs;
   cudaStream_t side = nullptr;  // capture / replay stream (the caller's stream may be the legacy default stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -182,25 +181,6 @@ int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* c
   net->conv_b.assign(conv_b, conv_b + n_convs);
   net->head_w = head_w;
   net->head_b = head_b;
-  if (c_pad == 16) {
-    // 7x7/s2 stem as 4x4 taps x (2x2 sub-pixels x 16 channels): the taps of the first row / column only use the
-    // second sub-pixel row / column -- 15 of the 64 (tap, sub-pixel) K steps carry no weights at all.  Read them off
-    // the packed weights so that any stem matrix (not only a 7x7-derived one) is handled correctly.
-    const size_t k_total = 16 * 64, n_el = 64 * k_total;
-    std::vector<uint16_t> hw(n_el);
-    MPX_CHECK_CUDA(cudaMemcpy(hw.data(), conv_w[0], n_el * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-    unsigned long long skip = 0;
-    for (int tap = 0; tap < 16; ++tap)
-      for (int k = 0; k < 4; ++k) {
-        bool zero = true;
-        for (int co = 0; co < 64 && zero; ++co)
-          for (int c = 0; c < 16; ++c)
-            if ((hw[co * k_total + tap * 64 + k * 16 + c] & 0x7fffu) != 0) { zero = false; break; }
-        if (zero) skip |= 1ull << (tap * 4 + k);
-      }
-    const char* env = getenv("MPX_STEM_KSKIP");  // diagnostic: MPX_STEM_KSKIP=0 executes every K step
-    net->stem_kskip = (env && env[0] == '0') ? 0ull : skip;
-  }
   *out = net;
   return MPX_OK;
 }
@@ -308,7 +288,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   int rc;
   // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input
   {
-    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, net->stem_kskip};
+    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1};
     rc = conv_forward(d, x, net->conv_w[ci], net->conv_b[ci], nullptr, buf_stem, 0, 0, stream);
     if (rc != MPX_OK) return rc;
     ++ci;

@@ -246,6 +246,46 @@ def test_small_batch_splitk_network_matches_unsplit(cfg_name, n):
         assert torch.equal(o, split[0])  # deterministic
 
 
+WIN2_CASES = [
+    # name, n, h, w, relu, use_res, max_ctas
+    ("l2_res", 4, 30, 40, True, True, 4),
+    ("l2_nores_many_per_cta", 9, 30, 40, True, False, 3),
+    ("odd_size", 3, 17, 23, False, True, 2),
+    ("tiny_images", 11, 5, 7, True, True, 2),
+    ("one_super_tile", 1, 12, 16, True, False, 1),
+]
+
+
+@pytest.mark.parametrize("case", WIN2_CASES, ids=[c[0] for c in WIN2_CASES])
+def test_layer2_window_kernel_agrees_with_im2col_and_torch(case):
+    """conv_window2_kernel (128 -> 128, 3x3: activations loaded once per 256-row super-tile, one weight pass for two
+    tiles, two MMA issuers) vs the im2col kernel (mode bit 8 = 256 disables it) and fp32 torch."""
+    name, n, h, w, relu, use_res, max_ctas = case
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(n, h, w, 128, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(128, 3, 3, 128, device="cuda", generator=g) / (9 * 128) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(128, device="cuda", generator=g)
+    res = torch.randn(n, h, w, 128, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    outs = []
+    try:
+        for mode in (DEFAULT_CONV_MODE, DEFAULT_CONV_MODE | 256):
+            _abi.lib().mpx_conv_set_mode(mode)
+            out = torch.full((n, h, w, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 128, _abi.ptr(wt.view(128, -1)), _abi.ptr(bias), 128, 3, 3,
+                                                  1, 1, 1, 1, 1, int(relu), _abi.ptr(res), _abi.ptr(out), 0, max_ctas,
+                                                  _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out.float())
+    finally:
+        _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
+    ref = _conv_ref(x, wt, bias, 1, (1, 1, 1, 1), relu, res)
+    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    assert not torch.isnan(outs[0]).any()
+    assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
+    # different K order (panel-major) than the im2col kernel: equal up to one bf16 rounding
+    assert (outs[0] - outs[1]).abs().max() <= 2 ** -7 * ref.abs().max().item()
+
+
 def test_graph_replay_equals_eager_launches():
     cfg = helpers.COARSE_CFG
     sd = helpers.make_state_dict(cfg, seed=2)
