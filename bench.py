@@ -260,17 +260,17 @@ def run_mpx_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = lib.mpx_launch_count()
     total_ms = timed(step_device, args.steps)
-    launches = torch.tensor([lib.mpx_launch_count() - l0], device="cuda", dtype=torch.float64)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        dist.all_reduce(launches)
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
-    # roofline of the dominant kernel (conv_igemm_kernel): CUDA events around every conv launch, same workload
+    # roofline of the dominant kernels (the convolutions of the 576-hypothesis coarse forward): CUDA events around every
+    # conv launch, same workload.  The coarse forward normally replays a CUDA graph (its launches cannot be timed one by
+    # one), so for this pass it is launched eagerly; the small-batch forwards (<= 64 rows) keep replaying graphs.
+    saved_gmb = est.coarse_model.graph_max_batch
+    est.coarse_model.graph_max_batch = 64
     lib.mpx_profile_enable(1)
     prof_steps = 2
     for _ in range(prof_steps):
@@ -278,6 +278,20 @@ def run_mpx_arm(args):
     conv_ms, conv_fl, conv_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     _abi.check(lib.mpx_profile_summary(ctypes.byref(conv_ms), ctypes.byref(conv_fl), ctypes.byref(conv_n)))
     lib.mpx_profile_enable(0)
+    est.coarse_model.graph_max_batch = saved_gmb
+    # kernels of libmpx.so per step: counted on one step launched eagerly (graph replays execute the same kernels but do
+    # not pass through the library's launch counter)
+    flags = (est.coarse_model.use_cuda_graphs, est.refiner_model.use_cuda_graphs)
+    est.coarse_model.use_cuda_graphs = est.refiner_model.use_cuda_graphs = False
+    lib.mpx_net_set_graphs(0)
+    l0 = lib.mpx_launch_count()
+    step_device()
+    torch.cuda.synchronize()
+    launches = torch.tensor([(lib.mpx_launch_count() - l0) * args.steps], device="cuda", dtype=torch.float64)
+    lib.mpx_net_set_graphs(1)
+    est.coarse_model.use_cuda_graphs, est.refiner_model.use_cuda_graphs = flags
+    if world > 1:
+        dist.all_reduce(launches)
     barrier()
 
     hyp_per_step = M_GRID * n_gpus

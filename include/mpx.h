@@ -190,9 +190,16 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                            void* d_out, int block_n, int splits, void* stream);
 
-/* kernel selection bits for block_n == 0 (auto), default 11: 1 = the shared-memory window kernel serves the
- * 64->64 channel stride-1 convolutions (stem, layer1); 2 = the CTA-pair kernel serves 256-wide tiles; 4 = and
- * 128-wide tiles; 8 = mpx_net_forward uses split-K for batches <= 64.  0 = single-CTA TMA-im2col kernel only */
+/* kernel selection bits for block_n == 0 (auto), default 11:
+ *   1   window kernels: 64->64 stride-1 convolutions (stem, layer1) and 128->128 3x3 (layer2) load their activations
+ *       once per tile as a contiguous window and address the filter taps as row-shifted operand descriptors
+ *   2   the CTA-pair (cta_group::2) kernel serves 256-wide tiles;  4  and 128-wide tiles
+ *   8   mpx_net_forward splits the K loop of layers 2-4 over a thread-block cluster for batches <= 64
+ *   16  a single epilogue warp set in the 64->64 window kernel (default two)
+ *   32  a single MMA-issuing thread in the 64->64 window kernel (default two);  64  three
+ *   128 three epilogue warp sets
+ *   256 disable the layer2 window kernel (TMA-im2col kernel instead)
+ * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 
 /* bring-up probe (tools/gpu_probe_rowshift.py): D[128,64] = A[r0:r0+128, :64] * B[64,64]^T with the UMMA

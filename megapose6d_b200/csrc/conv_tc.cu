@@ -1349,7 +1349,7 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit.
 static int conv_window2_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
                             void* out, int max_ctas, cudaStream_t stream) {
-  if ((g_conv_mode & 256) != 0) return MPX_ERR_UNSUPPORTED;  // mode bit 8 (256): disable
+  if ((g_conv_mode & 1) == 0 || (g_conv_mode & 256) != 0) return MPX_ERR_UNSUPPORTED;
   if (d.stride != 1 || d.C_in != 128 || d.C_out != 128 || d.R != 3 || d.S != 3) return MPX_ERR_UNSUPPORTED;
   if (d.pad_lo_h != 1 || d.pad_lo_w != 1 || d.pad_hi_h != 1 || d.pad_hi_w != 1) return MPX_ERR_UNSUPPORTED;
   Win2Params p;

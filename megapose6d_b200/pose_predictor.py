@@ -129,7 +129,7 @@ class PosePredictor(nn.Module):
         self._nhwc4_bufs: Dict[Tuple[int, ...], torch.Tensor] = {}
         self._graphs: Dict[Any, Dict[str, Any]] = {}
         self.use_cuda_graphs = True   # replay the refinement loop as one CUDA graph for small batches
-        self.graph_max_batch = 64
+        self.graph_max_batch = 1024
         self._x_cache: Dict[Tuple[int, int, int], torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------
