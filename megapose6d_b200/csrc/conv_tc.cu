@@ -414,10 +414,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // activations / residual of the previous kernel are complete from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -607,25 +609,9 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvP
   int grid = p.m_tiles * p.n_tiles * p.splits;
   int cap = max_ctas > 0 ? max_ctas : sm_count();
   ProfileSlot* slot = profile_begin(stream);
-  if (p.splits > 1) {
-    // one work item per CTA, the k-splits of a tile form a cluster
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(256, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.splits;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    MPX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N>, ma, mb, p));
-  } else {
-    if (grid > cap) grid = cap;
-    conv_igemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(ma, mb, p);
-  }
+  // split-K: one work item per CTA, the k-splits of a tile form a cluster
+  if (p.splits == 1 && grid > cap) grid = cap;
+  MPX_CHECK_CUDA(launch_pdl(conv_igemm_kernel<BLOCK_N>, dim3(grid), dim3(256), Cfg::kSmemBytes, stream, p.splits, ma, mb, p));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * p.M_total * p.C_out * p.num_k_blocks * kBlockK);
@@ -864,11 +850,13 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int hpwp = p.Hp * p.Wp;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1113,7 +1101,8 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
                                           227 * 1024));                                                          \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    conv_window_kernel<E><<<grid, 128 + 128 * E, smem_bytes, stream>>>(map_a, map_b, p, stages, n_taps);           \
+    MPX_CHECK_CUDA(launch_pdl(conv_window_kernel<E>, dim3(grid), dim3(128 + 128 * E), smem_bytes, stream, 1, map_a, map_b, \
+                              p, stages, n_taps));                                                             \
   } while (0)
   if (epi_sets == 1) MPX_WIN_LAUNCH(1);
   else if (epi_sets == 2) MPX_WIN_LAUNCH(2);
@@ -1212,11 +1201,13 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int hpwp = p.Hp * p.Wp;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== window producer =====================
@@ -1415,7 +1406,7 @@ static int conv_window2_try(const ConvDesc& d, const void* x, const void* w, con
   const int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
   ProfileSlot* slot = profile_begin(stream);
-  conv_window2_kernel<<<grid, 384, smem_bytes, stream>>>(map_a, map_b, p);
+  MPX_CHECK_CUDA(launch_pdl(conv_window2_kernel, dim3(grid), dim3(384), smem_bytes, stream, 1, map_a, map_b, p));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 128.0 * kW2Taps * 128.0);

@@ -80,6 +80,44 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while its stream predecessor is
+// still running, as soon as every CTA of the predecessor has executed pdl_trigger() (or exited).  It must call pdl_wait()
+// before it touches memory the predecessor writes (or writes memory the predecessor reads); everything before that --
+// barrier / TMEM set-up, descriptor prefetch, constant loads -- overlaps with the predecessor's tail.  The chains of
+// small-batch kernels (36 convolutions of ~6-10 us each per network forward) are bound by exactly that fixed cost.
+// Without a PDL-aware predecessor both calls are no-ops.  mpx_conv_set_mode bit 9 (512) launches without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+int conv_get_mode();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if ((conv_get_mode() & 512) == 0) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // cross-file declarations (conv_tc.cu, net.cu)
 // ---------------------------------------------------------------------------------------------
 extern long long g_launches;  // kernels launched by this library (host-side counter)

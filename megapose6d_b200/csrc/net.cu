@@ -16,6 +16,8 @@ namespace mpx {
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h,
                                     int w, int c8, int ho, int wo) {
   const long long total = static_cast<long long>(n) * ho * wo * c8;
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int cc = static_cast<int>(i % c8);
@@ -63,8 +65,8 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
   long long blocks = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  maxpool3x3s2_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo);
+  MPX_CHECK_CUDA(launch_pdl(maxpool3x3s2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, 1,
+                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;
@@ -84,6 +86,8 @@ avgpool_linear_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c, const 
   extern __shared__ float smem_pool[];  // [G][c] partial sums, then [c] pooled
   const int img = blockIdx.x;
   const __nv_bfloat16* xi = x + static_cast<size_t>(img) * hw * c;
+  pdl_trigger();
+  pdl_wait();
   const int nq = c >> 2;
   const int G = nq >= kPoolThreads ? 1 : kPoolThreads / nq;
   float* part = smem_pool;
@@ -129,8 +133,8 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
   const int G = nq >= kPoolThreads ? 1 : kPoolThreads / nq;
   const size_t smem = static_cast<size_t>(G + 1) * c * sizeof(float);
   MPX_REQUIRE(smem <= 48 * 1024, "avgpool_linear: C=%d needs %zu bytes of shared memory", c, smem);
-  avgpool_linear_kernel<<<n, kPoolThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), hw, c, w, b,
-                                                           out_dim, out);
+  MPX_CHECK_CUDA(launch_pdl(avgpool_linear_kernel, dim3(n), dim3(kPoolThreads), smem, stream, 1,
+                            reinterpret_cast<const __nv_bfloat16*>(x), hw, c, w, b, out_dim, out));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;
