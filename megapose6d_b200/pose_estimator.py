@@ -331,6 +331,96 @@ class PoseEstimator(torch.nn.Module):
                 labels_rows=[l for l in labels for _ in range(M)])
         return ent
 
+    def _coarse_stage(self, images: torch.Tensor, K_obs: torch.Tensor, bboxes_det: torch.Tensor, rows_c: dict, B: int,
+                      M: int, Kh: int) -> dict:
+        """Device work of the coarse stage on tensors only: pose initialisation, the coarse model over all B*M rows, and
+        the top-K rows per detection ordered like `sort_values(descending).groupby().head(K)`.  No host synchronisation
+        and no pointer-dependent input besides K_obs / bboxes_det (capturable as a CUDA graph)."""
+        coarse_model = self.coarse_model
+        batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
+        K_rows = K_obs[batch_im_ids]
+        bboxes = bboxes_det[rows_c["bbox_ids"]]
+        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes, coarse_model.mesh_db.points, label_idx, K_rows, rows_c["R"])
+        timing = defaultdict(float)
+        logits = coarse_model._iterate(images, rows_c["im_idx32"], K_rows.float().contiguous(), rows_c["label_idx32"],
+                                       TCO.float().contiguous(), 1, timing)[0]["out"]
+        scores = torch.sigmoid(logits)
+        flat = logits.flatten()
+        top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()                       # [B, Kh]
+        rows = (top + rows_c["group_base"]).flatten()
+        rows = rows[torch.sort(flat[rows], descending=True, stable=True).indices]
+        packed_c = torch.cat((flat.double(), scores.flatten().double(), rows.double()))
+        return dict(K_rows=K_rows, bboxes=bboxes, TCO=TCO, logits=logits, scores=scores, rows=rows, packed_c=packed_c,
+                    TCO_sel=TCO[rows], bim_sel=batch_im_ids[rows], lab_sel=label_idx[rows], K_sel=K_rows[rows],
+                    bboxes_sel=bboxes[rows], out=dict(render_time=timing["render"], model_time=timing["model"]))
+
+    def _coarse_stage_graphed(self, observation: ObservationTensor, bboxes_det: torch.Tensor, rows_c: dict, B: int, M: int,
+                              Kh: int) -> dict:
+        """`_coarse_stage`, replayed as one CUDA graph when this process owns all rows (no collective inside) and the
+        stage fits one launch: the ~25 small launches in front of the first large kernel otherwise leave the GPU idle for
+        ~0.5 ms per step.  First sight of a configuration runs eagerly, the second captures, later ones replay."""
+        cm = self.coarse_model
+        images = observation.images
+        n = B * M
+        K_obs = observation.K.float()
+        if "im_idx32" not in rows_c:
+            rows_c["im_idx32"] = rows_c["batch_im_ids"].to(torch.int32).contiguous()
+            rows_c["label_idx32"] = rows_c["label_idx"].to(torch.int32).contiguous()
+        cm._nhwc4(images, refresh=True)
+        graphable = (not self.sharder.enabled and cm.use_cuda_graphs and n <= min(cm.graph_max_batch, cm.max_batch)
+                     and not (cm.keep_images or cm.debug))
+        if not graphable:
+            if self.sharder.enabled or n > cm.max_batch:
+                return self._coarse_stage_sharded(observation, bboxes_det, rows_c, B, M, Kh)
+            return dict(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh), static=False)
+        key = (id(rows_c), Kh, tuple(images.shape), cm._nhwc4(images).data_ptr(), tuple(K_obs.shape))
+        graphs = self.__dict__.setdefault("_coarse_graphs", {})
+        entry = graphs.get(key)
+        if entry is None:
+            if len(graphs) >= 8:
+                graphs.clear()
+            graphs[key] = dict(graph=None, K=K_obs.clone(), bboxes=bboxes_det.clone(), rows_c=rows_c)
+            return dict(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh), static=False)
+        prev = self.__dict__.get("_coarse_copies_done")
+        if prev is not None:
+            torch.cuda.current_stream(images.device).wait_event(prev)  # the previous step's copies out of the static buffers
+        entry["K"].copy_(K_obs)
+        entry["bboxes"].copy_(bboxes_det)
+        if entry["graph"] is None:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    out = self._coarse_stage(images, entry["K"], entry["bboxes"], rows_c, B, M, Kh)
+            except Exception:  # noqa: BLE001 -- capture not possible here: stay eager
+                torch.cuda.synchronize()
+                graphs.pop(key, None)
+                cm.use_cuda_graphs = False
+                return dict(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh), static=False)
+            entry["graph"], entry["out"] = graph, out
+        entry["graph"].replay()
+        return dict(entry["out"], static=True)
+
+    def _coarse_stage_sharded(self, observation: ObservationTensor, bboxes_det: torch.Tensor, rows_c: dict, B: int, M: int,
+                              Kh: int) -> dict:
+        """The coarse stage with the rows split over ranks (one all_gather of the logits) or over several launches."""
+        coarse_model = self.coarse_model
+        device = observation.images.device
+        batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
+        K_rows = observation.K[batch_im_ids]
+        bboxes = bboxes_det[rows_c["bbox_ids"]]
+        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes, coarse_model.mesh_db.points, label_idx, K_rows, rows_c["R"])
+        logits, out_c = self._score(observation, rows_c["labels_rows"], batch_im_ids, TCO, False, False, label_idx)
+        scores = torch.sigmoid(logits)
+        flat = logits.flatten()
+        top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()
+        rows = (top + rows_c["group_base"]).flatten()
+        rows = rows[torch.sort(flat[rows], descending=True, stable=True).indices]
+        packed_c = torch.cat((flat.double(), scores.flatten().double(), rows.double()))
+        return dict(K_rows=K_rows, bboxes=bboxes, TCO=TCO, logits=logits, scores=scores, rows=rows, packed_c=packed_c,
+                    TCO_sel=TCO[rows], bim_sel=batch_im_ids[rows], lab_sel=label_idx[rows], K_sel=K_rows[rows],
+                    bboxes_sel=bboxes[rows], out=out_c, static=False)
+
     def _pinned(self, name: str, n: int) -> torch.Tensor:
         bufs = self.__dict__.setdefault("_pinned_bufs", {})
         buf = bufs.get(name)
@@ -368,18 +458,11 @@ class PoseEstimator(torch.nn.Module):
         # ---- coarse: B*M rows, row = detection * M + hypothesis
         rows_c = self._pipeline_rows(df, device)
         batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
-        K_rows = observation.K[batch_im_ids]
-        bboxes = detections.bboxes.to(device)[rows_c["bbox_ids"]]
-        TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes.float(), coarse_model.mesh_db.points, label_idx, K_rows,
-                                                         rows_c["R"])
-        logits, out_c = self._score(observation, rows_c["labels_rows"], batch_im_ids, TCO, False, False, label_idx)
-        scores = torch.sigmoid(logits)
-        # ---- top-K per detection on the device, rows ordered by descending logit like sort_values().groupby().head()
-        flat = logits.flatten()
-        top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()                       # [B, Kh]
-        rows = (top + rows_c["group_base"]).flatten()
-        rows = rows[torch.sort(flat[rows], descending=True, stable=True).indices]
-        packed_c = torch.cat((flat.double(), scores.flatten().double(), rows.double()))
+        bboxes_det = detections.bboxes.to(device).float()
+        st = self._coarse_stage_graphed(observation, bboxes_det, rows_c, B, M, Kh)
+        K_rows, bboxes, TCO, logits, scores, rows, packed_c = (st[k] for k in ("K_rows", "bboxes", "TCO", "logits", "scores",
+                                                                               "rows", "packed_c"))
+        out_c = st["out"]
         pin_c = self._pinned("coarse", packed_c.numel())
         ev_c = torch.cuda.Event()
         ev_c.record(main)
@@ -388,9 +471,20 @@ class PoseEstimator(torch.nn.Module):
             pin_c.copy_(packed_c, non_blocking=True)
             ev_c_done = torch.cuda.Event()
             ev_c_done.record(side)
+            if st["static"]:
+                # the stage's outputs live in the replayed graph's static buffers: what is handed to the caller is copied
+                # out here, off the critical path (the next replay waits for these copies)
+                K_rows, bboxes, TCO, logits, scores = (t.clone() for t in (K_rows, bboxes, TCO, logits, scores))
+                sel_user = {k: st[k].clone() for k in ("TCO_sel", "K_sel", "bboxes_sel")}
+                ev_copies = torch.cuda.Event()
+                ev_copies.record(side)
+                self.__dict__["_coarse_copies_done"] = ev_copies
+                for t in (K_rows, bboxes, TCO, logits, scores, *sel_user.values()):
+                    t.record_stream(main)
+            else:
+                sel_user = {k: st[k] for k in ("TCO_sel", "K_sel", "bboxes_sel")}
         packed_c.record_stream(side)
-        TCO_sel, bim_sel, lab_sel, K_sel = TCO[rows], batch_im_ids[rows], label_idx[rows], K_rows[rows]
-        bboxes_sel = bboxes[rows]
+        TCO_sel, bim_sel, lab_sel, K_sel = st["TCO_sel"], st["bim_sel"], st["lab_sel"], st["K_sel"]
         # ---- refiner on the selected rows (sharded), then scoring, all enqueued without a host round trip
         s0, s1 = self.sharder.span(n_sel)
         iters = refiner.refine_tensors(observation.images, bim_sel[s0:s1], K_sel[s0:s1], lab_sel[s0:s1], TCO_sel[s0:s1],
@@ -404,7 +498,7 @@ class PoseEstimator(torch.nn.Module):
             for f, src in fields.items():
                 loc = iters[n][src] if iters else torch.empty((0,) + tails[f], device=device)
                 tensors[f] = self.sharder.gather_rows(loc, n_sel)
-            tensors["K"] = K_sel
+            tensors["K"] = sel_user["K_sel"]
             refined.append(tensors)
         TCO_ref = refined[-1]["poses"] if n_refiner_iterations > 0 else TCO_sel
         t_ref = time.time()
@@ -422,6 +516,8 @@ class PoseEstimator(torch.nn.Module):
         packed_f = torch.cat((pl.double(), pose_scores.flatten().double(), keep.double()))
         pin_f = self._pinned("final", packed_f.numel())
         pin_f.copy_(packed_f, non_blocking=True)
+        if st["static"]:
+            main.wait_event(self.__dict__["_coarse_copies_done"])  # later work on this stream sees the copied-out tensors
         ev_f_done = torch.cuda.Event()
         ev_f_done.record(main)
 
@@ -445,7 +541,7 @@ class PoseEstimator(torch.nn.Module):
                                       f"render_time: {out_c['render_time']:.2f}"}
         df_sel = df_hyp.iloc[rows_np].copy()
         df_sel.index = pd.RangeIndex(n_sel)
-        data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=TCO_sel, bboxes=bboxes_sel))
+        data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=sel_user["TCO_sel"], bboxes=sel_user["bboxes_sel"]))
         df_ref = df_sel.copy()
         df_ref["refiner_batch_idx"] = np.arange(n_sel) // max(1, self.bsz_objects)
         df_ref["refiner_instance_idx"] = np.arange(n_sel) % max(1, self.bsz_objects)

@@ -249,3 +249,43 @@ def test_fused_pipeline_equals_staged_pipeline(setup):
             assert torch.equal(getattr(a, t), getattr(b, t)), (it, t)
     assert torch.equal(fa.poses, fb.poses)
     pd.testing.assert_frame_equal(fa.infos[fb.infos.columns], fb.infos, check_dtype=False)
+
+
+def test_fused_pipeline_graph_replay_tracks_its_inputs(setup):
+    """The coarse stage of the fused path runs eagerly on first sight of a configuration, is captured as a CUDA graph on the
+    second call and replayed afterwards: replays return the same results, results handed out earlier are not overwritten,
+    and new detections / intrinsics are honoured by the replayed graph."""
+    ds, images, K = setup["ds"], setup["images"][:, :3].contiguous(), setup["K"]
+    est = load_model.load_named_model("megapose-1.0-RGB-multi-hypothesis", ds, models_root=setup["root"])
+    est.load_SO3_grid(72)
+    labels = [ds[0].label, ds[1].label]
+    TCO_gt = torch.from_numpy(procedural.random_poses(2, 31)).float()
+    TCO_gt[:, 2, 3] = torch.tensor([0.55, 0.7])
+    bboxes = torch.stack([helpers.detection_for_pose(K[0], TCO_gt[i], torch.from_numpy(ds.get_object_by_label(labels[i]).mesh.vertices).float())
+                          for i in range(2)])
+    det_df = pd.DataFrame(dict(label=labels, batch_im_id=0))
+
+    def run(bb, Kc, fused=True):
+        est.fused_pipeline = fused
+        obs = ObservationTensor(images.clone(), Kc.clone()).cuda()
+        det = PandasTensorCollection(det_df.copy(), bboxes=bb.cuda())
+        return est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=2, n_pose_hypotheses=2)
+
+    first = [run(bboxes, K) for _ in range(4)]  # eager, capture, replay, replay
+    kept = first[0][1]["coarse"]["preds"].poses.clone(), first[0][1]["coarse_filter"]["preds"].poses.clone()
+    for f, e in first[1:]:
+        assert torch.equal(f.poses, first[0][0].poses)
+        assert torch.equal(e["coarse"]["data"]["logits"], first[0][1]["coarse"]["data"]["logits"])
+        pd.testing.assert_frame_equal(f.infos, first[0][0].infos)
+    bb2 = bboxes + torch.tensor([[6.0, -4.0, 9.0, 3.0], [-5.0, 2.0, -1.0, 8.0]])
+    K2 = K.clone()
+    K2[:, 0, 2] += 3.0
+    f2, e2 = run(bb2, K2)                      # replay with new inputs
+    # tensors handed out by earlier calls still hold their values
+    assert torch.equal(first[0][1]["coarse"]["preds"].poses, kept[0])
+    assert torch.equal(first[0][1]["coarse_filter"]["preds"].poses, kept[1])
+    fs, es = run(bb2, K2, fused=False)         # staged path on the same inputs
+    assert not torch.equal(e2["coarse"]["data"]["logits"], first[0][1]["coarse"]["data"]["logits"])
+    assert torch.equal(e2["coarse"]["data"]["logits"], es["coarse"]["data"]["logits"])
+    assert torch.equal(f2.poses, fs.poses)
+    pd.testing.assert_frame_equal(f2.infos[fs.infos.columns], fs.infos, check_dtype=False)
