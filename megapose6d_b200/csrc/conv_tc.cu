@@ -1024,25 +1024,46 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
   // mode bit 4 (16) selects a single set
   const int epi_sets = (g_conv_mode & 16) != 0 ? 1 : ((g_conv_mode & 128) != 0 ? 3 : 2);
   const int smem_limit = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, bias*/;
-  // choose the number of filter rows per window: largest row group whose windows fit at least twice
-  int rg = d.R, stages = 0;
-  for (; rg >= 1; --rg) {
-    if (d.R % rg) continue;
-    const int rows = kBlockM + (rg - 1) * p.Wp + (d.S - 1);
+  // Choose the number of filter rows per window.  The two MMA issuers work on alternating tiles, so what matters is how
+  // many TILES' worth of windows fit the ring (2 = both issuers always have a resident tile); ties go to the larger row
+  // group (fewer halo rows re-loaded).  layer1: rg = 3, one 38 KB window per tile, 4 stages.  Coarse stem (16 resident
+  // weight tiles = 128 KB): rg = 2 fits 2 stages = 1 tile, rg = 1 fits 5 windows of 17 KB = 1.25 tiles.
+  int rg = 0, stages = 0;
+  double best = 0.0;
+  for (int cand = d.R; cand >= 1; --cand) {
+    if (d.R % cand) continue;
+    const int rows = kBlockM + (cand - 1) * p.Wp + (d.S - 1);
     const int n_chunks = (rows + 255) / 256;
     const int chunk = ((rows + n_chunks - 1) / n_chunks + 7) & ~7;
     const int win_bytes = chunk * n_chunks * 128;
-    stages = (smem_limit - b_bytes) / win_bytes;
-    if (stages >= 2) {
+    int st = (smem_limit - b_bytes) / win_bytes;
+    if (st > 8) st = 8;
+    if (st < 2) continue;
+    double tiles = static_cast<double>(st) / (d.R / cand);
+    if (tiles > 2.0) tiles = 2.0;
+    if (tiles > best + 1e-9) {
+      best = tiles;
+      rg = cand;
+      stages = st;
       p.win_rows = rows;
       p.n_chunks = n_chunks;
       p.chunk_rows = chunk;
       p.win_bytes = win_bytes;
-      break;
+    }
+  }
+  if ((g_conv_mode & 1024) != 0 && d.R % 2 == 0) {  // diagnostic (mode bit 10): force the pre-r01 choice rg = R / 2
+    const int cand = d.R / 2;
+    const int rows = kBlockM + (cand - 1) * p.Wp + (d.S - 1);
+    const int n_chunks = (rows + 255) / 256;
+    const int chunk = ((rows + n_chunks - 1) / n_chunks + 7) & ~7;
+    const int win_bytes = chunk * n_chunks * 128;
+    const int st = (smem_limit - b_bytes) / win_bytes;
+    if (st >= 2) {
+      rg = cand; stages = st > 8 ? 8 : st;
+      p.win_rows = rows; p.n_chunks = n_chunks; p.chunk_rows = chunk; p.win_bytes = win_bytes;
     }
   }
   if (rg < 1 || stages < 2) return MPX_ERR_UNSUPPORTED;
-  if (stages > 4) stages = 4;
   p.rg = rg;
   p.n_windows = d.R / rg;
   p.taps_per_win = rg * d.S;
