@@ -13,61 +13,68 @@ namespace mpx {
 // ---------------------------------------------------------------------------------------------
 // 3x3 / stride 2 / pad 1 max pool on bf16 NHWC; one thread = 8 channels (16 B) of one output pixel
 // ---------------------------------------------------------------------------------------------
-__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h,
-                                    int w, int c8, int ho, int wo) {
-  const long long total = static_cast<long long>(n) * ho * wo * c8;
+// one CTA per output row (img, oy): threads walk (ox, channel group) with 32-bit index math only -- the flat
+// grid-stride form spent most of its instructions on 64-bit div / mod of the element index
+__global__ void __launch_bounds__(512)
+maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int c8, int ho, int wo) {
   pdl_trigger();
   pdl_wait();
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cc = static_cast<int>(i % c8);
-    long long t = i / c8;
-    const int ox = static_cast<int>(t % wo);
-    t /= wo;
-    const int oy = static_cast<int>(t % ho);
-    const int img = static_cast<int>(t / ho);
-    float m[8];
+  const int row_items = wo * c8;
+  for (int row = blockIdx.x; row < n * ho; row += gridDim.x) {
+    const int img = row / ho, oy = row - img * ho;
+    const int iy0 = oy * 2 - 1;
+    const uint4* xin = x + static_cast<size_t>(img) * h * w * c8;
+    uint4* orow = out + static_cast<size_t>(row) * row_items;
+    for (int t = threadIdx.x; t < row_items; t += blockDim.x) {
+      const int ox = t / c8, cc = t - ox * c8;
+      const int ix0 = ox * 2 - 1;
+      float m[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+      for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int iy = oy * 2 - 1 + dy;
-      if (iy < 0 || iy >= h) continue;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int iy = iy0 + dy;
+        if (iy < 0 || iy >= h) continue;
+        const uint4* xr = xin + static_cast<size_t>(iy) * w * c8 + cc;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int ix = ox * 2 - 1 + dx;
-        if (ix < 0 || ix >= w) continue;
-        const uint4 v = __ldg(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c8 + cc);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        for (int dx = 0; dx < 3; ++dx) {
+          const int ix = ix0 + dx;
+          if (ix < 0 || ix >= w) continue;
+          const uint4 v = __ldg(xr + ix * c8);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(u[j]);
-          m[2 * j] = fmaxf(m[2 * j], f.x);
-          m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(u[j]);
+            m[2 * j] = fmaxf(m[2 * j], f.x);
+            m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+          }
         }
       }
+      uint4 o;
+      o.x = pack_bf16x2(m[0], m[1]);
+      o.y = pack_bf16x2(m[2], m[3]);
+      o.z = pack_bf16x2(m[4], m[5]);
+      o.w = pack_bf16x2(m[6], m[7]);
+      orow[t] = o;
     }
-    uint4 o;
-    o.x = pack_bf16x2(m[0], m[1]);
-    o.y = pack_bf16x2(m[2], m[3]);
-    o.z = pack_bf16x2(m[4], m[5]);
-    o.w = pack_bf16x2(m[6], m[7]);
-    out[i] = o;
   }
 }
 
 int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream) {
   MPX_REQUIRE(c % 8 == 0, "maxpool: C=%d must be a multiple of 8", c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
-  if (total == 0) return MPX_OK;
-  const int threads = 256;
-  long long blocks = (total + threads - 1) / threads;
-  const long long cap = static_cast<long long>(sm_count()) * 16;
+  const long long rows = static_cast<long long>(n) * ho;
+  if (rows == 0) return MPX_OK;
+  MPX_REQUIRE(rows < (1LL << 31), "maxpool: too many rows");
+  const int row_items = wo * (c / 8);
+  int threads = ((row_items + 31) / 32) * 32;
+  if (threads > 512) threads = ((row_items + 1) / 2 + 31) / 32 * 32;  // two passes per row
+  if (threads > 512) threads = 512;
+  long long blocks = rows;
+  const long long cap = static_cast<long long>(sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   MPX_CHECK_CUDA(launch_pdl(maxpool3x3s2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, 1,
                             reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo));
-  MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;
 }

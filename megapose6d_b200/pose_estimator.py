@@ -331,19 +331,32 @@ class PoseEstimator(torch.nn.Module):
                 labels_rows=[l for l in labels for _ in range(M)])
         return ent
 
-    def _coarse_stage(self, images: torch.Tensor, K_obs: torch.Tensor, bboxes_det: torch.Tensor, rows_c: dict, B: int,
-                      M: int, Kh: int) -> dict:
-        """Device work of the coarse stage on tensors only: pose initialisation, the coarse model over all B*M rows, and
-        the top-K rows per detection ordered like `sort_values(descending).groupby().head(K)`.  No host synchronisation
-        and no pointer-dependent input besides K_obs / bboxes_det (capturable as a CUDA graph)."""
+    def _coarse_local(self, images: torch.Tensor, K_obs: torch.Tensor, bboxes_det: torch.Tensor, rows_c: dict, s0: int,
+                      s1: int) -> dict:
+        """Device work of the coarse stage up to this rank's logits, on tensors only: per-row intrinsics / boxes, pose
+        initialisation of all B*M rows, the coarse model over rows [s0, s1).  No host synchronisation, no collective, no
+        pointer-dependent input besides K_obs / bboxes_det: capturable as a CUDA graph."""
         coarse_model = self.coarse_model
         batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
         K_rows = K_obs[batch_im_ids]
         bboxes = bboxes_det[rows_c["bbox_ids"]]
         TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes, coarse_model.mesh_db.points, label_idx, K_rows, rows_c["R"])
         timing = defaultdict(float)
-        logits = coarse_model._iterate(images, rows_c["im_idx32"], K_rows.float().contiguous(), rows_c["label_idx32"],
-                                       TCO.float().contiguous(), 1, timing)[0]["out"]
+        if s1 > s0:
+            logits_local = coarse_model._iterate(images, rows_c["im_idx32"][s0:s1].contiguous(),
+                                                 K_rows[s0:s1].float().contiguous(),
+                                                 rows_c["label_idx32"][s0:s1].contiguous(),
+                                                 TCO[s0:s1].float().contiguous(), 1, timing)[0]["out"]
+        else:
+            logits_local = torch.empty(0, 1, device=TCO.device)
+        return dict(K_rows=K_rows, bboxes=bboxes, TCO=TCO, logits_local=logits_local,
+                    out=dict(render_time=timing["render"], model_time=timing["model"]))
+
+    def _coarse_select(self, st: dict, logits: torch.Tensor, rows_c: dict, B: int, M: int, Kh: int) -> dict:
+        """Scores and the top-K rows per detection, ordered like `sort_values(descending).groupby().head(K)`, on the
+        device; `logits` are the gathered logits of all B*M rows."""
+        batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
+        K_rows, bboxes, TCO = st["K_rows"], st["bboxes"], st["TCO"]
         scores = torch.sigmoid(logits)
         flat = logits.flatten()
         top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()                       # [B, Kh]
@@ -352,13 +365,20 @@ class PoseEstimator(torch.nn.Module):
         packed_c = torch.cat((flat.double(), scores.flatten().double(), rows.double()))
         return dict(K_rows=K_rows, bboxes=bboxes, TCO=TCO, logits=logits, scores=scores, rows=rows, packed_c=packed_c,
                     TCO_sel=TCO[rows], bim_sel=batch_im_ids[rows], lab_sel=label_idx[rows], K_sel=K_rows[rows],
-                    bboxes_sel=bboxes[rows], out=dict(render_time=timing["render"], model_time=timing["model"]))
+                    bboxes_sel=bboxes[rows], out=st["out"])
+
+    def _coarse_stage(self, images, K_obs, bboxes_det, rows_c, B, M, Kh, s0, s1, whole: bool) -> dict:
+        st = self._coarse_local(images, K_obs, bboxes_det, rows_c, s0, s1)
+        if whole:  # this process owns every row: selection inside the same (graph-capturable) region
+            return self._coarse_select(st, st["logits_local"], rows_c, B, M, Kh)
+        return st
 
     def _coarse_stage_graphed(self, observation: ObservationTensor, bboxes_det: torch.Tensor, rows_c: dict, B: int, M: int,
                               Kh: int) -> dict:
-        """`_coarse_stage`, replayed as one CUDA graph when this process owns all rows (no collective inside) and the
-        stage fits one launch: the ~25 small launches in front of the first large kernel otherwise leave the GPU idle for
-        ~0.5 ms per step.  First sight of a configuration runs eagerly, the second captures, later ones replay."""
+        """The coarse stage, with its device work up to the (local) logits -- and, when this process owns all rows, the
+        selection too -- replayed as one CUDA graph: the ~25 small launches in front of the first large kernel otherwise
+        leave the GPU idle for ~0.5 ms per step.  First sight of a configuration runs eagerly, the second captures, later
+        ones replay.  With several ranks the logits are all-gathered (outside the graph) before the selection."""
         cm = self.coarse_model
         images = observation.images
         n = B * M
@@ -366,21 +386,28 @@ class PoseEstimator(torch.nn.Module):
         if "im_idx32" not in rows_c:
             rows_c["im_idx32"] = rows_c["batch_im_ids"].to(torch.int32).contiguous()
             rows_c["label_idx32"] = rows_c["label_idx"].to(torch.int32).contiguous()
+        s0, s1 = self.sharder.span(n)
+        whole = not self.sharder.enabled
+        if s1 - s0 > cm.max_batch:  # several launches per rank: the chunked reference-style path
+            return self._coarse_stage_chunked(observation, bboxes_det, rows_c, B, M, Kh)
         cm._nhwc4(images, refresh=True)
-        graphable = (not self.sharder.enabled and cm.use_cuda_graphs and n <= min(cm.graph_max_batch, cm.max_batch)
-                     and not (cm.keep_images or cm.debug))
+
+        def finish(st: dict, static: bool) -> dict:
+            if not whole:
+                st = self._coarse_select(st, self.sharder.gather_rows(st["logits_local"], n), rows_c, B, M, Kh)
+            return dict(st, static=static)
+
+        graphable = cm.use_cuda_graphs and (s1 - s0) <= cm.graph_max_batch and not (cm.keep_images or cm.debug)
         if not graphable:
-            if self.sharder.enabled or n > cm.max_batch:
-                return self._coarse_stage_sharded(observation, bboxes_det, rows_c, B, M, Kh)
-            return dict(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh), static=False)
-        key = (id(rows_c), Kh, tuple(images.shape), cm._nhwc4(images).data_ptr(), tuple(K_obs.shape))
+            return finish(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh, s0, s1, whole), False)
+        key = (id(rows_c), Kh, s0, s1, whole, tuple(images.shape), cm._nhwc4(images).data_ptr(), tuple(K_obs.shape))
         graphs = self.__dict__.setdefault("_coarse_graphs", {})
         entry = graphs.get(key)
         if entry is None:
             if len(graphs) >= 8:
                 graphs.clear()
             graphs[key] = dict(graph=None, K=K_obs.clone(), bboxes=bboxes_det.clone(), rows_c=rows_c)
-            return dict(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh), static=False)
+            return finish(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh, s0, s1, whole), False)
         prev = self.__dict__.get("_coarse_copies_done")
         if prev is not None:
             torch.cuda.current_stream(images.device).wait_event(prev)  # the previous step's copies out of the static buffers
@@ -391,35 +418,27 @@ class PoseEstimator(torch.nn.Module):
             graph = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(graph):
-                    out = self._coarse_stage(images, entry["K"], entry["bboxes"], rows_c, B, M, Kh)
+                    out = self._coarse_stage(images, entry["K"], entry["bboxes"], rows_c, B, M, Kh, s0, s1, whole)
             except Exception:  # noqa: BLE001 -- capture not possible here: stay eager
                 torch.cuda.synchronize()
                 graphs.pop(key, None)
                 cm.use_cuda_graphs = False
-                return dict(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh), static=False)
+                return finish(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh, s0, s1, whole), False)
             entry["graph"], entry["out"] = graph, out
         entry["graph"].replay()
-        return dict(entry["out"], static=True)
+        return finish(dict(entry["out"]), True)
 
-    def _coarse_stage_sharded(self, observation: ObservationTensor, bboxes_det: torch.Tensor, rows_c: dict, B: int, M: int,
+    def _coarse_stage_chunked(self, observation: ObservationTensor, bboxes_det: torch.Tensor, rows_c: dict, B: int, M: int,
                               Kh: int) -> dict:
-        """The coarse stage with the rows split over ranks (one all_gather of the logits) or over several launches."""
+        """The coarse stage when a rank's share of the rows needs several launches (`PosePredictor.max_batch`)."""
         coarse_model = self.coarse_model
-        device = observation.images.device
         batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
         K_rows = observation.K[batch_im_ids]
         bboxes = bboxes_det[rows_c["bbox_ids"]]
         TCO = lib3d.TCO_init_from_boxes_autodepth_with_R(bboxes, coarse_model.mesh_db.points, label_idx, K_rows, rows_c["R"])
         logits, out_c = self._score(observation, rows_c["labels_rows"], batch_im_ids, TCO, False, False, label_idx)
-        scores = torch.sigmoid(logits)
-        flat = logits.flatten()
-        top = lib3d.topk_per_group(logits.reshape(B, M), Kh).long()
-        rows = (top + rows_c["group_base"]).flatten()
-        rows = rows[torch.sort(flat[rows], descending=True, stable=True).indices]
-        packed_c = torch.cat((flat.double(), scores.flatten().double(), rows.double()))
-        return dict(K_rows=K_rows, bboxes=bboxes, TCO=TCO, logits=logits, scores=scores, rows=rows, packed_c=packed_c,
-                    TCO_sel=TCO[rows], bim_sel=batch_im_ids[rows], lab_sel=label_idx[rows], K_sel=K_rows[rows],
-                    bboxes_sel=bboxes[rows], out=out_c, static=False)
+        st = dict(K_rows=K_rows, bboxes=bboxes, TCO=TCO, out=out_c)
+        return dict(self._coarse_select(st, logits, rows_c, B, M, Kh), static=False)
 
     def _pinned(self, name: str, n: int) -> torch.Tensor:
         bufs = self.__dict__.setdefault("_pinned_bufs", {})
@@ -493,13 +512,29 @@ class PoseEstimator(torch.nn.Module):
                       boxes_crop="boxes_crop")
         tails = dict(poses=(4, 4), poses_input=(4, 4), K_crop=(3, 3), boxes_rend=(4,), boxes_crop=(4,))
         refined = []
-        for n in range(n_refiner_iterations):
-            tensors = dict()
-            for f, src in fields.items():
-                loc = iters[n][src] if iters else torch.empty((0,) + tails[f], device=device)
-                tensors[f] = self.sharder.gather_rows(loc, n_sel)
-            tensors["K"] = sel_user["K_sel"]
-            refined.append(tensors)
+        if self.sharder.world > 1:
+            # one all_gather for every field of every iteration: rows -> [n_loc, n_iter * 49] floats
+            widths = {f: int(np.prod(tails[f])) for f in fields}
+            n_loc = s1 - s0
+            if iters:
+                local = torch.cat([iters[n][src].reshape(n_loc, -1).float() for n in range(n_refiner_iterations)
+                                   for src in fields.values()], dim=1)
+            else:
+                local = torch.empty(0, n_refiner_iterations * sum(widths.values()), device=device)
+            full = self.sharder.gather_rows(local, n_sel)
+            col = 0
+            for n in range(n_refiner_iterations):
+                tensors = dict()
+                for f in fields:
+                    tensors[f] = full[:, col:col + widths[f]].reshape((n_sel,) + tails[f])
+                    col += widths[f]
+                tensors["K"] = sel_user["K_sel"]
+                refined.append(tensors)
+        else:
+            for n in range(n_refiner_iterations):
+                tensors = {f: iters[n][src] for f, src in fields.items()}
+                tensors["K"] = sel_user["K_sel"]
+                refined.append(tensors)
         TCO_ref = refined[-1]["poses"] if n_refiner_iterations > 0 else TCO_sel
         t_ref = time.time()
         pose_logits, out_s = self._score(observation, [""] * n_sel, bim_sel, TCO_ref, False, False, lab_sel)
