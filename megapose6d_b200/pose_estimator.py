@@ -159,7 +159,7 @@ class PoseEstimator(torch.nn.Module):
         assert self.coarse_model is not None
         device = observation.images.device
         df = data_TCO.infos
-        batch_im_ids = torch.as_tensor(df["batch_im_id"].to_numpy(), device=device)
+        batch_im_ids = torch.as_tensor(np.array(df["batch_im_id"].to_numpy(), copy=True), device=device)
         logits, out_ = self._score(observation, df["label"].tolist(), batch_im_ids, data_TCO.poses.to(device), cuda_timer,
                                    return_debug_data)
         scores = torch.sigmoid(logits)
@@ -192,7 +192,7 @@ class PoseEstimator(torch.nn.Module):
         df = detections.infos
         # device-side row tables straight from the B detections (row = detection * M + hypothesis) ...
         det_labels = df["label"].tolist()
-        bim = torch.as_tensor(df["batch_im_id"].to_numpy(), device=device)
+        bim = torch.as_tensor(np.array(df["batch_im_id"].to_numpy(), copy=True), device=device)
         batch_im_ids = bim.repeat_interleave(M)
         bbox_ids = torch.arange(B, device=device).repeat_interleave(M)
         m_idx = torch.arange(M, device=device).repeat(B)
@@ -322,7 +322,7 @@ class PoseEstimator(torch.nn.Module):
             if len(cache) >= 8:
                 cache.clear()
             B = len(df)
-            bim = torch.as_tensor(np.ascontiguousarray(df["batch_im_id"].to_numpy()), device=device)
+            bim = torch.as_tensor(np.array(df["batch_im_id"].to_numpy(), copy=True), device=device)
             det_label_idx = self.coarse_model.mesh_db.label_ids(list(labels), device)
             ent = cache[key] = dict(
                 batch_im_ids=bim.repeat_interleave(M), bbox_ids=torch.arange(B, device=device).repeat_interleave(M),
