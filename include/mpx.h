@@ -55,6 +55,15 @@ int mpx_meshdb_create(int n_meshes, const float* h_verts, const float* h_normals
                       const int64_t* h_face_offsets, mpx_meshdb** out);
 int mpx_meshdb_destroy(mpx_meshdb* db);
 
+/* Optional diffuse textures (what Panda3D / Assimp load from the model's material,
+ * panda3d_renderer/panda3d_scene_renderer.py:195-208).  Host arrays: h_uv [sum_nv,2] per-vertex texture coordinates
+ * (v up), h_tex all RGB8 images back to back (row 0 = top), h_tex_offsets [n+1] byte offsets, h_tex_dims [n,2] =
+ * (height, width), (0,0) for an untextured mesh, h_tex_modulate [n] (may be NULL): 1 = multiply the texture with the
+ * interpolated vertex colours.  Sampling: repeat wrap, bilinear over texel centres, no mip-mapping.  Call once, after
+ * mpx_meshdb_create. */
+int mpx_meshdb_set_textures(mpx_meshdb* db, const float* h_uv, const uint8_t* h_tex, const int64_t* h_tex_offsets,
+                            const int32_t* h_tex_dims, const int32_t* h_tex_modulate);
+
 /* ---- rasteriser ------------------------------------------------------------------------------
  * Replaces Panda3dBatchRenderer.render (panda3d_renderer/panda3d_batch_renderer.py:217-282) and
  * everything under it (worker_loop :89-150, Panda3dSceneRenderer.render_scene

@@ -30,6 +30,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_last_error.restype = c_char_p
     lib.mpx_meshdb_create.argtypes = [c_int, vp, vp, vp, vp, vp, vp, POINTER(vp)]
     lib.mpx_meshdb_destroy.argtypes = [vp]
+    lib.mpx_meshdb_set_textures.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mpx_raster_workspace_bytes.argtypes = [c_int, c_int]
     lib.mpx_raster_workspace_bytes.restype = c_size_t
     lib.mpx_raster_render.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_uint32, vp, vp, vp, vp, c_size_t, vp]
@@ -77,7 +78,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 EXPORTS = [
     "mpx_abi_version", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
-    "mpx_meshdb_create", "mpx_meshdb_destroy",
+    "mpx_meshdb_create", "mpx_meshdb_destroy", "mpx_meshdb_set_textures",
     "mpx_raster_workspace_bytes", "mpx_raster_set_mode", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",

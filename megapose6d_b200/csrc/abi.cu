@@ -66,6 +66,13 @@ int mpx_meshdb_destroy(mpx_meshdb* db) {
   return MPX_OK;
 }
 
+int mpx_meshdb_set_textures(mpx_meshdb* db, const float* uv, const uint8_t* tex, const int64_t* tex_offsets,
+                            const int32_t* tex_dims, const int32_t* tex_modulate) {
+  MPX_NOT_NULL(db);
+  return meshdb_set_textures(db->db, uv, tex, tex_offsets, tex_dims, tex_modulate);
+}
+
+
 // ---- rasteriser ----
 size_t mpx_raster_workspace_bytes(int h, int w) { return raster_workspace_bytes(h, w); }
 

@@ -163,6 +163,12 @@ struct MeshDb {
   long long* face_offsets;  // [n+1]
   int4* vtx_cache;          // [slots, nv_max] {X, Y, 1/z bits, behind}
   int slots;
+  // optional textures (meshdb_set_textures): per-vertex uv, RGB8 images back to back, per mesh {byte offset, th, tw,
+  // modulate-with-vertex-colours}; tex_info == nullptr: no mesh is textured
+  float* uv;                // [sum_nv,2]
+  unsigned char* tex;
+  long long* tex_offsets;   // [n]
+  int4* tex_info;           // [n] {th, tw, modulate, 0}; th == 0: untextured
 };
 struct RasterOut {
   float* rgb;      // contract planes (fp32 NCHW), any may be null
@@ -182,6 +188,8 @@ int meshdb_create(int n_meshes, const float* verts, const float* normals, const 
                   const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
                   MeshDb** out);
 void meshdb_destroy(MeshDb* db);
+int meshdb_set_textures(MeshDb* db, const float* uv, const unsigned char* tex, const int64_t* tex_offsets,
+                        const int32_t* tex_dims, const int32_t* tex_modulate);
 size_t raster_workspace_bytes(int h, int w);
 void raster_set_scatter(int on);
 int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, const float* K, int n_views,

@@ -29,6 +29,7 @@
 // shades and writes the outputs.  In the fused single-view mode the resolve pass also computes the
 // observation crop of its pixel (roi_align) and stores the complete channel vector of the network
 // input with 16-byte stores.
+#include <vector>
 #include "crop_device.cuh"
 
 namespace mpx {
@@ -84,6 +85,42 @@ __device__ __forceinline__ float quant8(float v, bool on) {
   v = fminf(fmaxf(v, 0.0f), 1.0f);
   if (!on) return v;
   return c_tables.q8[__float2int_rn(__fmul_rn(v, 255.0f))];
+}
+
+// Diffuse texture of a mesh (contract in oracle/raster_ref.c): uv wrapped to [0,1) (repeat), v up, bilinear over texel
+// centres, texel = byte / 255 (the k/255 table), every step a single correctly rounded operation in a fixed order.
+struct TexRef {
+  const float* uv;           // this mesh's [nv,2]
+  const unsigned char* tex;  // [th,tw,3], nullptr = untextured
+  int th, tw, modulate;
+};
+__device__ __forceinline__ int wrap_idx(int i, int n) {
+  const int r = i % n;
+  return r < 0 ? r + n : r;
+}
+__device__ __forceinline__ void texture_sample(const TexRef& t, float u, float v, float (&out)[3]) {
+  if (!(u == u)) u = 0.f;
+  if (!(v == v)) v = 0.f;
+  u = __fsub_rn(u, floorf(u));
+  v = __fsub_rn(v, floorf(v));
+  const float x = __fmaf_rn(u, static_cast<float>(t.tw), -0.5f);
+  const float y = __fmaf_rn(__fsub_rn(1.0f, v), static_cast<float>(t.th), -0.5f);
+  const float x0 = floorf(x), y0 = floorf(y);
+  const float fx = __fsub_rn(x, x0), fy = __fsub_rn(y, y0);
+  const int i0 = wrap_idx(static_cast<int>(x0), t.tw), i1 = wrap_idx(static_cast<int>(x0) + 1, t.tw);
+  const int r0 = wrap_idx(static_cast<int>(y0), t.th), r1 = wrap_idx(static_cast<int>(y0) + 1, t.th);
+  const unsigned char* p00 = t.tex + (static_cast<size_t>(r0) * t.tw + i0) * 3;
+  const unsigned char* p10 = t.tex + (static_cast<size_t>(r0) * t.tw + i1) * 3;
+  const unsigned char* p01 = t.tex + (static_cast<size_t>(r1) * t.tw + i0) * 3;
+  const unsigned char* p11 = t.tex + (static_cast<size_t>(r1) * t.tw + i1) * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float c00 = c_tables.q8[__ldg(p00 + k)], c10 = c_tables.q8[__ldg(p10 + k)];
+    const float c01 = c_tables.q8[__ldg(p01 + k)], c11 = c_tables.q8[__ldg(p11 + k)];
+    const float top = __fmaf_rn(fx, __fsub_rn(c10, c00), c00);
+    const float bot = __fmaf_rn(fx, __fsub_rn(c11, c01), c01);
+    out[k] = __fmaf_rn(fy, __fsub_rn(bot, top), top);
+  }
 }
 
 struct TriSetup {
@@ -262,13 +299,28 @@ __device__ __forceinline__ void load_view(const MeshDb& db, const int* __restric
   sK[0] = Kv[0]; sK[1] = Kv[2]; sK[2] = Kv[4]; sK[3] = Kv[5];
 }
 
+__device__ __forceinline__ TexRef mesh_texture(const MeshDb& db, int lab, long long v_off, bool valid) {
+  TexRef t;
+  t.uv = nullptr; t.tex = nullptr; t.th = t.tw = t.modulate = 0;
+  if (valid && db.tex_info != nullptr) {
+    const int4 info = db.tex_info[lab];
+    if (info.x > 0 && info.y > 0) {
+      t.uv = db.uv + 2 * v_off;
+      t.tex = db.tex + db.tex_offsets[lab];
+      t.th = info.x; t.tw = info.y; t.modulate = info.z;
+    }
+  }
+  return t;
+}
+
 // (D) resolve + shade + write for rows [row_lo, row_hi] of one view.  Called by every thread of the CTA (contains
 // barriers when the crop is fused).
-template <bool CACHED>
+template <bool CACHED, bool TEXTURED>
 __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __restrict__ faces,
                                              const float* __restrict__ colors, const float* __restrict__ normals,
-                                             const unsigned long long* __restrict__ vis, int view, int row_lo, int row_hi,
-                                             int h, int w, bool q8, bool gl_axes, const RasterOut& out, AxisW* s_axis) {
+                                             const TexRef& texref, const unsigned long long* __restrict__ vis, int view,
+                                             int row_lo, int row_hi, int h, int w, bool q8, bool gl_axes,
+                                             const RasterOut& out, AxisW* s_axis) {
   const int npix = h * w;
   const float* sR = src.sR;
   // (D) resolve + shade + write
@@ -319,6 +371,16 @@ __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __res
                            __fmaf_rn(b1, __ldg(vcol + 3 * ib + k), __fmul_rn(b2, __ldg(vcol + 3 * ic + k))));
         nrm[k] = __fmaf_rn(b0, __ldg(vnrm + 3 * ia + k),
                            __fmaf_rn(b1, __ldg(vnrm + 3 * ib + k), __fmul_rn(b2, __ldg(vnrm + 3 * ic + k))));
+      }
+      if (TEXTURED && texref.tex != nullptr) {
+        const float* uv = texref.uv;
+        const float tu = __fmaf_rn(b0, __ldg(uv + 2 * ia), __fmaf_rn(b1, __ldg(uv + 2 * ib), __fmul_rn(b2, __ldg(uv + 2 * ic))));
+        const float tv = __fmaf_rn(b0, __ldg(uv + 2 * ia + 1),
+                                   __fmaf_rn(b1, __ldg(uv + 2 * ib + 1), __fmul_rn(b2, __ldg(uv + 2 * ic + 1))));
+        float tc[3];
+        texture_sample(texref, tu, tv, tc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) col[k] = texref.modulate ? __fmul_rn(tc[k], col[k]) : tc[k];
       }
       r = quant8(col[0], q8);
       g = quant8(col[1], q8);
@@ -409,6 +471,7 @@ __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __res
   }
 }
 
+template <bool TEXTURED>  // instantiated for mesh stores with / without textures: the untextured kernel keeps its registers
 __global__ void __launch_bounds__(kRasterThreads, 2)
 raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
               const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out,
@@ -465,8 +528,9 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     cover_big_triangles<true>(src, faces, min(s_big_count, kBigQueue), s_big, row_lo, row_hi, h, w, vis);
     __syncthreads();
 
-    resolve_rows<true>(src, faces, db.colors + 3 * v_off, db.normals + 3 * v_off, vis, view, row_lo, row_hi, h, w, q8,
-                       gl_axes, out, s_axis);
+    resolve_rows<true, TEXTURED>(src, faces, db.colors + 3 * v_off, db.normals + 3 * v_off,
+                                 TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0}, vis, view,
+                                 row_lo, row_hi, h, w, q8, gl_axes, out, s_axis);
   }
 }
 
@@ -512,6 +576,7 @@ raster_cover_kernel(const MeshDb db, const int* __restrict__ label_idx, const fl
   cover_big_triangles<false>(src, faces, min(s_big_count, kBigQueue), s_big, 0, h - 1, h, w, vis);
 }
 
+template <bool TEXTURED>
 __global__ void __launch_bounds__(kRasterThreads, 2)
 raster_resolve_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
                       const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out,
@@ -536,9 +601,10 @@ raster_resolve_kernel(const MeshDb db, const int* __restrict__ label_idx, const 
   src.sR = sR;
   src.fx = sK[0]; src.cx = sK[1]; src.fy = sK[2]; src.cy = sK[3];
   // an invalid view has an untouched (all ~0) visibility buffer: every pixel resolves to background
-  resolve_rows<false>(src, db.faces + 3 * f_off, db.colors + 3 * v_off, db.normals + 3 * v_off,
-                      vis_all + static_cast<size_t>(view) * h * w, view, row_lo, row_hi, h, w, (flags & 1u) != 0,
-                      (flags & 2u) != 0, out, s_axis);
+  resolve_rows<false, TEXTURED>(src, db.faces + 3 * f_off, db.colors + 3 * v_off, db.normals + 3 * v_off,
+                                TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0},
+                                vis_all + static_cast<size_t>(view) * h * w, view, row_lo, row_hi, h, w, (flags & 1u) != 0,
+                                (flags & 2u) != 0, out, s_axis);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -598,8 +664,42 @@ int meshdb_create(int n_meshes, const float* verts, const float* normals, const 
   return MPX_OK;
 }
 
+int meshdb_set_textures(MeshDb* db, const float* uv, const unsigned char* tex, const int64_t* tex_offsets,
+                        const int32_t* tex_dims, const int32_t* tex_modulate) {
+  MPX_REQUIRE(db != nullptr && uv != nullptr && tex != nullptr && tex_offsets != nullptr && tex_dims != nullptr,
+              "meshdb_set_textures: null argument");
+  MPX_REQUIRE(db->tex_info == nullptr, "meshdb_set_textures: textures already set");
+  const int n = db->n_meshes;
+  std::vector<long long> vo(n + 1);
+  MPX_CHECK_CUDA(cudaMemcpy(vo.data(), db->vert_offsets, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost));
+  std::vector<int4> info(n);
+  std::vector<long long> offs(n);
+  for (int i = 0; i < n; ++i) {
+    const int th = tex_dims[2 * i], tw = tex_dims[2 * i + 1];
+    MPX_REQUIRE(th >= 0 && tw >= 0 && th <= 16384 && tw <= 16384, "meshdb_set_textures: mesh %d texture %dx%d", i, th, tw);
+    MPX_REQUIRE(tex_offsets[i + 1] - tex_offsets[i] == static_cast<int64_t>(th) * tw * 3,
+                "meshdb_set_textures: mesh %d texture bytes do not match its size", i);
+    info[i] = make_int4(th, tw, tex_modulate ? tex_modulate[i] : 0, 0);
+    offs[i] = tex_offsets[i];
+  }
+  const long long nv = vo[n], bytes = tex_offsets[n];
+  MPX_CHECK_CUDA(cudaMalloc(&db->uv, sizeof(float) * 2 * (nv > 0 ? nv : 1)));
+  MPX_CHECK_CUDA(cudaMalloc(&db->tex, bytes > 0 ? bytes : 1));
+  MPX_CHECK_CUDA(cudaMalloc(&db->tex_offsets, sizeof(long long) * n));
+  MPX_CHECK_CUDA(cudaMalloc(&db->tex_info, sizeof(int4) * n));
+  MPX_CHECK_CUDA(cudaMemcpy(db->uv, uv, sizeof(float) * 2 * nv, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->tex, tex, bytes, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->tex_offsets, offs.data(), sizeof(long long) * n, cudaMemcpyHostToDevice));
+  MPX_CHECK_CUDA(cudaMemcpy(db->tex_info, info.data(), sizeof(int4) * n, cudaMemcpyHostToDevice));
+  return MPX_OK;
+}
+
 void meshdb_destroy(MeshDb* db) {
   if (!db) return;
+  cudaFree(db->uv);
+  cudaFree(db->tex);
+  cudaFree(db->tex_offsets);
+  cudaFree(db->tex_info);
   cudaFree(db->verts);
   cudaFree(db->normals);
   cudaFree(db->colors);
@@ -649,8 +749,12 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
     if (strips > h) strips = h;
     const int rows = (h + strips - 1) / strips;
     strips = (h + rows - 1) / rows;  // no empty strips
-    raster_resolve_kernel<<<n_views * strips, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w,
-                                                                          flags, out, vis, strips);
+    if (db->tex_info != nullptr)
+      raster_resolve_kernel<true><<<n_views * strips, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w,
+                                                                                  flags, out, vis, strips);
+    else
+      raster_resolve_kernel<false><<<n_views * strips, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w,
+                                                                                   flags, out, vis, strips);
     MPX_CHECK_CUDA(cudaGetLastError());
     g_launches += 2;
     return MPX_OK;
@@ -663,8 +767,12 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
   }
   const long long items = static_cast<long long>(n_views) * strips;
   const int grid = items < db->slots ? static_cast<int>(items) : db->slots;
-  raster_kernel<<<grid, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out,
-                                                     reinterpret_cast<unsigned long long*>(workspace), strips);
+  if (db->tex_info != nullptr)
+    raster_kernel<true><<<grid, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out,
+                                                             reinterpret_cast<unsigned long long*>(workspace), strips);
+  else
+    raster_kernel<false><<<grid, kRasterThreads, 0, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out,
+                                                              reinterpret_cast<unsigned long long*>(workspace), strips);
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;

@@ -5,7 +5,10 @@ Host-side mirror of the reference's MeshDataBase / BatchedMeshes / Meshes
 what the Panda3D side of the reference does when it loads a model for rendering
 (src/megapose/panda3d_renderer/panda3d_scene_renderer.py:195-208: scale to metres, apply
 `ypr_offset_deg`).  The reference reads mesh files with trimesh / Assimp; here a small PLY/OBJ reader
-covers vertex positions, normals, colours and triangular faces (textures: SURVEY 8f "next").
+covers vertex positions, normals, colours, texture coordinates (per vertex or per face corner) and the
+diffuse texture named by the OBJ's MTL (`map_Kd`) or the PLY's `comment TextureFile` (the two forms the
+BOP / YCB-V / HOPE model sets use).  Corners that share a position but not a texture coordinate or
+normal become separate vertices, as they do in trimesh and Assimp.
 """
 from __future__ import annotations
 
@@ -29,12 +32,18 @@ class TriMesh:
     faces: np.ndarray  # [nf,3] int32
     vertex_normals: Optional[np.ndarray] = None  # [nv,3]
     vertex_colors: Optional[np.ndarray] = None  # [nv,3] in [0,1]
+    uv: Optional[np.ndarray] = None  # [nv,2] texture coordinates (v up)
+    texture: Optional[np.ndarray] = None  # [th,tw,3] uint8, row 0 = top of the image
+    texture_modulate: bool = False  # multiply the texture with the vertex colours (set when the file has both)
 
     def with_defaults(self) -> "TriMesh":
         normals = self.vertex_normals if self.vertex_normals is not None else compute_vertex_normals(self.vertices, self.faces)
         colors = self.vertex_colors if self.vertex_colors is not None else np.full((len(self.vertices), 3), 0.8)
+        textured = self.texture is not None and self.uv is not None
         return TriMesh(np.asarray(self.vertices, np.float64), np.asarray(self.faces, np.int32), np.asarray(normals, np.float64),
-                       np.asarray(colors, np.float64))
+                       np.asarray(colors, np.float64), np.asarray(self.uv, np.float64) if textured else None,
+                       np.ascontiguousarray(self.texture[..., :3], dtype=np.uint8) if textured else None,
+                       bool(textured and self.vertex_colors is not None and self.texture_modulate))
 
 
 def compute_vertex_normals(vertices: np.ndarray, faces: np.ndarray) -> np.ndarray:
@@ -81,6 +90,12 @@ def load_ply(path: Path) -> TriMesh:
     body = data[end:]
     verts: Dict[str, np.ndarray] = {}
     faces: List[List[int]] = []
+    face_uv: List[Optional[List[float]]] = []  # per-face texcoord list (u0 v0 u1 v1 ...), PLY `texcoord` property
+    texture_file = None
+    for line in header:
+        tok = line.split()
+        if len(tok) >= 3 and tok[0] == "comment" and tok[1].lower() == "texturefile":
+            texture_file = line.split(None, 2)[2].strip()
     if fmt == "ascii":
         lines = body.decode("ascii", "replace").split("\n")
         li = 0
@@ -90,10 +105,21 @@ def load_ply(path: Path) -> TriMesh:
                 arr = np.array([lines[li + i].split() for i in range(el["count"])], dtype=np.float64)
                 verts = {n: arr[:, k] for k, n in enumerate(names)}
             elif el["name"] == "face":
+                list_names = [p[3] for p in el["props"] if p[0] == "list"]
                 for i in range(el["count"]):
                     tok = lines[li + i].split()
-                    n = int(tok[0])
-                    faces.append([int(t) for t in tok[1:1 + n]])
+                    pos, row, tc = 0, None, None
+                    for name in list_names:
+                        n = int(tok[pos])
+                        vals = tok[pos + 1:pos + 1 + n]
+                        pos += 1 + n
+                        if name in ("vertex_indices", "vertex_index"):
+                            row = [int(t) for t in vals]
+                        elif name == "texcoord":
+                            tc = [float(t) for t in vals]
+                    if row is not None:
+                        faces.append(row)
+                        face_uv.append(tc)
             li += el["count"]
     else:
         endian = "<" if fmt == "binary_little_endian" else ">"
@@ -107,7 +133,7 @@ def load_ply(path: Path) -> TriMesh:
                     verts = {n: arr[n].astype(np.float64) for n in arr.dtype.names}
             else:
                 for _ in range(el["count"]):
-                    row = None
+                    row, tc = None, None
                     for p in el["props"]:
                         if p[0] == "list":
                             (n,) = struct.unpack_from(endian + _PLY_TYPES[p[1]], body, off)
@@ -116,21 +142,98 @@ def load_ply(path: Path) -> TriMesh:
                             off += struct.calcsize(_PLY_TYPES[p[2]]) * n
                             if p[3] in ("vertex_indices", "vertex_index"):
                                 row = list(vals)
+                            elif p[3] == "texcoord":
+                                tc = list(vals)
                         else:
                             off += struct.calcsize(_PLY_TYPES[p[1]])
                     if el["name"] == "face" and row is not None:
                         faces.append(row)
+                        face_uv.append(tc)
     v = np.stack([verts["x"], verts["y"], verts["z"]], axis=1)
     normals = np.stack([verts["nx"], verts["ny"], verts["nz"]], axis=1) if "nx" in verts else None
     colors = None
     if "red" in verts:
         colors = np.stack([verts["red"], verts["green"], verts["blue"]], axis=1) / 255.0
-    return TriMesh(v, _triangulate(faces), normals, colors)
+    uv = None
+    for un, vn in (("texture_u", "texture_v"), ("s", "t"), ("u", "v")):
+        if un in verts and vn in verts:
+            uv = np.stack([verts[un], verts[vn]], axis=1)
+            break
+    texture = _load_texture(Path(path).parent / texture_file) if texture_file else None
+    if uv is None and texture is not None and faces and all(t is not None and len(t) == 2 * len(f) for t, f in zip(face_uv, faces)):
+        # per-corner texture coordinates: one vertex per distinct (position index, u, v)
+        corners = [(f[k], float(t[2 * k]), float(t[2 * k + 1])) for f, t in zip(faces, face_uv) for k in range(len(f))]
+        new_faces, src, uv = _split_corners(corners, [len(f) for f in faces])
+        v = v[src]
+        normals = normals[src] if normals is not None else None
+        colors = colors[src] if colors is not None else None
+        faces = new_faces
+        uv = np.asarray(uv, np.float64)
+    if texture is None:
+        uv = None
+    return TriMesh(v, _triangulate(faces), normals, colors, uv, texture, texture_modulate=colors is not None)
+
+
+def _load_texture(path: Path) -> Optional[np.ndarray]:
+    """RGB uint8 [th,tw,3], row 0 = top; None when the file is missing (the mesh then renders with its vertex colours)."""
+    path = Path(path)
+    if not path.is_file():
+        return None
+    from PIL import Image  # local import: only textured meshes need it
+
+    with Image.open(path) as im:
+        return np.ascontiguousarray(np.asarray(im.convert("RGB"), dtype=np.uint8))
+
+
+def _split_corners(corners: Sequence[tuple], face_sizes: Sequence[int]):
+    """Distinct corner keys -> new vertex ids (first-seen order).  Returns (faces as lists of new ids, source position index
+    per new vertex, the remaining key fields per new vertex)."""
+    ids: Dict[tuple, int] = {}
+    src: List[int] = []
+    rest: List[tuple] = []
+    flat: List[int] = []
+    for key in corners:
+        k = ids.get(key)
+        if k is None:
+            k = ids[key] = len(src)
+            src.append(key[0])
+            rest.append(key[1:])
+        flat.append(k)
+    faces, pos = [], 0
+    for n in face_sizes:
+        faces.append(flat[pos:pos + n])
+        pos += n
+    return faces, np.asarray(src, np.int64), rest
+
+
+def _parse_mtl(path: Path) -> Dict[str, dict]:
+    mats: Dict[str, dict] = {}
+    cur = None
+    if not Path(path).is_file():
+        return mats
+    for line in Path(path).read_text(errors="replace").splitlines():
+        tok = line.split()
+        if not tok or tok[0].startswith("#"):
+            continue
+        if tok[0] == "newmtl":
+            cur = mats.setdefault(" ".join(tok[1:]), {})
+        elif cur is not None and tok[0] == "Kd" and len(tok) >= 4:
+            cur["Kd"] = [float(t) for t in tok[1:4]]
+        elif cur is not None and tok[0] == "map_Kd":
+            cur["map_Kd"] = line.split(None, 1)[1].strip().split()[-1]  # options (-s, -o ...) precede the file name
+    return mats
 
 
 def load_obj(path: Path) -> TriMesh:
-    vs, cols, faces = [], [], []
-    for line in Path(path).read_text(errors="replace").splitlines():
+    """Wavefront OBJ: v (optionally with r g b), vt, vn, f with v, v/vt, v//vn or v/vt/vn corners, mtllib / usemtl.  One
+    diffuse texture per mesh (the first material with a `map_Kd`, as the single-object model files of BOP / HOPE have)."""
+    path = Path(path)
+    vs, cols, vts, vns = [], [], [], []
+    corners: List[tuple] = []
+    sizes: List[int] = []
+    mats: Dict[str, dict] = {}
+    used: List[str] = []
+    for line in path.read_text(errors="replace").splitlines():
         tok = line.split()
         if not tok:
             continue
@@ -138,11 +241,50 @@ def load_obj(path: Path) -> TriMesh:
             vs.append([float(t) for t in tok[1:4]])
             if len(tok) >= 7:
                 cols.append([float(t) for t in tok[4:7]])
+        elif tok[0] == "vt":
+            vts.append([float(tok[1]), float(tok[2]) if len(tok) > 2 else 0.0])
+        elif tok[0] == "vn":
+            vns.append([float(t) for t in tok[1:4]])
+        elif tok[0] == "mtllib":
+            mats.update(_parse_mtl(path.parent / line.split(None, 1)[1].strip()))
+        elif tok[0] == "usemtl":
+            used.append(" ".join(tok[1:]))
         elif tok[0] == "f":
-            idx = [int(t.split("/")[0]) for t in tok[1:]]
-            faces.append([i - 1 if i > 0 else len(vs) + i for i in idx])
+            n = 0
+            for t in tok[1:]:
+                parts = (t.split("/") + ["", ""])[:3]
+                vi = int(parts[0])
+                ti = int(parts[1]) if parts[1] else 0
+                ni = int(parts[2]) if parts[2] else 0
+                corners.append((vi - 1 if vi > 0 else len(vs) + vi,
+                                (ti - 1 if ti > 0 else len(vts) + ti) if ti else -1,
+                                (ni - 1 if ni > 0 else len(vns) + ni) if ni else -1))
+                n += 1
+            sizes.append(n)
+    v = np.asarray(vs, np.float64).reshape(-1, 3)
     colors = np.asarray(cols) if len(cols) == len(vs) and vs else None
-    return TriMesh(np.asarray(vs, np.float64), _triangulate(faces), None, colors)
+    texture = None
+    for name in used + list(mats):
+        m = mats.get(name)
+        if m and "map_Kd" in m:
+            texture = _load_texture(path.parent / m["map_Kd"])
+            if texture is not None:
+                break
+    has_vt = bool(vts) and all(c[1] >= 0 for c in corners)
+    has_vn = bool(vns) and all(c[2] >= 0 for c in corners)
+    if not (has_vt and texture is not None) and not has_vn:
+        faces, pos = [], 0
+        for n in sizes:
+            faces.append([c[0] for c in corners[pos:pos + n]])
+            pos += n
+        return TriMesh(v, _triangulate(faces), None, colors)
+    keys = [(c[0], c[1] if has_vt and texture is not None else -1, c[2] if has_vn else -1) for c in corners]
+    faces, src, rest = _split_corners(keys, sizes)
+    rest = np.asarray(rest, np.int64).reshape(-1, 2)
+    uv = np.asarray(vts, np.float64)[rest[:, 0]] if has_vt and texture is not None else None
+    normals = np.asarray(vns, np.float64)[rest[:, 1]] if has_vn else None
+    return TriMesh(v[src], _triangulate(faces), normals, colors[src] if colors is not None else None, uv, texture,
+                   texture_modulate=colors is not None)
 
 
 def _triangulate(faces: Sequence[Sequence[int]]) -> np.ndarray:
@@ -291,6 +433,25 @@ class BatchedMeshes:
                 fo.ctypes.data, ctypes.byref(out)))
             self._handle = out
             self.host_arrays = dict(verts=v, normals=n, colors=c, faces=f, vert_offsets=vo, face_offsets=fo)
+            meshes = [self._mesh_db.meshes[str(label)] for label in self.labels]
+            if any(m.texture is not None for m in meshes):
+                uv_all, tex_all, t_off, dims, mod = [], [], [0], [], []
+                for m in meshes:
+                    has = m.texture is not None and m.uv is not None
+                    uv_all.append(np.asarray(m.uv, np.float32) if has else np.zeros((len(m.vertices), 2), np.float32))
+                    if has:
+                        tex_all.append(np.ascontiguousarray(m.texture, np.uint8).reshape(-1))
+                    dims.append(m.texture.shape[:2] if has else (0, 0))
+                    t_off.append(t_off[-1] + (tex_all[-1].size if has else 0))
+                    mod.append(1 if (has and m.texture_modulate) else 0)
+                uv = np.ascontiguousarray(np.concatenate(uv_all), np.float32)
+                tex = np.ascontiguousarray(np.concatenate(tex_all), np.uint8)
+                to = np.asarray(t_off, np.int64)
+                td = np.ascontiguousarray(np.asarray(dims, np.int32))
+                tm = np.ascontiguousarray(np.asarray(mod, np.int32))
+                _abi.check(_abi.lib().mpx_meshdb_set_textures(out, uv.ctypes.data, tex.ctypes.data, to.ctypes.data,
+                                                              td.ctypes.data, tm.ctypes.data))
+                self.host_arrays.update(uv=uv, tex=tex, tex_offsets=to, tex_dims=td, tex_modulate=tm)
         return self._handle
 
     def __del__(self):

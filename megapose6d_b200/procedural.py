@@ -57,6 +57,43 @@ def bumpy_sphere(n_seg: int = 100, n_lat: int = 51, radius: float = 0.05, bump: 
     return TriMesh(verts, faces_a, compute_vertex_normals(verts, faces_a), col)
 
 
+def checker_texture(th: int = 48, tw: int = 64, cell: int = 8, seed: int = 0) -> np.ndarray:
+    """RGB uint8 [th,tw,3]: a coloured checkerboard over a smooth gradient (every texel distinct from its neighbours)."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:th, 0:tw]
+    check = ((yy // cell + xx // cell) % 2).astype(np.float64)
+    base = np.stack([xx / max(tw - 1, 1), yy / max(th - 1, 1), 1.0 - xx / max(tw - 1, 1)], axis=-1)
+    tint = rs.uniform(0.35, 1.0, size=(3,))
+    img = (0.25 + 0.75 * check[..., None]) * (0.4 + 0.6 * base) * tint
+    return np.clip(np.round(img * 255.0), 0, 255).astype(np.uint8)
+
+
+def textured_box(size=(0.10, 0.07, 0.05), seed: int = 0, with_vertex_colors: bool = False) -> TriMesh:
+    """Axis-aligned box, 4 vertices per face (24 in all) so that every face carries its own patch of the texture."""
+    sx, sy, sz = (0.5 * s for s in size)
+    faces_def = [  # (normal, 4 corners counter-clockwise seen from outside)
+        ((1, 0, 0), [(sx, -sy, -sz), (sx, sy, -sz), (sx, sy, sz), (sx, -sy, sz)]),
+        ((-1, 0, 0), [(-sx, sy, -sz), (-sx, -sy, -sz), (-sx, -sy, sz), (-sx, sy, sz)]),
+        ((0, 1, 0), [(sx, sy, -sz), (-sx, sy, -sz), (-sx, sy, sz), (sx, sy, sz)]),
+        ((0, -1, 0), [(-sx, -sy, -sz), (sx, -sy, -sz), (sx, -sy, sz), (-sx, -sy, sz)]),
+        ((0, 0, 1), [(-sx, -sy, sz), (sx, -sy, sz), (sx, sy, sz), (-sx, sy, sz)]),
+        ((0, 0, -1), [(-sx, sy, -sz), (sx, sy, -sz), (sx, -sy, -sz), (-sx, -sy, -sz)]),
+    ]
+    v, n, uv, f = [], [], [], []
+    for k, (nrm, corners) in enumerate(faces_def):
+        u0, v0 = (k % 3) / 3.0, (k // 3) / 2.0  # 3 x 2 atlas; deliberately reaching outside [0,1] on the last column
+        quad_uv = [(u0, v0), (u0 + 0.4, v0), (u0 + 0.4, v0 + 0.55), (u0, v0 + 0.55)]
+        base = len(v)
+        v += corners
+        n += [nrm] * 4
+        uv += quad_uv
+        f += [[base, base + 1, base + 2], [base, base + 2, base + 3]]
+    rs = np.random.RandomState(seed + 100)
+    colors = rs.uniform(0.3, 1.0, size=(len(v), 3)).round(3) if with_vertex_colors else None
+    return TriMesh(np.asarray(v, np.float64), np.asarray(f, np.int32), np.asarray(n, np.float64), colors,
+                   np.asarray(uv, np.float64), checker_texture(seed=seed), texture_modulate=with_vertex_colors)
+
+
 def make_object_dataset(n_objects: int = 1, seed: int = 0, n_seg: int = 100, n_lat: int = 51) -> RigidObjectDataset:
     objs = []
     for i in range(n_objects):

@@ -82,7 +82,7 @@ class ObservationTensor:
                    K: Optional[np.ndarray] = None) -> "ObservationTensor":
         """rgb [H,W,3] uint8, depth [H,W] float (metres), K [3,3]."""
         assert rgb.dtype == np.uint8
-        rgb_tensor = torch.as_tensor(rgb).float() / 255
+        rgb_tensor = torch.as_tensor(np.array(rgb, copy=True)).float() / 255
         if rgb_tensor.shape[-1] == 3:
             rgb_tensor = rgb_tensor.permute(2, 0, 1)
         if depth is not None:

@@ -47,6 +47,7 @@ def raster_lib() -> ctypes.CDLL:
     if _LIB is None:
         _LIB = ctypes.CDLL(str(build_raster_lib()))
         _LIB.raster_ref_render_batch.restype = ctypes.c_int
+        _LIB.raster_ref_render_batch_tex.restype = ctypes.c_int
         _LIB.raster_ref_render.restype = ctypes.c_int
     return _LIB
 
@@ -55,8 +56,10 @@ class RefMeshes:
     """Host arrays in the layout of mpx_meshdb_create + the [L, Nv, 3] point database."""
 
     def __init__(self, labels: Sequence[str], verts: List[np.ndarray], normals: List[np.ndarray],
-                 colors: List[np.ndarray], faces: List[np.ndarray]):
+                 colors: List[np.ndarray], faces: List[np.ndarray], uvs: Optional[List[Optional[np.ndarray]]] = None,
+                 textures: Optional[List[Optional[np.ndarray]]] = None, modulate: Optional[Sequence[bool]] = None):
         self.labels = list(labels)
+        self.set_textures(verts, uvs, textures, modulate)
         self.label_to_id = {l: i for i, l in enumerate(self.labels)}
         self.verts = np.ascontiguousarray(np.concatenate(verts), np.float32)
         self.normals = np.ascontiguousarray(np.concatenate(normals), np.float32)
@@ -67,9 +70,36 @@ class RefMeshes:
         # points database as MeshDataBase.batched() (lib3d/rigid_mesh_database.py:90-130): float64 scale, pad, float32
         self.points = L.pad_stack_points([torch.tensor(np.asarray(v, np.float64)) for v in verts]).float()
 
+    def set_textures(self, verts, uvs, textures, modulate) -> None:
+        """Optional per-mesh texture: uv [nv,2] and an RGB uint8 image [th,tw,3] (row 0 = top); layout of
+        mpx_meshdb_set_textures."""
+        n = len(verts)
+        self.uv = self.tex = self.tex_offsets = self.tex_dims = self.tex_modulate = None
+        if not textures or all(t is None for t in textures):
+            return
+        uv_all, tex_all, offs, dims = [], [], [0], []
+        for i in range(n):
+            has = textures[i] is not None and uvs is not None and uvs[i] is not None
+            uv_all.append(np.asarray(uvs[i], np.float32) if has else np.zeros((len(verts[i]), 2), np.float32))
+            if has:
+                t = np.ascontiguousarray(textures[i][..., :3], np.uint8)
+                tex_all.append(t.reshape(-1))
+                dims.append(t.shape[:2])
+            else:
+                dims.append((0, 0))
+            offs.append(offs[-1] + (tex_all[-1].size if has else 0))
+        self.uv = np.ascontiguousarray(np.concatenate(uv_all), np.float32)
+        self.tex = np.ascontiguousarray(np.concatenate(tex_all), np.uint8)
+        self.tex_offsets = np.asarray(offs, np.int64)
+        self.tex_dims = np.ascontiguousarray(np.asarray(dims, np.int32))
+        self.tex_modulate = np.ascontiguousarray(np.asarray(modulate if modulate is not None else [0] * n, np.int32))
+
     @staticmethod
     def from_host_arrays(labels, arrays: Dict[str, np.ndarray], points: torch.Tensor) -> "RefMeshes":
         m = RefMeshes.__new__(RefMeshes)
+        m.uv = arrays.get("uv")
+        m.tex, m.tex_offsets = arrays.get("tex"), arrays.get("tex_offsets")
+        m.tex_dims, m.tex_modulate = arrays.get("tex_dims"), arrays.get("tex_modulate")
         m.labels = list(labels)
         m.label_to_id = {l: i for i, l in enumerate(m.labels)}
         m.verts, m.normals, m.colors, m.faces = arrays["verts"], arrays["normals"], arrays["colors"], arrays["faces"]
@@ -107,11 +137,13 @@ class RefRenderer:
         nrm = np.zeros((n, 3, h, w), np.float32) if render_normals else None
         dep = np.zeros((n, 1, h, w), np.float32) if render_depth else None
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None  # noqa: E731
-        rc = raster_lib().raster_ref_render_batch(
+        rc = raster_lib().raster_ref_render_batch_tex(
             ctypes.c_int(len(m.labels)), p(m.verts), p(m.normals), p(m.colors), p(m.vert_offsets), p(m.faces),
-            p(m.face_offsets), p(idx), p(T), p(Kn), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w),
-            ctypes.c_uint(self.flags), p(rgb), p(nrm), p(dep), ctypes.c_int(self.n_threads))
-        assert rc == 0, f"raster_ref_render_batch failed ({rc})"
+            p(m.face_offsets), p(getattr(m, "uv", None)), p(getattr(m, "tex", None)), p(getattr(m, "tex_offsets", None)),
+            p(getattr(m, "tex_dims", None)), p(getattr(m, "tex_modulate", None)), p(idx), p(T), p(Kn), ctypes.c_int(n),
+            ctypes.c_int(h), ctypes.c_int(w), ctypes.c_uint(self.flags), p(rgb), p(nrm), p(dep),
+            ctypes.c_int(self.n_threads))
+        assert rc == 0, f"raster_ref_render_batch_tex failed ({rc})"
         return dict(rgbs=torch.from_numpy(rgb), normals=torch.from_numpy(nrm) if nrm is not None else None,
                     depths=torch.from_numpy(dep) if dep is not None else None)
 

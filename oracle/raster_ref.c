@@ -23,6 +23,10 @@
  *     are dropped (no near-plane clipping)
  *   - 1/z linear in screen space, attributes perspective-correct (b_k = l_k/z_k * z, z = 1/(1/z))
  *   - single sample per pixel (the reference's 4x MSAA is not modelled)
+ *   - textured meshes (panda3d_scene_renderer.py:195-208 loads the model with its material / texture): per-vertex
+ *     (u, v) interpolated like the other attributes, wrapped to [0, 1) (repeat), v up (image row = (1 - v) * th - 0.5),
+ *     bilinear filter over texel centres without mip-mapping, texel = byte / 255; the texture replaces the albedo, or
+ *     modulates the interpolated vertex colours when the mesh has them
  * Every float operation is a single correctly-rounded IEEE operation in a fixed order (compile with
  * -ffp-contract=off) so that the device kernel can reproduce the results exactly.
  */
@@ -79,6 +83,42 @@ static float quant8(float v, int on) {
   return (float)lrintf(v * 255.0f) / 255.0f; /* uint8 level k, read back as k / 255 */
 }
 
+/* optional texture of one mesh: uv [nv,2], tex [th,tw,3] uint8 (row 0 = top of the image), modulate = multiply with the
+ * interpolated vertex colours */
+typedef struct {
+  const float* uv;
+  const uint8_t* tex;
+  int th, tw;
+  int modulate;
+} tex_t;
+
+static int wrap_idx(int i, int n) {
+  int r = i % n;
+  return r < 0 ? r + n : r;
+}
+
+static void texture_sample(const tex_t* t, float u, float v, float* out3) {
+  if (!(u == u)) u = 0.f;
+  if (!(v == v)) v = 0.f;
+  u = u - floorf(u);
+  v = v - floorf(v);
+  const float x = fmaf(u, (float)t->tw, -0.5f);
+  const float y = fmaf(1.0f - v, (float)t->th, -0.5f);
+  const float x0 = floorf(x), y0 = floorf(y);
+  const float fx = x - x0, fy = y - y0;
+  const int i0 = wrap_idx((int)x0, t->tw), i1 = wrap_idx((int)x0 + 1, t->tw);
+  const int r0 = wrap_idx((int)y0, t->th), r1 = wrap_idx((int)y0 + 1, t->th);
+  for (int k = 0; k < 3; ++k) {
+    const float c00 = (float)t->tex[((size_t)r0 * t->tw + i0) * 3 + k] / 255.0f;
+    const float c10 = (float)t->tex[((size_t)r0 * t->tw + i1) * 3 + k] / 255.0f;
+    const float c01 = (float)t->tex[((size_t)r1 * t->tw + i0) * 3 + k] / 255.0f;
+    const float c11 = (float)t->tex[((size_t)r1 * t->tw + i1) * 3 + k] / 255.0f;
+    const float top = fmaf(fx, c10 - c00, c00);
+    const float bot = fmaf(fx, c11 - c01, c01);
+    out3[k] = fmaf(fy, bot - top, top);
+  }
+}
+
 static tri_t load_tri(const vtx_t* vtx, const int32_t* faces, int tri) {
   tri_t t;
   const vtx_t a = vtx[faces[3 * tri]], b = vtx[faces[3 * tri + 1]], c = vtx[faces[3 * tri + 2]];
@@ -114,9 +154,9 @@ static int imax(int a, int b) { return a > b ? a : b; }
  * flags: bit0 quantize8, bit1 GL eye axes.  Outputs (any may be NULL): rgb [3,h,w], nrm [3,h,w],
  * depth [h,w], tri_id [h,w] (-1 = background).  Returns 0, or -1 on allocation failure.
  */
-int raster_ref_render(const float* verts, const float* normals, const float* colors, int nv,
-                      const int32_t* faces, int nf, const float* TCO, const float* K, int h, int w,
-                      unsigned flags, float* rgb, float* nrm, float* depth, int32_t* tri_id) {
+static int render_view(const float* verts, const float* normals, const float* colors, int nv,
+                       const int32_t* faces, int nf, const float* TCO, const float* K, int h, int w,
+                       unsigned flags, const tex_t* texture, float* rgb, float* nrm, float* depth, int32_t* tri_id) {
   const int npix = h * w;
   const int q8 = (flags & 1u) != 0, gl_axes = (flags & 2u) != 0;
   int valid = 1;
@@ -194,6 +234,14 @@ int raster_ref_render(const float* verts, const float* normals, const float* col
       col[k] = fmaf(b0, colors[3 * ia + k], fmaf(b1, colors[3 * ib + k], b2 * colors[3 * ic + k]));
       nn[k] = fmaf(b0, normals[3 * ia + k], fmaf(b1, normals[3 * ib + k], b2 * normals[3 * ic + k]));
     }
+    if (texture && texture->tex) {
+      const float* uv = texture->uv;
+      const float tu = fmaf(b0, uv[2 * ia], fmaf(b1, uv[2 * ib], b2 * uv[2 * ic]));
+      const float tv = fmaf(b0, uv[2 * ia + 1], fmaf(b1, uv[2 * ib + 1], b2 * uv[2 * ic + 1]));
+      float tc[3];
+      texture_sample(texture, tu, tv, tc);
+      for (int k = 0; k < 3; ++k) col[k] = texture->modulate ? tc[k] * col[k] : tc[k];
+    }
     if (rgb) {
       rgb[pix] = quant8(col[0], q8);
       rgb[npix + pix] = quant8(col[1], q8);
@@ -226,6 +274,23 @@ int raster_ref_render(const float* verts, const float* normals, const float* col
   return 0;
 }
 
+int raster_ref_render(const float* verts, const float* normals, const float* colors, int nv,
+                      const int32_t* faces, int nf, const float* TCO, const float* K, int h, int w,
+                      unsigned flags, float* rgb, float* nrm, float* depth, int32_t* tri_id) {
+  return render_view(verts, normals, colors, nv, faces, nf, TCO, K, h, w, flags, NULL, rgb, nrm, depth, tri_id);
+}
+
+/* the same with a texture: uv [nv,2], tex [th,tw,3] uint8 */
+int raster_ref_render_tex(const float* verts, const float* normals, const float* colors, const float* uv, int nv,
+                          const int32_t* faces, int nf, const uint8_t* tex, int th, int tw, int modulate,
+                          const float* TCO, const float* K, int h, int w, unsigned flags, float* rgb, float* nrm,
+                          float* depth, int32_t* tri_id) {
+  tex_t t;
+  t.uv = uv; t.tex = tex; t.th = th; t.tw = tw; t.modulate = modulate;
+  return render_view(verts, normals, colors, nv, faces, nf, TCO, K, h, w, flags, (tex && uv) ? &t : NULL, rgb, nrm,
+                     depth, tri_id);
+}
+
 /* Batched convenience: n views of (possibly different) meshes given by offsets, as the device API.
  * Views are spread over n_threads POSIX threads (<= 0: one thread). */
 #include <pthread.h>
@@ -238,6 +303,12 @@ typedef struct {
   int n_views, h, w;
   unsigned flags;
   float *rgb, *nrm, *depth;
+  /* optional textures: uv [sum_nv,2]; tex = all textures back to back; per mesh byte offset, (th, tw), modulate flag */
+  const float* uv;
+  const uint8_t* tex;
+  const int64_t* tex_offsets;
+  const int32_t* tex_dims;
+  const int32_t* tex_modulate;
   int next;  /* work counter, protected by lock */
   int status;
   pthread_mutex_t lock;
@@ -253,12 +324,22 @@ static void* batch_worker(void* arg) {
     if (v >= b->n_views) break;
     const int lab = b->label_idx[v];
     const int64_t vo = b->vert_offsets[lab], fo = b->face_offsets[lab];
-    const int rc = raster_ref_render(b->verts + 3 * vo, b->normals + 3 * vo, b->colors + 3 * vo,
-                                     (int)(b->vert_offsets[lab + 1] - vo), b->faces + 3 * fo,
-                                     (int)(b->face_offsets[lab + 1] - fo), b->TCO + 16 * v, b->K + 9 * v,
-                                     b->h, b->w, b->flags, b->rgb ? b->rgb + 3 * npix * v : NULL,
-                                     b->nrm ? b->nrm + 3 * npix * v : NULL,
-                                     b->depth ? b->depth + npix * v : NULL, NULL);
+    tex_t t;
+    const tex_t* tp = NULL;
+    if (b->tex && b->uv && b->tex_dims[2 * lab] > 0 && b->tex_dims[2 * lab + 1] > 0) {
+      t.uv = b->uv + 2 * vo;
+      t.tex = b->tex + b->tex_offsets[lab];
+      t.th = b->tex_dims[2 * lab];
+      t.tw = b->tex_dims[2 * lab + 1];
+      t.modulate = b->tex_modulate ? b->tex_modulate[lab] : 0;
+      tp = &t;
+    }
+    const int rc = render_view(b->verts + 3 * vo, b->normals + 3 * vo, b->colors + 3 * vo,
+                               (int)(b->vert_offsets[lab + 1] - vo), b->faces + 3 * fo,
+                               (int)(b->face_offsets[lab + 1] - fo), b->TCO + 16 * v, b->K + 9 * v,
+                               b->h, b->w, b->flags, tp, b->rgb ? b->rgb + 3 * npix * v : NULL,
+                               b->nrm ? b->nrm + 3 * npix * v : NULL,
+                               b->depth ? b->depth + npix * v : NULL, NULL);
     if (rc != 0) {
       pthread_mutex_lock(&b->lock);
       b->status = rc;
@@ -268,13 +349,32 @@ static void* batch_worker(void* arg) {
   return NULL;
 }
 
+int raster_ref_render_batch_tex(int n_meshes, const float* verts, const float* normals, const float* colors,
+                                const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
+                                const float* uv, const uint8_t* tex, const int64_t* tex_offsets,
+                                const int32_t* tex_dims, const int32_t* tex_modulate, const int32_t* label_idx,
+                                const float* TCO, const float* K, int n_views, int h, int w, unsigned flags,
+                                float* rgb, float* nrm, float* depth, int n_threads);
+
 int raster_ref_render_batch(int n_meshes, const float* verts, const float* normals, const float* colors,
                             const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
                             const int32_t* label_idx, const float* TCO, const float* K, int n_views, int h,
                             int w, unsigned flags, float* rgb, float* nrm, float* depth, int n_threads) {
+  return raster_ref_render_batch_tex(n_meshes, verts, normals, colors, vert_offsets, faces, face_offsets, NULL, NULL,
+                                     NULL, NULL, NULL, label_idx, TCO, K, n_views, h, w, flags, rgb, nrm, depth,
+                                     n_threads);
+}
+
+int raster_ref_render_batch_tex(int n_meshes, const float* verts, const float* normals, const float* colors,
+                                const int64_t* vert_offsets, const int32_t* faces, const int64_t* face_offsets,
+                                const float* uv, const uint8_t* tex, const int64_t* tex_offsets,
+                                const int32_t* tex_dims, const int32_t* tex_modulate, const int32_t* label_idx,
+                                const float* TCO, const float* K, int n_views, int h, int w, unsigned flags,
+                                float* rgb, float* nrm, float* depth, int n_threads) {
   for (int v = 0; v < n_views; ++v)
     if (label_idx[v] < 0 || label_idx[v] >= n_meshes) return -2;
   batch_t b;
+  b.uv = uv; b.tex = tex; b.tex_offsets = tex_offsets; b.tex_dims = tex_dims; b.tex_modulate = tex_modulate;
   b.verts = verts; b.normals = normals; b.colors = colors;
   b.vert_offsets = vert_offsets; b.face_offsets = face_offsets;
   b.faces = faces; b.label_idx = label_idx; b.TCO = TCO; b.K = K;

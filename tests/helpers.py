@@ -25,7 +25,7 @@ def make_scene(n_objects=1, seed=0, h=480, w=640, with_depth=False, n_seg=100, n
 
 
 def ref_meshes_from_dataset(ds) -> pipeline_ref.RefMeshes:
-    labels, v, n, c, f = [], [], [], [], []
+    labels, v, n, c, f, uv, tex, mod = [], [], [], [], [], [], [], []
     for obj in ds.list_objects:
         m = obj.mesh.with_defaults()
         labels.append(obj.label)
@@ -33,7 +33,10 @@ def ref_meshes_from_dataset(ds) -> pipeline_ref.RefMeshes:
         n.append(m.vertex_normals)
         c.append(np.clip(m.vertex_colors, 0, 1))
         f.append(m.faces)
-    return pipeline_ref.RefMeshes(labels, v, n, c, f)
+        uv.append(m.uv)
+        tex.append(m.texture)
+        mod.append(1 if m.texture_modulate else 0)
+    return pipeline_ref.RefMeshes(labels, v, n, c, f, uv, tex, mod)
 
 
 COARSE_CFG = dict(n_rendered_views=1, multiview_type="TCO", render_normals=True, render_depth=False, input_depth=False,
