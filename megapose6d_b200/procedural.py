@@ -94,6 +94,18 @@ def textured_box(size=(0.10, 0.07, 0.05), seed: int = 0, with_vertex_colors: boo
                    np.asarray(uv, np.float64), checker_texture(seed=seed), texture_modulate=with_vertex_colors)
 
 
+def textured_sphere(n_seg: int = 100, n_lat: int = 51, radius: float = 0.05, seed: int = 0) -> TriMesh:
+    """`bumpy_sphere` with longitude / latitude texture coordinates and the checker texture instead of vertex colours.  No
+    seam duplication: the last column interpolates u from (n_seg-1)/n_seg back to 0 across the texture, which is fine for
+    tests (both implementations must agree on it)."""
+    m = bumpy_sphere(n_seg, n_lat, radius, seed=seed)
+    d = m.vertices / (radius * np.array([1.0, 0.8, 0.6]))
+    d = d / np.linalg.norm(d, axis=1, keepdims=True)
+    u = (np.arctan2(d[:, 1], d[:, 0]) / (2 * np.pi)) % 1.0
+    v = 1.0 - np.arccos(np.clip(d[:, 2], -1, 1)) / np.pi
+    return TriMesh(m.vertices, m.faces, m.vertex_normals, None, np.stack([u, v], 1), checker_texture(64, 128, 8, seed))
+
+
 def make_object_dataset(n_objects: int = 1, seed: int = 0, n_seg: int = 100, n_lat: int = 51) -> RigidObjectDataset:
     objs = []
     for i in range(n_objects):

@@ -26,8 +26,9 @@ def _write_obj(path, mesh, scale_to_mm=1000.0):
         (path.parent / "material.mtl").write_text("newmtl m0\nmap_Kd texture.png\n")
 
 
-def _make_example_dir(root, rgb):
-    box = procedural.textured_box(seed=3).with_defaults()
+def _make_example_dir(root, rgb, dense=False):
+    # `dense`: enough vertices for the pipeline's 2000-point subsets (the reference samples without replacement too)
+    box = (procedural.textured_sphere(seed=3) if dense else procedural.textured_box(seed=3)).with_defaults()
     (root / "meshes" / "box").mkdir(parents=True)
     _write_obj(root / "meshes" / "box" / "box.obj", box)
     (root / "inputs").mkdir()
@@ -77,7 +78,7 @@ def test_example_runs_end_to_end(tmp_path):
     from tests import helpers
 
     rgb = (np.random.RandomState(2).rand(480, 640, 3) * 255).astype(np.uint8)
-    _make_example_dir(tmp_path, rgb)
+    _make_example_dir(tmp_path, rgb, dense=True)
     models = tmp_path / "models"
     load_model.write_run(models, "coarse-rgb-906902141", helpers.make_state_dict(helpers.COARSE_CFG, 1))
     load_model.write_run(models, "refiner-rgb-653307694", helpers.make_state_dict(helpers.REFINER_CFG, 2))
