@@ -77,9 +77,10 @@ int mpx_meshdb_set_textures(mpx_meshdb* db, const float* h_uv, const uint8_t* h_
 
 size_t mpx_raster_workspace_bytes(int h, int w);
 
-/* kernel selection, default 1: bit 0 = batches of at most SMs/8 views (refiner iterations, final scoring) spread
+/* kernel selection, default 3: bit 0 = batches of at most SMs/8 views (refiner iterations, final scoring) spread
  * the triangles of each view over many CTAs (coverage kernel + resolve kernel) instead of one CTA per
- * (view, row strip); 0 = always the one-kernel path.  Both produce identical pixels. */
+ * (view, row strip); bit 1 = visibility through a fire-and-forget 64-bit min reduction instead of read-then-atomic.
+ * All combinations produce identical pixels. */
 int mpx_raster_set_mode(int mode);
 
 /* contract output: float32 NCHW planes; any of d_rgb [N,3,h,w], d_normals [N,3,h,w],

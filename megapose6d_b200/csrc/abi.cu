@@ -78,7 +78,7 @@ size_t mpx_raster_workspace_bytes(int h, int w) { return raster_workspace_bytes(
 
 int mpx_raster_set_mode(int mode) {
   raster_set_scatter(mode & 1);
-  return MPX_OK;
+  return raster_set_red_only(mode & 2);
 }
 
 int mpx_raster_render(const mpx_meshdb* db, const int32_t* d_label_idx, const float* d_TCO, const float* d_K,

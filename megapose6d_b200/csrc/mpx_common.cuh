@@ -192,6 +192,7 @@ int meshdb_set_textures(MeshDb* db, const float* uv, const unsigned char* tex, c
                         const int32_t* tex_dims, const int32_t* tex_modulate);
 size_t raster_workspace_bytes(int h, int w);
 void raster_set_scatter(int on);
+int raster_set_red_only(int on);
 int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, const float* K, int n_views,
                   int h, int w, unsigned flags, const RasterOut& out, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream);

@@ -125,14 +125,14 @@ def _render_both(ds, rm, labels, TCO, K, res, depth=True):
     return out, ref
 
 
-@pytest.fixture(params=[1, 0], ids=["scatter", "strips"])
+@pytest.fixture(params=[3, 2, 0], ids=["scatter", "strips", "strips_read_then_atomic"])
 def raster_mode(request):
     """Small batches have two implementations (include/mpx.h mpx_raster_set_mode): triangles scattered over many CTAs
     + resolve kernel (default), or one CTA per (view, row strip).  Both must match the oracle bit for bit."""
     from megapose6d_b200 import _abi
     _abi.lib().mpx_raster_set_mode(request.param)
     yield request.param
-    _abi.lib().mpx_raster_set_mode(1)
+    _abi.lib().mpx_raster_set_mode(3)
 
 
 def test_raster_bit_exact_vs_oracle(scene, raster_mode):
