@@ -69,12 +69,6 @@ __device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, int
          static_cast<long long>(by - ay) * static_cast<long long>(px - ax);
 }
 
-__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
-  int q = a / b;
-  if ((a % b != 0) && (a < 0)) --q;
-  return q;
-}
-
 // 32-level sawtooth of the reference's eye-normal texture with linear filtering and repeat wrap
 __device__ __forceinline__ float normal_texture(float s) {
   const float u = __fmaf_rn(s, 32.0f, -0.5f);
@@ -192,8 +186,10 @@ __device__ __forceinline__ TriSetup load_tri(const VtxSrc& src, const int* __res
 }
 
 // interpolated 1/z of a covered sample from its (orientation-corrected) edge values
-__device__ __forceinline__ float sample_iz(const TriSetup& t, long long w0, long long w1, long long w2, float& l0,
-                                           float& l1, float& l2) {
+// W = long long, or int when the edge values are known to fit (same integers, same correctly rounded conversions: the
+// 64-bit integer adds and int64 -> float conversions were a large part of the coverage loop's instructions)
+template <typename W>
+__device__ __forceinline__ float sample_iz(const TriSetup& t, W w0, W w1, W w2, float& l0, float& l1, float& l2) {
   l0 = __fmul_rn(static_cast<float>(w0), t.inv_area);
   l1 = __fmul_rn(static_cast<float>(w1), t.inv_area);
   l2 = __fmul_rn(static_cast<float>(w2), t.inv_area);
@@ -204,14 +200,15 @@ __device__ __forceinline__ void raster_bbox(const TriSetup& t, int h, int w, int
                                             int& i1) {
   const int minx = min(t.ax, min(t.bx, t.cx)), maxx = max(t.ax, max(t.bx, t.cx));
   const int miny = min(t.ay, min(t.by, t.cy)), maxy = max(t.ay, max(t.by, t.cy));
-  // pixel j has its centre at j*256 + 128
-  j0 = max(0, -floor_div(-(minx - kHalf), kSub));  // ceil((minx-128)/256)
-  j1 = min(w - 1, floor_div(maxx - kHalf, kSub));
-  i0 = max(0, -floor_div(-(miny - kHalf), kSub));
-  i1 = min(h - 1, floor_div(maxy - kHalf, kSub));
+  // pixel j has its centre at j*256 + 128; kSub is a power of two: floor division = arithmetic shift
+  j0 = max(0, (minx - kHalf + kSub - 1) >> kSubBits);  // ceil((minx-128)/256)
+  j1 = min(w - 1, (maxx - kHalf) >> kSubBits);
+  i0 = max(0, (miny - kHalf + kSub - 1) >> kSubBits);
+  i1 = min(h - 1, (maxy - kHalf) >> kSubBits);
 }
 
-__device__ __forceinline__ void emit_fragment(const TriSetup& t, long long w0, long long w1, long long w2, int tri,
+template <typename W>
+__device__ __forceinline__ void emit_fragment(const TriSetup& t, W w0, W w1, W w2, int tri,
                                               unsigned long long* __restrict__ cell) {
   if ((w0 | w1 | w2) < 0) return;
   float l0, l1, l2;
@@ -258,10 +255,29 @@ __device__ __forceinline__ void cover_triangle(const VtxSrc& src, const int* __r
   const long long dx0 = -sgn * static_cast<long long>(t.cy - t.by) * kSub, dy0 = sgn * static_cast<long long>(t.cx - t.bx) * kSub;
   const long long dx1 = -sgn * static_cast<long long>(t.ay - t.cy) * kSub, dy1 = sgn * static_cast<long long>(t.ax - t.cx) * kSub;
   const long long dx2 = -sgn * static_cast<long long>(t.by - t.ay) * kSub, dy2 = sgn * static_cast<long long>(t.bx - t.ax) * kSub;
+  // Triangles spanning at most 64 pixels in x and y (practically all of them): every edge value at a pixel centre inside
+  // the bounding box is below 2 * 2^14 * 2^14 = 2^29 in magnitude and every step below 2^22, so the walk runs in 32 bits
+  const int ext_x = max(t.ax, max(t.bx, t.cx)) - min(t.ax, min(t.bx, t.cx));
+  const int ext_y = max(t.ay, max(t.by, t.cy)) - min(t.ay, min(t.by, t.cy));
+  if (ext_x <= 16384 && ext_y <= 16384) {
+    int s0 = static_cast<int>(r0), s1 = static_cast<int>(r1), s2 = static_cast<int>(r2);
+    const int ex0 = static_cast<int>(dx0), ex1 = static_cast<int>(dx1), ex2 = static_cast<int>(dx2);
+    const int ey0 = static_cast<int>(dy0), ey1 = static_cast<int>(dy1), ey2 = static_cast<int>(dy2);
+    for (int i = i0; i <= i1; ++i) {
+      int w0 = s0, w1 = s1, w2 = s2;
+      unsigned long long* row = vis + i * w;
+      for (int j = j0; j <= j1; ++j) {
+        emit_fragment<int>(t, w0, w1, w2, tri, row + j);
+        w0 += ex0; w1 += ex1; w2 += ex2;
+      }
+      s0 += ey0; s1 += ey1; s2 += ey2;
+    }
+    return;
+  }
   for (int i = i0; i <= i1; ++i) {
     long long w0 = r0, w1 = r1, w2 = r2;
     for (int j = j0; j <= j1; ++j) {
-      emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
+      emit_fragment<long long>(t, w0, w1, w2, tri, vis + i * w + j);
       w0 += dx0; w1 += dx1; w2 += dx2;
     }
     r0 += dy0; r1 += dy1; r2 += dy2;
@@ -289,7 +305,7 @@ __device__ __forceinline__ void cover_big_triangles(const VtxSrc& src, const int
       long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
       long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
       if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
-      emit_fragment(t, w0, w1, w2, tri, vis + i * w + j);
+      emit_fragment<long long>(t, w0, w1, w2, tri, vis + i * w + j);
     }
   }
 }
@@ -369,7 +385,9 @@ __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __res
       long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
       if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
       float l0, l1, l2;
-      const float iz = sample_iz(t, w0, w1, w2, l0, l1, l2);
+      const float iz = (((w0 | w1 | w2) >> 31) == 0)
+                           ? sample_iz<int>(t, static_cast<int>(w0), static_cast<int>(w1), static_cast<int>(w2), l0, l1, l2)
+                           : sample_iz<long long>(t, w0, w1, w2, l0, l1, l2);
       const float z = __frcp_rn(iz);
       const float b0 = __fmul_rn(__fmul_rn(l0, t.iza), z);
       const float b1 = __fmul_rn(__fmul_rn(l1, t.izb), z);
