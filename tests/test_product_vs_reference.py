@@ -106,3 +106,43 @@ def test_instance_ids_and_detection_filter_match_the_reference(ref):
             assert fa.infos["label"].tolist() == fb.infos["label"].tolist()
             assert fa.infos["score"].tolist() == fb.infos["score"].tolist()
             assert torch.equal(fa.bboxes, fb.bboxes)
+
+
+class _AttrDict(dict):
+    """OmegaConf-like config for the reference function: attribute access, `in`, `del`, hasattr."""
+    __getattr__ = lambda self, k: self[k] if k in self else (_ for _ in ()).throw(AttributeError(k))  # noqa: E731
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+
+def test_check_update_config_matches_the_reference():
+    """training/pose_models_cfg.py:36-87 executed from the reference source (its module imports Panda3D, so only the
+    function body is compiled) against load_model.check_update_config on legacy and current run configurations."""
+    import logging
+    import re
+
+    from megapose6d_b200 import load_model
+
+    src = (refload.REF_ROOT / "training/pose_models_cfg.py").read_text()
+    body = src[src.index("def check_update_config"):src.index("def create_model_pose")]
+    body = re.sub(r"\(cfg: TrainingConfig\) -> TrainingConfig", "(cfg)", body)
+    ns = dict(logger=logging.getLogger("ref"))
+    exec(compile(body, "pose_models_cfg.py", "exec"), ns)
+    cases = [
+        dict(load_model.ZOO_CONFIGS["coarse-rgb-906902141"]),
+        dict(load_model.ZOO_CONFIGS["refiner-rgbd-288182519"]),
+        dict(input_strategy="input=obs+one_render", multiview_type="TCO", backbone_str="vanilla_resnet34"),
+        dict(multiview_type="front_3views", n_views=4, backbone_str="vanilla_resnet34"),
+        dict(multiview_type="front_5views", n_rendered_views=6, render_normals=True, depth_augmentation=True,
+             depth_normalization_type="tCR_scale_clamp_center"),
+    ]
+    for case in cases:
+        want = ns["check_update_config"](_AttrDict(case))
+        got = load_model.check_update_config(load_model.Cfg(dict(case)))
+        for key in ("is_coarse_compat", "n_rendered_views", "multiview_type", "predict_rendered_views_logits",
+                    "remove_TCO_rendering", "predict_pose_update", "render_normals", "render_depth", "input_depth",
+                    "renderer"):
+            assert got[key] == want[key], (case, key, got[key], want[key])
+        if "depth_normalization_type" in want:
+            assert got["depth_normalization_type"] == want["depth_normalization_type"], case
+        assert "n_views" not in got
