@@ -209,6 +209,9 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
  *   32  a single MMA-issuing thread in the 64->64 window kernel (default two);  64  three
  *   128 three epilogue warp sets
  *   256 disable the layer2 window kernel (TMA-im2col kernel instead)
+ *   512 launch without programmatic dependent launch;  1024 older row-group choice of the window kernel (diagnostic)
+ *   2048 window kernel: a stage is refilled only after every MMA issuer has seen its fill (experimental)
+ *   4096 window + CTA-pair kernel for the 3x3 stride-1 convolutions of layer3 / layer4 (experimental, unmeasured)
  * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 

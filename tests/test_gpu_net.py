@@ -340,3 +340,68 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
     tol = 2 ** -7 * ref.abs().max().item() + 1e-2
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
     assert torch.equal(outs[0], outs[1])  # same products, same K order, fp32 accumulation in TMEM
+
+
+EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("MPX_EXPERIMENTAL") != "1",
+                                  reason="kernel variants that are off by default and not yet measured "
+                                         "(set MPX_EXPERIMENTAL=1 to run)")
+
+PAIR_WINDOW_CASES = [
+    # name, n, h, w, c_in, c_out, relu, use_res, max_ctas
+    ("l3", 6, 15, 20, 256, 256, True, True, 4),
+    ("l3_nores_many_per_pair", 13, 15, 20, 256, 256, True, False, 2),
+    ("l4_two_cout_tiles", 9, 8, 10, 512, 512, True, True, 4),
+    ("odd_size", 5, 9, 13, 128, 256, False, True, 2),
+]
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize("case", PAIR_WINDOW_CASES, ids=[c[0] for c in PAIR_WINDOW_CASES])
+def test_experimental_pair_window_kernel(case):
+    """conv_window2p_kernel (mode bit 12 = 4096) vs the default kernels and fp32 torch."""
+    name, n, h, w, cin, cout, relu, use_res, max_ctas = case
+    g = torch.Generator(device="cuda").manual_seed(29)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    res = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    outs = []
+    try:
+        for mode in (DEFAULT_CONV_MODE | 4096, DEFAULT_CONV_MODE):
+            _abi.lib().mpx_conv_set_mode(mode)
+            out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, 3,
+                                                  3, 1, 1, 1, 1, 1, int(relu), _abi.ptr(res), _abi.ptr(out), 0, max_ctas,
+                                                  _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out.float())
+    finally:
+        _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
+    ref = _conv_ref(x, wt, bias, 1, (1, 1, 1, 1), relu, res)
+    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    assert not torch.isnan(outs[0]).any()
+    assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
+    assert (outs[0] - outs[1]).abs().max() <= 2 ** -7 * ref.abs().max().item()
+
+
+@EXPERIMENTAL
+def test_experimental_window_observers_arrive():
+    """Window kernel with refills gated on every issuer's arrival (mode bit 11 = 2048): same results as the default."""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    for (n, h, w, r, pads) in ((7, 60, 80, 3, (1, 1, 1, 1)), (3, 120, 160, 4, (2, 2, 1, 1))):
+        x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16)
+        wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(torch.bfloat16)
+        bias = torch.randn(64, device="cuda", generator=g)
+        outs = []
+        try:
+            for mode in (DEFAULT_CONV_MODE | 2048, DEFAULT_CONV_MODE):
+                _abi.lib().mpx_conv_set_mode(mode)
+                out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+                _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
+                                                      1, pads[0], pads[1], pads[2], pads[3], 1, None, _abi.ptr(out), 0, 5,
+                                                      _abi.stream_ptr()))
+                torch.cuda.synchronize()
+                outs.append(out)
+        finally:
+            _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
+        assert torch.equal(outs[0], outs[1])
