@@ -29,43 +29,94 @@ from .types import DetectionsType, ObservationTensor, PoseEstimatesType
 
 @dataclass
 class CameraData:
-    """datasets/scene_dataset.py:122-180 (the fields the example uses)."""
-    K: np.ndarray
-    resolution: Tuple[int, int]
+    """datasets/scene_dataset.py:122-180.  Transforms are 4x4 float64 matrices here; on disk `[quaternion xyzw, translation]`."""
+    K: Optional[np.ndarray] = None
+    resolution: Optional[Tuple[int, int]] = None
+    TWC: Optional[np.ndarray] = None
+    camera_id: Optional[str] = None
+    TWC_init: Optional[np.ndarray] = None
 
     @staticmethod
     def from_json(text: str) -> "CameraData":
         d = json.loads(text)
-        K = np.asarray(d["K"], dtype=np.float64)
-        assert K.shape == (3, 3), "camera_data.json: K must be 3x3"
-        h, w = d["resolution"]
-        return CameraData(K=K, resolution=(int(h), int(w)))
+        assert isinstance(d, dict), "camera_data.json must hold one object"
+        out = CameraData()
+        for key in ("TWC", "TWC_init"):
+            if key in d:
+                quat, trans = d[key]
+                setattr(out, key, transform_from_quat_trans(quat, trans))
+        if "camera_id" in d:
+            out.camera_id = d["camera_id"]
+        if "K" in d:
+            out.K = np.asarray(d["K"], dtype=np.float64)
+            assert out.K.shape == (3, 3), "camera_data.json: K must be 3x3"
+        if "resolution" in d:
+            h, w = d["resolution"]
+            assert isinstance(h, int) and isinstance(w, int), "camera_data.json: resolution must be two integers [h, w]"
+            out.resolution = (h, w)
+        return out
+
+    def to_json(self) -> str:
+        d: dict = {}
+        for key in ("TWC", "TWC_init"):
+            T = getattr(self, key)
+            if T is not None:
+                d[key] = transform_to_list(T)
+        if self.K is not None:
+            d["K"] = np.asarray(self.K).tolist()
+        if self.camera_id is not None:
+            d["camera_id"] = self.camera_id
+        if self.resolution is not None:
+            d["resolution"] = [int(self.resolution[0]), int(self.resolution[1])]
+        return json.dumps(d)
 
 
 @dataclass
 class ObjectData:
-    """datasets/scene_dataset.py:71-120: label + modal bounding box in, label + TWO out."""
+    """datasets/scene_dataset.py:71-120: label + boxes in, label + TWO out."""
     label: str
-    bbox_modal: Optional[np.ndarray] = None
     TWO: Optional[np.ndarray] = None  # 4x4
+    unique_id: Optional[int] = None
+    bbox_amodal: Optional[np.ndarray] = None  # [xmin, ymin, xmax, ymax]
+    bbox_modal: Optional[np.ndarray] = None
+    visib_fract: Optional[float] = None
+    TWO_init: Optional[np.ndarray] = None
 
     @staticmethod
     def from_json(d: dict) -> "ObjectData":
-        out = ObjectData(label=str(d["label"]))
-        if "bbox_modal" in d:
-            out.bbox_modal = np.asarray(d["bbox_modal"], dtype=np.float64)
-        if "TWO" in d:
-            quat, trans = d["TWO"]
-            out.TWO = transform_from_quat_trans(quat, trans)
+        assert isinstance(d, dict) and isinstance(d["label"], str)
+        out = ObjectData(label=d["label"])
+        for key in ("TWO", "TWO_init"):
+            if key in d:
+                quat, trans = d[key]
+                setattr(out, key, transform_from_quat_trans(quat, trans))
+        for key in ("unique_id", "visib_fract"):
+            if key in d:
+                setattr(out, key, d[key])
+        for key in ("bbox_amodal", "bbox_modal"):
+            if key in d:
+                setattr(out, key, np.asarray(d[key], dtype=np.float64))
         return out
 
     def to_json(self) -> dict:
         d: dict = dict(label=self.label)
-        if self.TWO is not None:
-            d["TWO"] = [rotmat_to_quat_xyzw(self.TWO[:3, :3]).tolist(), self.TWO[:3, 3].tolist()]
-        if self.bbox_modal is not None:
-            d["bbox_modal"] = np.asarray(self.bbox_modal).tolist()
+        for key in ("TWO", "TWO_init"):
+            T = getattr(self, key)
+            if T is not None:
+                d[key] = transform_to_list(T)
+        for key in ("bbox_amodal", "bbox_modal"):
+            if getattr(self, key) is not None:
+                d[key] = np.asarray(getattr(self, key)).tolist()
+        for key in ("visib_fract", "unique_id"):
+            if getattr(self, key) is not None:
+                d[key] = getattr(self, key)
         return d
+
+
+def transform_to_list(T: np.ndarray) -> list:
+    """4x4 -> [quaternion xyzw, translation] (datasets/scene_dataset.py:67-68)."""
+    T = np.asarray(T, dtype=np.float64)
+    return [rotmat_to_quat_xyzw(T[:3, :3]).tolist(), T[:3, 3].tolist()]
 
 
 def rotmat_to_quat_xyzw(R: np.ndarray) -> np.ndarray:
@@ -107,6 +158,7 @@ def load_observation(example_dir: Path, load_depth: bool = False) -> Tuple[np.nd
     camera = CameraData.from_json((example_dir / "camera_data.json").read_text())
     with Image.open(example_dir / "image_rgb.png") as im:
         rgb = np.asarray(im.convert("RGB"), dtype=np.uint8)
+    assert camera.K is not None and camera.resolution is not None, "camera_data.json needs K and resolution"
     assert rgb.shape[:2] == camera.resolution, f"image {rgb.shape[:2]} != camera resolution {camera.resolution}"
     depth = None
     if load_depth:
