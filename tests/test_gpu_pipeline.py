@@ -11,6 +11,8 @@ Tolerances (stated):
   * refined poses: with the engine's network output substituted into the oracle's update the poses agree to
     1e-5 (geometry only); free-running, each iteration is compared from the engine's own input pose.
 """
+from pathlib import Path
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -163,6 +165,13 @@ def test_pipeline_matches_oracle(setup):
     for _, row in final.infos.iterrows():
         grp = scored[(scored["label"] == row["label"]) & (scored["instance_id"] == row["instance_id"])]
         assert row["pose_logit"] == grp["pose_logit"].max()
+    # the same scenario as run by the reference's own PoseEstimator (tests/golden/pipeline.npz, tools/make_golden.py):
+    # initial poses to fp32 rounding, survivors wherever the reference's margin is clear of the bf16 noise
+    golden = np.load(Path(__file__).resolve().parent / "golden" / "pipeline.npz")
+    kept_rows = extra["coarse_filter"]["preds"].infos
+    kept = [sorted(kept_rows[kept_rows["bbox_id"] == det]["hypothesis_id"]) for det in range(2)]
+    print("pipeline vs the reference's fixture:", helpers.check_pipeline_against_golden(golden, coarse.poses, lg, kept,
+                                                                                        exact_network=False))
 
 
 def test_refiner_graph_replay_equals_eager(setup):

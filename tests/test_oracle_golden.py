@@ -61,3 +61,34 @@ def test_bf16_emulation_tracks_fp32():
     with torch.no_grad():
         a, b = resnet_ref.forward(sd, x), resnet_ref.forward_bf16_emulated(sd, x)
     assert (a - b).abs().max() < 0.08 * max(a.std().item(), 0.1) + 0.05
+
+
+def test_pipeline_golden():
+    """The oracle pipeline against the outputs of the reference's own PoseEstimator.run_inference_pipeline on the shared
+    two-object scenario (tests/golden/pipeline.npz) -- runs without /root/reference, so also on the GPU box."""
+    from oracle import pipeline_ref
+
+    sc = helpers.pipeline_scenario()
+    golden = np.load(G / "pipeline.npz")
+    meshes = helpers.ref_meshes_from_dataset(sc["ds"])
+    oc = pipeline_ref.RefPosePredictor(sc["sd_coarse"], helpers.COARSE_CFG, meshes, pipeline_ref.RefRenderer(meshes))
+    orf = pipeline_ref.RefPosePredictor(sc["sd_refiner"], helpers.REFINER_CFG, meshes, pipeline_ref.RefRenderer(meshes))
+    est = pipeline_ref.RefPoseEstimator(oc, orf, bsz_images=64, bsz_objects=2, SO3_grid_size=sc["grid"])
+    got = est.run_inference_pipeline(sc["images"], sc["K"], sc["det_df"].copy(), sc["bboxes"],
+                                     n_refiner_iterations=sc["n_refiner_iterations"], n_pose_hypotheses=sc["n_pose_hypotheses"])
+    assert got["coarse_df"]["hypothesis_id"].tolist() == golden["coarse_hypothesis"].tolist()
+    f = got["filtered_df"]
+    kept = [sorted(f[f["bbox_id"] == d]["hypothesis_id"]) for d in range(2)]
+    info = helpers.check_pipeline_against_golden(golden, got["coarse_poses"], got["coarse_df"]["coarse_logit"].values, kept,
+                                                 exact_network=True, final_labels=got["final_df"]["label"].values,
+                                                 final_hypotheses=got["final_df"]["hypothesis_id"].values,
+                                                 final_poses=got["final_poses"])
+    assert info["survivors_checked"] == 2
+    # scored hypotheses: same refined poses and logits, row for row after sorting by (label, hypothesis)
+    s = got["scored_df"]
+    key_g = sorted(range(len(s)), key=lambda i: (s["label"].iloc[i], s["hypothesis_id"].iloc[i]))
+    key_w = sorted(range(4), key=lambda i: (golden["scored_label"][i], golden["scored_hypothesis"][i]))
+    assert np.allclose(s["pose_logit"].values[key_g], golden["scored_pose_logit"][key_w], rtol=1e-4, atol=1e-4)
+    # the checker's bf16 branch (what the GPU test runs) accepts the same data
+    helpers.check_pipeline_against_golden(golden, got["coarse_poses"], got["coarse_df"]["coarse_logit"].values, kept,
+                                          exact_network=False)

@@ -69,7 +69,40 @@ def main():
         with torch.no_grad():
             y = torch.nn.functional.linear(net(x), sd[head + ".weight"], sd[head + ".bias"])
         np.savez(OUT / f"resnet_{name}.npz", y=y.numpy())
+    pipeline_fixture(ref)
     print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
+
+
+def pipeline_fixture(ref):
+    """The reference's own PoseEstimator.run_inference_pipeline on tests/helpers.pipeline_scenario() (fp32, CPU).  Only the
+    renderer is not the reference's: Panda3D is absent, the C rasteriser of oracle/raster_ref.c stands in."""
+    from oracle import pipeline_ref
+    from tests.test_oracle_vs_reference import _reference_predictor
+
+    sc = helpers.pipeline_scenario()
+    meshes = helpers.ref_meshes_from_dataset(sc["ds"])
+    coarse = _reference_predictor(ref, helpers.COARSE_CFG, sc["sd_coarse"], meshes)
+    refiner = _reference_predictor(ref, helpers.REFINER_CFG, sc["sd_refiner"], meshes)
+    coarse.cfg = refiner.cfg = None
+    with refload.cpu_cuda_patch():
+        est = ref.pose_estimator.PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=2, bsz_images=64,
+                                               SO3_grid_size=sc["grid"])
+        detections = ref.tensor_collection.PandasTensorCollection(sc["det_df"].copy(), bboxes=sc["bboxes"])
+        obs = ref.types.ObservationTensor(sc["images"], sc["K"])
+        final, extra = est.run_inference_pipeline(obs, detections=detections, n_refiner_iterations=sc["n_refiner_iterations"],
+                                                  n_pose_hypotheses=sc["n_pose_hypotheses"])
+    c = extra["coarse"]["preds"]
+    f = extra["coarse_filter"]["preds"].infos
+    n_det = len(sc["labels"])
+    assert c.infos["bbox_id"].tolist() == sorted(c.infos["bbox_id"].tolist()), "rows are detection-major"
+    kept = np.stack([np.sort(f[f["bbox_id"] == d]["hypothesis_id"].values) for d in range(n_det)])
+    scored = extra["scoring"]["preds"]
+    np.savez(OUT / "pipeline.npz", coarse_poses=c.poses.numpy(), coarse_logit=c.infos["coarse_logit"].values.astype(np.float32),
+             coarse_hypothesis=c.infos["hypothesis_id"].values.astype(np.int64), kept_hypotheses=kept.astype(np.int64),
+             scored_label=np.array(scored.infos["label"].tolist(), dtype="U"), scored_hypothesis=scored.infos["hypothesis_id"].values.astype(np.int64),
+             scored_pose_logit=scored.infos["pose_logit"].values.astype(np.float32), scored_poses=scored.poses.numpy(),
+             final_label=np.array(final.infos["label"].tolist(), dtype="U"), final_hypothesis=final.infos["hypothesis_id"].values.astype(np.int64),
+             final_poses=final.poses.numpy(), final_pose_logit=final.infos["pose_logit"].values.astype(np.float32))
 
 
 if __name__ == "__main__":
