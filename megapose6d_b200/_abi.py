@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 from typing import Optional
 
@@ -14,6 +14,7 @@ import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libmpx.so"
 _lib: Optional[ctypes.CDLL] = None
+ABI_VERSION = 1  # MPX_ABI_VERSION of include/mpx.h this binding was written against
 
 
 class MpxError(RuntimeError):
@@ -98,6 +99,9 @@ def lib() -> ctypes.CDLL:
             )
         handle = ctypes.CDLL(str(_LIB_PATH))
         _declare(handle)
+        if handle.mpx_abi_version() != ABI_VERSION:
+            raise MpxError(f"{_LIB_PATH} has ABI version {handle.mpx_abi_version()}, this package needs {ABI_VERSION}: "
+                           "rebuild it with `python -m megapose6d_b200.build --force`")
         _lib = handle
     return _lib
 

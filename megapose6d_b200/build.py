@@ -33,8 +33,9 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for name in sorted(SOURCES + ["mpx_common.cuh"]):
-        h.update((CSRC / name).read_bytes())
+    for path in sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")):
+        h.update(path.name.encode())
+        h.update(path.read_bytes())
     h.update((CSRC.parent.parent / "include" / "mpx.h").read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

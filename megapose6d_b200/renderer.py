@@ -8,7 +8,7 @@ render_normals) -> BatchRenderOutput(rgbs, normals, depths)` contract, `.stop()`
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 

@@ -76,7 +76,6 @@ def main():
 def pipeline_fixture(ref):
     """The reference's own PoseEstimator.run_inference_pipeline on tests/helpers.pipeline_scenario() (fp32, CPU).  Only the
     renderer is not the reference's: Panda3D is absent, the C rasteriser of oracle/raster_ref.c stands in."""
-    from oracle import pipeline_ref
     from tests.test_oracle_vs_reference import _reference_predictor
 
     sc = helpers.pipeline_scenario()
