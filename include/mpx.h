@@ -212,6 +212,8 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
  *   512 launch without programmatic dependent launch;  1024 older row-group choice of the window kernel (diagnostic)
  *   2048 window kernel: a stage is refilled only after every MMA issuer has seen its fill (experimental)
  *   4096 window + CTA-pair kernel for the 3x3 stride-1 convolutions of layer3 / layer4 (experimental, unmeasured)
+ *   8192 the same kernel with 128-wide tiles for the 128 -> 128 convolutions of layer2, ahead of the layer2 window
+ *        kernel (experimental, unmeasured)
  * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 

@@ -649,6 +649,10 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   if (block_n_override == 0) {  // auto: the window kernel serves the 64 -> 64 stride-1 layers
     rc = conv_window_try(d, x, w, bias, residual, out, max_ctas, stream);
     if (rc != MPX_ERR_UNSUPPORTED) return rc;
+    if ((conv_mode() & 8192) != 0 && d.C_out == 128) {  // experimental: pair-window kernel ahead of conv_window2_kernel
+      rc = conv_window2p_try(d, x, w, bias, residual, out, max_ctas, stream);
+      if (rc != MPX_ERR_UNSUPPORTED) return rc;
+    }
     rc = conv_window2_try(d, x, w, bias, residual, out, max_ctas, stream);
     if (rc != MPX_ERR_UNSUPPORTED) return rc;
     rc = conv_window2p_try(d, x, w, bias, residual, out, max_ctas, stream);
@@ -1922,11 +1926,10 @@ conv_window2p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
-// Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit or the mode bit is off.
-static int conv_window2p_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
-                             void* out, int max_ctas, cudaStream_t stream) {
-  constexpr int BLOCK_N = 256;
-  if ((g_conv_mode & 4096) == 0) return MPX_ERR_UNSUPPORTED;
+// Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit.
+template <int BLOCK_N>
+static int conv_window2p_launch(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
+                                void* out, int max_ctas, cudaStream_t stream) {
   if (d.stride != 1 || d.R != 3 || d.S != 3 || d.C_out % BLOCK_N != 0 || d.C_out > 512 || d.C_in % 64 != 0 || d.C_in < 128)
     return MPX_ERR_UNSUPPORTED;
   if (d.pad_lo_h != 1 || d.pad_lo_w != 1 || d.pad_hi_h != 1 || d.pad_hi_w != 1) return MPX_ERR_UNSUPPORTED;
@@ -2005,6 +2008,18 @@ static int conv_window2p_try(const ConvDesc& d, const void* x, const void* w, co
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * static_cast<double>(d.C_out) * 9.0 * d.C_in);
   return MPX_OK;
+}
+
+// bit 12 (4096): C_out = 256 / 512 (layer3, layer4) with 256-wide tiles; bit 13 (8192): C_out = 128 (layer2) with 128-wide
+// tiles, tried BEFORE conv_window2_kernel (per SM and 256x128x16 MMA the tensor core then reads 4 KB of A + 2 KB of B from
+// shared memory instead of 4 + 4 KB).  Both off by default.
+static int conv_window2p_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
+                             void* out, int max_ctas, cudaStream_t stream) {
+  if ((g_conv_mode & 8192) != 0 && d.C_out == 128)
+    return conv_window2p_launch<128>(d, x, w, bias, residual, out, max_ctas, stream);
+  if ((g_conv_mode & 4096) != 0 && d.C_out >= 256)
+    return conv_window2p_launch<256>(d, x, w, bias, residual, out, max_ctas, stream);
+  return MPX_ERR_UNSUPPORTED;
 }
 
 

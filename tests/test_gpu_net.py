@@ -347,19 +347,24 @@ EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("MPX_EXPERIMENTAL
                                          "(set MPX_EXPERIMENTAL=1 to run)")
 
 PAIR_WINDOW_CASES = [
-    # name, n, h, w, c_in, c_out, relu, use_res, max_ctas
-    ("l3", 6, 15, 20, 256, 256, True, True, 4),
-    ("l3_nores_many_per_pair", 13, 15, 20, 256, 256, True, False, 2),
-    ("l4_two_cout_tiles", 9, 8, 10, 512, 512, True, True, 4),
-    ("odd_size", 5, 9, 13, 128, 256, False, True, 2),
+    # name, n, h, w, c_in, c_out, relu, use_res, max_ctas, mode bit
+    ("l3", 6, 15, 20, 256, 256, True, True, 4, 4096),
+    ("l3_nores_many_per_pair", 13, 15, 20, 256, 256, True, False, 2, 4096),
+    ("l4_two_cout_tiles", 9, 8, 10, 512, 512, True, True, 4, 4096),
+    ("odd_size", 5, 9, 13, 128, 256, False, True, 2, 4096),
+    ("l2_128wide", 4, 30, 40, 128, 128, True, True, 4, 8192),
+    ("l2_128wide_many_per_pair", 9, 30, 40, 128, 128, True, False, 2, 8192),
+    ("l2_128wide_odd_size", 3, 17, 23, 128, 128, False, True, 2, 8192),
+    ("l2_128wide_tiny_images", 11, 5, 7, 128, 128, True, True, 2, 8192),
 ]
 
 
 @EXPERIMENTAL
 @pytest.mark.parametrize("case", PAIR_WINDOW_CASES, ids=[c[0] for c in PAIR_WINDOW_CASES])
 def test_experimental_pair_window_kernel(case):
-    """conv_window2p_kernel (mode bit 12 = 4096) vs the default kernels and fp32 torch."""
-    name, n, h, w, cin, cout, relu, use_res, max_ctas = case
+    """conv_window2p_kernel (mode bit 12 = 4096: 256-wide tiles for layer3/4; bit 13 = 8192: 128-wide tiles for layer2) vs the
+    default kernels and fp32 torch."""
+    name, n, h, w, cin, cout, relu, use_res, max_ctas, bit = case
     g = torch.Generator(device="cuda").manual_seed(29)
     x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
     wt = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(torch.bfloat16)
@@ -367,7 +372,7 @@ def test_experimental_pair_window_kernel(case):
     res = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
     outs = []
     try:
-        for mode in (DEFAULT_CONV_MODE | 4096, DEFAULT_CONV_MODE):
+        for mode in (DEFAULT_CONV_MODE | bit, DEFAULT_CONV_MODE):
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
             _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, 3,

@@ -5,8 +5,8 @@ that every setting returns the same survivor and a pose within tolerance of the 
 
     python tools/gpu_ab.py --conv 11,2059,4107 --raster 3 --steps 20 --rounds 3 --out gpurun_out/ab_modes.json
 
-Mode bits: include/mpx.h (`mpx_conv_set_mode`, `mpx_raster_set_mode`); 2048 = arrival-gated window refills, 4096 = pair-window
-kernel for layer3/4 (both written without a GPU at hand: run `MPX_EXPERIMENTAL=1 pytest tests/test_gpu_net.py -k experimental`
+Mode bits: include/mpx.h (`mpx_conv_set_mode`, `mpx_raster_set_mode`); 2048 = arrival-gated window refills, 4096 / 8192 = pair-window
+kernel for layer3/4 / layer2 (all written without a GPU at hand: run `MPX_EXPERIMENTAL=1 pytest tests/test_gpu_net.py -k experimental`
 first).  A setting that traps or hangs is killed by the per-process timeout and reported as failed."""
 import argparse
 import json
