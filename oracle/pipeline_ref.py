@@ -275,12 +275,12 @@ class RefPoseEstimator:
         logits, TCO_all = [], []
         for s in range(0, n, self.bsz_images):
             d = df.iloc[s:s + self.bsz_images]
-            im_ids = torch.as_tensor(d["batch_im_id"].values)
+            im_ids = torch.as_tensor(d["batch_im_id"].to_numpy(copy=True))
             labels = d["label"].tolist()
             K_ = K[im_ids]
-            TCO_init = L.TCO_init_from_boxes_autodepth_with_R(bboxes[torch.as_tensor(d["bbox_id"].values)].float(),
+            TCO_init = L.TCO_init_from_boxes_autodepth_with_R(bboxes[torch.as_tensor(d["bbox_id"].to_numpy(copy=True))].float(),
                                                               self.coarse.meshes.select_points(labels), K_,
-                                                              self.SO3_grid[torch.as_tensor(d["hypothesis_id"].values)])
+                                                              self.SO3_grid[torch.as_tensor(d["hypothesis_id"].to_numpy(copy=True))])
             out = self.coarse.forward_coarse(images[im_ids], K_, labels, TCO_init)
             logits.append(out["logits"])
             TCO_all.append(TCO_init)
@@ -299,7 +299,7 @@ class RefPoseEstimator:
         outs = defaultdict(list)
         for s in range(0, len(df), self.bsz_objects):
             d = df.iloc[s:s + self.bsz_objects]
-            im_ids = torch.as_tensor(d["batch_im_id"].values)
+            im_ids = torch.as_tensor(d["batch_im_id"].to_numpy(copy=True))
             o = self.refiner.forward(images[im_ids], K[im_ids], d["label"].tolist(), TCO[s:s + self.bsz_objects], n_iterations)
             for k, v in o.items():
                 outs[k].append(v)
@@ -312,7 +312,7 @@ class RefPoseEstimator:
         logits = []
         for s in range(0, len(df), self.bsz_images):
             d = df.iloc[s:s + self.bsz_images]
-            im_ids = torch.as_tensor(d["batch_im_id"].values)
+            im_ids = torch.as_tensor(d["batch_im_id"].to_numpy(copy=True))
             logits.append(self.coarse.forward_coarse(images[im_ids], K[im_ids], d["label"].tolist(), TCO[s:s + self.bsz_images])["logits"])
         return torch.cat(logits)
 
