@@ -135,7 +135,7 @@ def check_pipeline_against_golden(golden, coarse_poses, coarse_logits, kept_hypo
     want_poses = torch.from_numpy(golden["coarse_poses"])
     assert torch.allclose(coarse_poses.float().cpu(), want_poses, rtol=2e-5, atol=2e-6)
     want = torch.from_numpy(golden["coarse_logit"]).float()
-    got = torch.as_tensor(np.asarray(coarse_logits)).float()
+    got = torch.as_tensor(np.array(torch.as_tensor(coarse_logits).cpu() if torch.is_tensor(coarse_logits) else coarse_logits, dtype=np.float32))
     err = (got - want).abs()
     if exact_network:
         assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), f"coarse logits: max err {err.max():.3g}"
