@@ -214,6 +214,7 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
  *   4096 window + CTA-pair kernel for the 3x3 stride-1 convolutions of layer3 / layer4 (experimental, unmeasured)
  *   8192 the same kernel with 128-wide tiles for the 128 -> 128 convolutions of layer2, ahead of the layer2 window
  *        kernel (experimental, unmeasured)
+ *   16384 the layer2 window kernel on CTA pairs (cta_group::2, two MMA issuers in the leader; experimental, unmeasured)
  * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 

@@ -356,14 +356,20 @@ PAIR_WINDOW_CASES = [
     ("l2_128wide_many_per_pair", 9, 30, 40, 128, 128, True, False, 2, 8192),
     ("l2_128wide_odd_size", 3, 17, 23, 128, 128, False, True, 2, 8192),
     ("l2_128wide_tiny_images", 11, 5, 7, 128, 128, True, True, 2, 8192),
+    # conv_window2q_kernel (bit 14): the layer2 window kernel on CTA pairs, two issuers
+    ("l2_pairs_odd_super_tiles", 4, 30, 40, 128, 128, True, True, 4, 16384),
+    ("l2_pairs_many_per_pair", 9, 30, 40, 128, 128, True, False, 2, 16384),
+    ("l2_pairs_odd_size", 3, 17, 23, 128, 128, False, True, 2, 16384),
+    ("l2_pairs_tiny_images", 11, 5, 7, 128, 128, True, True, 2, 16384),
+    ("l2_pairs_one_item_peer_idle", 1, 12, 16, 128, 128, True, False, 1, 16384),
 ]
 
 
 @EXPERIMENTAL
 @pytest.mark.parametrize("case", PAIR_WINDOW_CASES, ids=[c[0] for c in PAIR_WINDOW_CASES])
 def test_experimental_pair_window_kernel(case):
-    """conv_window2p_kernel (mode bit 12 = 4096: 256-wide tiles for layer3/4; bit 13 = 8192: 128-wide tiles for layer2) vs the
-    default kernels and fp32 torch."""
+    """conv_window2p_kernel (mode bit 12 = 4096: 256-wide tiles for layer3/4; bit 13 = 8192: 128-wide tiles for layer2) and
+    conv_window2q_kernel (bit 14 = 16384: the layer2 window kernel on CTA pairs) vs the default kernels and fp32 torch."""
     name, n, h, w, cin, cout, relu, use_res, max_ctas, bit = case
     g = torch.Generator(device="cuda").manual_seed(29)
     x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
