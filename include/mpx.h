@@ -215,6 +215,7 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
  *   8192 the same kernel with 128-wide tiles for the 128 -> 128 convolutions of layer2, ahead of the layer2 window
  *        kernel (experimental, unmeasured)
  *   16384 the layer2 window kernel on CTA pairs (cta_group::2, two MMA issuers in the leader; experimental, unmeasured)
+ *   32768 the 64 -> 64 window kernel (stem, layer1) on CTA pairs (experimental, unmeasured)
  * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 

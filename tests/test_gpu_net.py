@@ -416,3 +416,45 @@ def test_experimental_window_observers_arrive():
         finally:
             _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
         assert torch.equal(outs[0], outs[1])
+
+
+PAIR_WINDOW64_CASES = [
+    # name, n, h, w, r, pads (lo_h, lo_w, hi_h, hi_w), relu, use_res, max_ctas
+    ("layer1", 7, 60, 80, 3, (1, 1, 1, 1), True, False, 6),
+    ("layer1_residual", 5, 60, 80, 3, (1, 1, 1, 1), True, True, 4),
+    ("stem_4x4", 3, 120, 160, 4, (2, 2, 1, 1), True, False, 6),
+    ("odd_size_odd_tiles", 3, 17, 23, 3, (1, 1, 1, 1), False, True, 2),
+    ("two_tiles_one_pair", 1, 12, 16, 3, (1, 1, 1, 1), True, False, 2),
+    ("one_by_one_taps", 4, 20, 24, 1, (0, 0, 0, 0), False, False, 4),
+]
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize("case", PAIR_WINDOW64_CASES, ids=[c[0] for c in PAIR_WINDOW64_CASES])
+def test_experimental_pair_window64_kernel(case):
+    """conv_windowq_kernel (mode bit 15 = 32768: the 64 -> 64 window kernel on CTA pairs) vs the default window kernel and
+    fp32 torch."""
+    name, n, h, w, r, pads, relu, use_res, max_ctas = case
+    g = torch.Generator(device="cuda").manual_seed(37)
+    x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(64, device="cuda", generator=g)
+    res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    outs = []
+    try:
+        for mode in (DEFAULT_CONV_MODE | 32768, DEFAULT_CONV_MODE):
+            _abi.lib().mpx_conv_set_mode(mode)
+            out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
+                                                  1, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(out),
+                                                  0, max_ctas, _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out.float())
+    finally:
+        _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
+    ref = _conv_ref(x, wt, bias, 1, pads, relu, res)
+    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    assert not torch.isnan(outs[0]).any()
+    assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
+    print(name, "bit-equal to the single-CTA window kernel:", torch.equal(outs[0], outs[1]))
+    assert (outs[0] - outs[1]).abs().max() <= 2 ** -7 * ref.abs().max().item()
