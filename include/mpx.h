@@ -216,6 +216,7 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
  *        kernel (experimental, unmeasured)
  *   16384 the layer2 window kernel on CTA pairs (cta_group::2, two MMA issuers in the leader; experimental, unmeasured)
  *   32768 the 64 -> 64 window kernel (stem, layer1) on CTA pairs (experimental, unmeasured)
+ *   65536 pair kernels of bits 14 / 15: request the whole residual row before waiting for the accumulator (experimental)
  * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 

@@ -195,6 +195,64 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bf
   }
 }
 
+// Variant for the experimental pair-window kernels (mode bit 16 = 65536): the WHOLE residual row (NCOLS <= 128: at most 16
+// 16-byte registers) is requested before the thread waits for the accumulator, so that no residual load is exposed
+// between two 32-column chunks (conv2 of a block is 0.09 / 0.035 ms slower than conv1 in layer1 / layer2 today).
+template <int NCOLS>
+__device__ __forceinline__ void load_res_row(const __nv_bfloat16* res_row, uint4 (&r)[NCOLS / 8]) {
+  const uint4* r4 = reinterpret_cast<const uint4*>(res_row);
+#pragma unroll
+  for (int i = 0; i < NCOLS / 8; ++i) r[i] = __ldg(r4 + i);
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_row_preloaded(uint32_t taddr, bool valid, __nv_bfloat16* out_row, bool has_res,
+                                                       const float* bias_s, int relu, const uint4 (&res)[NCOLS / 8]) {
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 32) {
+    uint32_t v[32];
+    tc_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+    tc_wait_ld();
+    if (valid) {
+      uint4* o4 = reinterpret_cast<uint4*>(out_row + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float f[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c + 8 * i);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 8 * i + 4);
+        f[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
+        f[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
+        f[2] = __uint_as_float(v[8 * i + 2]) + b0.z;
+        f[3] = __uint_as_float(v[8 * i + 3]) + b0.w;
+        f[4] = __uint_as_float(v[8 * i + 4]) + b1.x;
+        f[5] = __uint_as_float(v[8 * i + 5]) + b1.y;
+        f[6] = __uint_as_float(v[8 * i + 6]) + b1.z;
+        f[7] = __uint_as_float(v[8 * i + 7]) + b1.w;
+        if (has_res) {
+          const uint4 rv = res[c / 8 + i];
+          const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 t = unpack_bf16x2(rr[j]);
+            f[2 * j] += t.x;
+            f[2 * j + 1] += t.y;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        o4[i] = o;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -2048,7 +2106,7 @@ constexpr int kW2qBHalf = (kW2N / 2) * 128;  // [64 c_out][64 c_in] bf16 = 8 KB 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const Win2Params p) {
+                     const Win2Params p, int res_preload) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -2217,11 +2275,20 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * kW2N);
       const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
-      uint4 res_cur[4];
-      if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
-      mbar_wait(&tmem_full[buf], static_cast<uint32_t>(local >> 1) & 1u);
-      tc_fence_after();
-      epilogue_row<kW2N>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
+      if (res_preload) {
+        uint4 res_all[kW2N / 8];
+        const bool has_res = valid && res_row != nullptr;
+        if (has_res) load_res_row<kW2N>(res_row, res_all);
+        mbar_wait(&tmem_full[buf], static_cast<uint32_t>(local >> 1) & 1u);
+        tc_fence_after();
+        epilogue_row_preloaded<kW2N>(taddr, valid, p.out + off, has_res, bias_s, p.relu, res_all);
+      } else {
+        uint4 res_cur[4];
+        if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
+        mbar_wait(&tmem_full[buf], static_cast<uint32_t>(local >> 1) & 1u);
+        tc_fence_after();
+        epilogue_row<kW2N>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -2309,7 +2376,7 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
   if (cap < 1) cap = 1;
   const int pairs = items < cap ? items : cap;
   ProfileSlot* slot = profile_begin(stream);
-  conv_window2q_kernel<<<2 * pairs, 384, smem_bytes, stream>>>(map_a, map_b, p);
+  conv_window2q_kernel<<<2 * pairs, 384, smem_bytes, stream>>>(map_a, map_b, p, (g_conv_mode & 65536) != 0 ? 1 : 0);
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 128.0 * kW2Taps * 128.0);
@@ -2332,7 +2399,7 @@ constexpr int kWinqBHalf = (kWinN / 2) * 128;  // one tap's weights for this CTA
 
 __global__ void __launch_bounds__(384, 1)
 conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const WinParams p, int stages, int n_taps) {
+                    const WinParams p, int stages, int n_taps, int res_preload) {
   constexpr int kEpiSets = 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -2498,11 +2565,20 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
       const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
-      uint4 res_cur[4];
-      if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      epilogue_row<kWinN>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
+      if (res_preload) {
+        uint4 res_all[kWinN / 8];
+        const bool has_res = valid && res_row != nullptr;
+        if (has_res) load_res_row<kWinN>(res_row, res_all);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        epilogue_row_preloaded<kWinN>(taddr, valid, p.out + off, has_res, bias_s, p.relu, res_all);
+      } else {
+        uint4 res_cur[4];
+        if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        epilogue_row<kWinN>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -2624,7 +2700,7 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
   const int pairs = n_ptiles < cap ? n_ptiles : cap;
   ProfileSlot* slot = profile_begin(stream);
   MPX_CHECK_CUDA(launch_pdl(conv_windowq_kernel, dim3(2 * pairs), dim3(384), smem_bytes, stream, 2, map_a, map_b, p, stages,
-                            n_taps));
+                            n_taps, (g_conv_mode & 65536) != 0 ? 1 : 0));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 64.0 * n_taps * 64.0);

@@ -9,5 +9,5 @@ echo "new tests: exit $?"; tail -3 gpurun_out/first_new_tests.log
 timeout 600 python -m pytest tests/test_gpu_net.py -k experimental -q > gpurun_out/first_experimental.log 2>&1
 echo "experimental kernels: exit $?"; tail -5 gpurun_out/first_experimental.log
 unset MPX_EXPERIMENTAL
-timeout 900 python tools/gpu_ab.py --conv 11,2059,4107,8203,16395,32779,49163 --steps 20 --rounds 3 --timeout 200 --out gpurun_out/ab_modes.json > gpurun_out/ab_modes.log 2>&1
+timeout 900 python tools/gpu_ab.py --conv 11,2059,4107,8203,16395,32779,49163,114699 --steps 20 --rounds 3 --timeout 200 --out gpurun_out/ab_modes.json > gpurun_out/ab_modes.log 2>&1
 echo "A/B: exit $?"; tail -40 gpurun_out/ab_modes.log
