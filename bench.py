@@ -261,10 +261,10 @@ def run_mpx_arm(args):
     if rank == 0:
         sampler.start()
     total_ms = timed(step_device, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
 
     # roofline of the dominant kernels (the convolutions of the 576-hypothesis coarse forward): CUDA events around every
     # conv launch, same workload.  The coarse forward normally replays a CUDA graph (its launches cannot be timed one by
