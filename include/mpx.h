@@ -25,10 +25,14 @@
 extern "C" {
 #endif
 
-#define MPX_ABI_VERSION 1
+#define MPX_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------------ */
 int mpx_abi_version(void);
+/* 16-bit storage type of weights / activations / the network input tensor ("act16" below): 0 = IEEE fp16 (default: the
+ * number format the reference's networks were trained under, training/train_megapose.py:299 torch.cuda.amp.autocast;
+ * conversions saturate at +-65504), 1 = bf16 (library built with -DMPX_ACT_BF16).  Accumulation is fp32 in both. */
+int mpx_act_dtype(void);
 const char* mpx_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (host-side counter) */
 long long mpx_launch_count(void);
@@ -90,7 +94,7 @@ int mpx_raster_render(const mpx_meshdb* db, const int32_t* d_label_idx, const fl
                       float* d_normals, float* d_depth, void* d_workspace, size_t workspace_bytes,
                       void* stream);
 
-/* fused output: writes bf16 channels straight into the network input tensor (see mpx_net):
+/* fused output: writes act16 channels straight into the network input tensor (see mpx_net):
  * view i belongs to sample i / views_per_sample, view slot v = i % views_per_sample and its
  * channels land at ch_offset + v * ch_per_view (+0..2 rgb, +3..5 normals, +6 depth if
  * ch_per_view == 7).  d_depth_norm_z [n_samples] (may be NULL) applies the reference's
@@ -165,7 +169,7 @@ int mpx_image_to_nhwc4(const float* d_images_nchw, int b, int c, int h, int w, f
 int mpx_roi_align(const float* d_img_nhwc4, int b, int h, int w, const int32_t* d_im_idx,
                   const float* d_boxes, int n, int c, int out_h, int out_w, float* d_out,
                   void* stream);
-/* fused output: bf16 channels 0..c-1 of the network input tensor; for c == 4 the depth channel is
+/* fused output: act16 channels 0..c-1 of the network input tensor; for c == 4 the depth channel is
  * normalised with d_depth_norm_z as in mpx_raster_render_fused. */
 int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int32_t* d_im_idx,
                         const float* d_boxes, int n, int c, int out_h, int out_w, void* d_x,
@@ -174,19 +178,19 @@ int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int
 /* ---- network -------------------------------------------------------------------------------------
  * ResNet-34 + fc + head of PosePredictor.net_forward (models/pose_rigid.py:314-334) with the
  * backbone of models/torchvision_resnet.py:181-316.  Weights are passed already BN-folded and
- * repacked (see megapose6d_b200/backbone.py): per conv a bf16 [C_out, R*S*C_in] matrix and an
+ * repacked (see megapose6d_b200/backbone.py): per conv an act16 [C_out, R*S*C_in] matrix and an
  * fp32 bias.
  *
- * Network input tensor ("x"): bf16, space-to-depth NHWC [n, H/2, W/2, 4*c_pad] with channel
+ * Network input tensor ("x"): act16, space-to-depth NHWC [n, H/2, W/2, 4*c_pad] with channel
  * index (dy*2+dx)*c_pad + c, c_pad = 16 (coarse, 9 real channels) or 32 (refiner, 27|32).
  */
 size_t mpx_net_input_bytes(int n, int h, int w, int c_pad);
 
 /* single convolution (also the unit the parity tests exercise):
- *   d_x [n,H,W,C_in] bf16, d_w [C_out, R*S*C_in] bf16, d_bias [C_out] fp32,
- *   d_residual / d_out [n,P,Q,C_out] bf16 (residual may be NULL)
+ *   d_x [n,H,W,C_in] act16, d_w [C_out, R*S*C_in] act16, d_bias [C_out] fp32,
+ *   d_residual / d_out [n,P,Q,C_out] act16 (residual may be NULL)
  *   block_n: 0 = auto, else 64|128|256; max_ctas: 0 = one per SM */
-int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
+int mpx_conv2d(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
                     const float* d_bias, int c_out, int r, int s, int stride, int pad_lo_h,
                     int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                     void* d_out, int block_n, int max_ctas, void* stream);
@@ -195,7 +199,7 @@ int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* 
  * cluster per output tile -- the form the network uses for small batches (refiner iterations: a handful of output
  * tiles, up to 72 serial k-blocks).  The partial tiles are reduced through distributed shared memory in rank order
  * (deterministic).  block_n must be explicit. */
-int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
+int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
                            const float* d_bias, int c_out, int r, int s, int stride, int pad_lo_h,
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                            void* d_out, int block_n, int splits, void* stream);
@@ -221,14 +225,14 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
 int mpx_conv_set_mode(int mode);
 
 /* bring-up probe (tools/gpu_probe_rowshift.py): D[128,64] = A[r0:r0+128, :64] * B[64,64]^T with the UMMA
- * A descriptor started r0 rows into a TMA-written 128B-swizzled tile; d_a [144,64] bf16, d_b [64,64] bf16 */
+ * A descriptor started r0 rows into a TMA-written 128B-swizzled tile; d_a [144,64] act16, d_b [64,64] act16 */
 int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out,
                             void* stream);
 
-/* 3x3/s2/p1 max pool, bf16 NHWC (torchvision_resnet.py:302) */
-int mpx_maxpool3x3s2_bf16(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream);
+/* 3x3/s2/p1 max pool, act16 NHWC (torchvision_resnet.py:302) */
+int mpx_maxpool3x3s2(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream);
 
-/* global average pool + folded (fc o head) linear: d_x [n, hw, c] bf16, d_w [out_dim, c] fp32,
+/* global average pool + folded (fc o head) linear: d_x [n, hw, c] act16, d_w [out_dim, c] fp32,
  * d_b [out_dim] fp32 -> d_out [n, out_dim] fp32 */
 int mpx_avgpool_linear(const void* d_x, int n, int hw, int c, const float* d_w, const float* d_b,
                        int out_dim, float* d_out, void* stream);

@@ -14,7 +14,7 @@ import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libmpx.so"
 _lib: Optional[ctypes.CDLL] = None
-ABI_VERSION = 1  # MPX_ABI_VERSION of include/mpx.h this binding was written against
+ABI_VERSION = 2  # MPX_ABI_VERSION of include/mpx.h this binding was written against
 
 
 class MpxError(RuntimeError):
@@ -28,6 +28,7 @@ def lib_path() -> Path:
 def _declare(lib: ctypes.CDLL) -> None:
     vp = c_void_p
     lib.mpx_abi_version.restype = c_int
+    lib.mpx_act_dtype.restype = c_int
     lib.mpx_last_error.restype = c_char_p
     lib.mpx_meshdb_create.argtypes = [c_int, vp, vp, vp, vp, vp, vp, POINTER(vp)]
     lib.mpx_meshdb_destroy.argtypes = [vp]
@@ -53,11 +54,11 @@ def _declare(lib: ctypes.CDLL) -> None:
                                         vp, vp]
     lib.mpx_net_input_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.mpx_net_input_bytes.restype = c_size_t
-    lib.mpx_conv2d_bf16.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
+    lib.mpx_conv2d.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp]
-    lib.mpx_conv2d_bf16_splitk.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
+    lib.mpx_conv2d_splitk.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,
                                            c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, vp]
-    lib.mpx_maxpool3x3s2_bf16.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
+    lib.mpx_maxpool3x3s2.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
     lib.mpx_avgpool_linear.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp, vp]
     lib.mpx_net_create.argtypes = [c_int, c_int, POINTER(vp), POINTER(vp), c_int, vp, vp, POINTER(vp)]
     lib.mpx_net_destroy.argtypes = [vp]
@@ -78,12 +79,12 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 
 EXPORTS = [
-    "mpx_abi_version", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
+    "mpx_abi_version", "mpx_act_dtype", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
     "mpx_meshdb_create", "mpx_meshdb_destroy", "mpx_meshdb_set_textures",
     "mpx_raster_workspace_bytes", "mpx_raster_set_mode", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",
-    "mpx_net_input_bytes", "mpx_conv2d_bf16", "mpx_conv2d_bf16_splitk", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2_bf16", "mpx_avgpool_linear",
+    "mpx_net_input_bytes", "mpx_conv2d", "mpx_conv2d_splitk", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_maxpool3x3s2", "mpx_avgpool_linear",
     "mpx_net_create", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_workspace_bytes", "mpx_net_forward",
 ]
 
@@ -104,6 +105,11 @@ def lib() -> ctypes.CDLL:
                            "rebuild it with `python -m megapose6d_b200.build --force`")
         _lib = handle
     return _lib
+
+
+def act_dtype() -> torch.dtype:
+    """torch dtype of the library's 16-bit weights / activations / network input (include/mpx.h: mpx_act_dtype)."""
+    return torch.float16 if lib().mpx_act_dtype() == 0 else torch.bfloat16
 
 
 def check(rc: int) -> None:

@@ -6,7 +6,8 @@ training/pose_models_cfg.py:106-109 with `num_classes=512, n_input_channels=C`) 
 (`pose_fc` or `views_logits_head`, models/pose_rigid.py:120-130) in the reference's state-dict
 layout and repacks them once for the tcgen05 kernels:
   * eval-mode BatchNorm folded into the preceding conv (w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps));
-  * conv weights OIHW fp32 -> [C_out, R*S*C_in] bf16, K ordered (r, s, c);
+  * conv weights OIHW fp32 -> [C_out, R*S*C_in] in the library's 16-bit type (`_abi.act_dtype()`: fp16 unless the
+    library was built for bf16), K ordered (r, s, c);
   * the 7x7/s2 stem rewritten as a 4x4/s1 conv over the space-to-depth input (channels padded to
     c_pad = 16 or 32, four sub-pixels -> 64 or 128 input channels);
   * avgpool -> fc(512x512) -> head(512 x 1|9) folded into one linear map (there is no
@@ -72,11 +73,12 @@ class ResNet34Engine:
         assert n_inputs <= 32, f"n_inputs={n_inputs} > 32 is not supported"
         assert sd["backbone.conv1.weight"].shape[1] == n_inputs, "checkpoint / config channel mismatch"
         self.device = torch.device(device)
+        self.act_dtype = _abi.act_dtype()
         self._weights: List[torch.Tensor] = []
         self._biases: List[torch.Tensor] = []
 
         def add(wmat: torch.Tensor, bias: torch.Tensor) -> None:
-            self._weights.append(wmat.to(torch.float32).to(self.device).to(torch.bfloat16).contiguous())
+            self._weights.append(wmat.to(torch.float32).to(self.device).to(self.act_dtype).contiguous())
             self._biases.append(bias.to(torch.float32).to(self.device).contiguous())
 
         w, b = _fold(sd, "backbone.conv1", "backbone.bn1")
@@ -105,6 +107,10 @@ class ResNet34Engine:
                                              _abi.ptr(self.head_b), ctypes.byref(handle)))
         self._handle = handle
         self._workspace: Optional[torch.Tensor] = None
+        # workspaces that were outgrown: CUDA graphs captured by the callers (PosePredictor._iterate_graphed,
+        # PoseEstimator._coarse_stage_graphed) have their addresses baked in, so they are kept alive, never freed;
+        # growth is geometric, the retired ones therefore sum to less than the live one
+        self._retired_workspaces: List[torch.Tensor] = []
         self._out_cache: Dict[int, torch.Tensor] = {}
 
     def __del__(self):
@@ -115,24 +121,27 @@ class ResNet34Engine:
             pass
 
     def alloc_input(self, n: int, h: int, w: int) -> torch.Tensor:
-        """Zero-initialised network input tensor [n, h/2, w/2, 4*c_pad] bf16 (pad channels stay 0)."""
-        return torch.zeros(n, h // 2, w // 2, 4 * self.c_pad, device=self.device, dtype=torch.bfloat16)
+        """Zero-initialised network input tensor [n, h/2, w/2, 4*c_pad] fp16|bf16 (pad channels stay 0)."""
+        return torch.zeros(n, h // 2, w // 2, 4 * self.c_pad, device=self.device, dtype=self.act_dtype)
 
     def pack_input(self, x_nchw: torch.Tensor) -> torch.Tensor:
-        """[n, C, h, w] float -> space-to-depth bf16 input (for tests and the non-fused API path)."""
+        """[n, C, h, w] float -> space-to-depth 16-bit input (for tests and the non-fused API path)."""
         n, c, h, w = x_nchw.shape
         assert c == self.n_inputs
         x = torch.zeros(n, self.c_pad, h, w, device=self.device, dtype=torch.float32)
         x[:, :c] = x_nchw.to(self.device).float()
         x = x.view(n, self.c_pad, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1)  # n, h/2, w/2, dy, dx, c
-        return x.reshape(n, h // 2, w // 2, 4 * self.c_pad).to(torch.bfloat16).contiguous()
+        return x.reshape(n, h // 2, w // 2, 4 * self.c_pad).clamp(-65504.0, 65504.0).to(self.act_dtype).contiguous()
 
     def forward(self, x: torch.Tensor, h: int, w: int) -> torch.Tensor:
         """x: network input tensor for n samples of size h x w -> [n, out_dim] float32."""
         n = x.shape[0]
-        assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape == (n, h // 2, w // 2, 4 * self.c_pad)
+        assert x.dtype == self.act_dtype and x.is_contiguous() and x.shape == (n, h // 2, w // 2, 4 * self.c_pad)
         need = _abi.lib().mpx_net_workspace_bytes(self._handle, n, h, w)
         if self._workspace is None or self._workspace.numel() < need:
+            if self._workspace is not None:
+                self._retired_workspaces.append(self._workspace)
+                need = max(need, 2 * self._workspace.numel())
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         # persistent output buffer per batch size: (x, out, workspace, shape) identify the cached CUDA graph
         out = self._out_cache.get(n)

@@ -22,6 +22,7 @@ using namespace mpx;
 extern "C" {
 
 int mpx_abi_version(void) { return MPX_ABI_VERSION; }
+int mpx_act_dtype(void) { return kActIsFp16 ? 0 : 1; }
 const char* mpx_last_error(void) { return g_err; }
 
 long long mpx_launch_count(void) { return g_launches; }
@@ -119,7 +120,7 @@ int mpx_raster_render_fused(const mpx_meshdb* db, const int32_t* d_label_idx, co
   }
   RasterOut out;
   memset(&out, 0, sizeof(out));
-  out.x = reinterpret_cast<__nv_bfloat16*>(d_x);
+  out.x = reinterpret_cast<act_t*>(d_x);
   out.c_pad = c_pad;
   out.ch_offset = ch_offset;
   out.ch_per_view = ch_per_view;
@@ -148,7 +149,7 @@ int mpx_render_crop_fused(const mpx_meshdb* db, const int32_t* d_label_idx, cons
   MPX_REQUIRE(b > 0 && im_h > 0 && im_w > 0, "mpx_render_crop_fused: empty observation");
   RasterOut out;
   memset(&out, 0, sizeof(out));
-  out.x = reinterpret_cast<__nv_bfloat16*>(d_x);
+  out.x = reinterpret_cast<act_t*>(d_x);
   out.c_pad = c_pad;
   out.ch_offset = c_in;
   out.ch_per_view = ch_per_view;
@@ -277,7 +278,7 @@ int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int
   MPX_REQUIRE(c <= c_pad, "mpx_roi_align_fused: c=%d > c_pad=%d", c, c_pad);
   CropOut out;
   memset(&out, 0, sizeof(out));
-  out.x = reinterpret_cast<__nv_bfloat16*>(d_x);
+  out.x = reinterpret_cast<act_t*>(d_x);
   out.c_pad = c_pad;
   out.depth_norm_z = d_depth_norm_z;
   return roi_align_launch(d_img_nhwc4, b, h, w, d_im_idx, d_boxes, n, c, out_h, out_w, out,
@@ -289,25 +290,25 @@ size_t mpx_net_input_bytes(int n, int h, int w, int c_pad) {
   return static_cast<size_t>(n) * (h / 2) * (w / 2) * 4 * c_pad * 2;
 }
 
-int mpx_conv2d_bf16(const void* d_x, int n, int h, int w, int c_in, const void* d_w, const float* d_bias,
+int mpx_conv2d(const void* d_x, int n, int h, int w, int c_in, const void* d_w, const float* d_bias,
                     int c_out, int r, int s, int stride, int pad_lo_h, int pad_lo_w, int pad_hi_h, int pad_hi_w,
                     int relu, const void* d_residual, void* d_out, int block_n, int max_ctas, void* stream) {
   MPX_NOT_NULL(d_x);
   MPX_NOT_NULL(d_w);
   MPX_NOT_NULL(d_bias);
   MPX_NOT_NULL(d_out);
-  MPX_REQUIRE(n > 0 && h > 0 && w > 0, "mpx_conv2d_bf16: empty input");
+  MPX_REQUIRE(n > 0 && h > 0 && w > 0, "mpx_conv2d: empty input");
   MPX_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_residual) & 15) == 0,
-              "mpx_conv2d_bf16: pointers must be 16-byte aligned");
+              "mpx_conv2d: pointers must be 16-byte aligned");
   ConvDesc d{n, h, w, c_in, c_out, r, s, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w, relu};
   return conv_forward(d, d_x, d_w, d_bias, d_residual, d_out, block_n, max_ctas,
                       static_cast<cudaStream_t>(stream));
 }
 
-int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w, const float* d_bias,
+int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void* d_w, const float* d_bias,
                            int c_out, int r, int s, int stride, int pad_lo_h, int pad_lo_w, int pad_hi_h,
                            int pad_hi_w, int relu, const void* d_residual, void* d_out, int block_n, int splits,
                            void* stream) {
@@ -315,14 +316,14 @@ int mpx_conv2d_bf16_splitk(const void* d_x, int n, int h, int w, int c_in, const
   MPX_NOT_NULL(d_w);
   MPX_NOT_NULL(d_bias);
   MPX_NOT_NULL(d_out);
-  MPX_REQUIRE(n > 0 && h > 0 && w > 0, "mpx_conv2d_bf16_splitk: empty input");
+  MPX_REQUIRE(n > 0 && h > 0 && w > 0, "mpx_conv2d_splitk: empty input");
   MPX_REQUIRE(splits == 0 || splits == 1 || splits == 2 || splits == 4 || splits == 8,
-              "mpx_conv2d_bf16_splitk: splits=%d must be 0 (heuristic), 1, 2, 4 or 8", splits);
-  MPX_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "mpx_conv2d_bf16_splitk: block_n must be 64|128|256");
+              "mpx_conv2d_splitk: splits=%d must be 0 (heuristic), 1, 2, 4 or 8", splits);
+  MPX_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "mpx_conv2d_splitk: block_n must be 64|128|256");
   MPX_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_residual) & 15) == 0,
-              "mpx_conv2d_bf16_splitk: pointers must be 16-byte aligned");
+              "mpx_conv2d_splitk: pointers must be 16-byte aligned");
   ConvDesc d{n, h, w, c_in, c_out, r, s, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w, relu};
   return conv_forward(d, d_x, d_w, d_bias, d_residual, d_out, block_n, 0, static_cast<cudaStream_t>(stream),
                       splits == 0 ? -1 : splits);
@@ -335,7 +336,7 @@ int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_o
   return umma_rowshift_probe(d_a, d_b, r0, base_offset, d_out, static_cast<cudaStream_t>(stream));
 }
 
-int mpx_maxpool3x3s2_bf16(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream) {
+int mpx_maxpool3x3s2(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream) {
   MPX_NOT_NULL(d_x);
   MPX_NOT_NULL(d_out);
   return maxpool3x3s2(d_x, n, h, w, c, d_out, static_cast<cudaStream_t>(stream));

@@ -23,6 +23,12 @@
 
 namespace mpx {
 
+#ifdef MPX_ACT_BF16
+#define kTmaActType CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#else
+#define kTmaActType CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------
@@ -89,8 +95,8 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers bf16 inputs with fp32 accumulation.
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+// D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers fp16 and bf16 inputs (InstrDescriptor a/b format) with fp32 accumulation.
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                             uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -134,15 +140,15 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // next 32-column chunk is requested before the current chunk is processed, and the caller requests the first
 // chunk before it waits for the accumulator, so that the global-load latency hides behind the MMAs.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_res_chunk(const __nv_bfloat16* res_row, int c, uint4 (&r)[4]) {
+__device__ __forceinline__ void load_res_chunk(const act_t* res_row, int c, uint4 (&r)[4]) {
   const uint4* r4 = reinterpret_cast<const uint4*>(res_row + c);
 #pragma unroll
   for (int i = 0; i < 4; ++i) r[i] = __ldg(r4 + i);
 }
 
 template <int NCOLS>
-__device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bfloat16* out_row,
-                                             const __nv_bfloat16* res_row, const float* bias_s, int relu,
+__device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, act_t* out_row,
+                                             const act_t* res_row, const float* bias_s, int relu,
                                              uint4 (&res_cur)[4]) {
   const bool has_res = valid && res_row != nullptr;
 #pragma unroll 1
@@ -171,7 +177,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bf
           const uint32_t rr[4] = {res_cur[i].x, res_cur[i].y, res_cur[i].z, res_cur[i].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 t = unpack_bf16x2(rr[j]);
+            const float2 t = unpack_act2(rr[j]);
             f[2 * j] += t.x;
             f[2 * j + 1] += t.y;
           }
@@ -181,10 +187,10 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bf
           for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]);
-        o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]);
-        o.w = pack_bf16x2(f[6], f[7]);
+        o.x = pack_act2(f[0], f[1]);
+        o.y = pack_act2(f[2], f[3]);
+        o.z = pack_act2(f[4], f[5]);
+        o.w = pack_act2(f[6], f[7]);
         o4[i] = o;
       }
     }
@@ -199,14 +205,14 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, __nv_bf
 // 16-byte registers) is requested before the thread waits for the accumulator, so that no residual load is exposed
 // between two 32-column chunks (conv2 of a block is 0.09 / 0.035 ms slower than conv1 in layer1 / layer2 today).
 template <int NCOLS>
-__device__ __forceinline__ void load_res_row(const __nv_bfloat16* res_row, uint4 (&r)[NCOLS / 8]) {
+__device__ __forceinline__ void load_res_row(const act_t* res_row, uint4 (&r)[NCOLS / 8]) {
   const uint4* r4 = reinterpret_cast<const uint4*>(res_row);
 #pragma unroll
   for (int i = 0; i < NCOLS / 8; ++i) r[i] = __ldg(r4 + i);
 }
 
 template <int NCOLS>
-__device__ __forceinline__ void epilogue_row_preloaded(uint32_t taddr, bool valid, __nv_bfloat16* out_row, bool has_res,
+__device__ __forceinline__ void epilogue_row_preloaded(uint32_t taddr, bool valid, act_t* out_row, bool has_res,
                                                        const float* bias_s, int relu, const uint4 (&res)[NCOLS / 8]) {
 #pragma unroll
   for (int c = 0; c < NCOLS; c += 32) {
@@ -233,7 +239,7 @@ __device__ __forceinline__ void epilogue_row_preloaded(uint32_t taddr, bool vali
           const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 t = unpack_bf16x2(rr[j]);
+            const float2 t = unpack_act2(rr[j]);
             f[2 * j] += t.x;
             f[2 * j + 1] += t.y;
           }
@@ -243,10 +249,10 @@ __device__ __forceinline__ void epilogue_row_preloaded(uint32_t taddr, bool vali
           for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]);
-        o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]);
-        o.w = pack_bf16x2(f[6], f[7]);
+        o.x = pack_act2(f[0], f[1]);
+        o.y = pack_act2(f[2], f[3]);
+        o.z = pack_act2(f[4], f[5]);
+        o.w = pack_act2(f[6], f[7]);
         o4[i] = o;
       }
     }
@@ -297,8 +303,8 @@ __device__ __forceinline__ void splitk_park_row(uint32_t taddr, uint32_t tile_sm
 // rows [rank*128/S, (rank+1)*128/S) of the tile: sum over the cluster, epilogue, store.  All threads of the CTA.
 template <int NCOLS>
 __device__ __forceinline__ void splitk_reduce_slice(uint32_t tile_smem, int splits, int rank, long long m0,
-                                                    int M_total, int C_out, int n0, __nv_bfloat16* __restrict__ out,
-                                                    const __nv_bfloat16* __restrict__ residual, const float* bias_s,
+                                                    int M_total, int C_out, int n0, act_t* __restrict__ out,
+                                                    const act_t* __restrict__ residual, const float* bias_s,
                                                     int relu) {
   constexpr int kVecPerRow = NCOLS / 4;
   const int rows_per = 128 / splits;
@@ -329,7 +335,7 @@ __device__ __forceinline__ void splitk_reduce_slice(uint32_t tile_smem, int spli
     const size_t off = static_cast<size_t>(m) * C_out + n0 + c;
     if (residual != nullptr) {
       const uint2 rr = __ldg(reinterpret_cast<const uint2*>(residual + off));
-      const float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y);
+      const float2 t0 = unpack_act2(rr.x), t1 = unpack_act2(rr.y);
       f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
     }
     if (relu) {
@@ -337,8 +343,8 @@ __device__ __forceinline__ void splitk_reduce_slice(uint32_t tile_smem, int spli
       for (int j = 0; j < 4; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     uint2 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
+    o.x = pack_act2(f[0], f[1]);
+    o.y = pack_act2(f[2], f[3]);
     *reinterpret_cast<uint2*>(out + off) = o;
   }
 }
@@ -405,8 +411,8 @@ struct ConvParams {
   int m_tiles, n_tiles;
   int relu;
   const float* bias;                // [C_out] folded BN shift
-  const __nv_bfloat16* residual;    // [M_total, C_out] or nullptr
-  __nv_bfloat16* out;               // [M_total, C_out]
+  const act_t* residual;    // [M_total, C_out] or nullptr
+  act_t* out;               // [M_total, C_out]
   // split-K: the `splits` (1, 2, 4 or 8) CTAs of a cluster share one output tile, each accumulating a contiguous
   // range of k-blocks; reduction through distributed shared memory (see SplitKTile)
   int splits;
@@ -524,9 +530,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // InstrDescriptor (cute/arch/mma_sm100_desc.hpp): c_format F32 [4,6)=1, a/b format BF16
-      // [7,10)=[10,13)=1, a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+      // InstrDescriptor (cute/arch/mma_sm100_desc.hpp): c_format F32 [4,6)=1, a/b format
+      // [7,10), [10,13) = kIdescAB (0 = F16, 1 = BF16), a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB |
                                  (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                  (static_cast<uint32_t>(kBlockM >> 4) << 24);
       int stage = 0;
@@ -549,7 +555,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+            tc_mma_f16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                         idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -576,7 +582,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool valid = m < p.M_total;
       const int n0 = n_tile * BLOCK_N;
       const size_t off = static_cast<size_t>(valid ? m : 0) * p.C_out + n0;
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       if (p.splits == 1) {
@@ -759,7 +765,7 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
     int lower[2] = {-d.pad_lo_w, -d.pad_lo_h};
     int upper[2] = {d.pad_hi_w - (d.S - 1), d.pad_hi_h - (d.R - 1)};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
-    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x),
+    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x),
                                  dims, strides, lower, upper, /*channelsPerPixel=*/kBlockK,
                                  /*pixelsPerColumn=*/kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -781,7 +787,7 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
     // the CTA-pair kernel loads half of the weight tile per CTA
     cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(use_pair ? block_n / 2 : block_n)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims,
                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -803,8 +809,8 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   p.n_tiles = d.C_out / block_n;
   p.relu = d.relu;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
   p.splits = 1;
   if (splitk != 0 && !use_pair) {
     // Few output tiles and a long K loop (deep layers at batch 1: one 80-row tile, 72 k-blocks): split K over a cluster.
@@ -869,8 +875,8 @@ struct WinParams {
   int mma_issuers;     // 1 or 2 issuing threads (tiles alternate)
   int observers_arrive;  // 1: a stage is refilled only after EVERY issuer has seen its fill (empty count = issuers)
   const float* bias;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out;
+  const act_t* residual;
+  act_t* out;
 };
 
 constexpr int kWinN = 64;          // C_out
@@ -971,7 +977,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int n_issuers = p.mma_issuers;
     const int which = warp == 1 ? 0 : (warp == 3 ? 1 : 2);  // warp 2 (TMEM allocator) doubles as the third issuer
     if (lane == 0 && which < n_issuers) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kWinN >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kWinN >> 3) << 17) |
                                  (static_cast<uint32_t>(kBlockM >> 4) << 24);
       mbar_wait(b_full, 0);
       int stage = 0;
@@ -1012,10 +1018,10 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int r = 0; r < p.rg; ++r) {
             uint64_t da = da_row;
             for (int s = 0; s < p.S; ++s) {
-              tc_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
               da += 8;
               db += kWinBTile / 16;
@@ -1053,7 +1059,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kWinN : 0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);  // in flight while the MMAs finish
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -1156,8 +1162,8 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
   p.mma_issuers = (g_conv_mode & 32) != 0 ? 1 : ((g_conv_mode & 64) != 0 ? 3 : 2);
   p.observers_arrive = (g_conv_mode & 2048) != 0 ? 1 : 0;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
@@ -1168,7 +1174,7 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
     int lower[2] = {-d.pad_lo_w, -d.pad_lo_h};
     int upper[2] = {d.pad_hi_w, d.pad_hi_h};  // the base pixel walks the whole padded image
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, kBlockK, static_cast<cuuint32_t>(p.chunk_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1184,7 +1190,7 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
     cuuint64_t strides[1] = {K_total * 2};
     cuuint32_t box[2] = {kBlockK, 64};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -1246,8 +1252,8 @@ struct Win2Params {
   int n_super;
   int relu;
   const float* bias;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out;
+  const act_t* residual;
+  act_t* out;
 };
 
 constexpr int kW2N = 128;                 // C_out = C_in
@@ -1355,7 +1361,7 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== MMA issuers: warp 1 -> rows 0-127 of the super-tile, warp 3 -> rows 128-255 ==========
     if (lane == 0) {
       const int ti = warp == 1 ? 0 : 1;
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kW2N >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kW2N >> 3) << 17) |
                                  (static_cast<uint32_t>(kBlockM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -1380,10 +1386,10 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               mbar_wait(&b_full[stage], phase);
               tc_fence_after();
               const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * kW2BTile));
-              tc_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
               tc_commit(&b_empty[stage]);
               if (++stage == kW2BStages) {
@@ -1419,7 +1425,7 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kW2N : 0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * kW2N);
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);  // in flight while the MMAs finish
       mbar_wait(&tmem_full[buf], static_cast<uint32_t>(local >> 1) & 1u);
@@ -1466,8 +1472,8 @@ static int conv_window2_try(const ConvDesc& d, const void* x, const void* w, con
   p.n_super = static_cast<int>(n_super);
   p.relu = d.relu;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
@@ -1478,7 +1484,7 @@ static int conv_window2_try(const ConvDesc& d, const void* x, const void* w, con
     int lower[2] = {-1, -1};
     int upper[2] = {1, 1};  // the base pixel walks the whole padded image
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, kBlockK, static_cast<cuuint32_t>(p.chunk_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1494,7 +1500,7 @@ static int conv_window2_try(const ConvDesc& d, const void* x, const void* w, con
     cuuint64_t strides[1] = {K_total * 2};
     cuuint32_t box[2] = {kBlockK, 128};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -1550,7 +1556,7 @@ __device__ __forceinline__ void tma2_load_im2col_4d(void* smem, const CUtensorMa
       "l"(kTmaCacheHintNormal)
       : "memory");
 }
-__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void tc2_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -1673,7 +1679,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -1691,7 +1697,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * Cfg::kBHalfBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            tc2_mma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+            tc2_mma_f16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
           }
           tc2_commit_mc(&empty_bar[stage]);
@@ -1717,7 +1723,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const bool valid = m < p.M_total;
       const int n0 = n_tile * BLOCK_N;
       const size_t off = static_cast<size_t>(valid ? m : 0) * p.C_out + n0;
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -1788,8 +1794,8 @@ struct Win2pParams {
   int n_super;
   int relu;
   const float* bias;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out;
+  const act_t* residual;
+  act_t* out;
 };
 
 constexpr int kW2pABufs = 4;
@@ -1905,7 +1911,7 @@ conv_window2p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -1927,10 +1933,10 @@ conv_window2p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               mbar_wait(&b_full[stage], phase);
               tc_fence_after();
               const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * kBHalf));
-              tc2_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc2_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc2_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc2_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc2_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc2_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc2_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc2_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
               tc2_commit_mc(&b_empty[stage]);
               if (++stage == kW2pBStages) {
@@ -1967,7 +1973,7 @@ conv_window2p_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         valid = (y >= 0) && (y < p.H) && (x >= 0) && (x < p.W);
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.C_out + n0 : 0;
       }
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
       mbar_wait(&tmem_full[acc], static_cast<uint32_t>(local >> 1) & 1u);
@@ -2023,8 +2029,8 @@ static int conv_window2p_launch(const ConvDesc& d, const void* x, const void* w,
   p.n_super = static_cast<int>(n_super);
   p.relu = d.relu;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
@@ -2037,7 +2043,7 @@ static int conv_window2p_launch(const ConvDesc& d, const void* x, const void* w,
     int lower[2] = {-1, -1};
     int upper[2] = {1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, kBlockK, static_cast<cuuint32_t>(p.chunk_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -2053,7 +2059,7 @@ static int conv_window2p_launch(const ConvDesc& d, const void* x, const void* w,
     cuuint64_t strides[1] = {K_total * 2};
     cuuint32_t box[2] = {kBlockK, BLOCK_N / 2};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -2211,7 +2217,7 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===================== MMA issuers (leader only): warp 1 -> rows 0-127 of both CTAs, warp 3 -> rows 128-255 ======
     if (leader && lane == 0) {
       const int ti = warp == 1 ? 0 : 1;
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kW2N >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kW2N >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -2235,10 +2241,10 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               mbar_wait(&b_full[stage], phase);
               tc_fence_after();
               const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * kW2qBHalf));
-              tc2_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc2_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc2_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc2_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc2_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc2_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc2_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc2_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
               tc2_commit_mc(&b_empty[stage]);
               if (++stage == kW2qBStages) {
@@ -2274,7 +2280,7 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kW2N : 0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * kW2N);
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       if (res_preload) {
         uint4 res_all[kW2N / 8];
         const bool has_res = valid && res_row != nullptr;
@@ -2333,8 +2339,8 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
   p.n_super = static_cast<int>(n_super);
   p.relu = d.relu;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
@@ -2345,7 +2351,7 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
     int lower[2] = {-1, -1};
     int upper[2] = {1, 1};  // the base pixel walks the whole padded image
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, kBlockK, static_cast<cuuint32_t>(p.chunk_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -2361,7 +2367,7 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
     cuuint64_t strides[1] = {K_total * 2};
     cuuint32_t box[2] = {kBlockK, kW2N / 2};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -2490,7 +2496,7 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== MMA issuers (leader only), pair tiles alternately =====================
     const int which = warp == 1 ? 0 : 1;
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kWinN >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kWinN >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       mbar_wait(b_full, 0);
       int stage = 0;
@@ -2523,10 +2529,10 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int r = 0; r < p.rg; ++r) {
             uint64_t da = da_row;
             for (int s = 0; s < p.S; ++s) {
-              tc2_mma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc2_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc2_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc2_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc2_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc2_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc2_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc2_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
               da += 8;
               db += kWinqBHalf / 16;
@@ -2564,7 +2570,7 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kWinN : 0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
-      const __nv_bfloat16* res_row = p.residual ? p.residual + off : nullptr;
+      const act_t* res_row = p.residual ? p.residual + off : nullptr;
       if (res_preload) {
         uint4 res_all[kWinN / 8];
         const bool has_res = valid && res_row != nullptr;
@@ -2655,8 +2661,8 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
   p.mma_issuers = 2;
   p.observers_arrive = 0;
   p.bias = bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
@@ -2667,7 +2673,7 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
     int lower[2] = {-d.pad_lo_w, -d.pad_lo_h};
     int upper[2] = {d.pad_hi_w, d.pad_hi_h};  // the base pixel walks the whole padded image
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x), dims, strides, lower,
                                  upper, kBlockK, static_cast<cuuint32_t>(p.chunk_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -2683,7 +2689,7 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
     cuuint64_t strides[1] = {K_total * 2};
     cuuint32_t box[2] = {kBlockK, kWinN / 2};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -2746,14 +2752,14 @@ umma_rowshift_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
     tma_load_2d(smem_b, &map_b, &bars[0], 0, 0);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(64 >> 3) << 17) |
+    constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(64 >> 3) << 17) |
                                (static_cast<uint32_t>(128 >> 4) << 24);
     const uint64_t da = make_sw128_desc(smem_u32(smem_a) + static_cast<uint32_t>(r0) * 128u) |
                         (static_cast<uint64_t>(base_off & 7) << 49);
     const uint64_t db = make_sw128_desc(smem_u32(smem_b));
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      tc_mma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+      tc_mma_f16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                   k > 0 ? 1u : 0u);
     tc_commit(&bars[1]);
   }
@@ -2787,7 +2793,7 @@ int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, floa
     cuuint64_t dims[2] = {64, 144};
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {64, 144};
-    CUresult r = g_encode_tiled(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a), dims, strides, box,
+    CUresult r = g_encode_tiled(&map_a, kTmaActType, 2, const_cast<void*>(a), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "probe: encode A failed (%d)", static_cast<int>(r));
@@ -2796,7 +2802,7 @@ int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, floa
     cuuint64_t dims[2] = {64, 64};
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {64, 64};
-    CUresult r = g_encode_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b), dims, strides, box,
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(b), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "probe: encode B failed (%d)", static_cast<int>(r));

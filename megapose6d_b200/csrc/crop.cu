@@ -74,15 +74,15 @@ roi_align_kernel(const float4* __restrict__ images, int b, int h, int w, const i
     }
     if (out.x) {
       const int hs = oh >> 1, ws = ow >> 1;
-      __nv_bfloat16* o = out.x + ((static_cast<size_t>(roi) * hs + (ph >> 1)) * ws + (pw >> 1)) * (4 * out.c_pad) +
+      act_t* o = out.x + ((static_cast<size_t>(roi) * hs + (ph >> 1)) * ws + (pw >> 1)) * (4 * out.c_pad) +
                          ((ph & 1) * 2 + (pw & 1)) * out.c_pad;
-      o[0] = __float2bfloat16_rn(acc.x);
-      o[1] = __float2bfloat16_rn(acc.y);
-      o[2] = __float2bfloat16_rn(acc.z);
+      o[0] = to_act(acc.x);
+      o[1] = to_act(acc.y);
+      o[2] = to_act(acc.z);
       if (c == 4) {
         float d = acc.w;
         if (out.depth_norm_z) d = fminf(fmaxf(d / __ldg(out.depth_norm_z + roi), 0.f), 2.f) - 1.f;
-        o[3] = __float2bfloat16_rn(d);
+        o[3] = to_act(d);
       }
     }
   }

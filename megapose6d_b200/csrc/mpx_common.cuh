@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -70,14 +71,47 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+// ---------------------------------------------------------------------------------------------
+// 16-bit storage type of weights and activations ("act").  fp16 by default: the tensor core runs fp16 and bf16 operands
+// at the same rate (tcgen05 kind::f16, fp32 accumulation either way), fp16 carries three more mantissa bits, and fp16 is
+// what the reference's networks were trained under (torch.cuda.amp.autocast, training/train_megapose.py:299).  The
+// narrower range is handled by a saturating conversion (values beyond +-65504 clamp instead of becoming inf).
+// -DMPX_ACT_BF16 selects bf16 (same kernels; diagnostic A/B of the two number formats).
+// ---------------------------------------------------------------------------------------------
+#ifdef MPX_ACT_BF16
+typedef __nv_bfloat16 act_t;
+typedef __nv_bfloat162 act_t2;
+constexpr int kActIsFp16 = 0;
+constexpr uint32_t kIdescAB = (1u << 7) | (1u << 10);  // InstrDescriptor a_format / b_format = BF16
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  act_t2 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+__device__ __forceinline__ float2 unpack_act2(uint32_t u) {
+  act_t2 v = *reinterpret_cast<act_t2*>(&u);
   return __bfloat1622float2(v);
 }
+__device__ __forceinline__ act_t to_act(float v) { return __float2bfloat16_rn(v); }
+#else
+typedef __half act_t;
+typedef __half2 act_t2;
+constexpr int kActIsFp16 = 1;
+constexpr uint32_t kIdescAB = 0u;                      // InstrDescriptor a_format / b_format = F16
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  uint32_t r;  // cvt packs its first source into the upper half
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_act2(uint32_t u) {
+  act_t2 v = *reinterpret_cast<act_t2*>(&u);
+  return __half22float2(v);
+}
+__device__ __forceinline__ act_t to_act(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while its stream predecessor is
@@ -174,7 +208,7 @@ struct RasterOut {
   float* rgb;      // contract planes (fp32 NCHW), any may be null
   float* normals;
   float* depth;
-  __nv_bfloat16* x;  // fused network input (bf16 s2d NHWC), may be null
+  act_t* x;  // fused network input (16-bit s2d NHWC), may be null
   int c_pad, ch_offset, ch_per_view, views_per_sample;
   const float* depth_norm_z;
   // optional: observation crop computed in the resolve pass (views_per_sample == 1), so that each
@@ -213,7 +247,7 @@ int topk_per_group(const float* logits, int n_groups, int m, int k, int* idx, cu
 // crop.cu
 struct CropOut {
   float* nchw;       // [n, c, oh, ow] or null
-  __nv_bfloat16* x;  // fused network input or null
+  act_t* x;  // fused network input or null
   int c_pad;
   const float* depth_norm_z;
 };

@@ -44,17 +44,17 @@ maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n,
           const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16x2(u[j]);
+            const float2 f = unpack_act2(u[j]);
             m[2 * j] = fmaxf(m[2 * j], f.x);
             m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
           }
         }
       }
       uint4 o;
-      o.x = pack_bf16x2(m[0], m[1]);
-      o.y = pack_bf16x2(m[2], m[3]);
-      o.z = pack_bf16x2(m[4], m[5]);
-      o.w = pack_bf16x2(m[6], m[7]);
+      o.x = pack_act2(m[0], m[1]);
+      o.y = pack_act2(m[2], m[3]);
+      o.z = pack_act2(m[4], m[5]);
+      o.w = pack_act2(m[6], m[7]);
       orow[t] = o;
     }
   }
@@ -88,11 +88,11 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
 // ---------------------------------------------------------------------------------------------
 constexpr int kPoolThreads = 512;
 __global__ void __launch_bounds__(kPoolThreads)
-avgpool_linear_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c, const float* __restrict__ w,
+avgpool_linear_kernel(const act_t* __restrict__ x, int hw, int c, const float* __restrict__ w,
                       const float* __restrict__ b, int out_dim, float* __restrict__ out) {
   extern __shared__ float smem_pool[];  // [G][c] partial sums, then [c] pooled
   const int img = blockIdx.x;
-  const __nv_bfloat16* xi = x + static_cast<size_t>(img) * hw * c;
+  const act_t* xi = x + static_cast<size_t>(img) * hw * c;
   pdl_trigger();
   pdl_wait();
   const int nq = c >> 2;
@@ -106,7 +106,7 @@ avgpool_linear_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c, const 
 #pragma unroll 4
       for (int p = g; p < hw; p += G) {
         const uint2 v = __ldg(reinterpret_cast<const uint2*>(xi + static_cast<size_t>(p) * c + 4 * q));
-        const float2 a = unpack_bf16x2(v.x), d = unpack_bf16x2(v.y);
+        const float2 a = unpack_act2(v.x), d = unpack_act2(v.y);
         s0 += a.x;
         s1 += a.y;
         s2 += d.x;
@@ -141,7 +141,7 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
   const size_t smem = static_cast<size_t>(G + 1) * c * sizeof(float);
   MPX_REQUIRE(smem <= 48 * 1024, "avgpool_linear: C=%d needs %zu bytes of shared memory", c, smem);
   MPX_CHECK_CUDA(launch_pdl(avgpool_linear_kernel, dim3(n), dim3(kPoolThreads), smem, stream, 1,
-                            reinterpret_cast<const __nv_bfloat16*>(x), hw, c, w, b, out_dim, out));
+                            reinterpret_cast<const act_t*>(x), hw, c, w, b, out_dim, out));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;

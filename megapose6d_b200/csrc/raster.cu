@@ -447,7 +447,7 @@ __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __res
     if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
     if (out.x) {
       const int hs = h >> 1, ws = w >> 1;
-      __nv_bfloat16* base = out.x +
+      act_t* base = out.x +
                             ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
                             ((i & 1) * 2 + (j & 1)) * out.c_pad;
       float dn = dep;
@@ -480,22 +480,22 @@ __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __res
         if (out.ch_per_view == 7) ch[c++] = dn;
         uint4* o4 = reinterpret_cast<uint4*>(base);
         uint4 v0, v1;
-        v0.x = pack_bf16x2(ch[0], ch[1]); v0.y = pack_bf16x2(ch[2], ch[3]);
-        v0.z = pack_bf16x2(ch[4], ch[5]); v0.w = pack_bf16x2(ch[6], ch[7]);
-        v1.x = pack_bf16x2(ch[8], ch[9]); v1.y = pack_bf16x2(ch[10], ch[11]);
-        v1.z = pack_bf16x2(ch[12], ch[13]); v1.w = pack_bf16x2(ch[14], ch[15]);
+        v0.x = pack_act2(ch[0], ch[1]); v0.y = pack_act2(ch[2], ch[3]);
+        v0.z = pack_act2(ch[4], ch[5]); v0.w = pack_act2(ch[6], ch[7]);
+        v1.x = pack_act2(ch[8], ch[9]); v1.y = pack_act2(ch[10], ch[11]);
+        v1.z = pack_act2(ch[12], ch[13]); v1.w = pack_act2(ch[14], ch[15]);
         o4[0] = v0;
         o4[1] = v1;
         for (int k = 2; k < out.c_pad / 8; ++k) o4[k] = make_uint4(0u, 0u, 0u, 0u);
       } else {
-        __nv_bfloat16* o = base + out.ch_offset + vslot * out.ch_per_view;
-        o[0] = __float2bfloat16_rn(r);
-        o[1] = __float2bfloat16_rn(g);
-        o[2] = __float2bfloat16_rn(b);
-        o[3] = __float2bfloat16_rn(n0);
-        o[4] = __float2bfloat16_rn(n1);
-        o[5] = __float2bfloat16_rn(n2);
-        if (out.ch_per_view == 7) o[6] = __float2bfloat16_rn(dn);
+        act_t* o = base + out.ch_offset + vslot * out.ch_per_view;
+        o[0] = to_act(r);
+        o[1] = to_act(g);
+        o[2] = to_act(b);
+        o[3] = to_act(n0);
+        o[4] = to_act(n1);
+        o[5] = to_act(n2);
+        if (out.ch_per_view == 7) o[6] = to_act(dn);
       }
     }
   }

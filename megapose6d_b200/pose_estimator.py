@@ -400,7 +400,9 @@ class PoseEstimator(torch.nn.Module):
         graphable = cm.use_cuda_graphs and (s1 - s0) <= cm.graph_max_batch and not (cm.keep_images or cm.debug)
         if not graphable:
             return finish(self._coarse_stage(images, K_obs, bboxes_det, rows_c, B, M, Kh, s0, s1, whole), False)
-        key = (id(rows_c), Kh, s0, s1, whole, tuple(images.shape), cm._nhwc4(images).data_ptr(), tuple(K_obs.shape))
+        cm._input_buffer(s1 - s0, *cm.render_size)  # may retire older buffers and the graphs over them (bumps the epoch)
+        key = (id(rows_c), Kh, s0, s1, whole, tuple(images.shape), cm._nhwc4(images).data_ptr(), tuple(K_obs.shape),
+               cm.graph_epoch)
         graphs = self.__dict__.setdefault("_coarse_graphs", {})
         entry = graphs.get(key)
         if entry is None:
@@ -547,12 +549,12 @@ class PoseEstimator(torch.nn.Module):
         pos = torch.arange(n_sel, device=device)
         first = torch.full((B,), n_sel, device=device, dtype=torch.long).scatter_reduce_(0, g_sorted, pos, "amin")
         keep = order[torch.sort(first).values]                                 # [B] rows of the scored collection
+        if st["static"]:
+            main.wait_event(self.__dict__["_coarse_copies_done"])  # the side-stream clones (K_sel ...) are read from here on
         final_tensors = {k: v[keep] for k, v in refined[-1].items()} if n_refiner_iterations > 0 else None
         packed_f = torch.cat((pl.double(), pose_scores.flatten().double(), keep.double()))
         pin_f = self._pinned("final", packed_f.numel())
         pin_f.copy_(packed_f, non_blocking=True)
-        if st["static"]:
-            main.wait_event(self.__dict__["_coarse_copies_done"])  # later work on this stream sees the copied-out tensors
         ev_f_done = torch.cuda.Event()
         ev_f_done.record(main)
 

@@ -5,7 +5,7 @@ constructor keywords, `forward` / `forward_coarse` / `forward_coarse_tensor` / `
 `compute_crops_multiview` / `render_images_multiview` / `net_forward` / `update_pose` /
 `normalize_images` with the same argument meaning and output structure (PosePredictorOutput).
 
-What differs underneath: one fused path.  The crop kernel and the rasteriser write bf16 channels
+What differs underneath: one fused path.  The crop kernel and the rasteriser write 16-bit channels
 straight into the network input tensor (no fp32 NCHW intermediates, no torch.cat, no host round
 trip for the multi-view cameras); the fp32 `images_crop` / `renders` tensors of the reference's
 outputs are only materialised on request (`keep_images=True` or `return_debug_data=True`).
@@ -131,6 +131,7 @@ class PosePredictor(nn.Module):
         self.use_cuda_graphs = True   # replay the refinement loop as one CUDA graph for small batches
         self.graph_max_batch = 1024
         self._x_cache: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self.graph_epoch = 0  # bumped whenever buffers that captured graphs point into are released
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -157,6 +158,20 @@ class PosePredictor(nn.Module):
         if refresh:
             lib3d.image_to_nhwc4(images, out=buf)
         return buf
+
+    def _input_buffer(self, n: int, h: int, w: int) -> torch.Tensor:
+        """Persistent network input per (batch size, render size).  Captured graphs (here and in
+        PoseEstimator._coarse_stage_graphed) have these addresses baked in, so a buffer is only ever released together
+        with every graph that may point into it: `graph_epoch` is part of the owners' graph keys."""
+        x = self._x_cache.get((n, h, w))
+        if x is None:
+            if len(self._x_cache) >= 32:
+                assert not torch.cuda.is_current_stream_capturing(), "input buffers must exist before capture"
+                self._graphs.clear()
+                self._x_cache.clear()
+                self.graph_epoch += 1
+            x = self._x_cache[(n, h, w)] = self.backbone.alloc_input(n, h, w)
+        return x
 
     def _label_idx(self, labels: List[str], device) -> torch.Tensor:
         return self.mesh_db.label_ids(labels, device)
@@ -268,11 +283,7 @@ class PosePredictor(nn.Module):
 
         # persistent network input per batch size: the pad channels are zeroed once, every real channel of every
         # pixel is rewritten by the crop and raster kernels on each call (background pixels included)
-        x = self._x_cache.get((n, h, w))
-        if x is None:
-            if len(self._x_cache) >= 8:
-                self._x_cache.clear()
-            x = self._x_cache[(n, h, w)] = self.backbone.alloc_input(n, h, w)
+        x = self._input_buffer(n, h, w)
         from . import _abi  # local import keeps the module import light
 
         nhwc4 = self._nhwc4(images)
@@ -393,7 +404,8 @@ class PosePredictor(nn.Module):
         ~60 launches per iteration, not by the GPU work.  One graph per (batch size, iterations, frame buffer)."""
         bsz = TCO0.shape[0]
         # the graph reads the frame from the persistent NHWC4 buffer of this shape (refreshed by forward())
-        key = (bsz, n_iterations, tuple(images.shape), self._nhwc4(images).data_ptr())
+        self._input_buffer(bsz, *self.render_size)  # may retire older buffers and the graphs over them (bumps the epoch)
+        key = (bsz, n_iterations, tuple(images.shape), self._nhwc4(images).data_ptr(), self.graph_epoch)
         entry = self._graphs.get(key)
         if entry is None:
             # first sight: run eagerly (allocates the persistent buffers, one-time CUDA set-up); capture next time

@@ -13,6 +13,7 @@ from tests import helpers
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16  # the library's 16-bit type
 
 
 def _poses(n, seed, **kw):
@@ -191,7 +192,7 @@ def test_raster_many_views_persistent_loop(scene):
 
 
 def test_fused_crop_render_matches_separate_kernels(scene, raster_mode):
-    """mpx_render_crop_fused writes the same bf16 network input as roi_align_fused + raster_render_fused."""
+    """mpx_render_crop_fused writes the same 16-bit network input as roi_align_fused + raster_render_fused."""
     from megapose6d_b200 import _abi
 
     ds, images, K, db, rm = scene
@@ -205,7 +206,7 @@ def test_fused_crop_render_matches_separate_kernels(scene, raster_mode):
                           [250, 150, 390, 255]]).cuda()
     im_idx = torch.zeros(n, dtype=torch.int32, device=DEV)
     nhwc4 = lib3d.image_to_nhwc4(images[:, :3].contiguous().cuda())
-    xa = torch.zeros(n, h // 2, w // 2, 4 * c_pad, device=DEV, dtype=torch.bfloat16)
+    xa = torch.zeros(n, h // 2, w // 2, 4 * c_pad, device=DEV, dtype=ACT)
     xb = torch.full_like(xa, 7.0)  # the fused kernel must overwrite every channel, pad included
     _abi.check(_abi.lib().mpx_roi_align_fused(_abi.ptr(nhwc4), 1, 480, 640, _abi.ptr(im_idx), _abi.ptr(boxes), n, 3, h, w,
                                               _abi.ptr(xa), c_pad, None, _abi.stream_ptr()))
@@ -250,12 +251,12 @@ def test_textured_meshes_many_views_and_fused_input():
     out, ref = _render_both(ds, rm, labels, TCO, Kc, (64, 80))
     assert torch.equal(out.rgbs.cpu(), ref["rgbs"]) and torch.equal(out.normals.cpu(), ref["normals"])
     assert torch.equal(out.depths.cpu(), ref["depths"])
-    # fused bf16 network input: channels 3..8 of each pixel vector are the bf16-rounded contract planes
+    # fused 16-bit network input: channels 3..8 of each pixel vector are the contract planes rounded to the 16-bit type
     r = BatchRenderer(object_dataset=ds)
     m, h, w, c_pad = 5, 64, 80, 16
-    x = torch.zeros(m, h // 2, w // 2, 4 * c_pad, device=DEV, dtype=torch.bfloat16)
+    x = torch.zeros(m, h // 2, w // 2, 4 * c_pad, device=DEV, dtype=ACT)
     lab = r.mesh_db.label_ids(labels[:m], DEV)
     r.render_fused(lab, TCO[:m].cuda().contiguous(), Kc[:m].cuda().contiguous(), 1, (h, w), x, c_pad, 3, 6, None)
     xs = x.view(m, h // 2, w // 2, 2, 2, c_pad).permute(0, 5, 1, 3, 2, 4).reshape(m, c_pad, h, w).float().cpu()
-    want = torch.cat((ref["rgbs"][:m], ref["normals"][:m]), dim=1).to(torch.bfloat16).float()
+    want = torch.cat((ref["rgbs"][:m], ref["normals"][:m]), dim=1).to(ACT).float()
     assert torch.equal(xs[:, 3:9], want)

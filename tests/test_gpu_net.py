@@ -1,12 +1,14 @@
 """GPU parity of the tcgen05 convolution and of the whole ResNet-34 engine.
 
 Tolerances (stated, floating point):
-  * single conv vs fp32 torch conv on the same bf16-rounded operands: |err| <= 2^-7 * max|ref| + 1e-2
-    (one bf16 rounding of the output; accumulation is fp32 on both sides);
-  * full network vs the fp32 oracle: |err_j| <= 2^-8 * sum_i |W_ji| |pooled_i| (one bf16 ulp of the folded head's
-    absolute-value condition bound, oracle/resnet_ref.py:bf16_forward_error_bound); vs the bf16-emulated oracle
-    (same quantisation points, only the accumulation order differs): a quarter of that.  The reference itself was
-    trained under fp16 autocast (train_megapose.py:299).
+  * single conv vs fp32 torch conv on the same 16-bit-rounded operands: |err| <= ULP * max|ref| + ATOL, one rounding
+    of the output in the library's 16-bit type (fp16: ULP = 2^-10, ATOL = 2e-3; bf16 build: 2^-7, 1e-2; accumulation
+    is fp32 on both sides);
+  * full network vs the fp32 oracle: |err_j| <= ACT16_EPS * sum_i |W_ji| |pooled_i| (fp16: 2^-13 of the folded head's
+    absolute-value condition bound ~ 0.14 logit standard deviations, about 3x the observed error;
+    oracle/resnet_ref.py:act16_forward_error_bound); vs the emulated oracle (same quantisation points, only the
+    accumulation order differs): half of that.  The reference itself was trained under fp16 autocast
+    (train_megapose.py:299).
 """
 import pytest
 import torch
@@ -18,6 +20,8 @@ from oracle import resnet_ref
 from tests import helpers
 
 pytestmark = pytest.mark.gpu
+ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
+ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
 DEFAULT_CONV_MODE = 11  # window | pair(256) | split-K in the network
 
 
@@ -51,21 +55,21 @@ def test_conv_vs_torch(case):
     torch.backends.cudnn.allow_tf32 = False
     name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, max_ctas = case
     g = torch.Generator(device="cuda").manual_seed(sum(map(ord, name)) % 1000)
-    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(ACT)
     bias = torch.randn(cout, device="cuda", generator=g)
     p = (h + pads[0] + pads[2] - r) // stride + 1
     q = (w + pads[1] + pads[3] - s) // stride + 1
-    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
-    out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
+    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(ACT) if use_res else None
+    out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=ACT)
+    _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
                                           stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
                                           _abi.ptr(out), block_n, max_ctas, _abi.stream_ptr()))
     torch.cuda.synchronize()
     ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
     err = (out.float() - ref).abs().max().item()
     assert not torch.isnan(out.float()).any()
-    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-2, err
+    assert err <= ULP * ref.abs().max().item() + ATOL, err
 
 
 SPLITK_CASES = [
@@ -86,63 +90,63 @@ def test_conv_splitk_matches_unsplit_and_reference(case):
     """K loop split over a thread-block cluster, partial tiles reduced through distributed shared memory."""
     name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res, block_n, splits = case
     g = torch.Generator(device="cuda").manual_seed(sum(map(ord, name)) % 1000)
-    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(ACT)
     bias = torch.randn(cout, device="cuda", generator=g)
     p = (h + pads[0] + pads[2] - r) // stride + 1
     q = (w + pads[1] + pads[3] - s) // stride + 1
-    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(ACT) if use_res else None
     lib = _abi.lib()
     outs = []
     for rep in range(2):
-        out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
-        _abi.check(lib.mpx_conv2d_bf16_splitk(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r,
+        out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=ACT)
+        _abi.check(lib.mpx_conv2d_splitk(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r,
                                               s, stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
                                               _abi.ptr(out), block_n, splits, _abi.stream_ptr()))
         torch.cuda.synchronize()
         outs.append(out.float())
-    unsplit = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _abi.check(lib.mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s, stride,
+    unsplit = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=ACT)
+    _abi.check(lib.mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s, stride,
                                    pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(unsplit), block_n, 0,
                                    _abi.stream_ptr()))
     torch.cuda.synchronize()
     ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
-    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    tol = ULP * ref.abs().max().item() + ATOL
     assert not torch.isnan(outs[0]).any()
     assert (outs[0] - ref).abs().max() <= tol
     # fp32 partial sums are combined in a different (fixed) order than the unsplit K loop: one bf16 rounding at most
-    assert (outs[0] - unsplit.float()).abs().max() <= 2 ** -7 * ref.abs().max().item()
+    assert (outs[0] - unsplit.float()).abs().max() <= ULP * ref.abs().max().item()
     assert torch.equal(outs[0], outs[1])  # partial tiles are summed in rank order: deterministic
 
 
 def test_conv_splitk_rejects_bad_split_count():
-    x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
-    w = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
+    x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=ACT)
+    w = torch.zeros(64, 64, device="cuda", dtype=ACT)
     b = torch.zeros(64, device="cuda")
-    out = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
-    rc = _abi.lib().mpx_conv2d_bf16_splitk(_abi.ptr(x), 1, 8, 8, 64, _abi.ptr(w), _abi.ptr(b), 64, 1, 1, 1, 0, 0, 0, 0, 0, None,
+    out = torch.zeros(1, 8, 8, 64, device="cuda", dtype=ACT)
+    rc = _abi.lib().mpx_conv2d_splitk(_abi.ptr(x), 1, 8, 8, 64, _abi.ptr(w), _abi.ptr(b), 64, 1, 1, 1, 0, 0, 0, 0, 0, None,
                                            _abi.ptr(out), 64, 3, _abi.stream_ptr())
     assert rc != 0 and b"splits" in _abi.lib().mpx_last_error()
 
 
 def test_conv_rejects_bad_arguments():
-    x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
-    w = torch.zeros(64, 48, device="cuda", dtype=torch.bfloat16)
+    x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=ACT)
+    w = torch.zeros(64, 48, device="cuda", dtype=ACT)
     b = torch.zeros(64, device="cuda")
-    out = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
-    rc = _abi.lib().mpx_conv2d_bf16(_abi.ptr(x), 1, 8, 8, 48, _abi.ptr(w), _abi.ptr(b), 64, 1, 1, 1, 0, 0, 0, 0, 0, None,
+    out = torch.zeros(1, 8, 8, 64, device="cuda", dtype=ACT)
+    rc = _abi.lib().mpx_conv2d(_abi.ptr(x), 1, 8, 8, 48, _abi.ptr(w), _abi.ptr(b), 64, 1, 1, 1, 0, 0, 0, 0, 0, None,
                                     _abi.ptr(out), 0, 0, _abi.stream_ptr())
     assert rc != 0 and b"multiple of 64" in _abi.lib().mpx_last_error()
 
 
 def test_maxpool_and_tail():
     g = torch.Generator(device="cuda").manual_seed(0)
-    x = torch.randn(3, 30, 40, 64, device="cuda", generator=g).to(torch.bfloat16)
-    out = torch.empty(3, 15, 20, 64, device="cuda", dtype=torch.bfloat16)
-    _abi.check(_abi.lib().mpx_maxpool3x3s2_bf16(_abi.ptr(x), 3, 30, 40, 64, _abi.ptr(out), _abi.stream_ptr()))
+    x = torch.randn(3, 30, 40, 64, device="cuda", generator=g).to(ACT)
+    out = torch.empty(3, 15, 20, 64, device="cuda", dtype=ACT)
+    _abi.check(_abi.lib().mpx_maxpool3x3s2(_abi.ptr(x), 3, 30, 40, 64, _abi.ptr(out), _abi.stream_ptr()))
     ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
     assert torch.equal(out.float(), ref)
-    f = torch.randn(5, 80, 512, device="cuda", generator=g).to(torch.bfloat16)
+    f = torch.randn(5, 80, 512, device="cuda", generator=g).to(ACT)
     W = torch.randn(9, 512, device="cuda", generator=g) * 0.05
     b = torch.randn(9, device="cuda", generator=g)
     o = torch.empty(5, 9, device="cuda")
@@ -160,23 +164,23 @@ def test_resnet34_engine_vs_oracle(cfg_name):
     eng = ResNet34Engine(sd, n_inputs=c, head=head)
     x = helpers._calibration_batch(c, 40, n=5)
     got = eng(x.cuda()).cpu()
-    emu = resnet_ref.forward_bf16_emulated(sd, x.cuda()).cpu()
+    emu = resnet_ref.forward_act16_emulated(sd, x.cuda(), ACT).cpu()
     with torch.no_grad():
         fp32 = resnet_ref.forward(sd, x)
-        bound = resnet_ref.bf16_forward_error_bound(sd, x, eps=2 ** -8)
+        bound = resnet_ref.act16_forward_error_bound(sd, x, dtype=ACT)
     e_emu = (got - emu).abs()
     e_fp = (got - fp32).abs()
     print(f"[{cfg_name}] max|engine-emulated|={e_emu.max():.4g} max|engine-fp32|={e_fp.max():.4g} "
-          f"bound(2^-8)={bound.min():.4g}..{bound.max():.4g} out std={fp32.std():.4g}")
-    assert (e_emu <= 0.25 * bound + 1e-3).all()   # same quantisation points: only accumulation order differs
-    assert (e_fp <= bound + 1e-3).all()           # stated bf16-vs-fp32 tolerance (resnet_ref.bf16_forward_error_bound)
+          f"bound={bound.min():.4g}..{bound.max():.4g} out std={fp32.std():.4g}")
+    assert (e_emu <= 0.5 * bound + 1e-4).all()   # same quantisation points: only accumulation order differs
+    assert (e_fp <= bound + 1e-4).all()           # stated 16-bit-vs-fp32 tolerance (resnet_ref.act16_forward_error_bound)
     # small input as well (stem / pooling edge handling): 64x96
     x2 = helpers._calibration_batch(c, 41, n=3, h=64, w=96)
     got2 = eng(x2.cuda()).cpu()
-    emu2 = resnet_ref.forward_bf16_emulated(sd, x2.cuda()).cpu()
+    emu2 = resnet_ref.forward_act16_emulated(sd, x2.cuda(), ACT).cpu()
     with torch.no_grad():
-        bound2 = resnet_ref.bf16_forward_error_bound(sd, x2, eps=2 ** -8)
-    assert ((got2 - emu2).abs() <= 0.25 * bound2 + 1e-3).all()
+        bound2 = resnet_ref.act16_forward_error_bound(sd, x2, dtype=ACT)
+    assert ((got2 - emu2).abs() <= 0.5 * bound2 + 1e-4).all()
 
 
 WINDOW_CASES = [
@@ -194,16 +198,16 @@ def test_window_and_im2col_kernels_agree(case):
     and each is within the stated tolerance of the fp32 reference."""
     name, n, h, w, r, s, pads, relu, use_res = case
     g = torch.Generator(device="cuda").manual_seed(7)
-    x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(64, r, s, 64, device="cuda", generator=g) / (r * s * 64) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(64, r, s, 64, device="cuda", generator=g) / (r * s * 64) ** 0.5).to(ACT)
     bias = torch.randn(64, device="cuda", generator=g)
-    res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
         for mode in (1, 0):
             _abi.lib().mpx_conv_set_mode(mode)
-            out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, s, 1,
+            out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
+            _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, s, 1,
                                                   pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(out), 0, 0,
                                                   _abi.stream_ptr()))
             torch.cuda.synchronize()
@@ -211,7 +215,7 @@ def test_window_and_im2col_kernels_agree(case):
     finally:
         _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, 1, pads, relu, res)
-    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    tol = ULP * ref.abs().max().item() + ATOL
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
     assert (outs[0] - outs[1]).abs().max() <= tol
 
@@ -239,10 +243,10 @@ def test_small_batch_splitk_network_matches_unsplit(cfg_name, n):
         lib.mpx_net_set_graphs(1)
         lib.mpx_conv_set_mode(DEFAULT_CONV_MODE)
     with torch.no_grad():
-        bound = resnet_ref.bf16_forward_error_bound(sd, helpers._calibration_batch(c, 5, n=n), eps=2 ** -8).cuda()
+        bound = resnet_ref.act16_forward_error_bound(sd, helpers._calibration_batch(c, 5, n=n), dtype=ACT).cuda()
     for o in split + graphed:
         assert torch.isfinite(o).all()
-        assert ((o - unsplit).abs() <= 0.1 * bound + 1e-6).all(), ((o - unsplit).abs().max(), bound.min())
+        assert ((o - unsplit).abs() <= 0.5 * bound + 1e-6).all(), ((o - unsplit).abs().max(), bound.min())
         assert torch.equal(o, split[0])  # deterministic
 
 
@@ -262,16 +266,16 @@ def test_layer2_window_kernel_agrees_with_im2col_and_torch(case):
     tiles, two MMA issuers) vs the im2col kernel (mode bit 8 = 256 disables it) and fp32 torch."""
     name, n, h, w, relu, use_res, max_ctas = case
     g = torch.Generator(device="cuda").manual_seed(23)
-    x = torch.randn(n, h, w, 128, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(128, 3, 3, 128, device="cuda", generator=g) / (9 * 128) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, 128, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(128, 3, 3, 128, device="cuda", generator=g) / (9 * 128) ** 0.5).to(ACT)
     bias = torch.randn(128, device="cuda", generator=g)
-    res = torch.randn(n, h, w, 128, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(n, h, w, 128, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
         for mode in (DEFAULT_CONV_MODE, DEFAULT_CONV_MODE | 256):
             _abi.lib().mpx_conv_set_mode(mode)
-            out = torch.full((n, h, w, 128), float("nan"), device="cuda", dtype=torch.bfloat16)
-            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 128, _abi.ptr(wt.view(128, -1)), _abi.ptr(bias), 128, 3, 3,
+            out = torch.full((n, h, w, 128), float("nan"), device="cuda", dtype=ACT)
+            _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 128, _abi.ptr(wt.view(128, -1)), _abi.ptr(bias), 128, 3, 3,
                                                   1, 1, 1, 1, 1, int(relu), _abi.ptr(res), _abi.ptr(out), 0, max_ctas,
                                                   _abi.stream_ptr()))
             torch.cuda.synchronize()
@@ -279,11 +283,11 @@ def test_layer2_window_kernel_agrees_with_im2col_and_torch(case):
     finally:
         _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, 1, (1, 1, 1, 1), relu, res)
-    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    tol = ULP * ref.abs().max().item() + ATOL
     assert not torch.isnan(outs[0]).any()
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
     # different K order (panel-major) than the im2col kernel: equal up to one bf16 rounding
-    assert (outs[0] - outs[1]).abs().max() <= 2 ** -7 * ref.abs().max().item()
+    assert (outs[0] - outs[1]).abs().max() <= ULP * ref.abs().max().item()
 
 
 def test_graph_replay_equals_eager_launches():
@@ -318,18 +322,18 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
     the single-CTA kernel."""
     name, n, h, w, cin, cout, r, s, stride, pads, relu, use_res = case
     g = torch.Generator(device="cuda").manual_seed(11)
-    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(cout, r, s, cin, device="cuda", generator=g) / (r * s * cin) ** 0.5).to(ACT)
     bias = torch.randn(cout, device="cuda", generator=g)
     p = (h + pads[0] + pads[2] - r) // stride + 1
     q = (w + pads[1] + pads[3] - s) // stride + 1
-    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
         for mode in (7, 1):
             _abi.lib().mpx_conv_set_mode(mode)
-            out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
-            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
+            out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=ACT)
+            _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
                                                   stride, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res),
                                                   _abi.ptr(out), 0, 0, _abi.stream_ptr()))
             torch.cuda.synchronize()
@@ -337,7 +341,7 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
     finally:
         _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, stride, pads, relu, res)
-    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    tol = ULP * ref.abs().max().item() + ATOL
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
     assert torch.equal(outs[0], outs[1])  # same products, same K order, fp32 accumulation in TMEM
 
@@ -372,18 +376,18 @@ def test_experimental_pair_window_kernel(case):
     conv_window2q_kernel (bit 14 = 16384: the layer2 window kernel on CTA pairs) vs the default kernels and fp32 torch."""
     name, n, h, w, cin, cout, relu, use_res, max_ctas, bit = case
     g = torch.Generator(device="cuda").manual_seed(29)
-    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(ACT)
     bias = torch.randn(cout, device="cuda", generator=g)
-    res = torch.randn(n, h, w, cout, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(n, h, w, cout, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
         # bit 16 (65536): whole residual row requested before the accumulator wait (pair kernels of bits 14 / 15 only)
         modes = [DEFAULT_CONV_MODE | bit] + ([DEFAULT_CONV_MODE | bit | 65536] if use_res and bit == 16384 else [])
         for mode in modes + [DEFAULT_CONV_MODE]:
             _abi.lib().mpx_conv_set_mode(mode)
-            out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
-            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, 3,
+            out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=ACT)
+            _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, 3,
                                                   3, 1, 1, 1, 1, 1, int(relu), _abi.ptr(res), _abi.ptr(out), 0, max_ctas,
                                                   _abi.stream_ptr()))
             torch.cuda.synchronize()
@@ -391,11 +395,11 @@ def test_experimental_pair_window_kernel(case):
     finally:
         _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, 1, (1, 1, 1, 1), relu, res)
-    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    tol = ULP * ref.abs().max().item() + ATOL
     for o in outs:
         assert not torch.isnan(o).any()
         assert (o - ref).abs().max() <= tol
-        assert (o - outs[-1]).abs().max() <= 2 ** -7 * ref.abs().max().item()
+        assert (o - outs[-1]).abs().max() <= ULP * ref.abs().max().item()
     if len(outs) == 3:
         assert torch.equal(outs[0], outs[1])  # the residual preload changes when the loads are issued, not the arithmetic
 
@@ -405,15 +409,15 @@ def test_experimental_window_observers_arrive():
     """Window kernel with refills gated on every issuer's arrival (mode bit 11 = 2048): same results as the default."""
     g = torch.Generator(device="cuda").manual_seed(31)
     for (n, h, w, r, pads) in ((7, 60, 80, 3, (1, 1, 1, 1)), (3, 120, 160, 4, (2, 2, 1, 1))):
-        x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16)
-        wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(torch.bfloat16)
+        x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT)
+        wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(ACT)
         bias = torch.randn(64, device="cuda", generator=g)
         outs = []
         try:
             for mode in (DEFAULT_CONV_MODE | 2048, DEFAULT_CONV_MODE):
                 _abi.lib().mpx_conv_set_mode(mode)
-                out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-                _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
+                out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
+                _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
                                                       1, pads[0], pads[1], pads[2], pads[3], 1, None, _abi.ptr(out), 0, 5,
                                                       _abi.stream_ptr()))
                 torch.cuda.synchronize()
@@ -441,17 +445,17 @@ def test_experimental_pair_window64_kernel(case):
     fp32 torch."""
     name, n, h, w, r, pads, relu, use_res, max_ctas = case
     g = torch.Generator(device="cuda").manual_seed(37)
-    x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16)
-    wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT)
+    wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(ACT)
     bias = torch.randn(64, device="cuda", generator=g)
-    res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
         modes = [DEFAULT_CONV_MODE | 32768] + ([DEFAULT_CONV_MODE | 32768 | 65536] if use_res else [])
         for mode in modes + [DEFAULT_CONV_MODE]:
             _abi.lib().mpx_conv_set_mode(mode)
-            out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-            _abi.check(_abi.lib().mpx_conv2d_bf16(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
+            out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
+            _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
                                                   1, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(out),
                                                   0, max_ctas, _abi.stream_ptr()))
             torch.cuda.synchronize()
@@ -459,11 +463,11 @@ def test_experimental_pair_window64_kernel(case):
     finally:
         _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
     ref = _conv_ref(x, wt, bias, 1, pads, relu, res)
-    tol = 2 ** -7 * ref.abs().max().item() + 1e-2
+    tol = ULP * ref.abs().max().item() + ATOL
     for o in outs:
         assert not torch.isnan(o).any()
         assert (o - ref).abs().max() <= tol
-        assert (o - outs[-1]).abs().max() <= 2 ** -7 * ref.abs().max().item()
+        assert (o - outs[-1]).abs().max() <= ULP * ref.abs().max().item()
     print(name, "bit-equal to the single-CTA window kernel:", torch.equal(outs[0], outs[-1]))
     if len(outs) == 3:
         assert torch.equal(outs[0], outs[1])  # residual preload: same arithmetic
