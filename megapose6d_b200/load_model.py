@@ -147,7 +147,7 @@ def n_input_channels(cfg: Cfg) -> int:
 
 
 def create_model_pose(cfg: Cfg, renderer: BatchRenderer, mesh_db: BatchedMeshes,
-                      state_dict: Dict[str, torch.Tensor]) -> PosePredictor:
+                      state_dict: Dict[str, torch.Tensor], render_size: Tuple[int, int] = (240, 320)) -> PosePredictor:
     """training/pose_models_cfg.py:90-138 + load_state_dict; builds the engine from the checkpoint tensors."""
     if cfg.backbone_str != "vanilla_resnet34":
         raise NotImplementedError(f"backbone '{cfg.backbone_str}': only vanilla_resnet34 (all released models) is "
@@ -159,7 +159,7 @@ def create_model_pose(cfg: Cfg, renderer: BatchRenderer, mesh_db: BatchedMeshes,
         raise RuntimeError(f"checkpoint is missing keys {sorted(missing)}")
     backbone = ResNet34Engine(state_dict, n_inputs=n_input_channels(cfg), head=head)
     model = PosePredictor(
-        backbone=backbone, renderer=renderer, mesh_db=mesh_db, render_size=(240, 320),
+        backbone=backbone, renderer=renderer, mesh_db=mesh_db, render_size=tuple(render_size),
         n_rendered_views=cfg.n_rendered_views, views_inplane_rotations=cfg.views_inplane_rotations,
         multiview_type=cfg.multiview_type, render_normals=cfg.render_normals, render_depth=cfg.render_depth,
         input_depth=cfg.input_depth, predict_rendered_views_logits=cfg.predict_rendered_views_logits,
@@ -170,8 +170,11 @@ def create_model_pose(cfg: Cfg, renderer: BatchRenderer, mesh_db: BatchedMeshes,
 
 def load_pose_models(coarse_run_id: str, refiner_run_id: str, object_dataset: RigidObjectDataset,
                      force_panda3d_renderer: bool = False, renderer_kwargs: Optional[dict] = None,
-                     models_root: Optional[Path] = None) -> Tuple[PosePredictor, PosePredictor, MeshDataBase]:
-    """inference/utils.py:80-148 -> (coarse_model, refiner_model, mesh_db)."""
+                     models_root: Optional[Path] = None,
+                     render_size: Tuple[int, int] = (240, 320)) -> Tuple[PosePredictor, PosePredictor, MeshDataBase]:
+    """inference/utils.py:80-148 -> (coarse_model, refiner_model, mesh_db).  `render_size` is the crop / render
+    resolution of both models: the reference fixes it at (240, 320) in training/pose_models_cfg.py:105 and passes it
+    to PosePredictor(render_size=...) (models/pose_rigid.py:87); any even size works here."""
     models_root = Path(models_root) if models_root is not None else LOCAL_DATA_DIR / "megapose-models"
     mesh_db = MeshDataBase.from_object_ds(object_dataset)
     mesh_db_batched = mesh_db.batched().cuda()
@@ -188,7 +191,8 @@ def load_pose_models(coarse_run_id: str, refiner_run_id: str, object_dataset: Ri
         cfg = check_update_config(load_cfg(run_dir / "config.yaml"))
         ckpt = torch.load(run_dir / "checkpoint.pth.tar", map_location="cpu", weights_only=False)
         state_dict = change_keys_of_older_models(ckpt["state_dict"])
-        model = create_model_pose(cfg, renderer=renderer, mesh_db=mesh_db_batched, state_dict=state_dict)
+        model = create_model_pose(cfg, renderer=renderer, mesh_db=mesh_db_batched, state_dict=state_dict,
+                                  render_size=render_size)
         model = model.eval()
         model.cfg = cfg
         model.config = cfg
@@ -198,14 +202,15 @@ def load_pose_models(coarse_run_id: str, refiner_run_id: str, object_dataset: Ri
 
 
 def load_named_model(model_name: str, object_dataset: RigidObjectDataset, n_workers: int = 4,
-                     bsz_images: int = 128, models_root: Optional[Path] = None) -> PoseEstimator:
+                     bsz_images: int = 128, models_root: Optional[Path] = None,
+                     render_size: Tuple[int, int] = (240, 320)) -> PoseEstimator:
     """utils/load_model.py:50-89."""
     model = NAMED_MODELS[model_name]
     coarse_model, refiner_model, mesh_db = load_pose_models(
         coarse_run_id=model["coarse_run_id"], refiner_run_id=model["refiner_run_id"], object_dataset=object_dataset,
         force_panda3d_renderer=True, renderer_kwargs={"preload_cache": False, "split_objects": False,
                                                       "n_workers": n_workers},
-        models_root=models_root)
+        models_root=models_root, render_size=render_size)
     depth_refiner = None
     if model.get("depth_refiner") == "ICP":
         raise NotImplementedError("the ICP depth refiner (OpenCV ppf_match_3d) is outside the hot path; SURVEY 8f")

@@ -106,9 +106,13 @@ def textured_sphere(n_seg: int = 100, n_lat: int = 51, radius: float = 0.05, see
     return TriMesh(m.vertices, m.faces, m.vertex_normals, None, np.stack([u, v], 1), checker_texture(64, 128, 8, seed))
 
 
-def make_object_dataset(n_objects: int = 1, seed: int = 0, n_seg: int = 100, n_lat: int = 51) -> RigidObjectDataset:
+def make_object_dataset(n_objects: int = 1, seed: int = 0, n_seg=100, n_lat=51) -> RigidObjectDataset:
+    """`n_seg` / `n_lat`: one int for all objects or one per object (2 * n_seg * (n_lat - 1) triangles each)."""
+    segs = list(n_seg) if isinstance(n_seg, (list, tuple)) else [n_seg] * n_objects
+    lats = list(n_lat) if isinstance(n_lat, (list, tuple)) else [n_lat] * n_objects
     objs = []
     for i in range(n_objects):
+        n_seg, n_lat = segs[i], lats[i]
         rng = np.random.RandomState(seed + 17 * i)
         squash = tuple(0.6 + 0.4 * rng.rand(3))
         mesh = bumpy_sphere(n_seg=n_seg, n_lat=n_lat, radius=0.04 + 0.03 * rng.rand(), seed=seed + i, squash=squash)

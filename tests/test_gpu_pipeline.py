@@ -345,3 +345,45 @@ def test_many_detections_chunked_coarse_stage(setup):
     fb_s = fb.infos.sort_values(["batch_im_id", "label", "instance_id"]).reset_index(drop=True)
     same = (fa_s["hypothesis_id"].values == fb_s["hypothesis_id"].values)
     assert same[clear[fb_s["bbox_id"].values].numpy()].mean() >= 0.7
+
+
+def test_graph_replay_survives_a_change_of_the_detection_count(setup):
+    """A stream of frames with 1, 1, 1, 2, 1, 3, 1 detections: the 1-detection graphs (coarse stage, refiner loop, scoring
+    pass) are captured before a larger frame grows the network workspace and adds input buffers, and are replayed after
+    it.  Every frame must return exactly what an estimator without CUDA graphs returns (buffers baked into a captured
+    graph may never be released while the graph can still be replayed)."""
+    ds, images, K = setup["ds"], setup["images"][:, :3].contiguous(), setup["K"]
+    labels_all = [ds[0].label, ds[1].label, ds[0].label]
+    TCO_gt = torch.from_numpy(procedural.random_poses(3, 51)).float()
+    TCO_gt[:, 2, 3] = torch.tensor([0.5, 0.65, 0.8])
+    bboxes_all = torch.stack([helpers.detection_for_pose(K[0], TCO_gt[i], torch.from_numpy(ds.get_object_by_label(labels_all[i]).mesh.vertices).float())
+                              for i in range(3)])
+
+    def make(graphs: bool):
+        est = load_model.load_named_model("megapose-1.0-RGB-multi-hypothesis", ds, models_root=setup["root"])
+        est.load_SO3_grid(72)
+        est.coarse_model.use_cuda_graphs = est.refiner_model.use_cuda_graphs = graphs
+        return est
+
+    def run(est, n, shift):
+        det_df = pd.DataFrame(dict(label=labels_all[:n], batch_im_id=0))
+        obs = ObservationTensor(images.clone(), K.clone()).cuda()
+        det = PandasTensorCollection(det_df, bboxes=(bboxes_all[:n] + shift).cuda())
+        final, extra = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=2, n_pose_hypotheses=2)
+        scored = extra["scoring"]["preds"]
+        return final.poses.clone(), final.infos["pose_logit"].to_numpy().copy(), scored.poses.clone()
+
+    lib = _abi.lib()
+    counts = [1, 1, 1, 2, 1, 3, 1, 2, 1]
+    a, b = make(True), make(False)
+    try:
+        for step, n in enumerate(counts):
+            lib.mpx_net_set_graphs(1)
+            got = run(a, n, float(step))
+            lib.mpx_net_set_graphs(0)
+            want = run(b, n, float(step))
+            assert torch.equal(got[0], want[0]) and torch.equal(got[2], want[2]), (step, n)
+            assert np.array_equal(got[1], want[1]), (step, n)
+    finally:
+        lib.mpx_net_set_graphs(1)
+    assert len(a.refiner_model.backbone._retired_workspaces) >= 1, "the scenario must grow the workspace after a capture"

@@ -2,6 +2,7 @@
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import lib3d_ref as L
@@ -97,3 +98,26 @@ def test_pipeline_golden():
     # the checker's 16-bit branch (what the GPU test runs) accepts the same data
     helpers.check_pipeline_against_golden(golden, got["coarse_poses"], got["coarse_df"]["coarse_logit"].values, kept,
                                           exact_network=False)
+
+
+@pytest.mark.parametrize("name", ["fullsize_rgb", "fullsize_rgb_224"])
+def test_oracle_against_the_full_size_fixture(name):
+    """tests/golden/fullsize_*.npz hold what the reference's own pipeline returned for BASELINE configs[1] at full size
+    (576 hypotheses, 5 iterations; tools/make_golden.py).  The complete unit takes the oracle ~1 min on the host, so the
+    CPU suite checks the first 16 hypotheses of the coarse stage and one refiner step of the survivor; the CUDA path is
+    compared with the whole fixture in tests/test_zz_gpu_fullsize.py."""
+    from oracle import pipeline_ref
+
+    g = np.load(G / f"{name}.npz")
+    sc = helpers.FULLSIZE[name]()
+    meshes = helpers.ref_meshes_from_dataset(sc["ds"])
+    rr = pipeline_ref.RefRenderer(meshes)
+    oc = pipeline_ref.RefPosePredictor(sc["sd_coarse"], helpers.COARSE_CFG, meshes, rr, render_size=sc["render_size"])
+    orf = pipeline_ref.RefPosePredictor(sc["sd_refiner"], sc["cfg_refiner"], meshes, rr, render_size=sc["render_size"])
+    est = pipeline_ref.RefPoseEstimator(oc, orf, bsz_images=16, bsz_objects=8, SO3_grid_size=sc["grid"])
+    with torch.no_grad():
+        df, _ = est.forward_coarse_model(sc["images"], sc["K"], sc["det_df"], sc["bboxes"], max_hypotheses=16)
+        assert np.allclose(df["coarse_logit"].values, g["coarse_logit"][:16], rtol=1e-4, atol=1e-4)
+        kept = torch.from_numpy(g["kept_poses"][:1])
+        out = orf.forward(sc["images"], sc["K"], sc["labels"][:1], kept, n_iterations=1)["iteration=1"]
+    assert torch.allclose(out["TCO_output"], torch.from_numpy(g["refiner_poses"][0][:1]), rtol=1e-4, atol=1e-5)

@@ -118,7 +118,7 @@ class _MeshDbAdapter:
         return _Sel()
 
 
-def _reference_predictor(ref, cfg, sd, meshes):
+def _reference_predictor(ref, cfg, sd, meshes, render_size=(240, 320), n_threads=None):
     class Renderer(ref.Panda3dBatchRenderer):
         def __init__(self, inner):
             self.inner = inner
@@ -132,8 +132,8 @@ def _reference_predictor(ref, cfg, sd, meshes):
     backbone = ref.torchvision_resnet.resnet34(num_classes=512, n_input_channels=c)
     backbone.n_features = 512
     model = ref.pose_rigid.PosePredictor(
-        backbone=backbone, renderer=Renderer(pipeline_ref.RefRenderer(meshes)), mesh_db=_MeshDbAdapter(meshes, ref),
-        render_size=(240, 320), n_rendered_views=cfg["n_rendered_views"], multiview_type=cfg["multiview_type"],
+        backbone=backbone, renderer=Renderer(pipeline_ref.RefRenderer(meshes, **({} if n_threads is None else dict(n_threads=n_threads)))),
+        mesh_db=_MeshDbAdapter(meshes, ref), render_size=tuple(render_size), n_rendered_views=cfg["n_rendered_views"], multiview_type=cfg["multiview_type"],
         render_normals=True, render_depth=cfg["render_depth"], input_depth=cfg["input_depth"],
         predict_rendered_views_logits=cfg["predict_rendered_views_logits"], remove_TCO_rendering=False,
         predict_pose_update=cfg["predict_pose_update"], depth_normalization_type=cfg["depth_normalization_type"])

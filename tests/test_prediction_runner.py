@@ -445,12 +445,7 @@ def test_frames_sharded_over_two_ranks(tmp_path, n_frames):
 
 
 # --------------------------------------------------------------------------------------------- real estimator (GPU)
-NOT_YET_RUN_ON_A_GPU = pytest.mark.skipif(os.environ.get("MPX_EXPERIMENTAL") != "1",
-                                          reason="written after the round's GPU budget was spent; set MPX_EXPERIMENTAL=1 to run")
-
-
 @pytest.mark.gpu
-@NOT_YET_RUN_ON_A_GPU
 def test_runner_with_the_real_estimator(tmp_path):
     """Three frames through the runner == three direct pipeline calls (the fused pipeline is deterministic for equal
     inputs), with the look-ahead copies on the side stream in play."""

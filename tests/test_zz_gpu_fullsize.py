@@ -1,91 +1,142 @@
-"""BASELINE configs[1] at FULL size on the GPU (1 object x 576 SO(3)-grid hypotheses, 5 refiner iterations, scoring) —
-the workload bench.py times — checked through size-independent properties (the CPU oracle needs ~30 s for this size, so it
-is not the checker here; it is the checker at 72 rotations in tests/test_gpu_pipeline.py):
+"""BASELINE configs[1..3] at FULL size on the GPU against what the REAL reference returned for the same inputs.
 
-  * idempotence: first call (eager), second (graph capture) and third (graph replay) return bit-identical results;
-  * host-buffer inputs (pinned memory, copies inside the call) give the same bits as device-resident inputs;
-  * the 576 coarse rows are the 576 grid rotations, one each; the survivor is the arg-max of the coarse logits;
-  * every returned pose is a rigid transform in front of the camera (R^T R = I to 1e-4, det = +1, t_z > 0);
-  * scores are the sigmoid of the logits; the final row is the scored row.
+tests/golden/fullsize_*.npz were written by tools/make_golden.py: the reference's own
+PoseEstimator.run_inference_pipeline (inference/pose_estimator.py:511-641; fp32 on the host, the C rasteriser of
+oracle/raster_ref.c standing in for Panda3D) on the scenarios of workloads/scenes.py:
 
-The file sorts last on purpose: it builds the same estimator as bench.py and allocates the full-size graphs."""
-import tempfile
+  fullsize_rgb      configs[1]: 1 object x 576 hypotheses + 5 refiner iterations + scoring, 240x320 (what bench.py times)
+  fullsize_rgb_224  the same at 224x224 crops / renders (the size BASELINE.json's metric names)
+  fullsize_rgbd32   configs[2]: RGB-D refiner, 32-object batch x 5 refiner iterations (72-rotation coarse grid)
+  fullsize_ycbv21   configs[3]: 21 objects x 576 hypotheses in one frame (12 096 coarse rows)
+
+Asserted, with the fp16-vs-fp32 tolerances stated here:
+  * every coarse logit within LOGIT_TOL_STD standard deviations of the reference's logits (max) and LOGIT_RMS_STD (rms);
+  * per detection the same surviving hypothesis as the reference -- or, where the reference's own margin between its
+    best candidates is inside twice the observed noise, one of those near-tied candidates (counted and bounded);
+  * for detections with the same survivor: the pose after every refiner iteration and the final pose within
+    ROT_TOL_DEG / TRANS_TOL_MM of the reference's, the scoring logit within the logit tolerance.
+Plus the size-independent properties of round 1 (idempotence over eager / capture / replay, host-resident inputs, rigid
+poses, score = sigmoid(logit)).  The file sorts last on purpose: it allocates the full-size buffers and graphs."""
 from pathlib import Path
 
 import numpy as np
 import pytest
 import torch
 
+from workloads import scenes
+
 pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+LOGIT_TOL_STD = 0.12   # max |logit error| / std of the reference's logits (observed with fp16: ~0.05-0.08)
+LOGIT_RMS_STD = 0.04   # rms
+ROT_TOL_DEG = 0.5
+TRANS_TOL_MM = 1.0
 
 
-@pytest.fixture(scope="module")
-def workload():
-    import bench
-    from megapose6d_b200 import load_model
-
-    ds, images, K, det_df, bboxes, sds = bench.build_scene(1)
-    with tempfile.TemporaryDirectory() as tmp:
-        for run_id, sd in sds.items():
-            load_model.write_run(tmp, run_id, sd)
-        est = load_model.load_named_model("megapose-1.0-RGB", ds, models_root=Path(tmp))
-    return dict(est=est, images=images, K=K, det_df=det_df, bboxes=bboxes, n_iters=bench.N_REFINER_ITERS, m=bench.M_GRID)
-
-
-def _run(w, pinned=False):
+def _run(est, sc, pinned=False):
     from megapose6d_b200.tensor_collection import PandasTensorCollection
     from megapose6d_b200.types import ObservationTensor
 
     if pinned:
-        images, K, bboxes = (t.pin_memory().cuda(non_blocking=True) for t in (w["images"], w["K"], w["bboxes"]))
+        images, K, bboxes = (t.pin_memory().cuda(non_blocking=True) for t in (sc["images"], sc["K"], sc["bboxes"]))
     else:
-        images, K, bboxes = w["images"].cuda(), w["K"].cuda(), w["bboxes"].cuda()
-    det = PandasTensorCollection(w["det_df"].copy(), bboxes=bboxes)
-    final, extra = w["est"].run_inference_pipeline(ObservationTensor(images, K), detections=det,
-                                                    n_refiner_iterations=w["n_iters"], n_pose_hypotheses=1)
+        images, K, bboxes = sc["images"].cuda(), sc["K"].cuda(), sc["bboxes"].cuda()
+    det = PandasTensorCollection(sc["det_df"].copy(), bboxes=bboxes)
+    final, extra = est.run_inference_pipeline(ObservationTensor(images, K), detections=det,
+                                              n_refiner_iterations=sc["n_refiner_iterations"],
+                                              n_pose_hypotheses=sc["n_pose_hypotheses"])
     torch.cuda.synchronize()
     return final, extra
 
 
+def _pose_err(a: torch.Tensor, b: torch.Tensor):
+    """geodesic rotation error [deg] and translation error [mm] between batches of 4x4 poses."""
+    a, b = a.double().cpu(), b.double().cpu()
+    dR = a[:, :3, :3].transpose(1, 2) @ b[:, :3, :3]
+    cos = ((dR.diagonal(dim1=1, dim2=2).sum(-1) - 1) / 2).clamp(-1, 1)
+    return torch.rad2deg(torch.acos(cos)), (a[:, :3, 3] - b[:, :3, 3]).norm(dim=-1) * 1000.0
+
+
 def _rigid(poses):
-    poses = poses.double().cpu()
-    R, t = poses[:, :3, :3], poses[:, :3, 3]
+    R = poses[:, :3, :3].double().cpu()
     eye = torch.eye(3, dtype=torch.float64).expand_as(R)
     assert torch.allclose(R.transpose(1, 2) @ R, eye, atol=1e-4), "rotation block is not orthonormal"
     assert torch.allclose(torch.linalg.det(R), torch.ones(len(R), dtype=torch.float64), atol=1e-4)
-    assert torch.equal(poses[:, 3], torch.tensor([0.0, 0, 0, 1], dtype=torch.float64).expand(len(poses), 4))
-    assert (t[:, 2] > 0).all(), "object behind the camera"
+    assert (poses[:, 2, 3] > 0).all() and torch.isfinite(poses).all()
 
 
-def test_full_size_pipeline_properties(workload):
-    w = workload
-    m = w["m"]
-    runs = [_run(w) for _ in range(3)] + [_run(w, pinned=True)]
-    final0, extra0 = runs[0]
-    coarse0 = extra0["coarse"]["preds"]
-    # shapes and bookkeeping of the reference's outputs
-    assert len(final0) == 1 and len(coarse0) == m and len(extra0["coarse_filter"]["preds"]) == 1
-    assert sorted(coarse0.infos["hypothesis_id"].tolist()) == list(range(m))
-    assert set(extra0["refiner_all_hypotheses"]["preds"].keys()) == {f"iteration={n + 1}" for n in range(w["n_iters"])}
-    logits = coarse0.infos["coarse_logit"].to_numpy()
-    assert np.isfinite(logits).all() and logits.std() > 0
-    kept = extra0["coarse_filter"]["preds"].infos
-    assert int(kept["hypothesis_id"].iloc[0]) == int(coarse0.infos["hypothesis_id"].iloc[int(np.argmax(logits))])
-    assert np.allclose(coarse0.infos["coarse_score"].to_numpy(), 1.0 / (1.0 + np.exp(-logits.astype(np.float64))), atol=1e-6)
-    # rigid transforms everywhere
-    _rigid(coarse0.poses)
-    for it in extra0["refiner_all_hypotheses"]["preds"].values():
-        _rigid(it.poses)
-    _rigid(final0.poses)
-    # the final row is the scored row of the surviving hypothesis
-    scored = extra0["scoring"]["preds"]
-    assert torch.equal(final0.poses, scored.poses) and final0.infos["pose_logit"].iloc[0] == scored.infos["pose_logit"].iloc[0]
-    pl = float(final0.infos["pose_logit"].iloc[0])
-    assert abs(float(final0.infos["pose_score"].iloc[0]) - 1.0 / (1.0 + np.exp(-pl))) < 1e-6
-    # idempotence over eager / capture / replay, and host-resident inputs
-    for final, extra in runs[1:]:
-        assert torch.equal(final.poses, final0.poses)
-        assert np.array_equal(extra["coarse"]["preds"].infos["coarse_logit"].to_numpy(), logits)
-        assert torch.equal(extra["coarse"]["preds"].poses, coarse0.poses)
-        assert final.infos["pose_logit"].iloc[0] == final0.infos["pose_logit"].iloc[0]
-        assert final.infos["hypothesis_id"].iloc[0] == final0.infos["hypothesis_id"].iloc[0]
+@pytest.mark.parametrize("name", list(scenes.FULLSIZE))
+def test_full_size_pipeline_matches_the_reference(name):
+    path = GOLDEN / f"{name}.npz"
+    if not path.exists():
+        pytest.skip(f"{path.name} has not been generated (tools/make_golden.py {name})")
+    g = np.load(path)
+    sc = scenes.FULLSIZE[name]()
+    est = scenes.build_estimator(sc)
+    B, M = len(sc["labels"]), sc["grid"]
+    runs = [_run(est, sc) for _ in range(3)]  # eager, graph capture, graph replay
+    final, extra = runs[-1]
+
+    # ---- size-independent properties
+    for f, _ in runs[:-1]:
+        assert torch.equal(f.poses, final.poses) and f.infos["pose_logit"].tolist() == final.infos["pose_logit"].tolist()
+    fp, _ = _run(est, sc, pinned=True)
+    assert torch.equal(fp.poses, final.poses)
+    coarse = extra["coarse"]["preds"]
+    assert len(coarse) == B * M and coarse.infos["hypothesis_id"].tolist() == list(range(M)) * B
+    _rigid(coarse.poses), _rigid(final.poses)
+    logits = coarse.infos["coarse_logit"].to_numpy().astype(np.float64)
+    assert np.allclose(coarse.infos["coarse_score"].to_numpy(), 1.0 / (1.0 + np.exp(-logits)), atol=1e-6)
+
+    # ---- coarse logits against the reference's
+    want = g["coarse_logit"].astype(np.float64)
+    assert np.array_equal(g["coarse_hypothesis"], coarse.infos["hypothesis_id"].to_numpy())
+    err = np.abs(logits - want)
+    std = want.std()
+    print(f"[{name}] coarse logits: max err {err.max():.4f} = {err.max() / std:.3f} std, rms {np.sqrt((err ** 2).mean()):.4f} "
+          f"= {np.sqrt((err ** 2).mean()) / std:.3f} std (reference std {std:.3f}, {B * M} rows)")
+    assert err.max() <= LOGIT_TOL_STD * std and np.sqrt((err ** 2).mean()) <= LOGIT_RMS_STD * std
+
+    # ---- survivors
+    kept = extra["coarse_filter"]["preds"].infos
+    noise = 2.0 * err.max()
+    same, near_tie = [], 0
+    for det in range(B):
+        w = want[det * M:(det + 1) * M]
+        got_h = int(kept[kept["bbox_id"] == det]["hypothesis_id"].iloc[0])
+        want_h = int(g["kept_hypothesis"][g["kept_bbox_id"] == det][0])
+        if got_h == want_h:
+            same.append(det)
+        else:
+            assert w[want_h] - w[got_h] <= noise, (det, got_h, want_h, w[want_h] - w[got_h], noise)
+            near_tie += 1
+    print(f"[{name}] survivors: {len(same)}/{B} identical to the reference's, {near_tie} near-ties inside {noise:.3f}")
+    assert near_tie <= max(1, B // 8)
+
+    # ---- refiner iterations, scoring logit and final pose of the detections with the reference's survivor
+    preds = extra["refiner_all_hypotheses"]["preds"]
+    n_it = sc["n_refiner_iterations"]
+    rows_g = [int(np.flatnonzero(g["kept_bbox_id"] == det)[0]) for det in same]
+    rows_o = [int(np.flatnonzero(kept["bbox_id"].to_numpy() == det)[0]) for det in same]
+    worst = (0.0, 0.0)
+    for it in range(n_it):
+        p = preds[f"iteration={it + 1}"].poses[rows_o]
+        rot, tr = _pose_err(p, torch.from_numpy(g["refiner_poses"][it][rows_g]))
+        print(f"[{name}] refiner iteration {it + 1}: max rotation error {rot.max():.4f} deg, max translation error {tr.max():.4f} mm")
+        worst = (max(worst[0], rot.max().item()), max(worst[1], tr.max().item()))
+    assert worst[0] <= ROT_TOL_DEG and worst[1] <= TRANS_TOL_MM, worst
+    scored = extra["scoring"]["preds"].infos
+    sl = scored["pose_logit"].to_numpy().astype(np.float64)[rows_o]
+    serr = np.abs(sl - g["scored_pose_logit"].astype(np.float64)[rows_g])
+    print(f"[{name}] scoring logits: max err {serr.max():.4f}")
+    assert serr.max() <= 2 * LOGIT_TOL_STD * std  # refined poses differ by the pose tolerance above on top of the network's
+    labels_final = final.infos["label"].tolist()
+    for det in same:
+        lab, inst = sc["det_df"]["label"].iloc[det], sc["det_df"]["instance_id"].iloc[det]
+        i_o = [i for i, (l, n) in enumerate(zip(labels_final, final.infos["instance_id"])) if l == lab and n == inst][0]
+        cand = np.flatnonzero(g["final_label"] == lab)
+        i_g = int(cand[list(sc["det_df"][sc["det_df"]["label"] == lab]["instance_id"]).index(inst)]) if len(cand) > 1 else int(cand[0])
+        rot, tr = _pose_err(final.poses[i_o:i_o + 1], torch.from_numpy(g["final_poses"][i_g:i_g + 1]))
+        assert rot.item() <= ROT_TOL_DEG and tr.item() <= TRANS_TOL_MM, (det, rot.item(), tr.item())
+        assert int(final.infos["hypothesis_id"].iloc[i_o]) == int(g["final_hypothesis"][i_g])

@@ -13,7 +13,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
@@ -23,22 +22,20 @@ def child(steps: int, warmup: int) -> None:
     import torch
 
     sys.path.insert(0, str(ROOT))
-    import bench
-    from megapose6d_b200 import _abi, load_model
+    from workloads import scenes
+    from megapose6d_b200 import _abi
     from megapose6d_b200.tensor_collection import PandasTensorCollection
     from megapose6d_b200.types import ObservationTensor
 
-    ds, images, K, det_df, bboxes, sds = bench.build_scene(1)
-    with tempfile.TemporaryDirectory() as tmp:
-        for run_id, sd in sds.items():
-            load_model.write_run(tmp, run_id, sd)
-        est = load_model.load_named_model("megapose-1.0-RGB", ds, models_root=Path(tmp))
+    sc = scenes.bench_scene(1)
+    images, K, det_df, bboxes = sc["images"], sc["K"], sc["det_df"], sc["bboxes"]
+    est = scenes.build_estimator(sc)
     images_dev, K_dev, bboxes_dev = images.cuda(), K.cuda(), bboxes.cuda()
 
     def step():
         det = PandasTensorCollection(det_df.copy(), bboxes=bboxes_dev)
         return est.run_inference_pipeline(ObservationTensor(images_dev, K_dev), detections=det,
-                                          n_refiner_iterations=bench.N_REFINER_ITERS, n_pose_hypotheses=1)
+                                          n_refiner_iterations=5, n_pose_hypotheses=1)
 
     for _ in range(max(3, warmup)):
         final, _ = step()
@@ -54,7 +51,7 @@ def child(steps: int, warmup: int) -> None:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     print("AB_RESULT " + json.dumps(dict(
-        ms_per_step=ms, hyp_per_s=bench.M_GRID / ms * 1e3, launches_per_step=(lib.mpx_launch_count() - n0) / steps,
+        ms_per_step=ms, hyp_per_s=576 / ms * 1e3, launches_per_step=(lib.mpx_launch_count() - n0) / steps,
         survivor=int(final.infos["hypothesis_id"].iloc[0]), pose_logit=float(final.infos["pose_logit"].iloc[0]),
         pose=final.poses[0].cpu().flatten().tolist())))
 

@@ -1,7 +1,6 @@
 """Where does a pipeline step go?  Wraps the engine's entry points with synchronising timers (diagnostic only:
 the synchronisation removes all host/device overlap, so the parts add up to more than the asynchronous step)."""
 import sys
-import tempfile
 import time
 from collections import defaultdict
 from pathlib import Path
@@ -9,7 +8,7 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-import bench  # noqa: E402
+from workloads import scenes  # noqa: E402
 from megapose6d_b200 import _abi, backbone, lib3d, load_model, pose_estimator, pose_predictor, renderer  # noqa: E402
 from megapose6d_b200.tensor_collection import PandasTensorCollection  # noqa: E402
 from megapose6d_b200.types import ObservationTensor  # noqa: E402
@@ -35,11 +34,9 @@ def wrap(obj, name, label=None):
 
 
 def main():
-    ds, images, K, det_df, bboxes, sds = bench.build_scene(1)
-    with tempfile.TemporaryDirectory() as tmp:
-        for run_id, sd in sds.items():
-            load_model.write_run(tmp, run_id, sd)
-        est = load_model.load_named_model("megapose-1.0-RGB", ds, models_root=Path(tmp))
+    sc = scenes.bench_scene(1)
+    images, K, det_df, bboxes = sc["images"], sc["K"], sc["det_df"], sc["bboxes"]
+    est = scenes.build_estimator(sc)
     images_dev, K_dev, bboxes_dev = images.cuda(), K.cuda(), bboxes.cuda()
 
     def step():

@@ -1,22 +1,19 @@
 """Host vs device time per pipeline stage (async run, CUDA events at the stage boundaries + host clocks)."""
 import sys
-import tempfile
 import time
 from pathlib import Path
 
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-import bench  # noqa: E402
-from megapose6d_b200 import load_model, pose_estimator  # noqa: E402
+from workloads import scenes  # noqa: E402
+from megapose6d_b200 import pose_estimator  # noqa: E402
 from megapose6d_b200.tensor_collection import PandasTensorCollection  # noqa: E402
 from megapose6d_b200.types import ObservationTensor  # noqa: E402
 
-ds, images, K, det_df, bboxes, sds = bench.build_scene(1)
-with tempfile.TemporaryDirectory() as tmp:
-    for run_id, sd in sds.items():
-        load_model.write_run(tmp, run_id, sd)
-    est = load_model.load_named_model("megapose-1.0-RGB", ds, models_root=Path(tmp))
+sc = scenes.bench_scene(1)
+images, K, det_df, bboxes = sc["images"], sc["K"], sc["det_df"], sc["bboxes"]
+est = scenes.build_estimator(sc)
 images_dev, K_dev, bboxes_dev = images.cuda(), K.cuda(), bboxes.cuda()
 marks = []
 

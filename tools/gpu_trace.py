@@ -1,24 +1,20 @@
 """Kernel timeline of one pipeline step (torch.profiler / CUPTI): busy time, idle gaps and where they are."""
 import sys
-import tempfile
 from pathlib import Path
 
 import torch
 from torch.profiler import ProfilerActivity, profile
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-import bench  # noqa: E402
-from megapose6d_b200 import load_model  # noqa: E402
+from workloads import scenes  # noqa: E402
 from megapose6d_b200.tensor_collection import PandasTensorCollection  # noqa: E402
 from megapose6d_b200.types import ObservationTensor  # noqa: E402
 
 
 def main():
-    ds, images, K, det_df, bboxes, sds = bench.build_scene(1)
-    with tempfile.TemporaryDirectory() as tmp:
-        for run_id, sd in sds.items():
-            load_model.write_run(tmp, run_id, sd)
-        est = load_model.load_named_model("megapose-1.0-RGB", ds, models_root=Path(tmp))
+    sc = scenes.bench_scene(1)
+    images, K, det_df, bboxes = sc["images"], sc["K"], sc["det_df"], sc["bboxes"]
+    est = scenes.build_estimator(sc)
     images_dev, K_dev, bboxes_dev = images.cuda(), K.cuda(), bboxes.cuda()
 
     def step():

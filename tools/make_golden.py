@@ -104,5 +104,61 @@ def pipeline_fixture(ref):
              final_poses=final.poses.numpy(), final_pose_logit=final.infos["pose_logit"].values.astype(np.float32))
 
 
+def fullsize_fixture(ref, name: str):
+    """The reference's own PoseEstimator.run_inference_pipeline (fp32, CPU, C rasteriser standing in for Panda3D) on one of
+    the full-size scenarios of workloads/scenes.py (BASELINE configs[1..3]) -> tests/golden/<name>.npz: every coarse logit,
+    the survivors, the refiner's pose after every iteration, the scoring logits and the final poses."""
+    import os
+    import time
+
+    from tests.test_oracle_vs_reference import _reference_predictor
+    from workloads import scenes, weights
+
+    sc = scenes.FULLSIZE[name]()
+    meshes = helpers.ref_meshes_from_dataset(sc["ds"])
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rgb = sc["images"][:, :3].contiguous()
+    coarse = _reference_predictor(ref, weights.COARSE_CFG, sc["sd_coarse"], meshes, sc["render_size"], threads)
+    refiner = _reference_predictor(ref, sc["cfg_refiner"], sc["sd_refiner"], meshes, sc["render_size"], threads)
+    coarse.cfg = refiner.cfg = None
+    t0 = time.time()
+    with refload.cpu_cuda_patch():
+        est = ref.pose_estimator.PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=8, bsz_images=128,
+                                               SO3_grid_size=sc["grid"])
+        detections = ref.tensor_collection.PandasTensorCollection(sc["det_df"].copy(), bboxes=sc["bboxes"])
+        obs = ref.types.ObservationTensor(sc["images"], sc["K"])
+        if sc["cfg_refiner"]["input_depth"]:
+            # the zoo pairs an RGB coarse model with the RGB-D refiner (utils/load_model.py:18-26); the reference's coarse
+            # model slices the RGB channels itself (models/pose_rigid.py:660-664 via input_rgb_dims)
+            pass
+        final, extra = est.run_inference_pipeline(obs, detections=detections, n_refiner_iterations=sc["n_refiner_iterations"],
+                                                  n_pose_hypotheses=sc["n_pose_hypotheses"], keep_all_refiner_outputs=False)
+    c = extra["coarse"]["preds"]
+    f = extra["coarse_filter"]["preds"]
+    n_det = len(sc["labels"])
+    assert c.infos["bbox_id"].tolist() == sorted(c.infos["bbox_id"].tolist()), "rows are detection-major"
+    preds = extra["refiner_all_hypotheses"]["preds"]
+    iters = np.stack([preds[f"iteration={n + 1}"].poses.numpy() for n in range(sc["n_refiner_iterations"])])
+    scored = extra["scoring"]["preds"]
+    np.savez_compressed(
+        OUT / f"{name}.npz", coarse_logit=c.infos["coarse_logit"].values.astype(np.float32),
+        coarse_bbox_id=c.infos["bbox_id"].values.astype(np.int32), coarse_hypothesis=c.infos["hypothesis_id"].values.astype(np.int32),
+        kept_bbox_id=f.infos["bbox_id"].values.astype(np.int32), kept_hypothesis=f.infos["hypothesis_id"].values.astype(np.int32),
+        kept_poses=f.poses.numpy(), refiner_poses=iters,
+        scored_label=np.array(scored.infos["label"].tolist(), dtype="U"), scored_hypothesis=scored.infos["hypothesis_id"].values.astype(np.int32),
+        scored_pose_logit=scored.infos["pose_logit"].values.astype(np.float32),
+        final_label=np.array(final.infos["label"].tolist(), dtype="U"), final_hypothesis=final.infos["hypothesis_id"].values.astype(np.int32),
+        final_poses=final.poses.numpy(), final_pose_logit=final.infos["pose_logit"].values.astype(np.float32),
+        grid=sc["grid"], n_refiner_iterations=sc["n_refiner_iterations"], render_size=np.asarray(sc["render_size"]),
+        seconds_on_host=time.time() - t0, host_threads=threads)
+    print(f"{name}: {n_det} detections x {sc['grid']} hypotheses, {time.time() - t0:.1f} s on {threads} threads", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:  # python tools/make_golden.py fullsize_rgb fullsize_rgb_224 ...
+        _ref = refload.load()
+        for _name in sys.argv[1:]:
+            fullsize_fixture(_ref, _name)
+    else:
+        main()

@@ -3,14 +3,13 @@ every kernel is an ordinary launch) with cudaProfilerStart/Stop.  `--stage coars
 coarse forward (for the --set full capture)."""
 import argparse
 import sys
-import tempfile
 from pathlib import Path
 
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-import bench  # noqa: E402
-from megapose6d_b200 import _abi, load_model  # noqa: E402
+from workloads import scenes  # noqa: E402
+from megapose6d_b200 import _abi  # noqa: E402
 from megapose6d_b200.tensor_collection import PandasTensorCollection  # noqa: E402
 from megapose6d_b200.types import ObservationTensor  # noqa: E402
 
@@ -19,11 +18,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", default="step", choices=("step", "coarse"))
     args = ap.parse_args()
-    ds, images, K, det_df, bboxes, sds = bench.build_scene(1)
-    with tempfile.TemporaryDirectory() as tmp:
-        for run_id, sd in sds.items():
-            load_model.write_run(tmp, run_id, sd)
-        est = load_model.load_named_model("megapose-1.0-RGB", ds, models_root=Path(tmp))
+    sc = scenes.bench_scene(1)
+    images, K, det_df, bboxes = sc["images"], sc["K"], sc["det_df"], sc["bboxes"]
+    est = scenes.build_estimator(sc)
     _abi.lib().mpx_net_set_graphs(0)
     est.coarse_model.use_cuda_graphs = False
     est.refiner_model.use_cuda_graphs = False
