@@ -81,10 +81,12 @@ int mpx_meshdb_set_textures(mpx_meshdb* db, const float* h_uv, const uint8_t* h_
 
 size_t mpx_raster_workspace_bytes(int h, int w);
 
-/* kernel selection, default 3: bit 0 = batches of at most SMs/8 views (refiner iterations, final scoring) spread
+/* kernel selection, default 7: bit 0 = batches of at most SMs/8 views (refiner iterations, final scoring) spread
  * the triangles of each view over many CTAs (coverage kernel + resolve kernel) instead of one CTA per
- * (view, row strip); bit 1 = visibility through a fire-and-forget 64-bit min reduction instead of read-then-atomic.
- * All combinations produce identical pixels. */
+ * (view, row strip); bit 1 = (untiled kernels) visibility through a fire-and-forget 64-bit min reduction instead of
+ * read-then-atomic; bit 2 = larger batches use the tiled kernel (triangles binned into screen strips, z-test of a strip in
+ * shared memory, candidate fragments dealt out evenly over the threads) instead of one CTA per view with a global
+ * visibility buffer.  All combinations produce identical pixels. */
 int mpx_raster_set_mode(int mode);
 
 /* contract output: float32 NCHW planes; any of d_rgb [N,3,h,w], d_normals [N,3,h,w],

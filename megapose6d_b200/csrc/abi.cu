@@ -79,6 +79,7 @@ size_t mpx_raster_workspace_bytes(int h, int w) { return raster_workspace_bytes(
 
 int mpx_raster_set_mode(int mode) {
   raster_set_scatter(mode & 1);
+  raster_set_tiled(mode & 4);
   return raster_set_red_only(mode & 2);
 }
 

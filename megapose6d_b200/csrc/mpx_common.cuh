@@ -197,6 +197,14 @@ struct MeshDb {
   long long* face_offsets;  // [n+1]
   int4* vtx_cache;          // [slots, nv_max] {X, Y, 1/z bits, behind}
   int slots;
+  int nf_max;
+  // packed copies for the kernels (same values as the arrays above): faces padded to 16 B, and two float4 per vertex
+  // {r, g, b, nx}, {ny, nz, u, v} so that a resolved pixel gathers its triangle with 1 + 6 16-byte loads
+  int4* faces4;             // [sum_nf] {ia, ib, ic, 0}
+  float4* vattr;            // [sum_nv, 2]
+  // per-CTA scratch of the tiled kernel: row-range word per triangle, per-strip triangle lists, large-triangle list
+  unsigned* tile_scratch;   // [slots, tile_words]
+  long long tile_words;
   // optional textures (meshdb_set_textures): per-vertex uv, RGB8 images back to back, per mesh {byte offset, th, tw,
   // modulate-with-vertex-colours}; tex_info == nullptr: no mesh is textured
   float* uv;                // [sum_nv,2]
@@ -226,6 +234,7 @@ int meshdb_set_textures(MeshDb* db, const float* uv, const unsigned char* tex, c
                         const int32_t* tex_dims, const int32_t* tex_modulate);
 size_t raster_workspace_bytes(int h, int w);
 void raster_set_scatter(int on);
+void raster_set_tiled(int on);
 int raster_set_red_only(int on);
 int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, const float* K, int n_views,
                   int h, int w, unsigned flags, const RasterOut& out, void* workspace, size_t workspace_bytes,

@@ -44,6 +44,14 @@ constexpr float kClampUV = 1048576.0f;  // 2^20 pixels
 constexpr int kRasterThreads = 512;
 constexpr int kBigQueue = 2048;
 constexpr long long kBigArea = 1024;  // pixels; larger bounding boxes go to the CTA-wide path
+// tiled kernel
+constexpr int kTileThreads = 512;
+constexpr int kTileBatch = kTileThreads;  // triangles set up per batch, one per thread
+constexpr int kTileMinRows = 16;          // fewer rows per strip than this: use the untiled kernel
+constexpr int kTileMaxSpan = 6;           // strips a triangle of <= 65 rows can overlap when a strip has >= 16 rows
+constexpr int kTileMaxStrips = 128;
+constexpr int kRecFields = 16;
+constexpr int kSmallExt = 16384;          // sub-pixel extent (64 px) up to which every edge value fits 32 bits
 
 // k / 255 (uint8 read-back levels of the reference) and the 32 texel values uint8(k*255/32) / 255
 struct QuantTables {
@@ -54,7 +62,9 @@ __constant__ QuantTables c_tables;
 __constant__ int c_red_only = 1;
 static bool g_tables_ready = false;
 static bool g_scatter = true;  // small-batch scatter path (raster_set_scatter)
+static bool g_tiled = true;    // tiled kernel for batches that fill the GPU (raster_set_tiled)
 void raster_set_scatter(int on) { g_scatter = on != 0; }
+void raster_set_tiled(int on) { g_tiled = on != 0; }
 int raster_set_red_only(int on) {
   const int v = on != 0;
   MPX_CHECK_CUDA(cudaMemcpyToSymbol(c_red_only, &v, sizeof(v)));
@@ -164,9 +174,10 @@ struct VtxSrc {
 };
 
 template <bool CACHED>
-__device__ __forceinline__ TriSetup load_tri(const VtxSrc& src, const int* __restrict__ faces, int tri) {
+__device__ __forceinline__ TriSetup load_tri(const VtxSrc& src, const int4* __restrict__ faces, int tri) {
   TriSetup t;
-  const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1), ic = __ldg(faces + 3 * tri + 2);
+  const int4 f = __ldg(faces + tri);
+  const int ia = f.x, ib = f.y, ic = f.z;
   int4 a, b, c;
   if (CACHED) {
     a = __ldcg(src.cache + ia); b = __ldcg(src.cache + ib); c = __ldcg(src.cache + ic);
@@ -228,7 +239,7 @@ __device__ __forceinline__ void emit_fragment(const TriSetup& t, W w0, W w1, W w
 // (C) coverage of one triangle restricted to rows [row_lo, row_hi]; bounding boxes above kBigArea pixels are queued
 // for the CTA-wide path
 template <bool CACHED>
-__device__ __forceinline__ void cover_triangle(const VtxSrc& src, const int* __restrict__ faces, int tri, int row_lo,
+__device__ __forceinline__ void cover_triangle(const VtxSrc& src, const int4* __restrict__ faces, int tri, int row_lo,
                                                int row_hi, int h, int w, unsigned long long* __restrict__ vis,
                                                int* s_big_count, int* s_big) {
   const TriSetup t = load_tri<CACHED>(src, faces, tri);
@@ -286,7 +297,7 @@ __device__ __forceinline__ void cover_triangle(const VtxSrc& src, const int* __r
 
 // queued large triangles: the whole CTA shares each bounding box
 template <bool CACHED>
-__device__ __forceinline__ void cover_big_triangles(const VtxSrc& src, const int* __restrict__ faces, int nbig,
+__device__ __forceinline__ void cover_big_triangles(const VtxSrc& src, const int4* __restrict__ faces, int nbig,
                                                     const int* s_big, int row_lo, int row_hi, int h, int w,
                                                     unsigned long long* __restrict__ vis) {
   for (int b = 0; b < nbig; ++b) {
@@ -341,163 +352,188 @@ __device__ __forceinline__ TexRef mesh_texture(const MeshDb& db, int lab, long l
   return t;
 }
 
-// (D) resolve + shade + write for rows [row_lo, row_hi] of one view.  Called by every thread of the CTA (contains
-// barriers when the crop is fused).
+// (D) resolve + shade + write.  ResolveCtx holds what is constant over a view (output slots, fused-crop tables);
+// resolve_pixel shades one pixel from its visibility key and writes every requested output.
+struct ResolveCtx {
+  int sample, vslot, npix;
+  bool fuse_crop, crop_collapsed;
+  RoiParams roi;
+  const float4* crop_img;
+  const AxisW* s_axis;
+};
+
+// Called by every thread of the CTA (contains a barrier when the crop is fused).
+__device__ __forceinline__ ResolveCtx make_resolve_ctx(const RasterOut& out, int view, int h, int w, AxisW* s_axis) {
+  ResolveCtx c;
+  c.npix = h * w;
+  c.sample = out.x ? view / out.views_per_sample : 0;
+  c.vslot = out.x ? view % out.views_per_sample : 0;
+  c.fuse_crop = out.x != nullptr && out.crop_images != nullptr;
+  c.crop_img = nullptr;
+  c.crop_collapsed = false;
+  c.s_axis = s_axis;
+  c.roi = RoiParams{0.f, 0.f, 0.f, 0.f};
+  if (c.fuse_crop) {
+    c.roi = make_roi(out.crop_boxes + 4 * c.sample, h, w);
+    const int im = out.crop_im_idx ? out.crop_im_idx[c.sample] : c.sample;
+    if (im >= 0 && im < out.crop_b) c.crop_img = out.crop_images + static_cast<size_t>(im) * out.crop_h * out.crop_w;
+    // block-uniform: every thread sees the same sample / image
+    if (c.crop_img != nullptr && h + w <= kAxisTableMax)
+      c.crop_collapsed = build_axis_tables(c.roi, h, w, out.crop_h, out.crop_w, s_axis, s_axis + h);
+  }
+  return c;
+}
+
 template <bool CACHED, bool TEXTURED>
-__device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int* __restrict__ faces,
-                                             const float* __restrict__ colors, const float* __restrict__ normals,
-                                             const TexRef& texref, const unsigned long long* __restrict__ vis, int view,
-                                             int row_lo, int row_hi, int h, int w, bool q8, bool gl_axes,
-                                             const RasterOut& out, AxisW* s_axis) {
-  const int npix = h * w;
+__device__ __forceinline__ void resolve_pixel(const ResolveCtx& ctx, const VtxSrc& src, const int4* __restrict__ faces,
+                                              const float4* __restrict__ vattr, const TexRef& texref,
+                                              unsigned long long key, int view, int i, int j, int h, int w, bool q8,
+                                              bool gl_axes, const RasterOut& out) {
+  const int npix = ctx.npix;
+  const int pix = i * w + j;
   const float* sR = src.sR;
-  // (D) resolve + shade + write
-  const float* vcol = colors;
-  const float* vnrm = normals;
   // d = a / z + b with a = 1 / (1/far - 1/near), b = -a / near (utils.py:44-55), as literals so
   // that host and device agree on the rounding
   const float dep_a = -0.10101010f;
   const float dep_b = 1.01010101f;
-  const int sample = out.x ? view / out.views_per_sample : 0;
-  const int vslot = out.x ? view % out.views_per_sample : 0;
-  const bool fuse_crop = out.x != nullptr && out.crop_images != nullptr;
-  RoiParams roi;
-  const float4* crop_img = nullptr;
-  bool crop_collapsed = false;
-  if (fuse_crop) {
-    roi = make_roi(out.crop_boxes + 4 * sample, h, w);
-    const int im = out.crop_im_idx ? out.crop_im_idx[sample] : sample;
-    if (im >= 0 && im < out.crop_b) crop_img = out.crop_images + static_cast<size_t>(im) * out.crop_h * out.crop_w;
-    // block-uniform: every thread sees the same sample / image
-    if (crop_img != nullptr && h + w <= kAxisTableMax)
-      crop_collapsed = build_axis_tables(roi, h, w, out.crop_h, out.crop_w, s_axis, s_axis + h);
+  const int sample = ctx.sample;
+  float r = 0.f, g = 0.f, b = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dep = 0.f;
+  if (key != ~0ull) {
+    const int tri = static_cast<int>(key & 0xffffffffu);
+    const TriSetup t = load_tri<CACHED>(src, faces, tri);
+    const int px = j * kSub + kHalf, py = i * kSub + kHalf;
+    long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+    long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+    long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+    if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+    float l0, l1, l2;
+    const float iz = (((w0 | w1 | w2) >> 31) == 0)
+                         ? sample_iz<int>(t, static_cast<int>(w0), static_cast<int>(w1), static_cast<int>(w2), l0, l1, l2)
+                         : sample_iz<long long>(t, w0, w1, w2, l0, l1, l2);
+    const float z = __frcp_rn(iz);
+    const float b0 = __fmul_rn(__fmul_rn(l0, t.iza), z);
+    const float b1 = __fmul_rn(__fmul_rn(l1, t.izb), z);
+    const float b2 = __fmul_rn(__fmul_rn(l2, t.izc), z);
+    const int4 f = __ldg(faces + tri);
+    // packed per-vertex attributes {r, g, b, nx}, {ny, nz, u, v}
+    const float4 a0 = __ldg(vattr + 2 * f.x), a1 = __ldg(vattr + 2 * f.x + 1);
+    const float4 c0 = __ldg(vattr + 2 * f.y), c1 = __ldg(vattr + 2 * f.y + 1);
+    const float4 e0 = __ldg(vattr + 2 * f.z), e1 = __ldg(vattr + 2 * f.z + 1);
+#define MPX_INTERP(A, B, C) __fmaf_rn(b0, (A), __fmaf_rn(b1, (B), __fmul_rn(b2, (C))))
+    float col[3], nrm[3];
+    col[0] = MPX_INTERP(a0.x, c0.x, e0.x);
+    col[1] = MPX_INTERP(a0.y, c0.y, e0.y);
+    col[2] = MPX_INTERP(a0.z, c0.z, e0.z);
+    nrm[0] = MPX_INTERP(a0.w, c0.w, e0.w);
+    nrm[1] = MPX_INTERP(a1.x, c1.x, e1.x);
+    nrm[2] = MPX_INTERP(a1.y, c1.y, e1.y);
+    if (TEXTURED && texref.tex != nullptr) {
+      const float tu = MPX_INTERP(a1.z, c1.z, e1.z);
+      const float tv = MPX_INTERP(a1.w, c1.w, e1.w);
+      float tc[3];
+      texture_sample(texref, tu, tv, tc);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) col[k] = texref.modulate ? __fmul_rn(tc[k], col[k]) : tc[k];
+    }
+#undef MPX_INTERP
+    r = quant8(col[0], q8);
+    g = quant8(col[1], q8);
+    b = quant8(col[2], q8);
+    // eye-space normal (OpenCV camera axes), normalised
+    float ex = __fmaf_rn(sR[0], nrm[0], __fmaf_rn(sR[1], nrm[1], __fmul_rn(sR[2], nrm[2])));
+    float ey = __fmaf_rn(sR[4], nrm[0], __fmaf_rn(sR[5], nrm[1], __fmul_rn(sR[6], nrm[2])));
+    float ez = __fmaf_rn(sR[8], nrm[0], __fmaf_rn(sR[9], nrm[1], __fmul_rn(sR[10], nrm[2])));
+    const float nn = __fsqrt_rn(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, __fmul_rn(ez, ez))));
+    if (nn > 0.f) {
+      const float inv = __frcp_rn(nn);
+      ex = __fmul_rn(ex, inv);
+      ey = __fmul_rn(ey, inv);
+      ez = __fmul_rn(ez, inv);
+    }
+    // Panda camera axes (x right, y forward, z up) or GL axes (x right, y up, z backward)
+    const float px_ = ex;
+    const float py_ = gl_axes ? -ey : ez;
+    const float pz_ = gl_axes ? -ez : -ey;
+    n0 = quant8(normal_texture(px_), q8);
+    n1 = quant8(normal_texture(py_), q8);
+    n2 = quant8(normal_texture(pz_), q8);
+    const float d = __fmaf_rn(dep_a, iz, dep_b);
+    dep = (d > 0.999f) ? 0.f : z;
   }
+  if (out.rgb) {
+    float* o = out.rgb + (static_cast<size_t>(view) * 3) * npix + pix;
+    o[0] = r; o[npix] = g; o[2 * npix] = b;
+  }
+  if (out.normals) {
+    float* o = out.normals + (static_cast<size_t>(view) * 3) * npix + pix;
+    o[0] = n0; o[npix] = n1; o[2 * npix] = n2;
+  }
+  if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
+  if (out.x) {
+    const int hs = h >> 1, ws = w >> 1;
+    act_t* base = out.x + ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
+                  ((i & 1) * 2 + (j & 1)) * out.c_pad;
+    float dn = dep;
+    if (out.ch_per_view == 7 && out.depth_norm_z) {
+      // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
+      dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
+    }
+    if (ctx.fuse_crop) {
+      // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float vacc = 0.f;
+      const AxisW* s_axis = ctx.s_axis;
+      if (ctx.crop_collapsed) {
+        if (out.crop_c == 4) roi_align_pixel_collapsed<true>(ctx.crop_img, out.crop_w, s_axis[i], s_axis[h + j], acc, vacc);
+        else roi_align_pixel_collapsed<false>(ctx.crop_img, out.crop_w, s_axis[i], s_axis[h + j], acc, vacc);
+      } else if (ctx.crop_img) {
+        if (out.crop_c == 4) roi_align_pixel<true>(ctx.crop_img, out.crop_h, out.crop_w, ctx.roi, i, j, acc, vacc);
+        else roi_align_pixel<false>(ctx.crop_img, out.crop_h, out.crop_w, ctx.roi, i, j, acc, vacc);
+      }
+      float ch[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ch[k] = 0.f;
+      int c = 0;
+      ch[c++] = acc.x; ch[c++] = acc.y; ch[c++] = acc.z;
+      if (out.crop_c == 4) {
+        float d4 = (vacc < 0.99f) ? 0.f : acc.w;
+        if (out.depth_norm_z) d4 = fminf(fmaxf(d4 / __ldg(out.depth_norm_z + sample), 0.f), 2.f) - 1.f;
+        ch[c++] = d4;
+      }
+      ch[c++] = r; ch[c++] = g; ch[c++] = b; ch[c++] = n0; ch[c++] = n1; ch[c++] = n2;
+      if (out.ch_per_view == 7) ch[c++] = dn;
+      uint4* o4 = reinterpret_cast<uint4*>(base);
+      uint4 v0, v1;
+      v0.x = pack_act2(ch[0], ch[1]); v0.y = pack_act2(ch[2], ch[3]);
+      v0.z = pack_act2(ch[4], ch[5]); v0.w = pack_act2(ch[6], ch[7]);
+      v1.x = pack_act2(ch[8], ch[9]); v1.y = pack_act2(ch[10], ch[11]);
+      v1.z = pack_act2(ch[12], ch[13]); v1.w = pack_act2(ch[14], ch[15]);
+      o4[0] = v0;
+      o4[1] = v1;
+      for (int k = 2; k < out.c_pad / 8; ++k) o4[k] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      act_t* o = base + out.ch_offset + ctx.vslot * out.ch_per_view;
+      o[0] = to_act(r);
+      o[1] = to_act(g);
+      o[2] = to_act(b);
+      o[3] = to_act(n0);
+      o[4] = to_act(n1);
+      o[5] = to_act(n2);
+      if (out.ch_per_view == 7) o[6] = to_act(dn);
+    }
+  }
+}
+
+// rows [row_lo, row_hi] of one view from a global visibility buffer.  Called by every thread of the CTA.
+template <bool CACHED, bool TEXTURED>
+__device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int4* __restrict__ faces,
+                                             const float4* __restrict__ vattr, const TexRef& texref,
+                                             const unsigned long long* __restrict__ vis, int view, int row_lo, int row_hi,
+                                             int h, int w, bool q8, bool gl_axes, const RasterOut& out, AxisW* s_axis) {
+  const ResolveCtx ctx = make_resolve_ctx(out, view, h, w, s_axis);
   for (int pix = row_lo * w + threadIdx.x; pix < (row_hi + 1) * w; pix += blockDim.x) {
     const int i = pix / w, j = pix - i * w;
-    const unsigned long long key = __ldcg(vis + pix);
-    float r = 0.f, g = 0.f, b = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, dep = 0.f;
-    if (key != ~0ull) {
-      const int tri = static_cast<int>(key & 0xffffffffu);
-      const TriSetup t = load_tri<CACHED>(src, faces, tri);
-      const int px = j * kSub + kHalf, py = i * kSub + kHalf;
-      long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
-      long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
-      long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
-      if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
-      float l0, l1, l2;
-      const float iz = (((w0 | w1 | w2) >> 31) == 0)
-                           ? sample_iz<int>(t, static_cast<int>(w0), static_cast<int>(w1), static_cast<int>(w2), l0, l1, l2)
-                           : sample_iz<long long>(t, w0, w1, w2, l0, l1, l2);
-      const float z = __frcp_rn(iz);
-      const float b0 = __fmul_rn(__fmul_rn(l0, t.iza), z);
-      const float b1 = __fmul_rn(__fmul_rn(l1, t.izb), z);
-      const float b2 = __fmul_rn(__fmul_rn(l2, t.izc), z);
-      const int ia = __ldg(faces + 3 * tri), ib = __ldg(faces + 3 * tri + 1),
-                ic = __ldg(faces + 3 * tri + 2);
-      float col[3], nrm[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        col[k] = __fmaf_rn(b0, __ldg(vcol + 3 * ia + k),
-                           __fmaf_rn(b1, __ldg(vcol + 3 * ib + k), __fmul_rn(b2, __ldg(vcol + 3 * ic + k))));
-        nrm[k] = __fmaf_rn(b0, __ldg(vnrm + 3 * ia + k),
-                           __fmaf_rn(b1, __ldg(vnrm + 3 * ib + k), __fmul_rn(b2, __ldg(vnrm + 3 * ic + k))));
-      }
-      if (TEXTURED && texref.tex != nullptr) {
-        const float* uv = texref.uv;
-        const float tu = __fmaf_rn(b0, __ldg(uv + 2 * ia), __fmaf_rn(b1, __ldg(uv + 2 * ib), __fmul_rn(b2, __ldg(uv + 2 * ic))));
-        const float tv = __fmaf_rn(b0, __ldg(uv + 2 * ia + 1),
-                                   __fmaf_rn(b1, __ldg(uv + 2 * ib + 1), __fmul_rn(b2, __ldg(uv + 2 * ic + 1))));
-        float tc[3];
-        texture_sample(texref, tu, tv, tc);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) col[k] = texref.modulate ? __fmul_rn(tc[k], col[k]) : tc[k];
-      }
-      r = quant8(col[0], q8);
-      g = quant8(col[1], q8);
-      b = quant8(col[2], q8);
-      // eye-space normal (OpenCV camera axes), normalised
-      float ex = __fmaf_rn(sR[0], nrm[0], __fmaf_rn(sR[1], nrm[1], __fmul_rn(sR[2], nrm[2])));
-      float ey = __fmaf_rn(sR[4], nrm[0], __fmaf_rn(sR[5], nrm[1], __fmul_rn(sR[6], nrm[2])));
-      float ez = __fmaf_rn(sR[8], nrm[0], __fmaf_rn(sR[9], nrm[1], __fmul_rn(sR[10], nrm[2])));
-      const float nn = __fsqrt_rn(__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, __fmul_rn(ez, ez))));
-      if (nn > 0.f) {
-        const float inv = __frcp_rn(nn);
-        ex = __fmul_rn(ex, inv);
-        ey = __fmul_rn(ey, inv);
-        ez = __fmul_rn(ez, inv);
-      }
-      // Panda camera axes (x right, y forward, z up) or GL axes (x right, y up, z backward)
-      const float px_ = ex;
-      const float py_ = gl_axes ? -ey : ez;
-      const float pz_ = gl_axes ? -ez : -ey;
-      n0 = quant8(normal_texture(px_), q8);
-      n1 = quant8(normal_texture(py_), q8);
-      n2 = quant8(normal_texture(pz_), q8);
-      const float d = __fmaf_rn(dep_a, iz, dep_b);
-      dep = (d > 0.999f) ? 0.f : z;
-    }
-    if (out.rgb) {
-      float* o = out.rgb + (static_cast<size_t>(view) * 3) * npix + pix;
-      o[0] = r; o[npix] = g; o[2 * npix] = b;
-    }
-    if (out.normals) {
-      float* o = out.normals + (static_cast<size_t>(view) * 3) * npix + pix;
-      o[0] = n0; o[npix] = n1; o[2 * npix] = n2;
-    }
-    if (out.depth) out.depth[static_cast<size_t>(view) * npix + pix] = dep;
-    if (out.x) {
-      const int hs = h >> 1, ws = w >> 1;
-      act_t* base = out.x +
-                            ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
-                            ((i & 1) * 2 + (j & 1)) * out.c_pad;
-      float dn = dep;
-      if (out.ch_per_view == 7 && out.depth_norm_z) {
-        // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
-        dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
-      }
-      if (fuse_crop) {
-        // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float vacc = 0.f;
-        if (crop_collapsed) {
-          if (out.crop_c == 4) roi_align_pixel_collapsed<true>(crop_img, out.crop_w, s_axis[i], s_axis[h + j], acc, vacc);
-          else roi_align_pixel_collapsed<false>(crop_img, out.crop_w, s_axis[i], s_axis[h + j], acc, vacc);
-        } else if (crop_img) {
-          if (out.crop_c == 4) roi_align_pixel<true>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
-          else roi_align_pixel<false>(crop_img, out.crop_h, out.crop_w, roi, i, j, acc, vacc);
-        }
-        float ch[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) ch[k] = 0.f;
-        int c = 0;
-        ch[c++] = acc.x; ch[c++] = acc.y; ch[c++] = acc.z;
-        if (out.crop_c == 4) {
-          float d4 = (vacc < 0.99f) ? 0.f : acc.w;
-          if (out.depth_norm_z) d4 = fminf(fmaxf(d4 / __ldg(out.depth_norm_z + sample), 0.f), 2.f) - 1.f;
-          ch[c++] = d4;
-        }
-        ch[c++] = r; ch[c++] = g; ch[c++] = b; ch[c++] = n0; ch[c++] = n1; ch[c++] = n2;
-        if (out.ch_per_view == 7) ch[c++] = dn;
-        uint4* o4 = reinterpret_cast<uint4*>(base);
-        uint4 v0, v1;
-        v0.x = pack_act2(ch[0], ch[1]); v0.y = pack_act2(ch[2], ch[3]);
-        v0.z = pack_act2(ch[4], ch[5]); v0.w = pack_act2(ch[6], ch[7]);
-        v1.x = pack_act2(ch[8], ch[9]); v1.y = pack_act2(ch[10], ch[11]);
-        v1.z = pack_act2(ch[12], ch[13]); v1.w = pack_act2(ch[14], ch[15]);
-        o4[0] = v0;
-        o4[1] = v1;
-        for (int k = 2; k < out.c_pad / 8; ++k) o4[k] = make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        act_t* o = base + out.ch_offset + vslot * out.ch_per_view;
-        o[0] = to_act(r);
-        o[1] = to_act(g);
-        o[2] = to_act(b);
-        o[3] = to_act(n0);
-        o[4] = to_act(n1);
-        o[5] = to_act(n2);
-        if (out.ch_per_view == 7) o[6] = to_act(dn);
-      }
-    }
+    resolve_pixel<CACHED, TEXTURED>(ctx, src, faces, vattr, texref, __ldcg(vis + pix), view, i, j, h, w, q8, gl_axes, out);
   }
 }
 
@@ -537,7 +573,7 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     const int nv = valid ? static_cast<int>(db.vert_offsets[lab + 1] - v_off) : 0;
     const long long f_off = valid ? db.face_offsets[lab] : 0;
     const int nf = valid ? static_cast<int>(db.face_offsets[lab + 1] - f_off) : 0;
-    const int* faces = db.faces + 3 * f_off;
+    const int4* faces = db.faces4 + f_off;
 
     // (A) clear visibility, (B) transform + snap vertices
     for (int i = row_lo * w + threadIdx.x; i < (row_hi + 1) * w; i += blockDim.x) vis[i] = ~0ull;
@@ -558,7 +594,7 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
     cover_big_triangles<true>(src, faces, min(s_big_count, kBigQueue), s_big, row_lo, row_hi, h, w, vis);
     __syncthreads();
 
-    resolve_rows<true, TEXTURED>(src, faces, db.colors + 3 * v_off, db.normals + 3 * v_off,
+    resolve_rows<true, TEXTURED>(src, faces, db.vattr + 2 * v_off,
                                  TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0}, vis, view,
                                  row_lo, row_hi, h, w, q8, gl_axes, out, s_axis);
   }
@@ -593,7 +629,7 @@ raster_cover_kernel(const MeshDb db, const int* __restrict__ label_idx, const fl
   const long long v_off = db.vert_offsets[lab];
   const long long f_off = db.face_offsets[lab];
   const int nf = static_cast<int>(db.face_offsets[lab + 1] - f_off);
-  const int* faces = db.faces + 3 * f_off;
+  const int4* faces = db.faces4 + f_off;
   unsigned long long* vis = vis_all + static_cast<size_t>(view) * h * w;
   VtxSrc src;
   src.cache = nullptr;
@@ -631,10 +667,289 @@ raster_resolve_kernel(const MeshDb db, const int* __restrict__ label_idx, const 
   src.sR = sR;
   src.fx = sK[0]; src.cx = sK[1]; src.fy = sK[2]; src.cy = sK[3];
   // an invalid view has an untouched (all ~0) visibility buffer: every pixel resolves to background
-  resolve_rows<false, TEXTURED>(src, db.faces + 3 * f_off, db.colors + 3 * v_off, db.normals + 3 * v_off,
+  resolve_rows<false, TEXTURED>(src, db.faces4 + f_off, db.vattr + 2 * v_off,
                                 TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0},
                                 vis_all + static_cast<size_t>(view) * h * w, view, row_lo, row_hi, h, w, (flags & 1u) != 0,
                                 (flags & 2u) != 0, out, s_axis);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled kernel: per-view vertex transform -> triangles binned into screen strips -> z-test of one strip at a time in
+// SHARED memory -> shade + coalesced stores.  No global visibility buffer (the untiled kernel keeps 2 x SMs of them, 182 MB at
+// 240x320: more than the L2, so its clear / min-reduce / read-back traffic reached DRAM).
+//
+// One CTA (512 threads, two per SM) per (view, group of strips):
+//   (B)  snap the vertices into the CTA's L2-resident cache;
+//   (C0) one thread per triangle: bounding rows -> a range word per triangle; triangles are counted per strip, the counts
+//        prefix-summed, and a second pass over the range words fills compact per-strip lists (global scratch, a few KB);
+//        triangles wider or taller than 64 px (edge values beyond 32 bits) go to a list handled by the whole CTA;
+//   per strip (rows_per_strip x w pixels, 64-bit keys in shared memory):
+//   (C1) batches of 512 listed triangles, one per thread: edge functions at the corner of the strip-clipped bounding box,
+//        per-pixel steps, 1/z, 1/area -> a record in shared memory; an exclusive scan of the boxes' pixel counts;
+//   (C2) the batch's candidate fragments are dealt out EVENLY: thread t takes fragments [t*c, (t+1)*c) of the concatenated
+//        boxes (binary search for its first triangle, then it walks boxes row by row).  One thread per triangle -- the
+//        untiled kernel -- idles most of a warp while its largest box is walked (r01: 62% of the instructions, 64% lane
+//        utilisation, warp time = the largest of 32 boxes);
+//   (D)  resolve_pixel on the strip: keys from shared memory, triangle + packed attributes gathered with 16-byte loads.
+// Same integers, same correctly rounded float operations, order-independent 64-bit minimum: bit-identical to
+// raster_kernel and to oracle/raster_ref.c.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void smem_min64(unsigned long long* cell, unsigned long long key) {
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(cell);
+  while (key < old) {
+    const unsigned long long prev = atomicCAS(cell, old, key);
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+template <typename W>
+__device__ __forceinline__ void emit_fragment_smem(W w0, W w1, W w2, float iza, float izb, float izc, float inv_area,
+                                                   int tri, unsigned long long* cell) {
+  if ((w0 | w1 | w2) < 0) return;
+  const float l0 = __fmul_rn(static_cast<float>(w0), inv_area);
+  const float l1 = __fmul_rn(static_cast<float>(w1), inv_area);
+  const float l2 = __fmul_rn(static_cast<float>(w2), inv_area);
+  const float iz = __fmaf_rn(l0, iza, __fmaf_rn(l1, izb, __fmul_rn(l2, izc)));
+  if (!(iz >= kIzMin && iz <= kIzMax)) return;
+  smem_min64(cell, (static_cast<unsigned long long>(~__float_as_uint(iz)) << 32) | static_cast<unsigned>(tri));
+}
+
+template <bool TEXTURED>
+__global__ void __launch_bounds__(kTileThreads, 2)
+raster_tiled_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* __restrict__ TCO,
+                    const float* __restrict__ K, int n_views, int h, int w, unsigned flags, RasterOut out, int R,
+                    int n_strips, int groups) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  unsigned long long* s_vis = reinterpret_cast<unsigned long long*>(s_dyn);
+  int* s_rec = reinterpret_cast<int*>(s_vis + static_cast<size_t>(R) * w);  // [kRecFields][kTileBatch]
+  int* s_start = s_rec + kRecFields * kTileBatch;                            // [kTileBatch + 1]
+  AxisW* s_axis = reinterpret_cast<AxisW*>(s_start + kTileBatch + 1);        // [h + w] when the crop is fused
+  __shared__ float sR[12];
+  __shared__ float sK[4];
+  __shared__ int s_valid;
+  __shared__ int s_nbig;
+  __shared__ int s_counts[kTileMaxStrips + 1];
+  __shared__ int s_cursor[kTileMaxStrips];
+  __shared__ int s_wsum[kTileThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int4* vtx = db.vtx_cache + static_cast<size_t>(blockIdx.x) * db.nv_max;
+  unsigned* scratch = db.tile_scratch + static_cast<size_t>(blockIdx.x) * db.tile_words;
+  unsigned* g_range = scratch;                                   // [nf_max] row-range word per triangle
+  unsigned* g_big = scratch + db.nf_max;                         // [nf_max] large triangles
+  unsigned* g_list = scratch + 2 * static_cast<size_t>(db.nf_max);  // [kTileMaxSpan * nf_max] per-strip lists, back to back
+  const bool q8 = (flags & 1u) != 0;
+  const bool gl_axes = (flags & 2u) != 0;
+  const int spg = (n_strips + groups - 1) / groups;
+
+  for (int item = blockIdx.x; item < n_views * groups; item += gridDim.x) {
+    const int view = item / groups, grp = item - view * groups;
+    const int s_lo = grp * spg, s_hi = min(n_strips, s_lo + spg);
+    const int grow_lo = s_lo * R, grow_hi = min(h, s_hi * R) - 1;
+    __syncthreads();  // previous item fully resolved before shared / global scratch is reused
+    if (tid == 0) {
+      load_view(db, label_idx, TCO, K, view, sR, sK, &s_valid);
+      s_nbig = 0;
+    }
+    for (int i = tid; i <= n_strips; i += kTileThreads) s_counts[i] = 0;
+    __syncthreads();
+    const bool valid = s_valid != 0;
+    const int lab = valid ? label_idx[view] : 0;
+    const long long v_off = valid ? db.vert_offsets[lab] : 0;
+    const int nv = valid ? static_cast<int>(db.vert_offsets[lab + 1] - v_off) : 0;
+    const long long f_off = valid ? db.face_offsets[lab] : 0;
+    const int nf = valid ? static_cast<int>(db.face_offsets[lab + 1] - f_off) : 0;
+    const int4* faces = db.faces4 + f_off;
+    const float4* vattr = db.vattr + 2 * v_off;
+
+    // (B) transform + snap vertices
+    const float fx = sK[0], cx = sK[1], fy = sK[2], cy = sK[3];
+    for (int i = tid; i < nv; i += kTileThreads) vtx[i] = snap_vertex(db.verts + 3 * (v_off + i), sR, fx, cx, fy, cy);
+    __syncthreads();
+    VtxSrc src;
+    src.cache = vtx;
+    src.verts = nullptr;
+    src.sR = sR;
+    src.fx = fx; src.cx = cx; src.fy = fy; src.cy = cy;
+
+    // (C0) rows of every triangle, strip counts
+    for (int tri = tid; tri < nf; tri += kTileThreads) {
+      const TriSetup t = load_tri<true>(src, faces, tri);
+      unsigned word = 0u;
+      if (t.ok) {
+        int j0, j1, i0, i1;
+        raster_bbox(t, h, w, j0, j1, i0, i1);
+        i0 = max(i0, grow_lo);
+        i1 = min(i1, grow_hi);
+        if (j0 <= j1 && i0 <= i1) {
+          const int ext_x = max(t.ax, max(t.bx, t.cx)) - min(t.ax, min(t.bx, t.cx));
+          const int ext_y = max(t.ay, max(t.by, t.cy)) - min(t.ay, min(t.by, t.cy));
+          const bool big = ext_x > kSmallExt || ext_y > kSmallExt;
+          word = 0x80000000u | (big ? 0x40000000u : 0u) | (static_cast<unsigned>(i1) << 12) | static_cast<unsigned>(i0);
+          if (big) {
+            g_big[atomicAdd(&s_nbig, 1)] = tri;
+          } else {
+            for (int s = i0 / R; s <= i1 / R; ++s) atomicAdd(&s_counts[s + 1], 1);
+          }
+        }
+      }
+      g_range[tri] = word;
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int s = 0; s < n_strips; ++s) s_counts[s + 1] += s_counts[s];  // s_counts[s] = first list entry of strip s
+    __syncthreads();
+    for (int i = tid; i < n_strips; i += kTileThreads) s_cursor[i] = s_counts[i];
+    __syncthreads();
+    for (int tri = tid; tri < nf; tri += kTileThreads) {
+      const unsigned word = g_range[tri];
+      if ((word & 0xC0000000u) == 0x80000000u) {
+        const int i0 = static_cast<int>(word & 0xfffu), i1 = static_cast<int>((word >> 12) & 0xfffu);
+        for (int s = i0 / R; s <= i1 / R; ++s) g_list[atomicAdd(&s_cursor[s], 1)] = static_cast<unsigned>(tri);
+      }
+    }
+    const ResolveCtx ctx = make_resolve_ctx(out, view, h, w, s_axis);
+    const TexRef texref = TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0};
+    __syncthreads();
+    const int nbig = s_nbig;
+
+    for (int s = s_lo; s < s_hi; ++s) {
+      const int row_lo = s * R, row_hi = min(h, row_lo + R) - 1;
+      const int strip_px = (row_hi - row_lo + 1) * w;
+      for (int i = tid; i < strip_px; i += kTileThreads) s_vis[i] = ~0ull;
+      const int seg0 = s_counts[s], seg1 = s_counts[s + 1];
+      for (int b0 = seg0; b0 < seg1; b0 += kTileBatch) {
+        const int n = min(kTileBatch, seg1 - b0);
+        // (C1) one triangle per thread: record + number of candidate fragments
+        int count = 0;
+        if (tid < n) {
+          const int tri = static_cast<int>(g_list[b0 + tid]);
+          const TriSetup t = load_tri<true>(src, faces, tri);
+          int j0, j1, i0, i1;
+          raster_bbox(t, h, w, j0, j1, i0, i1);
+          i0 = max(i0, row_lo);
+          i1 = min(i1, row_hi);
+          const int px0 = j0 * kSub + kHalf, py0 = i0 * kSub + kHalf;
+          const long long sgn = t.flip ? -1 : 1;
+          // exact integers; below 2^29 in magnitude for a triangle of at most 64 x 64 px (see cover_triangle)
+          s_rec[0 * kTileBatch + tid] = static_cast<int>(sgn * edge_fn(t.bx, t.by, t.cx, t.cy, px0, py0));
+          s_rec[1 * kTileBatch + tid] = static_cast<int>(sgn * edge_fn(t.cx, t.cy, t.ax, t.ay, px0, py0));
+          s_rec[2 * kTileBatch + tid] = static_cast<int>(sgn * edge_fn(t.ax, t.ay, t.bx, t.by, px0, py0));
+          const int isg = t.flip ? -1 : 1;
+          s_rec[3 * kTileBatch + tid] = -isg * (t.cy - t.by) * kSub;
+          s_rec[4 * kTileBatch + tid] = -isg * (t.ay - t.cy) * kSub;
+          s_rec[5 * kTileBatch + tid] = -isg * (t.by - t.ay) * kSub;
+          s_rec[6 * kTileBatch + tid] = isg * (t.cx - t.bx) * kSub;
+          s_rec[7 * kTileBatch + tid] = isg * (t.ax - t.cx) * kSub;
+          s_rec[8 * kTileBatch + tid] = isg * (t.bx - t.ax) * kSub;
+          s_rec[9 * kTileBatch + tid] = __float_as_int(t.iza);
+          s_rec[10 * kTileBatch + tid] = __float_as_int(t.izb);
+          s_rec[11 * kTileBatch + tid] = __float_as_int(t.izc);
+          s_rec[12 * kTileBatch + tid] = __float_as_int(t.inv_area);
+          s_rec[13 * kTileBatch + tid] = (i0 - row_lo) * w + j0;  // strip-relative index of the box corner
+          const int bw = j1 - j0 + 1;
+          s_rec[14 * kTileBatch + tid] = bw;
+          s_rec[15 * kTileBatch + tid] = tri;
+          count = bw * (i1 - i0 + 1);
+        }
+        // exclusive scan of the counts over the CTA
+        int incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+          int v = lane < kTileThreads / 32 ? s_wsum[lane] : 0;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+          }
+          if (lane < kTileThreads / 32) s_wsum[lane] = v;  // inclusive over warps
+        }
+        __syncthreads();
+        const int excl = incl - count + (wid > 0 ? s_wsum[wid - 1] : 0);
+        s_start[tid] = excl;
+        if (tid == kTileThreads - 1) s_start[kTileBatch] = excl + count;
+        __syncthreads();
+        // (C2) fragments dealt out evenly
+        const int T = s_start[kTileBatch];
+        const int c = (T + kTileThreads - 1) / kTileThreads;
+        int f = tid * c;
+        const int f1 = min(T, f + c);
+        if (f < f1) {
+          int lo = 0, hi = kTileBatch;  // s_start[lo] <= f < s_start[hi]
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_start[mid] <= f) lo = mid; else hi = mid;
+          }
+          int k = lo;
+          while (f < f1) {
+            const int st = s_start[k], en = s_start[k + 1];
+            if (en <= f) { ++k; continue; }  // empty box
+            const int r0 = s_rec[0 * kTileBatch + k], r1 = s_rec[1 * kTileBatch + k], r2 = s_rec[2 * kTileBatch + k];
+            const int ex0 = s_rec[3 * kTileBatch + k], ex1 = s_rec[4 * kTileBatch + k], ex2 = s_rec[5 * kTileBatch + k];
+            const int ey0 = s_rec[6 * kTileBatch + k], ey1 = s_rec[7 * kTileBatch + k], ey2 = s_rec[8 * kTileBatch + k];
+            const float iza = __int_as_float(s_rec[9 * kTileBatch + k]), izb = __int_as_float(s_rec[10 * kTileBatch + k]);
+            const float izc = __int_as_float(s_rec[11 * kTileBatch + k]), inv_area = __int_as_float(s_rec[12 * kTileBatch + k]);
+            const int corner = s_rec[13 * kTileBatch + k], bw = s_rec[14 * kTileBatch + k], tri = s_rec[15 * kTileBatch + k];
+            const int off = f - st;
+            const int nfr = min(en, f1) - f;
+            int di = off / bw, dj = off - di * bw;
+            int w0 = r0 + dj * ex0 + di * ey0, w1 = r1 + dj * ex1 + di * ey1, w2 = r2 + dj * ex2 + di * ey2;
+            int idx = corner + di * w + dj;
+            for (int q = 0; q < nfr; ++q) {
+              emit_fragment_smem<int>(w0, w1, w2, iza, izb, izc, inv_area, tri, s_vis + idx);
+              ++dj; ++idx;
+              w0 += ex0; w1 += ex1; w2 += ex2;
+              if (dj == bw) {
+                dj = 0; ++di;
+                idx += w - bw;
+                w0 = r0 + di * ey0; w1 = r1 + di * ey1; w2 = r2 + di * ey2;
+              }
+            }
+            f += nfr;
+            ++k;
+          }
+        }
+        __syncthreads();  // the next batch overwrites the records
+      }
+      // large triangles (rare): the whole CTA shares each strip-clipped bounding box, 64-bit edge functions
+      for (int b = 0; b < nbig; ++b) {
+        const int tri = static_cast<int>(g_big[b]);
+        const TriSetup t = load_tri<true>(src, faces, tri);
+        int j0, j1, i0, i1;
+        raster_bbox(t, h, w, j0, j1, i0, i1);
+        i0 = max(i0, row_lo);
+        i1 = min(i1, row_hi);
+        if (i0 > i1) continue;
+        const int bw = j1 - j0 + 1;
+        const int cnt = bw * (i1 - i0 + 1);
+        for (int k = tid; k < cnt; k += kTileThreads) {
+          const int di = k / bw;
+          const int i = i0 + di, j = j0 + (k - di * bw);
+          const int px = j * kSub + kHalf, py = i * kSub + kHalf;
+          long long w0 = edge_fn(t.bx, t.by, t.cx, t.cy, px, py);
+          long long w1 = edge_fn(t.cx, t.cy, t.ax, t.ay, px, py);
+          long long w2 = edge_fn(t.ax, t.ay, t.bx, t.by, px, py);
+          if (t.flip) { w0 = -w0; w1 = -w1; w2 = -w2; }
+          emit_fragment_smem<long long>(w0, w1, w2, t.iza, t.izb, t.izc, t.inv_area, tri, s_vis + (i - row_lo) * w + j);
+        }
+      }
+      __syncthreads();
+      // (D) resolve + shade + write the strip
+      for (int p = tid; p < strip_px; p += kTileThreads) {
+        const int di = p / w;
+        resolve_pixel<true, TEXTURED>(ctx, src, faces, vattr, texref, s_vis[p], view, row_lo + di, p - di * w, h, w, q8,
+                                      gl_axes, out);
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -675,6 +990,12 @@ int meshdb_create(int n_meshes, const float* verts, const float* normals, const 
   }
   db->nv_max = nv_max > 0 ? nv_max : 1;
   db->slots = 2 * sm_count();
+  int nf_max = 1;
+  for (int i = 0; i < n_meshes; ++i) {
+    const long long c = face_offsets[i + 1] - face_offsets[i];
+    if (c > nf_max) nf_max = static_cast<int>(c);
+  }
+  db->nf_max = nf_max;
   MPX_CHECK_CUDA(cudaMalloc(&db->verts, sizeof(float) * 3 * (nv > 0 ? nv : 1)));
   MPX_CHECK_CUDA(cudaMalloc(&db->normals, sizeof(float) * 3 * (nv > 0 ? nv : 1)));
   MPX_CHECK_CUDA(cudaMalloc(&db->colors, sizeof(float) * 3 * (nv > 0 ? nv : 1)));
@@ -690,6 +1011,24 @@ int meshdb_create(int n_meshes, const float* verts, const float* normals, const 
                             cudaMemcpyHostToDevice));
   MPX_CHECK_CUDA(cudaMemcpy(db->face_offsets, face_offsets, sizeof(long long) * (n_meshes + 1),
                             cudaMemcpyHostToDevice));
+  // packed copies: 16-byte faces, two float4 of attributes per vertex (uv filled in by meshdb_set_textures)
+  {
+    std::vector<int4> f4(nf > 0 ? nf : 1);
+    for (long long f = 0; f < nf; ++f) f4[f] = make_int4(faces[3 * f], faces[3 * f + 1], faces[3 * f + 2], 0);
+    std::vector<float4> va(2 * (nv > 0 ? nv : 1));
+    for (long long v = 0; v < nv; ++v) {
+      va[2 * v] = make_float4(colors[3 * v], colors[3 * v + 1], colors[3 * v + 2], normals[3 * v]);
+      va[2 * v + 1] = make_float4(normals[3 * v + 1], normals[3 * v + 2], 0.f, 0.f);
+    }
+    MPX_CHECK_CUDA(cudaMalloc(&db->faces4, sizeof(int4) * f4.size()));
+    MPX_CHECK_CUDA(cudaMalloc(&db->vattr, sizeof(float4) * va.size()));
+    MPX_CHECK_CUDA(cudaMemcpy(db->faces4, f4.data(), sizeof(int4) * f4.size(), cudaMemcpyHostToDevice));
+    MPX_CHECK_CUDA(cudaMemcpy(db->vattr, va.data(), sizeof(float4) * va.size(), cudaMemcpyHostToDevice));
+  }
+  // tiled kernel scratch per CTA slot: range word per triangle, strip lists (a small triangle is at most 65 px tall:
+  // <= kTileMaxSpan strips), list of large triangles
+  db->tile_words = static_cast<long long>(nf_max) * (2 + kTileMaxSpan);
+  MPX_CHECK_CUDA(cudaMalloc(&db->tile_scratch, sizeof(unsigned) * db->tile_words * db->slots));
   *out = db;
   return MPX_OK;
 }
@@ -718,6 +1057,15 @@ int meshdb_set_textures(MeshDb* db, const float* uv, const unsigned char* tex, c
   MPX_CHECK_CUDA(cudaMalloc(&db->tex_offsets, sizeof(long long) * n));
   MPX_CHECK_CUDA(cudaMalloc(&db->tex_info, sizeof(int4) * n));
   MPX_CHECK_CUDA(cudaMemcpy(db->uv, uv, sizeof(float) * 2 * nv, cudaMemcpyHostToDevice));
+  {  // texture coordinates into the packed per-vertex attributes
+    std::vector<float4> va(2 * (nv > 0 ? nv : 1));
+    MPX_CHECK_CUDA(cudaMemcpy(va.data(), db->vattr, sizeof(float4) * 2 * nv, cudaMemcpyDeviceToHost));
+    for (long long v = 0; v < nv; ++v) {
+      va[2 * v + 1].z = uv[2 * v];
+      va[2 * v + 1].w = uv[2 * v + 1];
+    }
+    MPX_CHECK_CUDA(cudaMemcpy(db->vattr, va.data(), sizeof(float4) * 2 * nv, cudaMemcpyHostToDevice));
+  }
   MPX_CHECK_CUDA(cudaMemcpy(db->tex, tex, bytes, cudaMemcpyHostToDevice));
   MPX_CHECK_CUDA(cudaMemcpy(db->tex_offsets, offs.data(), sizeof(long long) * n, cudaMemcpyHostToDevice));
   MPX_CHECK_CUDA(cudaMemcpy(db->tex_info, info.data(), sizeof(int4) * n, cudaMemcpyHostToDevice));
@@ -737,6 +1085,9 @@ void meshdb_destroy(MeshDb* db) {
   cudaFree(db->vert_offsets);
   cudaFree(db->face_offsets);
   cudaFree(db->vtx_cache);
+  cudaFree(db->faces4);
+  cudaFree(db->vattr);
+  cudaFree(db->tile_scratch);
   delete db;
 }
 
@@ -788,6 +1139,34 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
     MPX_CHECK_CUDA(cudaGetLastError());
     g_launches += 2;
     return MPX_OK;
+  }
+  if (g_tiled && h < 4096 && w < 4096) {
+    // rows per strip from the shared memory left for the 64-bit visibility strip with two CTAs per SM
+    const bool axis = out.crop_images != nullptr && h + w <= kAxisTableMax;
+    const size_t fixed = static_cast<size_t>(kRecFields * kTileBatch + kTileBatch + 1) * sizeof(int) +
+                         (axis ? static_cast<size_t>(h + w) * sizeof(AxisW) : 0) + 16;
+    const size_t budget = 110 * 1024;
+    int R = fixed < budget ? static_cast<int>((budget - fixed) / (sizeof(unsigned long long) * w)) : 0;
+    if (R > h) R = h;
+    if (R >= kTileMinRows) {
+      int n_strips = (h + R - 1) / R;
+      R = (h + n_strips - 1) / n_strips;
+      n_strips = (h + R - 1) / R;
+      if (n_strips <= kTileMaxStrips && R >= kTileMinRows) {
+        int groups = 1;
+        if (n_views < db->slots) groups = db->slots / n_views;
+        if (groups > n_strips) groups = n_strips;
+        const long long items = static_cast<long long>(n_views) * groups;
+        const int grid = items < db->slots ? static_cast<int>(items) : db->slots;
+        const size_t dyn = static_cast<size_t>(R) * w * sizeof(unsigned long long) + fixed;
+        auto kern = db->tex_info != nullptr ? raster_tiled_kernel<true> : raster_tiled_kernel<false>;
+        MPX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+        kern<<<grid, kTileThreads, dyn, stream>>>(*db, label_idx, TCO, K, n_views, h, w, flags, out, R, n_strips, groups);
+        MPX_CHECK_CUDA(cudaGetLastError());
+        ++g_launches;
+        return MPX_OK;
+      }
+    }
   }
   int strips = 1;
   if (n_views < db->slots) {

@@ -126,14 +126,63 @@ def _render_both(ds, rm, labels, TCO, K, res, depth=True):
     return out, ref
 
 
-@pytest.fixture(params=[3, 2, 0], ids=["scatter", "strips", "strips_read_then_atomic"])
+@pytest.fixture(params=[7, 2, 0], ids=["scatter", "strips", "strips_read_then_atomic"])
 def raster_mode(request):
     """Small batches have two implementations (include/mpx.h mpx_raster_set_mode): triangles scattered over many CTAs
     + resolve kernel (default), or one CTA per (view, row strip).  Both must match the oracle bit for bit."""
     from megapose6d_b200 import _abi
     _abi.lib().mpx_raster_set_mode(request.param)
     yield request.param
-    _abi.lib().mpx_raster_set_mode(3)
+    _abi.lib().mpx_raster_set_mode(7)
+
+
+@pytest.fixture(params=[7, 3], ids=["tiled", "untiled"])
+def big_batch_mode(request):
+    """Batches that fill the GPU: the tiled kernel (triangles binned into screen strips, z-test in shared memory; default)
+    or one CTA per view with a global visibility buffer.  Same pixels, bit for bit."""
+    from megapose6d_b200 import _abi
+    _abi.lib().mpx_raster_set_mode(request.param)
+    yield request.param
+    _abi.lib().mpx_raster_set_mode(7)
+
+
+def _assert_same_render(out, ref, what=""):
+    for name, got, want in (("rgb", out.rgbs, ref["rgbs"]), ("normals", out.normals, ref["normals"]),
+                            ("depth", out.depths, ref["depths"])):
+        got = got.cpu()
+        mism = (got != want).flatten(1).any(dim=0).sum().item() if got.numel() else 0
+        assert torch.equal(got, want), f"{what}{name}: {mism} differing pixel positions, max |d|={(got - want).abs().max()}"
+
+
+def test_raster_big_batch_bit_exact_vs_oracle(scene, big_batch_mode):
+    """40 views of 10k-triangle meshes at 240x320: ten strips per view, several CTAs per view (strip groups), triangles
+    that straddle strips, a view at the near plane, one mostly outside the frustum, one with an invalid pose."""
+    ds, images, K, db, rm = scene
+    n = 40
+    labels = [ds[i % 3].label for i in range(n)]
+    TCO = _poses(n, 121, z_range=(0.25, 0.9))
+    TCO[3, 2, 3] = 0.12
+    TCO[4, 0, 3] = 0.35
+    TCO[7, 1, 1] = float("nan")
+    Kc = torch.tensor([[1500.0, 0, 160], [0, 1500, 120], [0, 0, 1]]).repeat(n, 1, 1)
+    Kc[5] = torch.tensor([[300.0, 0, 150.3], [0, 310, 118.9], [0, 0, 1]])
+    out, ref = _render_both(ds, rm, labels, TCO, Kc, (240, 320))
+    _assert_same_render(out, ref)
+    assert (out.depths > 0).float().mean() > 0.05 and out.rgbs[7].abs().sum() == 0
+
+
+def test_raster_big_batch_low_poly_and_odd_size(big_batch_mode):
+    """Boxes of 12 triangles (every triangle is 'large': the CTA-wide path of each kernel) next to a sphere, at a
+    resolution that does not divide into equal strips; more views than CTA slots so that the persistent loop runs."""
+    ds = RigidObjectDataset([RigidObject("box", mesh=procedural.textured_box(seed=1)),
+                             RigidObject("ball", mesh=procedural.bumpy_sphere(n_seg=40, n_lat=21))])
+    rm = helpers.ref_meshes_from_dataset(ds)
+    n = 2 * 148 + 5
+    labels = [ds[i % 2].label for i in range(n)]
+    TCO = _poses(n, 9, z_range=(0.2, 0.6))
+    Kc = torch.tensor([[420.0, 0, 75], [0, 420, 50], [0, 0, 1]]).repeat(n, 1, 1)
+    out, ref = _render_both(ds, rm, labels, TCO, Kc, (103, 150))
+    _assert_same_render(out, ref)
 
 
 def test_raster_bit_exact_vs_oracle(scene, raster_mode):
