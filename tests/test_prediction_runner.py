@@ -474,7 +474,11 @@ def test_runner_with_the_real_estimator(tmp_path):
     rows = 0
     for i in runner.sampler:
         f = frames[i]
-        obs = ObservationTensor.from_numpy(f.rgb, None, K).cuda()
+        # same conversion as the runner's (and the reference runner's, evaluation/prediction_runner.py:104-112): uint8 ->
+        # float32 / 255 ON THE DEVICE -- torch's CUDA division by a scalar multiplies by the reciprocal, one ulp away from
+        # the host's true division on a third of the 256 levels
+        obs = ObservationTensor.from_torch_batched(torch.from_numpy(f.rgb).permute(2, 0, 1).unsqueeze(0).cuda(), None,
+                                                   torch.as_tensor(K).unsqueeze(0).cuda())
         det = make_detections_from_object_data(f.object_datas).cuda()
         want, _ = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=2, n_pose_hypotheses=1,
                                              bsz_images=576, bsz_objects=16)

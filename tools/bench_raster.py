@@ -1,7 +1,8 @@
 """BASELINE.json configs[4]: rasteriser microbench -- one 10k-triangle mesh x 4096 views @224x224, rgb + normals.
 
 Reports the contract bytes written (fp32 NCHW planes, 6 channels: 1 204 224 B/view) per second against the
-measured HBM copy bandwidth, and the same for the fused bf16 output path.  Inputs are resident in HBM; CUDA events.
+measured HBM copy bandwidth, and the same for the fused 16-bit output path, for the tiled kernel (default, raster mode 7)
+and the untiled one (mode 3).  Inputs are resident in HBM; CUDA events.
 """
 import json
 import sys
@@ -43,13 +44,16 @@ def main(n_views=4096, h=224, w=224, iters=5):
         _abi.check(lib.mpx_raster_render(r.mesh_db.handle, _abi.ptr(lab), _abi.ptr(TCO), _abi.ptr(K), n_views, h, w, r.flags,
                                          _abi.ptr(rgbs), _abi.ptr(nrms), None, _abi.ptr(ws), ws.numel(), _abi.stream_ptr()))
 
-    x = torch.zeros(n_views, h // 2, w // 2, 64, device="cuda", dtype=torch.bfloat16)
+    x = torch.zeros(n_views, h // 2, w // 2, 64, device="cuda", dtype=_abi.act_dtype())
 
     def fused():
         r.render_fused(lab, TCO, K, 1, (h, w), x, 16, 3, 6)
 
     res = {}
-    for name, fn, nbytes in (("contract_fp32_nchw", contract, 4 * h * w * 6 + 100), ("fused_bf16", fused, 2 * h * w * 6 + 100)):
+    for mode, name, fn, nbytes in ((7, "contract_fp32_nchw", contract, 4 * h * w * 6 + 100), (7, "fused_16bit", fused, 2 * h * w * 6 + 100),
+                                   (3, "untiled_contract_fp32_nchw", contract, 4 * h * w * 6 + 100),
+                                   (3, "untiled_fused_16bit", fused, 2 * h * w * 6 + 100)):
+        lib.mpx_raster_set_mode(mode)
         for _ in range(2):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,6 +64,7 @@ def main(n_views=4096, h=224, w=224, iters=5):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         res[name] = {"ms": ms, "views_per_s": n_views / ms * 1e3, "GBps": nbytes * n_views / ms / 1e6, "bytes_per_view": nbytes}
+    lib.mpx_raster_set_mode(7)
     peaks = ROOT / "MEASURED_PEAKS.json"
     peak = json.loads(peaks.read_text())["hbm_gbs"] if peaks.exists() else 6650.0
     for v in res.values():

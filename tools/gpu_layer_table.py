@@ -61,12 +61,16 @@ def main():
     ap.add_argument("--batch", type=int, default=576)
     ap.add_argument("--render-size", default="240x320")
     ap.add_argument("--out", type=Path, default=Path("gpurun_out/layer_table.json"))
+    ap.add_argument("--mpx-only", action="store_true", help="skip the torch / cuDNN columns")
+    ap.add_argument("--conv-modes", default="", help="comma-separated mpx_conv_set_mode values to time side by side")
     args = ap.parse_args()
     h, w = (int(v) for v in args.render_size.split("x"))
     n = args.batch
     lib = _abi.lib()
     act = _abi.act_dtype()
     torch.backends.cudnn.benchmark = True
+    import os
+    default_mode = int(os.environ.get("MPX_CONV_MODE", "11"))
     rows = []
     g = torch.Generator(device="cuda").manual_seed(0)
     for name, count, H, Wd, cin, cout, r, stride, pad, use_res in layers(h, w, 9):
@@ -75,7 +79,7 @@ def main():
         rec = dict(layer=name, count=count, M=n * P * Q, N=cout, K=r * r * cin, gflop=flops / 1e9)
         x_nchw = torch.randn(n, cin, H, Wd, device="cuda", generator=g)
         wt = torch.randn(cout, cin, r, r, device="cuda", generator=g) / (r * r * cin) ** 0.5
-        for prec, (dt, cl, tf32) in T.PRECISIONS.items():
+        for prec, (dt, cl, tf32) in ({} if args.mpx_only else T.PRECISIONS).items():
             torch.backends.cudnn.allow_tf32 = tf32
             xx, ww = x_nchw.to(dt), wt.to(dt)
             if cl:
@@ -107,16 +111,21 @@ def main():
 
         ms = time_ms(run_mpx)
         rec["mpx_ms"], rec["mpx_tflops"] = ms, flops / ms / 1e9
-        best = min(rec[f"torch_{p}_ms"] for p in T.PRECISIONS)
-        rec["speedup_vs_best_torch"] = best / ms
-        rec["speedup_vs_torch_fp32_strict"] = rec["torch_fp32_strict_ms"] / ms
+        for mode in [int(m) for m in args.conv_modes.split(",") if m]:
+            lib.mpx_conv_set_mode(mode)
+            rec[f"mpx_mode{mode}_ms"] = time_ms(run_mpx)
+        lib.mpx_conv_set_mode(default_mode)
+        if not args.mpx_only:
+            best = min(rec[f"torch_{p}_ms"] for p in T.PRECISIONS)
+            rec["speedup_vs_best_torch"] = best / ms
+            rec["speedup_vs_torch_fp32_strict"] = rec["torch_fp32_strict_ms"] / ms
         rows.append(rec)
         print(json.dumps(rec), flush=True)
         del xm, wm, out, res
         torch.cuda.empty_cache()
     # whole network forward at this batch
     sd = W.make_state_dict(W.COARSE_CFG, 1)
-    net = {p: T.time_forward(sd, n, h, w, p) for p in T.PRECISIONS}
+    net = {} if args.mpx_only else {p: T.time_forward(sd, n, h, w, p) for p in T.PRECISIONS}
     eng = ResNet34Engine(sd, n_inputs=9, head="views_logits_head")
     x = eng.alloc_input(n, h, w)
     x.copy_(torch.rand(x.shape, device="cuda").to(act))
