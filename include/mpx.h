@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MPX_ABI_VERSION 2
+#define MPX_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------------------------ */
 int mpx_abi_version(void);
@@ -78,6 +78,16 @@ int mpx_meshdb_set_textures(mpx_meshdb* db, const float* h_uv, const uint8_t* h_
  */
 #define MPX_RASTER_QUANTIZE8 1u      /* round colour/normal channels to k/255 (uint8 read-back)  */
 #define MPX_RASTER_NORMALS_GL 2u     /* eye normals in GL Y-up axes instead of Panda Z-up axes  */
+#define MPX_RASTER_POINT_LIGHTS 4u   /* rgb lit by make_scene_lights() (ambient 0.1 + six point lights of 0.4 on the object's
+                                      * axes at 10 bounding radii, panda3d_scene_renderer.py:104-136) instead of ambient 1.0:
+                                      * what models with render_normals=False are fed (models/pose_rigid.py:374-378) */
+/* depth normalisation of the fused depth channels (PosePredictor.normalize_depth, models/pose_rigid.py:466-496), applied
+ * with d_depth_norm_z[sample] = tCR_z; raster entry points carry it in flags bits 8-9, mpx_roi_align_fused as an argument */
+#define MPX_DEPTH_NORM_TCR_SCALE_CLAMP_CENTER 0  /* clamp(depth / z, 0, 2) - 1 (the released RGB-D refiner) */
+#define MPX_DEPTH_NORM_TCR_SCALE 1               /* depth / z */
+#define MPX_DEPTH_NORM_TCR_CENTER_CLAMP 2        /* clamp(depth - z, -2, 2) */
+#define MPX_DEPTH_NORM_NONE 3
+#define MPX_RASTER_DEPTH_NORM_SHIFT 8
 
 size_t mpx_raster_workspace_bytes(int h, int w);
 
@@ -98,10 +108,10 @@ int mpx_raster_render(const mpx_meshdb* db, const int32_t* d_label_idx, const fl
 
 /* fused output: writes act16 channels straight into the network input tensor (see mpx_net):
  * view i belongs to sample i / views_per_sample, view slot v = i % views_per_sample and its
- * channels land at ch_offset + v * ch_per_view (+0..2 rgb, +3..5 normals, +6 depth if
- * ch_per_view == 7).  d_depth_norm_z [n_samples] (may be NULL) applies the reference's
- * "tCR_scale_clamp_center" depth normalisation (models/pose_rigid.py:466-496) to the depth
- * channel. */
+ * channels land at ch_offset + v * ch_per_view: ch_per_view = 3 (rgb), 4 (rgb, depth), 6 (rgb, normals) or
+ * 7 (rgb, normals, depth), i.e. what render_normals / render_depth select (models/pose_rigid.py:394-404).
+ * d_depth_norm_z [n_samples] (may be NULL = none) applies the depth normalisation selected by flags bits 8-9
+ * to the depth channel. */
 int mpx_raster_render_fused(const mpx_meshdb* db, const int32_t* d_label_idx, const float* d_TCO,
                             const float* d_K, int n_views, int views_per_sample, int h, int w,
                             uint32_t flags, void* d_x, int c_pad, int ch_offset, int ch_per_view,
@@ -175,7 +185,7 @@ int mpx_roi_align(const float* d_img_nhwc4, int b, int h, int w, const int32_t* 
  * normalised with d_depth_norm_z as in mpx_raster_render_fused. */
 int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int32_t* d_im_idx,
                         const float* d_boxes, int n, int c, int out_h, int out_w, void* d_x,
-                        int c_pad, const float* d_depth_norm_z, void* stream);
+                        int c_pad, const float* d_depth_norm_z, int depth_norm_kind, void* stream);
 
 /* ---- network -------------------------------------------------------------------------------------
  * ResNet-34 + fc + head of PosePredictor.net_forward (models/pose_rigid.py:314-334) with the
@@ -184,7 +194,8 @@ int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int
  * fp32 bias.
  *
  * Network input tensor ("x"): act16, space-to-depth NHWC [n, H/2, W/2, 4*c_pad] with channel
- * index (dy*2+dx)*c_pad + c, c_pad = 16 (coarse, 9 real channels) or 32 (refiner, 27|32).
+ * index (dy*2+dx)*c_pad + c, c_pad = the channel count rounded up to a multiple of 16: 16 (coarse, 9 real channels) or
+ * 32 (refiner, 27|32) for the released models, up to 256 for configurations with more rendered views.
  */
 size_t mpx_net_input_bytes(int n, int h, int w, int c_pad);
 

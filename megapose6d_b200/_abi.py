@@ -14,7 +14,7 @@ import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libmpx.so"
 _lib: Optional[ctypes.CDLL] = None
-ABI_VERSION = 2  # MPX_ABI_VERSION of include/mpx.h this binding was written against
+ABI_VERSION = 3  # MPX_ABI_VERSION of include/mpx.h this binding was written against
 
 
 class MpxError(RuntimeError):
@@ -51,7 +51,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_image_to_nhwc4.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
     lib.mpx_roi_align.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
     lib.mpx_roi_align_fused.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, c_int,
-                                        vp, vp]
+                                        vp, c_int, vp]
     lib.mpx_net_input_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.mpx_net_input_bytes.restype = c_size_t
     lib.mpx_conv2d.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int,

@@ -9,7 +9,7 @@ layout and repacks them once for the tcgen05 kernels:
   * conv weights OIHW fp32 -> [C_out, R*S*C_in] in the library's 16-bit type (`_abi.act_dtype()`: fp16 unless the
     library was built for bf16), K ordered (r, s, c);
   * the 7x7/s2 stem rewritten as a 4x4/s1 conv over the space-to-depth input (channels padded to
-    c_pad = 16 or 32, four sub-pixels -> 64 or 128 input channels);
+    c_pad = a multiple of 16 (16 | 32 for the released models), four sub-pixels -> 4 * c_pad input channels);
   * avgpool -> fc(512x512) -> head(512 x 1|9) folded into one linear map (there is no
     non-linearity between fc and the head, models/pose_rigid.py:323-334).
 """
@@ -69,8 +69,8 @@ class ResNet34Engine:
         sd = state_dict
         self.n_inputs = n_inputs
         self.n_features = 512
-        self.c_pad = 16 if n_inputs <= 16 else 32
-        assert n_inputs <= 32, f"n_inputs={n_inputs} > 32 is not supported"
+        self.c_pad = 16 * ((n_inputs + 15) // 16)  # 16 (coarse), 32 (refiner) for the released models
+        assert n_inputs <= 256, f"n_inputs={n_inputs} > 256 is not supported"
         assert sd["backbone.conv1.weight"].shape[1] == n_inputs, "checkpoint / config channel mismatch"
         self.device = torch.device(device)
         self.act_dtype = _abi.act_dtype()

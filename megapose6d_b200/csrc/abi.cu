@@ -127,6 +127,7 @@ int mpx_raster_render_fused(const mpx_meshdb* db, const int32_t* d_label_idx, co
   out.ch_per_view = ch_per_view;
   out.views_per_sample = views_per_sample;
   out.depth_norm_z = d_depth_norm_z;
+  out.depth_norm_kind = static_cast<int>((flags >> MPX_RASTER_DEPTH_NORM_SHIFT) & 3u);
   return raster_launch(db->db, d_label_idx, d_TCO, d_K, n_views, h, w, flags, out, d_workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
 }
@@ -156,6 +157,7 @@ int mpx_render_crop_fused(const mpx_meshdb* db, const int32_t* d_label_idx, cons
   out.ch_per_view = ch_per_view;
   out.views_per_sample = 1;
   out.depth_norm_z = d_depth_norm_z;
+  out.depth_norm_kind = static_cast<int>((flags >> MPX_RASTER_DEPTH_NORM_SHIFT) & 3u);
   out.crop_images = reinterpret_cast<const float4*>(d_img_nhwc4);
   out.crop_b = b;
   out.crop_h = im_h;
@@ -269,8 +271,9 @@ int mpx_roi_align(const float* d_img_nhwc4, int b, int h, int w, const int32_t* 
 
 int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int32_t* d_im_idx,
                         const float* d_boxes, int n, int c, int out_h, int out_w, void* d_x, int c_pad,
-                        const float* d_depth_norm_z, void* stream) {
+                        const float* d_depth_norm_z, int depth_norm_kind, void* stream) {
   MPX_REQUIRE(n >= 0, "mpx_roi_align_fused: n < 0");
+  MPX_REQUIRE(depth_norm_kind >= 0 && depth_norm_kind <= 3, "mpx_roi_align_fused: depth_norm_kind=%d", depth_norm_kind);
   if (n > 0) {
     MPX_NOT_NULL(d_img_nhwc4);
     MPX_NOT_NULL(d_boxes);
@@ -282,6 +285,7 @@ int mpx_roi_align_fused(const float* d_img_nhwc4, int b, int h, int w, const int
   out.x = reinterpret_cast<act_t*>(d_x);
   out.c_pad = c_pad;
   out.depth_norm_z = d_depth_norm_z;
+  out.depth_norm_kind = depth_norm_kind;
   return roi_align_launch(d_img_nhwc4, b, h, w, d_im_idx, d_boxes, n, c, out_h, out_w, out,
                           static_cast<cudaStream_t>(stream));
 }

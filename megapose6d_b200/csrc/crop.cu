@@ -81,7 +81,7 @@ roi_align_kernel(const float4* __restrict__ images, int b, int h, int w, const i
       o[2] = to_act(acc.z);
       if (c == 4) {
         float d = acc.w;
-        if (out.depth_norm_z) d = fminf(fmaxf(d / __ldg(out.depth_norm_z + roi), 0.f), 2.f) - 1.f;
+        if (out.depth_norm_z) d = depth_norm(d, __ldg(out.depth_norm_z + roi), out.depth_norm_kind);
         o[3] = to_act(d);
       }
     }

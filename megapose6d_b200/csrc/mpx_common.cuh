@@ -113,6 +113,15 @@ __device__ __forceinline__ act_t to_act(float v) {
 }
 #endif
 
+// depth normalisation of PosePredictor.normalize_depth (models/pose_rigid.py:466-496); kind as in include/mpx.h
+// (MPX_DEPTH_NORM_*): 0 tCR_scale_clamp_center, 1 tCR_scale, 2 tCR_center_clamp, 3 none
+__device__ __forceinline__ float depth_norm(float d, float z, int kind) {
+  if (kind == 0) return fminf(fmaxf(__fdiv_rn(d, z), 0.f), 2.f) - 1.f;
+  if (kind == 1) return __fdiv_rn(d, z);
+  if (kind == 2) return fminf(fmaxf(d - z, -2.f), 2.f);
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while its stream predecessor is
 // still running, as soon as every CTA of the predecessor has executed pdl_trigger() (or exited).  It must call pdl_wait()
@@ -202,6 +211,7 @@ struct MeshDb {
   // {r, g, b, nx}, {ny, nz, u, v} so that a resolved pixel gathers its triangle with 1 + 6 16-byte loads
   int4* faces4;             // [sum_nf] {ia, ib, ic, 0}
   float4* vattr;            // [sum_nv, 2]
+  float* radius;            // [n_meshes] max |vertex| (point lights sit at 10 radii, panda3d_scene_renderer.py:104-136)
   // per-CTA scratch of the tiled kernel: row-range word per triangle, per-strip triangle lists, large-triangle list
   unsigned* tile_scratch;   // [slots, tile_words]
   long long tile_words;
@@ -217,8 +227,9 @@ struct RasterOut {
   float* normals;
   float* depth;
   act_t* x;  // fused network input (16-bit s2d NHWC), may be null
-  int c_pad, ch_offset, ch_per_view, views_per_sample;
+  int c_pad, ch_offset, ch_per_view, views_per_sample;  // ch_per_view: 3 rgb | 4 rgb+depth | 6 rgb+normals | 7 all
   const float* depth_norm_z;
+  int depth_norm_kind;  // MPX_DEPTH_NORM_*
   // optional: observation crop computed in the resolve pass (views_per_sample == 1), so that each
   // pixel's whole channel vector (crop | render | zero pad) is written with 16-byte stores
   const float4* crop_images;  // [crop_b, crop_h, crop_w] NHWC4, nullptr = no fused crop
@@ -259,6 +270,7 @@ struct CropOut {
   act_t* x;  // fused network input or null
   int c_pad;
   const float* depth_norm_z;
+  int depth_norm_kind;
 };
 int image_to_nhwc4(const float* in, int b, int c, int h, int w, float* out, cudaStream_t stream);
 int roi_align_launch(const float* images, int b, int h, int w, const int* im_idx, const float* boxes, int n,

@@ -182,7 +182,7 @@ constexpr int kNumConvs = 36;  // stem + 2 per block (16 blocks) + 3 downsample
 
 int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* const* conv_b,
                int n_convs, const float* head_w, const float* head_b, Net** out) {
-  MPX_REQUIRE(c_pad == 16 || c_pad == 32, "net: c_pad=%d must be 16 or 32", c_pad);
+  MPX_REQUIRE(c_pad >= 16 && c_pad <= 256 && c_pad % 16 == 0, "net: c_pad=%d must be a multiple of 16 in [16, 256]", c_pad);
   MPX_REQUIRE(n_convs == kNumConvs, "net: expected %d conv tensors, got %d", kNumConvs, n_convs);
   MPX_REQUIRE(out_dim >= 1 && out_dim <= 512, "net: out_dim=%d unsupported", out_dim);
   Net* net = new Net();

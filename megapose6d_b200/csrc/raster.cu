@@ -356,6 +356,8 @@ __device__ __forceinline__ TexRef mesh_texture(const MeshDb& db, int lab, long l
 // resolve_pixel shades one pixel from its visibility key and writes every requested output.
 struct ResolveCtx {
   int sample, vslot, npix;
+  const float* verts;  // model vertices of this view's mesh, for the point-light shading (nullptr: ambient light)
+  float light_dist;    // 10 x bounding radius
   bool fuse_crop, crop_collapsed;
   RoiParams roi;
   const float4* crop_img;
@@ -363,9 +365,12 @@ struct ResolveCtx {
 };
 
 // Called by every thread of the CTA (contains a barrier when the crop is fused).
-__device__ __forceinline__ ResolveCtx make_resolve_ctx(const RasterOut& out, int view, int h, int w, AxisW* s_axis) {
+__device__ __forceinline__ ResolveCtx make_resolve_ctx(const RasterOut& out, int view, int h, int w, AxisW* s_axis,
+                                                        const float* verts = nullptr, float radius = 0.f) {
   ResolveCtx c;
   c.npix = h * w;
+  c.verts = verts;
+  c.light_dist = __fmul_rn(radius, 10.0f);
   c.sample = out.x ? view / out.views_per_sample : 0;
   c.vslot = out.x ? view % out.views_per_sample : 0;
   c.fuse_crop = out.x != nullptr && out.crop_images != nullptr;
@@ -435,6 +440,38 @@ __device__ __forceinline__ void resolve_pixel(const ResolveCtx& ctx, const VtxSr
 #pragma unroll
       for (int k = 0; k < 3; ++k) col[k] = texref.modulate ? __fmul_rn(tc[k], col[k]) : tc[k];
     }
+    if (ctx.verts != nullptr) {
+      // render_normals=False models: ambient 0.1 + six white point lights of 0.4 on the object's axes at 10 bounding radii
+      // (make_scene_lights, panda3d_scene_renderer.py:104-136), Lambert term per fragment with the interpolated unit
+      // normal and position in the object frame, no attenuation, no normal flip on back faces (contract: oracle/raster_ref.c)
+      const float* pa = ctx.verts + 3 * f.x;
+      const float* pb = ctx.verts + 3 * f.y;
+      const float* pc = ctx.verts + 3 * f.z;
+      const float p0 = MPX_INTERP(__ldg(pa), __ldg(pb), __ldg(pc));
+      const float p1 = MPX_INTERP(__ldg(pa + 1), __ldg(pb + 1), __ldg(pc + 1));
+      const float p2 = MPX_INTERP(__ldg(pa + 2), __ldg(pb + 2), __ldg(pc + 2));
+      float u0 = nrm[0], u1 = nrm[1], u2 = nrm[2];
+      const float ul = __fsqrt_rn(__fmaf_rn(u0, u0, __fmaf_rn(u1, u1, __fmul_rn(u2, u2))));
+      if (ul > 0.f) {
+        const float inv = __frcp_rn(ul);
+        u0 = __fmul_rn(u0, inv); u1 = __fmul_rn(u1, inv); u2 = __fmul_rn(u2, inv);
+      }
+      float shade = 0.1f;
+#pragma unroll
+      for (int li = 0; li < 6; ++li) {
+        const float sgn = (li & 1) ? -ctx.light_dist : ctx.light_dist;
+        const float d0 = __fsub_rn(li < 2 ? sgn : 0.f, p0);
+        const float d1 = __fsub_rn((li >> 1) == 1 ? sgn : 0.f, p1);
+        const float d2 = __fsub_rn(li >= 4 ? sgn : 0.f, p2);
+        const float dist = __fsqrt_rn(__fmaf_rn(d0, d0, __fmaf_rn(d1, d1, __fmul_rn(d2, d2))));
+        if (dist > 0.f) {
+          const float ndl = __fdiv_rn(__fmaf_rn(u0, d0, __fmaf_rn(u1, d1, __fmul_rn(u2, d2))), dist);
+          shade = __fmaf_rn(0.4f, fmaxf(ndl, 0.f), shade);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) col[k] = __fmul_rn(col[k], shade);
+    }
 #undef MPX_INTERP
     r = quant8(col[0], q8);
     g = quant8(col[1], q8);
@@ -473,11 +510,9 @@ __device__ __forceinline__ void resolve_pixel(const ResolveCtx& ctx, const VtxSr
     const int hs = h >> 1, ws = w >> 1;
     act_t* base = out.x + ((static_cast<size_t>(sample) * hs + (i >> 1)) * ws + (j >> 1)) * (4 * out.c_pad) +
                   ((i & 1) * 2 + (j & 1)) * out.c_pad;
+    const bool has_n = out.ch_per_view >= 6, has_d = out.ch_per_view == 4 || out.ch_per_view == 7;
     float dn = dep;
-    if (out.ch_per_view == 7 && out.depth_norm_z) {
-      // tCR_scale_clamp_center: clamp(depth / z, 0, 2) - 1
-      dn = fminf(fmaxf(__fdiv_rn(dep, __ldg(out.depth_norm_z + sample)), 0.f), 2.f) - 1.f;
-    }
+    if (has_d && out.depth_norm_z) dn = depth_norm(dep, __ldg(out.depth_norm_z + sample), out.depth_norm_kind);
     if (ctx.fuse_crop) {
       // whole pixel vector: [crop rgb(d) | render rgb, normals(, depth) | zero pad], c_pad/8 16-byte stores
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -497,11 +532,12 @@ __device__ __forceinline__ void resolve_pixel(const ResolveCtx& ctx, const VtxSr
       ch[c++] = acc.x; ch[c++] = acc.y; ch[c++] = acc.z;
       if (out.crop_c == 4) {
         float d4 = (vacc < 0.99f) ? 0.f : acc.w;
-        if (out.depth_norm_z) d4 = fminf(fmaxf(d4 / __ldg(out.depth_norm_z + sample), 0.f), 2.f) - 1.f;
+        if (out.depth_norm_z) d4 = depth_norm(d4, __ldg(out.depth_norm_z + sample), out.depth_norm_kind);
         ch[c++] = d4;
       }
-      ch[c++] = r; ch[c++] = g; ch[c++] = b; ch[c++] = n0; ch[c++] = n1; ch[c++] = n2;
-      if (out.ch_per_view == 7) ch[c++] = dn;
+      ch[c++] = r; ch[c++] = g; ch[c++] = b;
+      if (has_n) { ch[c++] = n0; ch[c++] = n1; ch[c++] = n2; }
+      if (has_d) ch[c++] = dn;
       uint4* o4 = reinterpret_cast<uint4*>(base);
       uint4 v0, v1;
       v0.x = pack_act2(ch[0], ch[1]); v0.y = pack_act2(ch[2], ch[3]);
@@ -516,10 +552,12 @@ __device__ __forceinline__ void resolve_pixel(const ResolveCtx& ctx, const VtxSr
       o[0] = to_act(r);
       o[1] = to_act(g);
       o[2] = to_act(b);
-      o[3] = to_act(n0);
-      o[4] = to_act(n1);
-      o[5] = to_act(n2);
-      if (out.ch_per_view == 7) o[6] = to_act(dn);
+      if (has_n) {
+        o[3] = to_act(n0);
+        o[4] = to_act(n1);
+        o[5] = to_act(n2);
+      }
+      if (has_d) o[has_n ? 6 : 3] = to_act(dn);
     }
   }
 }
@@ -529,8 +567,9 @@ template <bool CACHED, bool TEXTURED>
 __device__ __forceinline__ void resolve_rows(const VtxSrc& src, const int4* __restrict__ faces,
                                              const float4* __restrict__ vattr, const TexRef& texref,
                                              const unsigned long long* __restrict__ vis, int view, int row_lo, int row_hi,
-                                             int h, int w, bool q8, bool gl_axes, const RasterOut& out, AxisW* s_axis) {
-  const ResolveCtx ctx = make_resolve_ctx(out, view, h, w, s_axis);
+                                             int h, int w, bool q8, bool gl_axes, const RasterOut& out, AxisW* s_axis,
+                                             const float* light_verts, float radius) {
+  const ResolveCtx ctx = make_resolve_ctx(out, view, h, w, s_axis, light_verts, radius);
   for (int pix = row_lo * w + threadIdx.x; pix < (row_hi + 1) * w; pix += blockDim.x) {
     const int i = pix / w, j = pix - i * w;
     resolve_pixel<CACHED, TEXTURED>(ctx, src, faces, vattr, texref, __ldcg(vis + pix), view, i, j, h, w, q8, gl_axes, out);
@@ -596,7 +635,8 @@ raster_kernel(const MeshDb db, const int* __restrict__ label_idx, const float* _
 
     resolve_rows<true, TEXTURED>(src, faces, db.vattr + 2 * v_off,
                                  TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0}, vis, view,
-                                 row_lo, row_hi, h, w, q8, gl_axes, out, s_axis);
+                                 row_lo, row_hi, h, w, q8, gl_axes, out, s_axis,
+                                 (flags & 4u) != 0 && valid ? db.verts + 3 * v_off : nullptr, valid ? db.radius[lab] : 0.f);
   }
 }
 
@@ -670,7 +710,8 @@ raster_resolve_kernel(const MeshDb db, const int* __restrict__ label_idx, const 
   resolve_rows<false, TEXTURED>(src, db.faces4 + f_off, db.vattr + 2 * v_off,
                                 TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0},
                                 vis_all + static_cast<size_t>(view) * h * w, view, row_lo, row_hi, h, w, (flags & 1u) != 0,
-                                (flags & 2u) != 0, out, s_axis);
+                                (flags & 2u) != 0, out, s_axis, (flags & 4u) != 0 && valid ? db.verts + 3 * v_off : nullptr,
+                                valid ? db.radius[lab] : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -809,7 +850,8 @@ raster_tiled_kernel(const MeshDb db, const int* __restrict__ label_idx, const fl
         for (int s = i0 / R; s <= i1 / R; ++s) g_list[atomicAdd(&s_cursor[s], 1)] = static_cast<unsigned>(tri);
       }
     }
-    const ResolveCtx ctx = make_resolve_ctx(out, view, h, w, s_axis);
+    const ResolveCtx ctx = make_resolve_ctx(out, view, h, w, s_axis, (flags & 4u) != 0 && valid ? db.verts + 3 * v_off : nullptr,
+                                            valid ? db.radius[lab] : 0.f);
     const TexRef texref = TEXTURED ? mesh_texture(db, lab, v_off, valid) : TexRef{nullptr, nullptr, 0, 0, 0};
     __syncthreads();
     const int nbig = s_nbig;
@@ -1011,6 +1053,17 @@ int meshdb_create(int n_meshes, const float* verts, const float* normals, const 
                             cudaMemcpyHostToDevice));
   MPX_CHECK_CUDA(cudaMemcpy(db->face_offsets, face_offsets, sizeof(long long) * (n_meshes + 1),
                             cudaMemcpyHostToDevice));
+  {  // bounding radius about the object origin, in float with the oracle's operation order
+    std::vector<float> rad(n_meshes, 0.f);
+    for (int i = 0; i < n_meshes; ++i)
+      for (long long v = vert_offsets[i]; v < vert_offsets[i + 1]; ++v) {
+        const float x = verts[3 * v], y = verts[3 * v + 1], z = verts[3 * v + 2];
+        const float r = sqrtf(fmaf(x, x, fmaf(y, y, z * z)));
+        if (r > rad[i]) rad[i] = r;
+      }
+    MPX_CHECK_CUDA(cudaMalloc(&db->radius, sizeof(float) * n_meshes));
+    MPX_CHECK_CUDA(cudaMemcpy(db->radius, rad.data(), sizeof(float) * n_meshes, cudaMemcpyHostToDevice));
+  }
   // packed copies: 16-byte faces, two float4 of attributes per vertex (uv filled in by meshdb_set_textures)
   {
     std::vector<int4> f4(nf > 0 ? nf : 1);
@@ -1088,6 +1141,7 @@ void meshdb_destroy(MeshDb* db) {
   cudaFree(db->faces4);
   cudaFree(db->vattr);
   cudaFree(db->tile_scratch);
+  cudaFree(db->radius);
   delete db;
 }
 
@@ -1103,7 +1157,8 @@ int raster_launch(const MeshDb* db, const int32_t* label_idx, const float* TCO, 
   MPX_REQUIRE(workspace_bytes >= raster_workspace_bytes(h, w), "raster: workspace too small");
   if (out.x) {
     MPX_REQUIRE(h % 2 == 0 && w % 2 == 0, "raster: fused output needs even resolution");
-    MPX_REQUIRE(out.ch_per_view == 6 || out.ch_per_view == 7, "raster: ch_per_view must be 6 or 7");
+    MPX_REQUIRE(out.ch_per_view == 3 || out.ch_per_view == 4 || out.ch_per_view == 6 || out.ch_per_view == 7,
+                "raster: ch_per_view must be 3 (rgb), 4 (+depth), 6 (+normals) or 7 (+normals, depth)");
     MPX_REQUIRE(out.views_per_sample >= 1 &&
                     out.ch_offset + out.views_per_sample * out.ch_per_view <= out.c_pad,
                 "raster: channels do not fit c_pad=%d", out.c_pad);

@@ -16,11 +16,24 @@ import torch
 
 from . import _abi
 
+def _sphere_26():
+    """get_26_views_TCO_pos_sphere (lib3d/multiview.py:149-160)."""
+    out = []
+    for y in (0, 1, 2):
+        for x in (0, -1, 1):
+            for z in (0, 1, -1):
+                if not (x == 0 and y == 1 and z == 0):
+                    out.append([x, y, z])
+    return out
+
+
 VIEW_OFFSETS = {
-    # lib3d/multiview.py:95-135
+    # camera positions wrt camera 0 in units of |tCR| (lib3d/multiview.py:95-160); make_TCO_multiview of the reference
+    # accepts "TCO+front_1view", "TCO+front_3views" and "sphere_26views" (:197-232)
     "TCO+front_1view": [[0, 0, 0]],
     "TCO+front_3views": [[0, 0, 0], [1, 0, 0], [-1, 0, 0]],
     "TCO+front_5views": [[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]],
+    "sphere_26views": _sphere_26(),
 }
 
 
@@ -72,12 +85,10 @@ def make_TCO_multiview(TCO: torch.Tensor, tCR: torch.Tensor, multiview_type: str
                        n_views: int = 4, remove_TCO_rendering: bool = False,
                        views_inplane_rotations: bool = False) -> torch.Tensor:
     """multiview.py:165-246 -> TCV_O [bsz, n_views, 4, 4]."""
-    if views_inplane_rotations:
-        raise NotImplementedError("views_inplane_rotations is not used by the released models")
     TCO, tCR = _f32(TCO), _f32(tCR)
     n = TCO.shape[0]
     if n_views == 1:
-        return TCO.unsqueeze(1).clone()
+        return _inplane(TCO.unsqueeze(1).clone(), remove_TCO_rendering) if views_inplane_rotations else TCO.unsqueeze(1).clone()
     if multiview_type not in VIEW_OFFSETS:
         raise ValueError(multiview_type)
     offs = np.ascontiguousarray(np.asarray(VIEW_OFFSETS[multiview_type], dtype=np.float32))
@@ -87,8 +98,23 @@ def make_TCO_multiview(TCO: torch.Tensor, tCR: torch.Tensor, multiview_type: str
                                                 _abi.ptr(out), _abi.stream_ptr()))
     if remove_TCO_rendering:
         out = out[:, 1:].contiguous()
+    if views_inplane_rotations:
+        return _inplane(out, remove_TCO_rendering)
     assert out.shape[1] == n_views, (out.shape, n_views)
     return out
+
+
+def _inplane(TCV_O: torch.Tensor, remove_TCO_rendering: bool) -> torch.Tensor:
+    """lib3d/multiview.py:236-246: every view also rotated in the image plane by 90, 180 and 270 degrees (the rotation
+    block only, as in the reference); 4x the views."""
+    assert remove_TCO_rendering
+    out = TCV_O.unsqueeze(2).repeat(1, 1, 4, 1, 1)
+    for idx, angle in enumerate((np.pi / 2, np.pi, 3 * np.pi / 2)):
+        c, s = float(np.cos(angle)), float(np.sin(angle))
+        # transforms3d.euler.euler2mat(0, 0, angle): rotation about z
+        dR = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], device=TCV_O.device, dtype=TCV_O.dtype)
+        out[:, :, idx + 1, :3, :3] = dR @ out[:, :, idx + 1, :3, :3]
+    return out.flatten(1, 2).contiguous()
 
 
 def update_pose(TCO: torch.Tensor, K_crop: torch.Tensor, pose_outputs: torch.Tensor, tCR: torch.Tensor) -> torch.Tensor:

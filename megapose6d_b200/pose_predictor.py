@@ -26,7 +26,8 @@ from torch import nn
 from . import lib3d
 from .backbone import ResNet34Engine
 from .meshes import BatchedMeshes
-from .renderer import BatchRenderer, Panda3dLightData
+from .renderer import (DEPTH_NORM_KINDS, DEPTH_NORM_SHIFT, RASTER_POINT_LIGHTS, BatchRenderer, Panda3dLightData,
+                       make_scene_lights)
 
 
 @dataclass
@@ -106,23 +107,22 @@ class PosePredictor(nn.Module):
         self.predict_rendered_views_logits = predict_rendered_views_logits
         self.remove_TCO_rendering = remove_TCO_rendering
         self.predict_pose_update = predict_pose_update
-        if not render_normals:
-            raise NotImplementedError("render_normals=False (point-light shading) is not implemented; "
-                                      "all released models use render_normals=True")
         if views_inplane_rotations:
-            raise NotImplementedError("views_inplane_rotations is not used by the released models")
+            assert remove_TCO_rendering, "views_inplane_rotations needs remove_TCO_rendering (lib3d/multiview.py:237)"
         if predict_pose_update:
             assert backbone.out_dim == 9 and not predict_rendered_views_logits
         if predict_rendered_views_logits:
             assert backbone.out_dim == n_rendered_views
         self._input_rgb_dims = [0, 1, 2]
         self._input_depth_dims = [3] if input_depth else []
-        self._n_single_render_channels = 3 + 3 + (1 if render_depth else 0)
+        self._n_single_render_channels = 3 + (3 if render_normals else 0) + (1 if render_depth else 0)
         n_inputs = (3 + (1 if input_depth else 0)) + self._n_single_render_channels * n_rendered_views
         assert n_inputs == backbone.n_inputs, (n_inputs, backbone.n_inputs)
-        if (input_depth or render_depth) and depth_normalization_type != "tCR_scale_clamp_center":
-            raise NotImplementedError("only depth_normalization_type='tCR_scale_clamp_center' (the released "
-                                      "RGB-D refiner) is fused into the crop/raster kernels")
+        if (input_depth or render_depth) and depth_normalization_type not in DEPTH_NORM_KINDS:
+            raise ValueError(f"Unknown depth_normalization_type = {depth_normalization_type}")
+        # what the fused crop / raster kernels need to know about this configuration (include/mpx.h)
+        self._depth_norm_kind = DEPTH_NORM_KINDS.get(depth_normalization_type, 3)
+        self._raster_flags = (0 if render_normals else RASTER_POINT_LIGHTS) | (self._depth_norm_kind << DEPTH_NORM_SHIFT)
         self.debug = False
         self.keep_images = False  # materialise fp32 images_crop / renders in the outputs
         self.max_batch = 1152     # hypotheses per fused launch (memory: ~9 MB each at 240x320)
@@ -215,11 +215,14 @@ class PosePredictor(nn.Module):
             raise NotImplementedError("random_ambient_light is a training-time augmentation")
         bsz, n_views = TCV_O.shape[:2]
         labels_mv = [labels[n] for n in range(bsz) for _ in range(n_views)]
-        lights = [[Panda3dLightData("ambient", (1.0, 1.0, 1.0, 1.0))] for _ in labels_mv]
+        if self.render_normals:  # pose_rigid.py:374-378
+            lights = [[Panda3dLightData("ambient", (1.0, 1.0, 1.0, 1.0))] for _ in labels_mv]
+        else:
+            lights = [make_scene_lights() for _ in labels_mv]
         data = self.renderer.render(labels=labels_mv, TCO=TCV_O.flatten(0, 1), K=KV.flatten(0, 1), light_datas=lights,
                                     resolution=self.render_size, render_normals=self.render_normals,
                                     render_depth=self.render_depth, render_mask=False)
-        cat = [data.rgbs, data.normals] + ([data.depths] if self.render_depth else [])
+        cat = [data.rgbs] + ([data.normals] if self.render_normals else []) + ([data.depths] if self.render_depth else [])
         renders = torch.cat(cat, dim=1)
         return renders.view(bsz, n_views, renders.shape[1], *renders.shape[-2:]).flatten(1, 2)
 
@@ -247,7 +250,7 @@ class PosePredictor(nn.Module):
         if self.input_depth:
             images[:, self._input_depth_dims] = self.normalize_depth(images[:, self._input_depth_dims], tCR)
         if self.render_depth:
-            dims = 6 + self._n_single_render_channels * torch.arange(0, self.n_rendered_views)
+            dims = (self._n_single_render_channels - 1) + self._n_single_render_channels * torch.arange(0, self.n_rendered_views)
             renders[:, dims] = self.normalize_depth(renders[:, dims], tCR)
         return images, renders
 
@@ -279,7 +282,7 @@ class PosePredictor(nn.Module):
         else:
             lab_mv = label_idx
             KV_crop = K_crop.unsqueeze(1)
-        depth_z = tCR[:, 2].contiguous() if (self.input_depth or self.render_depth) else None
+        depth_z = tCR[:, 2].contiguous() if (self.input_depth or self.render_depth) and self._depth_norm_kind != 3 else None
 
         # persistent network input per batch size: the pad channels are zeroed once, every real channel of every
         # pixel is rewritten by the crop and raster kernels on each call (background pixels included)
@@ -294,16 +297,16 @@ class PosePredictor(nn.Module):
             self.renderer.render_crop_fused(lab_mv, TCV_O.reshape(-1, 4, 4).contiguous(),
                                             KV_crop.reshape(-1, 3, 3).contiguous(), self.render_size, nhwc4, im_idx,
                                             boxes_crop, c_in, x, self.backbone.c_pad, self._n_single_render_channels,
-                                            depth_z)
+                                            depth_z, self._raster_flags)
         else:
             _abi.check(_abi.lib().mpx_roi_align_fused(
                 _abi.ptr(nhwc4), nhwc4.shape[0], nhwc4.shape[1], nhwc4.shape[2], _abi.ptr(im_idx), _abi.ptr(boxes_crop),
                 n, c_in, h, w, _abi.ptr(x), self.backbone.c_pad, _abi.ptr(depth_z if self.input_depth else None),
-                _abi.stream_ptr()))
+                self._depth_norm_kind, _abi.stream_ptr()))
             self.renderer.render_fused(lab_mv, TCV_O.reshape(-1, 4, 4).contiguous(),
                                        KV_crop.reshape(-1, 3, 3).contiguous(), n_views, self.render_size, x,
                                        self.backbone.c_pad, c_in, self._n_single_render_channels,
-                                       depth_z if self.render_depth else None)
+                                       depth_z if self.render_depth else None, self._raster_flags)
         timing["render"] += t_r.stop()
         t_m = _Timer(cuda_timer)
         t_m.start()
@@ -387,7 +390,8 @@ class PosePredictor(nn.Module):
             tCR = TCO_input[:, :3, 3].contiguous()  # tOR = 0 (pose_rigid.py:527-529)
             TCV_O = lib3d.make_TCO_multiview(TCO_input, tCR, multiview_type=self.multiview_type,
                                              n_views=self.n_rendered_views,
-                                             remove_TCO_rendering=self.remove_TCO_rendering)
+                                             remove_TCO_rendering=self.remove_TCO_rendering,
+                                             views_inplane_rotations=self.views_inplane_rotations)
             step = self._step(images, im_idx, K, label_idx, TCO_input, tCR, TCV_O, timing, cuda_timer)
             if self.predict_pose_update:
                 TCO_output = self.update_pose(TCO_input, step["K_crop"], step["out"], tCR)

@@ -18,12 +18,31 @@ from .object_dataset import RigidObjectDataset
 
 RASTER_QUANTIZE8 = 1
 RASTER_NORMALS_GL = 2
+RASTER_POINT_LIGHTS = 4
+DEPTH_NORM_KINDS = {"tCR_scale_clamp_center": 0, "tCR_scale": 1, "tCR_center_clamp": 2, "none": 3, None: 3}
+DEPTH_NORM_SHIFT = 8
+
+
+def is_scene_lights(lights) -> bool:
+    """True for the light set of `make_scene_lights()` (ambient + point lights, what models with render_normals=False
+    render under, models/pose_rigid.py:374-378), False for a single ambient light."""
+    kinds = [getattr(light, "light_type", "ambient") for light in lights]
+    return "point" in kinds
+
+
+def make_scene_lights(ambient_light_color=(0.1, 0.1, 0.1, 1.0), point_lights_color=(0.4, 0.4, 0.4, 1.0)):
+    """panda3d_scene_renderer.py:104-136: 1 ambient light + 6 point lights on the object's axes at 10 bounding radii."""
+    lights = [Panda3dLightData("ambient", ambient_light_color)]
+    for axis in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+        lights.append(Panda3dLightData("point", point_lights_color, positioning_function=axis))
+    return lights
 
 
 @dataclass
 class Panda3dLightData:
-    """Light description of the reference API (panda3d_renderer/types.py:108-130); only ambient
-    white light (the zoo models' render_normals=True path) is rendered."""
+    """Light description of the reference API (panda3d_renderer/types.py:108-130).  Two light sets are rendered, the two
+    the reference's models use: one white ambient light (render_normals=True, all released models) and
+    `make_scene_lights()` (render_normals=False)."""
 
     light_type: str = "ambient"
     color: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
@@ -60,20 +79,32 @@ class BatchRenderer:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
         return self._workspace
 
-    def _check_lights(self, light_datas) -> None:
-        if light_datas is None:
-            return
+    def _light_flags(self, light_datas) -> int:
+        """0 for white ambient light, RASTER_POINT_LIGHTS for make_scene_lights(); the whole batch uses one light set."""
+        if light_datas is None or len(light_datas) == 0:
+            return 0
+        kinds = {is_scene_lights(lights) for lights in light_datas}
+        if len(kinds) > 1:
+            raise NotImplementedError("a batch must use one light set (ambient, or make_scene_lights())")
+        if not kinds.pop():
+            for lights in light_datas:
+                for light in lights:
+                    c = tuple(getattr(light, "color", (1.0, 1.0, 1.0, 1.0)))[:3]
+                    if c != (1.0, 1.0, 1.0):
+                        raise NotImplementedError("ambient light colours other than white are a training-time augmentation")
+            return 0
+        ref = make_scene_lights()
         for lights in light_datas:
-            for light in lights:
-                if getattr(light, "light_type", "ambient") != "ambient":
-                    raise NotImplementedError("only ambient lighting (render_normals=True models) is implemented")
+            if [(l.light_type, tuple(l.color)) for l in lights] != [(l.light_type, tuple(l.color)) for l in ref]:
+                raise NotImplementedError("point lights other than make_scene_lights() are not implemented")
+        return RASTER_POINT_LIGHTS
 
     def render(self, labels: List[str], TCO: torch.Tensor, K: torch.Tensor, light_datas=None,
                resolution: Tuple[int, int] = (240, 320), render_depth: bool = False, render_mask: bool = False,
                render_normals: bool = False) -> BatchRenderOutput:
         if render_mask:
             raise NotImplementedError
-        self._check_lights(light_datas)
+        flags = self.flags | self._light_flags(light_datas)
         n = TCO.shape[0]
         assert TCO.shape == (n, 4, 4) and K.shape == (n, 3, 3) and len(labels) == n
         h, w = resolution
@@ -86,19 +117,21 @@ class BatchRenderer:
         depths = torch.empty(n, 1, h, w, device=dev, dtype=torch.float32) if render_depth else None
         ws = self.workspace(h, w, dev)
         _abi.check(_abi.lib().mpx_raster_render(self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K),
-                                                n, h, w, self.flags, _abi.ptr(rgbs), _abi.ptr(normals),
+                                                n, h, w, flags, _abi.ptr(rgbs), _abi.ptr(normals),
                                                 _abi.ptr(depths), _abi.ptr(ws), ws.numel(), _abi.stream_ptr()))
         return BatchRenderOutput(rgbs=rgbs, normals=normals, depths=depths)
 
     def render_fused(self, label_idx: torch.Tensor, TCO: torch.Tensor, K: torch.Tensor, views_per_sample: int,
                      resolution: Tuple[int, int], x: torch.Tensor, c_pad: int, ch_offset: int, ch_per_view: int,
-                     depth_norm_z: Optional[torch.Tensor] = None) -> None:
-        """Render straight into the network input tensor `x` (see include/mpx.h)."""
+                     depth_norm_z: Optional[torch.Tensor] = None, extra_flags: int = 0) -> None:
+        """Render straight into the network input tensor `x` (see include/mpx.h); `extra_flags`: RASTER_POINT_LIGHTS,
+        depth-normalisation kind << DEPTH_NORM_SHIFT."""
         n = TCO.shape[0]
         h, w = resolution
         ws = self.workspace(h, w, TCO.device)
         _abi.check(_abi.lib().mpx_raster_render_fused(
-            self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K), n, views_per_sample, h, w, self.flags,
+            self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K), n, views_per_sample, h, w,
+            self.flags | extra_flags,
             _abi.ptr(x), c_pad, ch_offset, ch_per_view, _abi.ptr(depth_norm_z), _abi.ptr(ws), ws.numel(),
             _abi.stream_ptr()))
 
@@ -106,13 +139,13 @@ class BatchRenderer:
     def render_crop_fused(self, label_idx: torch.Tensor, TCO: torch.Tensor, K_crop: torch.Tensor,
                           resolution: Tuple[int, int], images_nhwc4: torch.Tensor, im_idx: torch.Tensor,
                           boxes_crop: torch.Tensor, c_in: int, x: torch.Tensor, c_pad: int, ch_per_view: int,
-                          depth_norm_z: Optional[torch.Tensor] = None) -> None:
+                          depth_norm_z: Optional[torch.Tensor] = None, extra_flags: int = 0) -> None:
         """Single-view samples: render + observation crop in one pass, whole pixel vectors written once."""
         n = TCO.shape[0]
         h, w = resolution
         ws = self.workspace(h, w, TCO.device)
         _abi.check(_abi.lib().mpx_render_crop_fused(
-            self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K_crop), n, h, w, self.flags,
+            self.mesh_db.handle, _abi.ptr(label_idx), _abi.ptr(TCO), _abi.ptr(K_crop), n, h, w, self.flags | extra_flags,
             _abi.ptr(images_nhwc4), images_nhwc4.shape[0], images_nhwc4.shape[1], images_nhwc4.shape[2], _abi.ptr(im_idx),
             _abi.ptr(boxes_crop), c_in, _abi.ptr(x), c_pad, ch_per_view, _abi.ptr(depth_norm_z), _abi.ptr(ws), ws.numel(),
             _abi.stream_ptr()))

@@ -281,8 +281,15 @@ def update_pose(TCO, K_crop, pose_outputs, tCR):
 # ---------------------------------------------------------------------------------------------
 _TCCGL = np.array([[1, 0, 0, 0], [0, 0, -1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float64)
 
+def _sphere_26():
+    """get_26_views_TCO_pos_sphere (lib3d/multiview.py:149-160)."""
+    return np.array([[x, y, z] for y in (0, 1, 2) for x in (0, -1, 1) for z in (0, 1, -1) if not (x == 0 and y == 1 and z == 0)],
+                    dtype=np.float64)
+
+
 VIEW_OFFSETS = {
-    # lib3d/multiview.py:95-135
+    # lib3d/multiview.py:95-160
+    "sphere_26views": _sphere_26(),
     "TCO+front_1view": np.array([[0, 0, 0]], dtype=np.float64),
     "TCO+front_3views": np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0]], dtype=np.float64),
     "TCO+front_5views": np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64),
@@ -327,12 +334,25 @@ def views_TC0_CV(TCO: np.ndarray, tCR: np.ndarray, offsets: np.ndarray):
     return out
 
 
+def _inplane_rotations(TCV_O: torch.Tensor, remove_TCO_rendering: bool) -> torch.Tensor:
+    """lib3d/multiview.py:236-246 (transforms3d.euler.euler2mat(0, 0, a) = rotation about z by a)."""
+    assert remove_TCO_rendering
+    TCV_O = TCV_O.unsqueeze(2).repeat(1, 1, 4, 1, 1)
+    for idx, angle in enumerate([np.pi / 2, np.pi, 3 * np.pi / 2]):
+        c, s = np.cos(angle), np.sin(angle)
+        dR = torch.as_tensor(np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]]), dtype=TCV_O.dtype)
+        TCV_O[:, :, idx + 1, :3, :3] = dR @ TCV_O[:, :, idx + 1, :3, :3]
+    return TCV_O.flatten(1, 2)
+
+
 def make_TCO_multiview(TCO: torch.Tensor, tCR: torch.Tensor, multiview_type: str = "TCO+front_3views",
-                       n_views: int = 4, remove_TCO_rendering: bool = False) -> torch.Tensor:
-    """lib3d/multiview.py:165-246 (n_views == 1 and the 'TCO+front_*' types)."""
+                       n_views: int = 4, remove_TCO_rendering: bool = False,
+                       views_inplane_rotations: bool = False) -> torch.Tensor:
+    """lib3d/multiview.py:165-246."""
     bsz = TCO.shape[0]
     if n_views == 1:
-        return TCO.unsqueeze(1).clone()
+        out = TCO.unsqueeze(1).clone()
+        return _inplane_rotations(out, remove_TCO_rendering) if views_inplane_rotations else out
     offsets = VIEW_OFFSETS[multiview_type]
     TCO_np, tCR_np = TCO.cpu().numpy(), tCR.cpu().numpy()
     all_views = []
@@ -341,7 +361,8 @@ def make_TCO_multiview(TCO: torch.Tensor, tCR: torch.Tensor, multiview_type: str
         views += views_TC0_CV(TCO_np[b], tCR_np[b], offsets)
         all_views.append(views)
     TC0_CV = torch.as_tensor(np.stack(all_views), dtype=TCO.dtype)
-    return invert_transform_matrices(TC0_CV) @ TCO.unsqueeze(1)
+    out = invert_transform_matrices(TC0_CV) @ TCO.unsqueeze(1)
+    return _inplane_rotations(out, remove_TCO_rendering) if views_inplane_rotations else out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -124,7 +124,9 @@ class RefRenderer:
         self.n_threads = n_threads or os.cpu_count() or 1
 
     def render(self, labels, TCO, K, light_datas=None, resolution=(240, 320), render_depth=False, render_mask=False,
-               render_normals=False):
+               render_normals=False, point_lights=False):
+        """`point_lights`: shade the albedo under make_scene_lights() (panda3d_scene_renderer.py:104-136) instead of white
+        ambient light -- what models with render_normals=False are fed (models/pose_rigid.py:374-378)."""
         if render_mask:
             raise NotImplementedError
         n = len(labels)
@@ -141,7 +143,7 @@ class RefRenderer:
             ctypes.c_int(len(m.labels)), p(m.verts), p(m.normals), p(m.colors), p(m.vert_offsets), p(m.faces),
             p(m.face_offsets), p(getattr(m, "uv", None)), p(getattr(m, "tex", None)), p(getattr(m, "tex_offsets", None)),
             p(getattr(m, "tex_dims", None)), p(getattr(m, "tex_modulate", None)), p(idx), p(T), p(Kn), ctypes.c_int(n),
-            ctypes.c_int(h), ctypes.c_int(w), ctypes.c_uint(self.flags), p(rgb), p(nrm), p(dep),
+            ctypes.c_int(h), ctypes.c_int(w), ctypes.c_uint(self.flags | (4 if point_lights else 0)), p(rgb), p(nrm), p(dep),
             ctypes.c_int(self.n_threads))
         assert rc == 0, f"raster_ref_render_batch_tex failed ({rc})"
         return dict(rgbs=torch.from_numpy(rgb), normals=torch.from_numpy(nrm) if nrm is not None else None,
@@ -163,7 +165,9 @@ class RefPosePredictor:
         self.multiview_type = cfg.get("multiview_type", "TCO")
         self.remove_TCO_rendering = cfg.get("remove_TCO_rendering", False)
         self.predict_pose_update = cfg.get("predict_pose_update", True)
-        self.n_render_ch = 6 + (1 if self.render_depth else 0)
+        self.render_normals = cfg.get("render_normals", True)
+        self.views_inplane_rotations = cfg.get("views_inplane_rotations", False)
+        self.n_render_ch = 3 + (3 if self.render_normals else 0) + (1 if self.render_depth else 0)
         self.net = net if net is not None else (lambda x: resnet_ref.forward(self.sd, x))
 
     # pose_rigid.py:180-247
@@ -194,8 +198,9 @@ class RefPosePredictor:
         bsz, n_views = TCV_O.shape[:2]
         labels_mv = [labels[n] for n in range(bsz) for _ in range(n_views)]
         d = self.renderer.render(labels_mv, TCV_O.flatten(0, 1), KV.flatten(0, 1), resolution=self.render_size,
-                                 render_normals=True, render_depth=self.render_depth)
-        cat = [d["rgbs"], d["normals"]] + ([d["depths"]] if self.render_depth else [])
+                                 render_normals=self.render_normals, render_depth=self.render_depth,
+                                 point_lights=not self.render_normals)
+        cat = [d["rgbs"]] + ([d["normals"]] if self.render_normals else []) + ([d["depths"]] if self.render_depth else [])
         r = torch.cat(cat, dim=1)
         return r.view(bsz, n_views, r.shape[1], *r.shape[-2:]).flatten(1, 2)
 
@@ -205,7 +210,8 @@ class RefPosePredictor:
         if self.input_depth:
             images[:, [3]] = L.normalize_depth(images[:, [3]], tCR, self.norm_type)
         if self.render_depth:
-            dims = 6 + self.n_render_ch * torch.arange(0, self.n_views)
+            n_views = renders.shape[1] // self.n_render_ch
+            dims = (self.n_render_ch - 1) + self.n_render_ch * torch.arange(0, n_views)
             renders[:, dims] = L.normalize_depth(renders[:, dims], tCR, self.norm_type)
         return images, renders
 
@@ -219,7 +225,8 @@ class RefPosePredictor:
         for n in range(n_iterations):
             TCO_input = L.normalize_T(TCO_input)
             tCR = TCO_input[..., :3, -1].clone()
-            TCV_O = L.make_TCO_multiview(TCO_input, tCR, self.multiview_type, self.n_views, self.remove_TCO_rendering)
+            TCV_O = L.make_TCO_multiview(TCO_input, tCR, self.multiview_type, self.n_views, self.remove_TCO_rendering,
+                                         self.views_inplane_rotations)
             tCV_R = TCV_O[..., :3, -1].clone()
             images_crop, K_crop, boxes_rend, boxes_crop = self.crop_inputs(images, K, TCO_input, tCR, labels)
             KV_crop = self.compute_crops_multiview(images, K, TCV_O, tCV_R, labels)

@@ -27,6 +27,10 @@
  *     (u, v) interpolated like the other attributes, wrapped to [0, 1) (repeat), v up (image row = (1 - v) * th - 0.5),
  *     bilinear filter over texel centres without mip-mapping, texel = byte / 255; the texture replaces the albedo, or
  *     modulates the interpolated vertex colours when the mesh has them
+ *   - flags bit 2 (4): the albedo is lit by make_scene_lights() (panda3d_scene_renderer.py:104-136: ambient 0.1 + six white
+ *     point lights of 0.4 at +-10 r on the object's axes, r = max |vertex|) instead of ambient 1.0: Lambert term per
+ *     fragment from the perspective-correct position and the normalised interpolated normal in the object frame, no
+ *     attenuation, no normal flip on back faces: rgb = albedo * (0.1 + 0.4 * sum_i max(0, n . (L_i - p) / |L_i - p|))
  * Every float operation is a single correctly-rounded IEEE operation in a fixed order (compile with
  * -ffp-contract=off) so that the device kernel can reproduce the results exactly.
  */
@@ -158,7 +162,17 @@ static int render_view(const float* verts, const float* normals, const float* co
                        const int32_t* faces, int nf, const float* TCO, const float* K, int h, int w,
                        unsigned flags, const tex_t* texture, float* rgb, float* nrm, float* depth, int32_t* tri_id) {
   const int npix = h * w;
-  const int q8 = (flags & 1u) != 0, gl_axes = (flags & 2u) != 0;
+  const int q8 = (flags & 1u) != 0, gl_axes = (flags & 2u) != 0, lights = (flags & 4u) != 0;
+  float light_dist = 0.f;
+  if (lights) {
+    float radius = 0.f;
+    for (int i = 0; i < nv; ++i) {
+      const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+      const float r = sqrtf(fmaf(x, x, fmaf(y, y, z * z)));
+      if (r > radius) radius = r;
+    }
+    light_dist = radius * 10.0f;
+  }
   int valid = 1;
   for (int i = 0; i < 16; ++i) valid = valid && isfinite(TCO[i]);
   for (int i = 0; i < 9; ++i) valid = valid && isfinite(K[i]);
@@ -241,6 +255,30 @@ static int render_view(const float* verts, const float* normals, const float* co
       float tc[3];
       texture_sample(texture, tu, tv, tc);
       for (int k = 0; k < 3; ++k) col[k] = texture->modulate ? tc[k] * col[k] : tc[k];
+    }
+    if (lights) {
+      float p[3];
+      for (int k = 0; k < 3; ++k)
+        p[k] = fmaf(b0, verts[3 * ia + k], fmaf(b1, verts[3 * ib + k], b2 * verts[3 * ic + k]));
+      float u0 = nn[0], u1 = nn[1], u2 = nn[2];
+      const float ul = sqrtf(fmaf(u0, u0, fmaf(u1, u1, u2 * u2)));
+      if (ul > 0.f) {
+        const float inv = 1.0f / ul;
+        u0 = u0 * inv; u1 = u1 * inv; u2 = u2 * inv;
+      }
+      float shade = 0.1f;
+      for (int li = 0; li < 6; ++li) {
+        const float sgn = (li & 1) ? -light_dist : light_dist;
+        const float d0 = (li < 2 ? sgn : 0.f) - p[0];
+        const float d1 = ((li >> 1) == 1 ? sgn : 0.f) - p[1];
+        const float d2 = (li >= 4 ? sgn : 0.f) - p[2];
+        const float dist = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+        if (dist > 0.f) {
+          const float ndl = fmaf(u0, d0, fmaf(u1, d1, u2 * d2)) / dist;
+          shade = fmaf(0.4f, fmaxf(ndl, 0.0f), shade);
+        }
+      }
+      for (int k = 0; k < 3; ++k) col[k] = col[k] * shade;
     }
     if (rgb) {
       rgb[pix] = quant8(col[0], q8);

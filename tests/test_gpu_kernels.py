@@ -258,7 +258,7 @@ def test_fused_crop_render_matches_separate_kernels(scene, raster_mode):
     xa = torch.zeros(n, h // 2, w // 2, 4 * c_pad, device=DEV, dtype=ACT)
     xb = torch.full_like(xa, 7.0)  # the fused kernel must overwrite every channel, pad included
     _abi.check(_abi.lib().mpx_roi_align_fused(_abi.ptr(nhwc4), 1, 480, 640, _abi.ptr(im_idx), _abi.ptr(boxes), n, 3, h, w,
-                                              _abi.ptr(xa), c_pad, None, _abi.stream_ptr()))
+                                              _abi.ptr(xa), c_pad, None, 0, _abi.stream_ptr()))
     r.render_fused(lab, TCO, Kc, 1, (h, w), xa, c_pad, 3, 6)
     r.render_crop_fused(lab, TCO, Kc, (h, w), nhwc4, im_idx, boxes, 3, xb, c_pad, 6)
     torch.cuda.synchronize()

@@ -88,3 +88,44 @@ def test_nearest_surface_wins_and_order_independent():
     centre = outs[0]["rgbs"][0, :, 120, 160]
     assert centre[0] == 1 and centre[1] == 0  # the red quad (z = 0.5) hides the green one (z = 0.52)
     assert abs(outs[0]["depths"][0, 0, 120, 160].item() - 0.5) < 1e-6
+
+
+def test_oracle_point_lights_and_multiview_variants():
+    """The contract's render_normals=False light set (ambient 0.1 + six axis lights of 0.4 at 10 radii): for far lights the
+    Lambert sum is |nx| + |ny| + |nz| of the normal, so lit / albedo lies in [0.5, 0.1 + 0.4 sqrt(3)]; and the extra
+    multiview types (26-view sphere, in-plane rotations) keep every view a rigid transform looking at the object."""
+    import numpy as np
+    import torch
+
+    from megapose6d_b200 import procedural
+    from oracle import lib3d_ref as L
+    from oracle import pipeline_ref
+    from tests import helpers
+
+    ds, _, _ = helpers.make_scene(1, seed=2)
+    rm = helpers.ref_meshes_from_dataset(ds)
+    TCO = torch.from_numpy(procedural.random_poses(2, 4, z_range=(0.3, 0.5), xy_range=0.01)).float()
+    K = torch.tensor([[600.0, 0, 80], [0, 600, 60], [0, 0, 1]]).repeat(2, 1, 1)
+    labels = [ds[0].label] * 2
+    r = pipeline_ref.RefRenderer(rm, quantize8=False)
+    amb = r.render(labels, TCO, K, None, (120, 160), render_depth=True)
+    lit = r.render(labels, TCO, K, None, (120, 160), render_depth=True, point_lights=True)
+    assert torch.equal(amb["depths"], lit["depths"])
+    cov = (amb["depths"][:, 0] > 0) & (amb["rgbs"].min(1).values > 0.05)
+    ratio = lit["rgbs"].permute(0, 2, 3, 1)[cov] / amb["rgbs"].permute(0, 2, 3, 1)[cov]
+    assert cov.sum() > 2000 and ratio.min() > 0.45 and ratio.max() < 0.1 + 0.4 * 3 ** 0.5 + 0.02
+    assert (ratio.max(1).values - ratio.min(1).values).max() < 1e-4  # one shade per pixel, applied to all three channels
+
+    T = torch.from_numpy(procedural.random_poses(3, 5)).float()
+    tCR = T[:, :3, 3].contiguous()
+    V = L.make_TCO_multiview(T, tCR, "sphere_26views", 27, False)
+    assert V.shape == (3, 27, 4, 4) and torch.allclose(V[:, 0], T)
+    R = V[..., :3, :3].double()
+    assert torch.allclose(R.transpose(-1, -2) @ R, torch.eye(3, dtype=torch.float64).expand_as(R), atol=1e-5)
+    # every extra camera sees the object origin (tCR = t, reference point = origin) on its optical axis
+    t = V[:, 1:, :3, 3]
+    assert (t[..., :2].abs().max() < 1e-5) and (t[..., 2] > 0).all()
+    W = L.make_TCO_multiview(T, tCR, "TCO+front_1view", 4, True, True)
+    assert W.shape == (3, 4, 4, 4)
+    Rz = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    assert torch.allclose(W[:, 1, :3, :3], Rz @ W[:, 0, :3, :3], atol=1e-6) and torch.equal(W[:, 1, :3, 3], W[:, 0, :3, 3])

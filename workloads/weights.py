@@ -27,7 +27,8 @@ REFINER_RGBD_CFG = dict(REFINER_CFG, render_depth=True, input_depth=True)
 
 
 def n_inputs(cfg) -> int:
-    return (3 + int(cfg["input_depth"])) + (6 + int(cfg["render_depth"])) * cfg["n_rendered_views"]
+    per_view = 3 + (3 if cfg.get("render_normals", True) else 0) + int(cfg["render_depth"])  # pose_models_cfg.py:95-103
+    return (3 + int(cfg["input_depth"])) + per_view * cfg["n_rendered_views"]
 
 
 def init_state_dict(n_inputs: int, head: str, head_dim: int, seed: int = 0) -> Dict[str, torch.Tensor]:
