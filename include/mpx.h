@@ -202,6 +202,8 @@ size_t mpx_net_input_bytes(int n, int h, int w, int c_pad);
 /* single convolution (also the unit the parity tests exercise):
  *   d_x [n,H,W,C_in] act16, d_w [C_out, R*S*C_in] act16, d_bias [C_out] fp32,
  *   d_residual / d_out [n,P,Q,C_out] act16 (residual may be NULL)
+ *   relu: bit 0 = ReLU; bit 1 = the weights are the space-to-depth form of the 7x7 stem (4x4 taps over C_in = 64: the 15 of
+ *   64 (tap, 16-channel) slices that are zero by construction are not multiplied, megapose6d_b200/backbone.py: _stem_s2d)
  *   block_n: 0 = auto, else 64|128|256; max_ctas: 0 = one per SM */
 int mpx_conv2d(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
                     const float* d_bias, int c_out, int r, int s, int stride, int pad_lo_h,
@@ -217,7 +219,7 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                            void* d_out, int block_n, int splits, void* stream);
 
-/* kernel selection bits for block_n == 0 (auto), default 11:
+/* kernel selection bits for block_n == 0 (auto), default 49163 = 1 + 2 + 8 + 16384 + 32768:
  *   1   window kernels: 64->64 stride-1 convolutions (stem, layer1) and 128->128 3x3 (layer2) load their activations
  *       once per tile as a contiguous window and address the filter taps as row-shifted operand descriptors
  *   2   the CTA-pair (cta_group::2) kernel serves 256-wide tiles;  4  and 128-wide tiles
@@ -225,15 +227,12 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
  *   16  a single epilogue warp set in the 64->64 window kernel (default two)
  *   32  a single MMA-issuing thread in the 64->64 window kernel (default two);  64  three
  *   128 three epilogue warp sets
- *   256 disable the layer2 window kernel (TMA-im2col kernel instead)
+ *   256 disable the single-CTA layer2 window kernel (TMA-im2col kernel instead)
  *   512 launch without programmatic dependent launch;  1024 older row-group choice of the window kernel (diagnostic)
- *   2048 window kernel: a stage is refilled only after every MMA issuer has seen its fill (experimental)
- *   4096 window + CTA-pair kernel for the 3x3 stride-1 convolutions of layer3 / layer4 (experimental, unmeasured)
- *   8192 the same kernel with 128-wide tiles for the 128 -> 128 convolutions of layer2, ahead of the layer2 window
- *        kernel (experimental, unmeasured)
- *   16384 the layer2 window kernel on CTA pairs (cta_group::2, two MMA issuers in the leader; experimental, unmeasured)
- *   32768 the 64 -> 64 window kernel (stem, layer1) on CTA pairs (experimental, unmeasured)
- *   65536 pair kernels of bits 14 / 15: request the whole residual row before waiting for the accumulator (experimental)
+ *   16384 the layer2 window kernel on CTA pairs (cta_group::2, two MMA issuers in the leader): layer2 0.167 -> 0.153 ms
+ *   32768 the 64 -> 64 window kernel (stem, layer1) on CTA pairs: layer1 0.255 -> 0.227 ms per convolution at batch 576
+ * (r02 A/B, profiles/r02_layer_table_mode_bits.json; the other round-1 candidates -- pair-window kernels for layer3/4 and
+ * 128-wide layer2 tiles, residual preload -- measured no gain and were removed.)
  * 0 = single-CTA TMA-im2col kernel only */
 int mpx_conv_set_mode(int mode);
 

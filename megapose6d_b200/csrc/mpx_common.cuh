@@ -176,6 +176,7 @@ struct ConvDesc {
   int C_out, R, S, stride;
   int pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
   int relu;
+  int s2d_stem;  // 1: the weights are the space-to-depth form of the 7x7 stem (zero slices are skipped), see conv_tc.cu
 };
 // splitk: 0 = never, -1 = heuristic (few output tiles, long K loop), 1|2|4|8 = that many k-splits (cluster size)
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,

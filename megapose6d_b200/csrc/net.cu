@@ -299,7 +299,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   int rc;
   // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input
   {
-    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1};
+    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, 1};
     rc = conv_forward(d, x, net->conv_w[ci], net->conv_b[ci], nullptr, buf_stem, 0, 0, stream);
     if (rc != MPX_OK) return rc;
     ++ci;

@@ -22,7 +22,8 @@ from tests import helpers
 pytestmark = pytest.mark.gpu
 ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
 ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
-DEFAULT_CONV_MODE = 11  # window | pair(256) | split-K in the network
+SINGLE_CTA_MODE = 11  # window | pair(256) | split-K, without the CTA-pair window kernels of bits 14 / 15
+DEFAULT_CONV_MODE = 49163  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15)
 
 
 def _conv_ref(x, w, bias, stride, pads, relu, residual):
@@ -272,7 +273,7 @@ def test_layer2_window_kernel_agrees_with_im2col_and_torch(case):
     res = torch.randn(n, h, w, 128, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        for mode in (DEFAULT_CONV_MODE, DEFAULT_CONV_MODE | 256):
+        for mode in (SINGLE_CTA_MODE, SINGLE_CTA_MODE | 256):  # single-CTA layer2 window kernel vs TMA-im2col kernel
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, 128), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 128, _abi.ptr(wt.view(128, -1)), _abi.ptr(bias), 128, 3, 3,
@@ -346,35 +347,22 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
     assert torch.equal(outs[0], outs[1])  # same products, same K order, fp32 accumulation in TMEM
 
 
-EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("MPX_EXPERIMENTAL") != "1",
-                                  reason="kernel variants that are off by default and not yet measured "
-                                         "(set MPX_EXPERIMENTAL=1 to run)")
-
 PAIR_WINDOW_CASES = [
-    # name, n, h, w, c_in, c_out, relu, use_res, max_ctas, mode bit
-    ("l3", 6, 15, 20, 256, 256, True, True, 4, 4096),
-    ("l3_nores_many_per_pair", 13, 15, 20, 256, 256, True, False, 2, 4096),
-    ("l4_two_cout_tiles", 9, 8, 10, 512, 512, True, True, 4, 4096),
-    ("odd_size", 5, 9, 13, 128, 256, False, True, 2, 4096),
-    ("l2_128wide", 4, 30, 40, 128, 128, True, True, 4, 8192),
-    ("l2_128wide_many_per_pair", 9, 30, 40, 128, 128, True, False, 2, 8192),
-    ("l2_128wide_odd_size", 3, 17, 23, 128, 128, False, True, 2, 8192),
-    ("l2_128wide_tiny_images", 11, 5, 7, 128, 128, True, True, 2, 8192),
-    # conv_window2q_kernel (bit 14): the layer2 window kernel on CTA pairs, two issuers
-    ("l2_pairs_odd_super_tiles", 4, 30, 40, 128, 128, True, True, 4, 16384),
-    ("l2_pairs_many_per_pair", 9, 30, 40, 128, 128, True, False, 2, 16384),
-    ("l2_pairs_odd_size", 3, 17, 23, 128, 128, False, True, 2, 16384),
-    ("l2_pairs_tiny_images", 11, 5, 7, 128, 128, True, True, 2, 16384),
-    ("l2_pairs_one_item_peer_idle", 1, 12, 16, 128, 128, True, False, 1, 16384),
+    # conv_window2q_kernel (bit 14 = 16384, default): the layer2 window kernel on CTA pairs, two issuers
+    # name, n, h, w, c_in, c_out, relu, use_res, max_ctas
+    ("l2_pairs_odd_super_tiles", 4, 30, 40, 128, 128, True, True, 4),
+    ("l2_pairs_many_per_pair", 9, 30, 40, 128, 128, True, False, 2),
+    ("l2_pairs_odd_size", 3, 17, 23, 128, 128, False, True, 2),
+    ("l2_pairs_tiny_images", 11, 5, 7, 128, 128, True, True, 2),
+    ("l2_pairs_one_item_peer_idle", 1, 12, 16, 128, 128, True, False, 1),
 ]
 
 
-@EXPERIMENTAL
 @pytest.mark.parametrize("case", PAIR_WINDOW_CASES, ids=[c[0] for c in PAIR_WINDOW_CASES])
-def test_experimental_pair_window_kernel(case):
-    """conv_window2p_kernel (mode bit 12 = 4096: 256-wide tiles for layer3/4; bit 13 = 8192: 128-wide tiles for layer2) and
-    conv_window2q_kernel (bit 14 = 16384: the layer2 window kernel on CTA pairs) vs the default kernels and fp32 torch."""
-    name, n, h, w, cin, cout, relu, use_res, max_ctas, bit = case
+def test_layer2_pair_window_kernel(case):
+    """conv_window2q_kernel (the layer2 window kernel on CTA pairs, default since r02) vs the single-CTA window kernel and
+    fp32 torch."""
+    name, n, h, w, cin, cout, relu, use_res, max_ctas = case
     g = torch.Generator(device="cuda").manual_seed(29)
     x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(ACT)
     wt = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(ACT)
@@ -382,14 +370,12 @@ def test_experimental_pair_window_kernel(case):
     res = torch.randn(n, h, w, cout, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        # bit 16 (65536): whole residual row requested before the accumulator wait (pair kernels of bits 14 / 15 only)
-        modes = [DEFAULT_CONV_MODE | bit] + ([DEFAULT_CONV_MODE | bit | 65536] if use_res and bit == 16384 else [])
-        for mode in modes + [DEFAULT_CONV_MODE]:
+        for mode in (DEFAULT_CONV_MODE, SINGLE_CTA_MODE):
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, 3,
-                                                  3, 1, 1, 1, 1, 1, int(relu), _abi.ptr(res), _abi.ptr(out), 0, max_ctas,
-                                                  _abi.stream_ptr()))
+                                             3, 1, 1, 1, 1, 1, int(relu), _abi.ptr(res), _abi.ptr(out), 0, max_ctas,
+                                             _abi.stream_ptr()))
             torch.cuda.synchronize()
             outs.append(out.float())
     finally:
@@ -400,31 +386,6 @@ def test_experimental_pair_window_kernel(case):
         assert not torch.isnan(o).any()
         assert (o - ref).abs().max() <= tol
         assert (o - outs[-1]).abs().max() <= ULP * ref.abs().max().item()
-    if len(outs) == 3:
-        assert torch.equal(outs[0], outs[1])  # the residual preload changes when the loads are issued, not the arithmetic
-
-
-@EXPERIMENTAL
-def test_experimental_window_observers_arrive():
-    """Window kernel with refills gated on every issuer's arrival (mode bit 11 = 2048): same results as the default."""
-    g = torch.Generator(device="cuda").manual_seed(31)
-    for (n, h, w, r, pads) in ((7, 60, 80, 3, (1, 1, 1, 1)), (3, 120, 160, 4, (2, 2, 1, 1))):
-        x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT)
-        wt = (torch.randn(64, r, r, 64, device="cuda", generator=g) / (r * r * 64) ** 0.5).to(ACT)
-        bias = torch.randn(64, device="cuda", generator=g)
-        outs = []
-        try:
-            for mode in (DEFAULT_CONV_MODE | 2048, DEFAULT_CONV_MODE):
-                _abi.lib().mpx_conv_set_mode(mode)
-                out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
-                _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
-                                                      1, pads[0], pads[1], pads[2], pads[3], 1, None, _abi.ptr(out), 0, 5,
-                                                      _abi.stream_ptr()))
-                torch.cuda.synchronize()
-                outs.append(out)
-        finally:
-            _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
-        assert torch.equal(outs[0], outs[1])
 
 
 PAIR_WINDOW64_CASES = [
@@ -438,11 +399,10 @@ PAIR_WINDOW64_CASES = [
 ]
 
 
-@EXPERIMENTAL
 @pytest.mark.parametrize("case", PAIR_WINDOW64_CASES, ids=[c[0] for c in PAIR_WINDOW64_CASES])
-def test_experimental_pair_window64_kernel(case):
-    """conv_windowq_kernel (mode bit 15 = 32768: the 64 -> 64 window kernel on CTA pairs) vs the default window kernel and
-    fp32 torch."""
+def test_pair_window64_kernel(case):
+    """conv_windowq_kernel (bit 15 = 32768, default since r02: the 64 -> 64 window kernel on CTA pairs) vs the single-CTA
+    window kernel and fp32 torch."""
     name, n, h, w, r, pads, relu, use_res, max_ctas = case
     g = torch.Generator(device="cuda").manual_seed(37)
     x = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT)
@@ -451,13 +411,12 @@ def test_experimental_pair_window64_kernel(case):
     res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        modes = [DEFAULT_CONV_MODE | 32768] + ([DEFAULT_CONV_MODE | 32768 | 65536] if use_res else [])
-        for mode in modes + [DEFAULT_CONV_MODE]:
+        for mode in (DEFAULT_CONV_MODE, SINGLE_CTA_MODE):
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
-                                                  1, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(out),
-                                                  0, max_ctas, _abi.stream_ptr()))
+                                             1, pads[0], pads[1], pads[2], pads[3], int(relu), _abi.ptr(res), _abi.ptr(out),
+                                             0, max_ctas, _abi.stream_ptr()))
             torch.cuda.synchronize()
             outs.append(out.float())
     finally:
@@ -468,6 +427,35 @@ def test_experimental_pair_window64_kernel(case):
         assert not torch.isnan(o).any()
         assert (o - ref).abs().max() <= tol
         assert (o - outs[-1]).abs().max() <= ULP * ref.abs().max().item()
-    print(name, "bit-equal to the single-CTA window kernel:", torch.equal(outs[0], outs[-1]))
-    if len(outs) == 3:
-        assert torch.equal(outs[0], outs[1])  # residual preload: same arithmetic
+
+
+@pytest.mark.parametrize("mode", [DEFAULT_CONV_MODE, SINGLE_CTA_MODE], ids=["cta_pairs", "single_cta"])
+def test_stem_space_to_depth_skips_zero_slices(mode):
+    """The 7x7 / stride-2 stem runs as a 4x4 convolution over the space-to-depth input; 15 of its 64 (tap, sub-pixel) weight
+    slices are zero by construction and are not multiplied (K = 784 instead of 1024).  Skipping them adds exact zeros less:
+    the output is bit-identical to the unskipped run and matches torch's 7x7 / stride-2 convolution."""
+    from megapose6d_b200.backbone import _stem_s2d
+
+    n, h, w, c, c_pad = 5, 96, 128, 9, 16
+    g = torch.Generator(device="cuda").manual_seed(41)
+    w7 = (torch.randn(64, c, 7, 7, device="cuda", generator=g) / (49 * c) ** 0.5).to(ACT)
+    x = torch.rand(n, c, h, w, device="cuda", generator=g).to(ACT)
+    bias = torch.randn(64, device="cuda", generator=g)
+    ws2d = _stem_s2d(w7.float().cpu(), c_pad).to(ACT).cuda().contiguous()
+    xp = torch.zeros(n, c_pad, h, w, device="cuda", dtype=ACT)
+    xp[:, :c] = x
+    xs = xp.view(n, c_pad, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(n, h // 2, w // 2, 4 * c_pad).contiguous()
+    outs = []
+    try:
+        for flags, m in ((3, mode), (1, mode), (3, mode | 131072)):
+            _abi.lib().mpx_conv_set_mode(m)
+            out = torch.full((n, h // 2, w // 2, 64), float("nan"), device="cuda", dtype=ACT)
+            _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(xs), n, h // 2, w // 2, 4 * c_pad, _abi.ptr(ws2d), _abi.ptr(bias), 64, 4, 4, 1,
+                                             2, 2, 1, 1, flags, None, _abi.ptr(out), 0, 6, _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = torch.relu(F.conv2d(x.float(), w7.float(), bias=bias, stride=2, padding=3)).permute(0, 2, 3, 1)
+    assert (outs[0].float() - ref).abs().max() <= ULP * ref.abs().max().item() + ATOL
