@@ -241,6 +241,10 @@ int mpx_conv_set_mode(int mode);
 int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out,
                             void* stream);
 
+/* measurement probe (tools/gpu_mma_probe.py): mean cycles per tcgen05.mma of shape (128 * cta_group) x n x 16, operands in
+ * shared memory, with `chains` independent accumulators interleaved by each of `issuers` (1|2) issuing threads; synchronous */
+int mpx_debug_mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* h_cycles_per_mma);
+
 /* 3x3/s2/p1 max pool, act16 NHWC (torchvision_resnet.py:302) */
 int mpx_maxpool3x3s2(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream);
 

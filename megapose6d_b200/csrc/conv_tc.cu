@@ -2451,4 +2451,118 @@ int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, floa
   return MPX_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe probe (tools/gpu_mma_probe.py): how many cycles one tcgen05.mma.kind::f16 of shape (128 x cta_group) x N x 16
+// costs with both operands in shared memory, as a function of N, of the number of independent accumulate chains one
+// issuing thread interleaves, and of the number of issuing threads.  Every SM (or SM pair) runs the same loop on its own
+// zero-filled operands; the result is the mean over CTAs of elapsed cycles / MMAs issued.  These are the floors the
+// convolution kernels are measured against in DESIGN.md.
+// ---------------------------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(128, 1)
+mma_probe_kernel(int N, int chains, int issuers, int n_mma, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;               // 128 rows x 128 B
+  uint8_t* smem_b = smem + 16384;       // N / CG rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + 32768);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zero fill -> async-proxy (tensor core) reads
+  if (warp == 2) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const bool leader = CG == 1 || cluster_ctarank() == 0;
+  const int which = warp == 1 ? 0 : (warp == 3 ? 1 : -1);
+  if (leader && lane == 0 && which >= 0 && which < issuers) {
+    const uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(N >> 3) << 17) |
+                           (static_cast<uint32_t>((128 * CG) >> 4) << 24);
+    const uint64_t da = make_sw128_desc(smem_u32(smem_a));
+    const uint64_t db = make_sw128_desc(smem_u32(smem_b));
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t d = tmem_base + static_cast<uint32_t>((which * chains + (i % chains)) * N);
+      const uint64_t ko = static_cast<uint64_t>(2 * (i & 3));
+      if (CG == 1) tc_mma_f16(d, da + ko, db + ko, idesc, 1u);
+      else tc2_mma_f16(d, da + ko, db + ko, idesc, 1u);
+    }
+    if (CG == 1) tc_commit(&bars[which]);
+    else tc2_commit_mc(&bars[which]);
+    mbar_wait(&bars[which], 0);
+    const long long t1 = clock64();
+    cycles[(blockIdx.x / CG) * 2 + which] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* cycles_per_mma) {
+  MPX_REQUIRE(cta_group == 1 || cta_group == 2, "mma_probe: cta_group must be 1 or 2");
+  MPX_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "mma_probe: N=%d", n);
+  MPX_REQUIRE(issuers >= 1 && issuers <= 2 && chains >= 1 && issuers * chains * n <= 512, "mma_probe: accumulators exceed TMEM");
+  MPX_REQUIRE(n_mma >= chains && n_mma <= (1 << 22), "mma_probe: n_mma=%d", n_mma);
+  const int ctas = (sm_count() / cta_group) * cta_group;
+  long long* d_cycles = nullptr;
+  MPX_CHECK_CUDA(cudaMalloc(&d_cycles, sizeof(long long) * 2 * ctas));
+  MPX_CHECK_CUDA(cudaMemset(d_cycles, 0, sizeof(long long) * 2 * ctas));
+  const int smem_bytes = 1024 + 16384 + 32768 + 64;
+  if (cta_group == 1) {
+    MPX_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    mma_probe_kernel<1><<<ctas, 128, smem_bytes>>>(n, chains, issuers, n_mma, d_cycles);
+  } else {
+    MPX_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MPX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mma_probe_kernel<2>, n, chains, issuers, n_mma, d_cycles));
+  }
+  MPX_CHECK_CUDA(cudaGetLastError());
+  MPX_CHECK_CUDA(cudaDeviceSynchronize());
+  std::vector<long long> h(2 * ctas);
+  MPX_CHECK_CUDA(cudaMemcpy(h.data(), d_cycles, sizeof(long long) * 2 * ctas, cudaMemcpyDeviceToHost));
+  cudaFree(d_cycles);
+  double sum = 0;
+  int cnt = 0;
+  for (int g = 0; g < ctas / cta_group; ++g) {
+    long long worst = 0;
+    for (int w = 0; w < issuers; ++w) worst = h[2 * g + w] > worst ? h[2 * g + w] : worst;
+    sum += static_cast<double>(worst) / (static_cast<double>(n_mma) * issuers);
+    ++cnt;
+  }
+  *cycles_per_mma = cnt ? sum / cnt : 0.0;
+  ++g_launches;
+  return MPX_OK;
+}
+
 }  // namespace mpx

@@ -183,6 +183,7 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
                  const void* residual, void* out, int block_n_override, int max_ctas,
                  cudaStream_t stream, int splitk = 0);
 int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride);
+int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* cycles_per_mma);
 int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, float* out, cudaStream_t stream);
 int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream);
 int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const float* b, int out_dim,
