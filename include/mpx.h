@@ -242,8 +242,11 @@ int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_o
                             void* stream);
 
 /* measurement probe (tools/gpu_mma_probe.py): mean cycles per tcgen05.mma of shape (128 * cta_group) x n x 16, operands in
- * shared memory, with `chains` independent accumulators interleaved by each of `issuers` (1|2) issuing threads; synchronous */
-int mpx_debug_mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* h_cycles_per_mma);
+ * shared memory, with `chains` (1|2|4) independent accumulators interleaved by each of `issuers` (1..4) issuing threads (one
+ * per warp); *h_cycles_per_mma = SM time per MMA, *h_issue_cycles_per_mma (may be NULL) = one thread's time per instruction
+ * issued, before the commit; synchronous */
+int mpx_debug_mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* h_cycles_per_mma,
+                        double* h_issue_cycles_per_mma);
 
 /* 3x3/s2/p1 max pool, act16 NHWC (torchvision_resnet.py:302) */
 int mpx_maxpool3x3s2(const void* d_x, int n, int h, int w, int c, void* d_out, void* stream);
@@ -258,6 +261,15 @@ typedef struct mpx_net mpx_net;
  * conv1, conv2, [downsample]); c_pad as above; d_head_w [out_dim,512] fp32, d_head_b [out_dim]. */
 int mpx_net_create(int c_pad, int out_dim, const void* const* h_conv_w, const float* const* h_conv_b,
                    int n_convs, const float* d_head_w, const float* d_head_b, mpx_net** out);
+/* Pre-activation backbones (WideResNet34 / WideResNet18 of models/wide_resnet.py:29-126, backbone_str "resnet34" /
+ * "resnet18", width 1): h_layer_blocks [4] blocks per layer; h_conv_w / h_conv_b: 1 + 2 * blocks + 3 DEVICE pointers in
+ * execution order (stem = the 5x5/s2 convolution as 3x3 over the space-to-depth input, bn1 folded; per block conv1 with
+ * bn2 folded, conv2 with a zero bias, [bare 1x1 downsample with a zero bias]); h_block_affine: per block a DEVICE pointer
+ * to [2, C_in] fp32 (scale, shift of the block's bn1, applied with ReLU to the block input); d_head_w [out_dim, 512] is
+ * the head itself (there is no fc). */
+int mpx_net_create_preact(int c_pad, int out_dim, const int32_t* h_layer_blocks, const void* const* h_conv_w,
+                          const float* const* h_conv_b, int n_convs, const float* const* h_block_affine, int n_blocks,
+                          const float* d_head_w, const float* d_head_b, mpx_net** out);
 int mpx_net_destroy(mpx_net* net);
 /* mpx_net_forward replays a cached CUDA graph per (buffers, shape) after the first call; 0 disables that
  * (every launch is then issued eagerly on the caller's stream). Default: enabled. */

@@ -40,7 +40,7 @@ def _declare(lib: ctypes.CDLL) -> None:
                                             c_int, c_int, vp, vp, c_size_t, vp]
     lib.mpx_render_crop_fused.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_uint32, vp, c_int, c_int, c_int, vp,
                                           vp, c_int, vp, c_int, c_int, vp, vp, c_size_t, vp]
-    lib.mpx_debug_mma_probe.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_double)]
+    lib.mpx_debug_mma_probe.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]
     lib.mpx_debug_umma_rowshift.argtypes = [vp, vp, c_int, c_int, vp, vp]
     lib.mpx_pose_init_autodepth.argtypes = [vp, c_int, vp, vp, vp, vp, c_int, vp, vp]
     lib.mpx_normalize_T.argtypes = [vp, c_int, vp, vp]
@@ -62,6 +62,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_maxpool3x3s2.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
     lib.mpx_avgpool_linear.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_int, vp, vp]
     lib.mpx_net_create.argtypes = [c_int, c_int, POINTER(vp), POINTER(vp), c_int, vp, vp, POINTER(vp)]
+    lib.mpx_net_create_preact.argtypes = [c_int, c_int, POINTER(ctypes.c_int32), POINTER(vp), POINTER(vp), c_int, POINTER(vp), c_int,
+                                          vp, vp, POINTER(vp)]
     lib.mpx_net_destroy.argtypes = [vp]
     lib.mpx_net_workspace_bytes.argtypes = [vp, c_int, c_int, c_int]
     lib.mpx_net_workspace_bytes.restype = c_size_t
@@ -86,7 +88,7 @@ EXPORTS = [
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",
     "mpx_net_input_bytes", "mpx_conv2d", "mpx_conv2d_splitk", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_debug_mma_probe", "mpx_maxpool3x3s2", "mpx_avgpool_linear",
-    "mpx_net_create", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_workspace_bytes", "mpx_net_forward",
+    "mpx_net_create", "mpx_net_create_preact", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_workspace_bytes", "mpx_net_forward",
 ]
 
 

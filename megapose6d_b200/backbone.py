@@ -62,13 +62,45 @@ def _stem_s2d(w: torch.Tensor, c_pad: int) -> torch.Tensor:
     return w2.reshape(co, -1).contiguous()
 
 
+def _stem_s2d_5x5(w: torch.Tensor, c_pad: int) -> torch.Tensor:
+    """5x5/s2/p2 weights [64, C, 5, 5] (WideResNet stem, models/wide_resnet.py:66-68) -> 3x3/s1/p1 weights over the s2d
+    input: w2[co, by+1, bx+1, (dy*2+dx)*c_pad + c] = w[co, c, 2*by+dy+2, 2*bx+dx+2] for by, bx in {-1, 0, 1} (zero outside
+    0..4)."""
+    co, c, _, _ = w.shape
+    w2 = torch.zeros(co, 3, 3, 4 * c_pad, dtype=w.dtype)
+    for by in (-1, 0, 1):
+        for dy in range(2):
+            kh = 2 * by + dy + 2
+            if not 0 <= kh <= 4:
+                continue
+            for bx in (-1, 0, 1):
+                for dx in range(2):
+                    kw = 2 * bx + dx + 2
+                    if not 0 <= kw <= 4:
+                        continue
+                    base = (dy * 2 + dx) * c_pad
+                    w2[:, by + 1, bx + 1, base:base + c] = w[:, :, kh, kw]
+    return w2.reshape(co, -1).contiguous()
+
+
+def is_wide_resnet(sd: Dict[str, torch.Tensor]) -> bool:
+    """Checkpoint of a WideResNet backbone (backbone_str "resnet34" / "resnet18", models/wide_resnet.py): pre-activation
+    blocks with their own bn1, no fc layer."""
+    return "backbone.layer1.0.bn1.weight" in sd and "backbone.fc.weight" not in sd
+
+
 class ResNet34Engine:
-    """Owns the repacked device weights and the mpx_net handle; `forward(x)` runs the whole network."""
+    """Owns the repacked device weights and the mpx_net handle; `forward(x)` runs the whole network.  Serves both backbone
+    families of training/pose_models_cfg.py:106-116: `vanilla_resnet34` (all released models) and the pre-activation
+    WideResNet34 / WideResNet18 of width 1."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], n_inputs: int, head: str, device="cuda"):
         sd = state_dict
         self.n_inputs = n_inputs
         self.n_features = 512
+        if is_wide_resnet(sd):
+            self._init_wide(sd, n_inputs, head, device)
+            return
         self.c_pad = 16 * ((n_inputs + 15) // 16)  # 16 (coarse), 32 (refiner) for the released models
         assert n_inputs <= 256, f"n_inputs={n_inputs} > 256 is not supported"
         assert sd["backbone.conv1.weight"].shape[1] == n_inputs, "checkpoint / config channel mismatch"
@@ -112,6 +144,55 @@ class ResNet34Engine:
         # growth is geometric, the retired ones therefore sum to less than the live one
         self._retired_workspaces: List[torch.Tensor] = []
         self._out_cache: Dict[int, torch.Tensor] = {}
+
+    def _init_wide(self, sd, n_inputs, head, device) -> None:
+        self.c_pad = 16 * ((n_inputs + 15) // 16)
+        assert n_inputs <= 256 and sd["backbone.conv1.weight"].shape[1] == n_inputs, "checkpoint / config channel mismatch"
+        assert sd["backbone.conv1.weight"].shape[0] == 64, "WideResNet width != 1 is not supported (C_out <= 512)"
+        self.device = torch.device(device)
+        self.act_dtype = _abi.act_dtype()
+        self._weights, self._biases, self._affines = [], [], []
+
+        def add(wmat, bias):
+            self._weights.append(wmat.to(torch.float32).to(self.device).to(self.act_dtype).contiguous())
+            self._biases.append(bias.to(torch.float32).to(self.device).contiguous())
+
+        w, b = _fold(sd, "backbone.conv1", "backbone.bn1")
+        add(_stem_s2d_5x5(w, self.c_pad), b)
+        layers = []
+        for li in range(4):
+            nb = 0
+            while f"backbone.layer{li + 1}.{nb}.conv1.weight" in sd:
+                p = f"backbone.layer{li + 1}.{nb}"
+                g, beta = sd[p + ".bn1.weight"].double().cpu(), sd[p + ".bn1.bias"].double().cpu()
+                mean, var = sd[p + ".bn1.running_mean"].double().cpu(), sd[p + ".bn1.running_var"].double().cpu()
+                scale = g / torch.sqrt(var + BN_EPS)
+                self._affines.append(torch.stack((scale, beta - mean * scale)).float().to(self.device).contiguous())
+                w, b = _fold(sd, p + ".conv1", p + ".bn2")
+                add(_pack(w), b)
+                w2 = sd[p + ".conv2.weight"].detach().double().cpu()
+                add(_pack(w2), torch.zeros(w2.shape[0], dtype=torch.float64))
+                if (p + ".downsample.weight") in sd:
+                    wd = sd[p + ".downsample.weight"].detach().double().cpu()
+                    add(_pack(wd), torch.zeros(wd.shape[0], dtype=torch.float64))
+                nb += 1
+            layers.append(nb)
+        self.head_w = sd[head + ".weight"].detach().float().to(self.device).contiguous()
+        self.head_b = sd[head + ".bias"].detach().float().to(self.device).contiguous()
+        self.out_dim = self.head_w.shape[0]
+        assert self.head_w.shape[1] == 512
+        n = len(self._weights)
+        wp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in self._weights])
+        bp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in self._biases])
+        ap = (ctypes.c_void_p * len(self._affines))(*[t.data_ptr() for t in self._affines])
+        lb = (ctypes.c_int32 * 4)(*layers)
+        handle = ctypes.c_void_p()
+        _abi.check(_abi.lib().mpx_net_create_preact(self.c_pad, self.out_dim, lb, wp, bp, n, ap, len(self._affines),
+                                                    _abi.ptr(self.head_w), _abi.ptr(self.head_b), ctypes.byref(handle)))
+        self._handle = handle
+        self._workspace = None
+        self._retired_workspaces = []
+        self._out_cache = {}
 
     def __del__(self):
         try:

@@ -334,9 +334,10 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
                       splits == 0 ? -1 : splits);
 }
 
-int mpx_debug_mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* h_cycles_per_mma) {
+int mpx_debug_mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* h_cycles_per_mma,
+                        double* h_issue_cycles_per_mma) {
   MPX_NOT_NULL(h_cycles_per_mma);
-  return mma_probe(cta_group, n, chains, issuers, n_mma, h_cycles_per_mma);
+  return mma_probe(cta_group, n, chains, issuers, n_mma, h_cycles_per_mma, h_issue_cycles_per_mma);
 }
 
 int mpx_debug_umma_rowshift(const void* d_a, const void* d_b, int r0, int base_offset, float* d_out, void* stream) {
@@ -382,6 +383,28 @@ int mpx_net_create(int c_pad, int out_dim, const void* const* h_conv_w, const fl
   return MPX_OK;
 }
 
+int mpx_net_create_preact(int c_pad, int out_dim, const int32_t* h_layer_blocks, const void* const* h_conv_w,
+                          const float* const* h_conv_b, int n_convs, const float* const* h_block_affine, int n_blocks,
+                          const float* d_head_w, const float* d_head_b, mpx_net** out) {
+  MPX_NOT_NULL(h_layer_blocks);
+  MPX_NOT_NULL(h_conv_w);
+  MPX_NOT_NULL(h_conv_b);
+  MPX_NOT_NULL(h_block_affine);
+  MPX_NOT_NULL(d_head_w);
+  MPX_NOT_NULL(d_head_b);
+  MPX_NOT_NULL(out);
+  for (int i = 0; i < n_convs; ++i)
+    MPX_REQUIRE(h_conv_w[i] != nullptr && h_conv_b[i] != nullptr, "mpx_net_create_preact: conv %d has a NULL tensor", i);
+  for (int i = 0; i < n_blocks; ++i)
+    MPX_REQUIRE(h_block_affine[i] != nullptr, "mpx_net_create_preact: block %d has no affine parameters", i);
+  int lb[4] = {h_layer_blocks[0], h_layer_blocks[1], h_layer_blocks[2], h_layer_blocks[3]};
+  Net* net = nullptr;
+  int rc = net_create_preact(c_pad, out_dim, lb, h_conv_w, h_conv_b, n_convs, h_block_affine, n_blocks, d_head_w, d_head_b, &net);
+  if (rc != MPX_OK) return rc;
+  *out = new mpx_net{net};
+  return MPX_OK;
+}
+
 int mpx_conv_set_mode(int mode) {
   conv_set_mode(mode);
   return MPX_OK;
@@ -401,8 +424,7 @@ int mpx_net_destroy(mpx_net* net) {
 }
 
 size_t mpx_net_workspace_bytes(const mpx_net* net, int n, int h, int w) {
-  (void)net;
-  return net_workspace_bytes(n, h, w);
+  return net_workspace_bytes(net ? net->net : nullptr, n, h, w);
 }
 
 int mpx_net_forward(const mpx_net* net, const void* d_x, int n, int h, int w, float* d_out, void* d_workspace,

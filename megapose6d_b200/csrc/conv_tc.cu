@@ -105,6 +105,27 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-uniform form: executed by ALL lanes of the issuing warp with warp-uniform operands; one lane is elected inside the
+// instruction.  With `if (lane == 0) tc_mma_f16(...)` ptxas cannot prove that the descriptors / TMEM address are uniform and
+// wraps every UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (three dependent uniform-datapath round trips per
+// instruction: ~150 cycles per MMA and issuing thread, tools/gpu_mma_probe.py).
+__device__ __forceinline__ void tc_mma_f16_u(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_u(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -2459,7 +2480,7 @@ int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, floa
 // convolution kernels are measured against in DESIGN.md.
 // ---------------------------------------------------------------------------------------------
 template <int CG>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(192, 1)
 mma_probe_kernel(int N, int chains, int issuers, int n_mma, long long* __restrict__ cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -2470,12 +2491,11 @@ mma_probe_kernel(int N, int chains, int issuers, int n_mma, long long* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zero fill -> async-proxy (tensor core) reads
-  if (warp == 2) {
+  if (warp == 4) {
     if (CG == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -2490,53 +2510,94 @@ mma_probe_kernel(int N, int chains, int issuers, int n_mma, long long* __restric
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const bool leader = CG == 1 || cluster_ctarank() == 0;
-  const int which = warp == 1 ? 0 : (warp == 3 ? 1 : -1);
-  if (leader && lane == 0 && which >= 0 && which < issuers) {
+  const bool uniform = (issuers & 0x100) != 0;  // warp-uniform issue path (elect.sync inside the instruction), cta_group 1
+  issuers &= 0xff;
+  const int which = __shfl_sync(0xffffffffu, warp, 0);  // issuing warps 0 .. issuers-1 (one per SM sub-partition)
+  if (CG == 1 && uniform) {
+    if (which < issuers) {
+      const uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+      const uint64_t da = make_sw128_desc(smem_u32(smem_a));
+      const uint64_t db = make_sw128_desc(smem_u32(smem_b));
+      const uint32_t d0 = __shfl_sync(0xffffffffu, tmem_base, 0) + static_cast<uint32_t>(which * chains * N);
+      const uint32_t cmask = static_cast<uint32_t>(chains - 1);
+      const long long t0 = clock64();
+      for (int i = 0; i < n_mma; i += 4) {
+        const uint32_t d = d0 + ((static_cast<uint32_t>(i) >> 2) & cmask) * static_cast<uint32_t>(N);
+        tc_mma_f16_u(d, da, db, idesc, 1u);
+        tc_mma_f16_u(d, da + 2, db + 2, idesc, 1u);
+        tc_mma_f16_u(d, da + 4, db + 4, idesc, 1u);
+        tc_mma_f16_u(d, da + 6, db + 6, idesc, 1u);
+      }
+      const long long t_issue = clock64();
+      tc_commit_u(&bars[which]);
+      mbar_wait(&bars[which], 0);
+      const long long t1 = clock64();
+      if (lane == 0) {
+        cycles[blockIdx.x * 8 + which] = t1 - t0;
+        cycles[blockIdx.x * 8 + 4 + which] = t_issue - t0;
+      }
+    }
+  } else if (leader && lane == 0 && which < issuers) {
     const uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(N >> 3) << 17) |
                            (static_cast<uint32_t>((128 * CG) >> 4) << 24);
     const uint64_t da = make_sw128_desc(smem_u32(smem_a));
     const uint64_t db = make_sw128_desc(smem_u32(smem_b));
+    const uint32_t d0 = tmem_base + static_cast<uint32_t>(which * chains * N);
+    const uint32_t cmask = static_cast<uint32_t>(chains - 1);  // chains is a power of two
     const long long t0 = clock64();
-    for (int i = 0; i < n_mma; ++i) {
-      const uint32_t d = tmem_base + static_cast<uint32_t>((which * chains + (i % chains)) * N);
-      const uint64_t ko = static_cast<uint64_t>(2 * (i & 3));
-      if (CG == 1) tc_mma_f16(d, da + ko, db + ko, idesc, 1u);
-      else tc2_mma_f16(d, da + ko, db + ko, idesc, 1u);
+    for (int i = 0; i < n_mma; i += 4) {
+      // four K steps of one 64-wide k-block, as the convolution kernels issue them
+      const uint32_t d = d0 + ((static_cast<uint32_t>(i) >> 2) & cmask) * static_cast<uint32_t>(N);
+      if (CG == 1) {
+        tc_mma_f16(d, da, db, idesc, 1u);
+        tc_mma_f16(d, da + 2, db + 2, idesc, 1u);
+        tc_mma_f16(d, da + 4, db + 4, idesc, 1u);
+        tc_mma_f16(d, da + 6, db + 6, idesc, 1u);
+      } else {
+        tc2_mma_f16(d, da, db, idesc, 1u);
+        tc2_mma_f16(d, da + 2, db + 2, idesc, 1u);
+        tc2_mma_f16(d, da + 4, db + 4, idesc, 1u);
+        tc2_mma_f16(d, da + 6, db + 6, idesc, 1u);
+      }
     }
+    const long long t_issue = clock64();
     if (CG == 1) tc_commit(&bars[which]);
     else tc2_commit_mc(&bars[which]);
     mbar_wait(&bars[which], 0);
     const long long t1 = clock64();
-    cycles[(blockIdx.x / CG) * 2 + which] = t1 - t0;
+    cycles[(blockIdx.x / CG) * 8 + which] = t1 - t0;
+    cycles[(blockIdx.x / CG) * 8 + 4 + which] = t_issue - t0;
   }
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();
-  if (warp == 2) {
+  if (warp == 4) {
     tc_fence_after();
     if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
-int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* cycles_per_mma) {
+int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* cycles_per_mma, double* issue_cycles_per_mma) {
   MPX_REQUIRE(cta_group == 1 || cta_group == 2, "mma_probe: cta_group must be 1 or 2");
   MPX_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "mma_probe: N=%d", n);
-  MPX_REQUIRE(issuers >= 1 && issuers <= 2 && chains >= 1 && issuers * chains * n <= 512, "mma_probe: accumulators exceed TMEM");
-  MPX_REQUIRE(n_mma >= chains && n_mma <= (1 << 22), "mma_probe: n_mma=%d", n_mma);
+  const int n_issuers = issuers & 0xff;
+  MPX_REQUIRE(n_issuers >= 1 && n_issuers <= 4 && (chains == 1 || chains == 2 || chains == 4) && n_issuers * chains * n <= 512,
+              "mma_probe: issuers in 1..4, chains in {1, 2, 4}, accumulators must fit the 512 TMEM columns");
+  MPX_REQUIRE(n_mma >= 4 && n_mma % 4 == 0 && n_mma <= (1 << 22), "mma_probe: n_mma=%d", n_mma);
   const int ctas = (sm_count() / cta_group) * cta_group;
   long long* d_cycles = nullptr;
-  MPX_CHECK_CUDA(cudaMalloc(&d_cycles, sizeof(long long) * 2 * ctas));
-  MPX_CHECK_CUDA(cudaMemset(d_cycles, 0, sizeof(long long) * 2 * ctas));
+  MPX_CHECK_CUDA(cudaMalloc(&d_cycles, sizeof(long long) * 8 * ctas));
+  MPX_CHECK_CUDA(cudaMemset(d_cycles, 0, sizeof(long long) * 8 * ctas));
   const int smem_bytes = 1024 + 16384 + 32768 + 64;
   if (cta_group == 1) {
     MPX_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    mma_probe_kernel<1><<<ctas, 128, smem_bytes>>>(n, chains, issuers, n_mma, d_cycles);
+    mma_probe_kernel<1><<<ctas, 192, smem_bytes>>>(n, chains, issuers, n_mma, d_cycles);
   } else {
     MPX_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = smem_bytes;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2549,18 +2610,23 @@ int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* 
   }
   MPX_CHECK_CUDA(cudaGetLastError());
   MPX_CHECK_CUDA(cudaDeviceSynchronize());
-  std::vector<long long> h(2 * ctas);
-  MPX_CHECK_CUDA(cudaMemcpy(h.data(), d_cycles, sizeof(long long) * 2 * ctas, cudaMemcpyDeviceToHost));
+  std::vector<long long> h(8 * ctas);
+  MPX_CHECK_CUDA(cudaMemcpy(h.data(), d_cycles, sizeof(long long) * 8 * ctas, cudaMemcpyDeviceToHost));
   cudaFree(d_cycles);
-  double sum = 0;
+  double sum = 0, sum_issue = 0;
   int cnt = 0;
   for (int g = 0; g < ctas / cta_group; ++g) {
-    long long worst = 0;
-    for (int w = 0; w < issuers; ++w) worst = h[2 * g + w] > worst ? h[2 * g + w] : worst;
-    sum += static_cast<double>(worst) / (static_cast<double>(n_mma) * issuers);
+    long long worst = 0, worst_issue = 0;
+    for (int w = 0; w < n_issuers; ++w) {
+      worst = h[8 * g + w] > worst ? h[8 * g + w] : worst;
+      worst_issue = h[8 * g + 4 + w] > worst_issue ? h[8 * g + 4 + w] : worst_issue;
+    }
+    sum += static_cast<double>(worst) / (static_cast<double>(n_mma) * n_issuers);
+    sum_issue += static_cast<double>(worst_issue) / static_cast<double>(n_mma);
     ++cnt;
   }
-  *cycles_per_mma = cnt ? sum / cnt : 0.0;
+  *cycles_per_mma = cnt ? sum / cnt : 0.0;                 // SM time per MMA with all issuers running
+  if (issue_cycles_per_mma) *issue_cycles_per_mma = cnt ? sum_issue / cnt : 0.0;  // one thread's time per instruction
   ++g_launches;
   return MPX_OK;
 }

@@ -183,7 +183,7 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
                  const void* residual, void* out, int block_n_override, int max_ctas,
                  cudaStream_t stream, int splitk = 0);
 int conv_out_dim(int in, int pad_lo, int pad_hi, int k, int stride);
-int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* cycles_per_mma);
+int mma_probe(int cta_group, int n, int chains, int issuers, int n_mma, double* cycles_per_mma, double* issue_cycles_per_mma);
 int umma_rowshift_probe(const void* a, const void* b, int r0, int base_off, float* out, cudaStream_t stream);
 int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStream_t stream);
 int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const float* b, int out_dim,
@@ -191,7 +191,10 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
 struct Net;
 int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* const* conv_b,
                int n_convs, const float* head_w, const float* head_b, Net** out);
-size_t net_workspace_bytes(int n, int h, int w);
+int net_create_preact(int c_pad, int out_dim, const int* layer_blocks, const void* const* conv_w, const float* const* conv_b,
+                      int n_convs, const float* const* block_affine, int n_blocks, const float* head_w, const float* head_b,
+                      Net** out);
+size_t net_workspace_bytes(const Net* net, int n, int h, int w);
 int net_forward(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream);
 void net_destroy(Net* net);

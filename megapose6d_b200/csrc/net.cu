@@ -80,6 +80,48 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
 }
 
 // ---------------------------------------------------------------------------------------------
+// per-channel affine + ReLU on a 16-bit NHWC tensor: a = relu(scale[c] * x + shift[c]) -- the pre-activation of the
+// WideResNet blocks (relu(bn1(x)), models/wide_resnet.py:53), whose input x is also the block's residual and therefore has to
+// stay unactivated.  One thread = 8 channels (16 B); fp32 arithmetic, one rounding.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+affine_relu_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long n8, int c8,
+                   const float* __restrict__ scale_shift /* [2, C] */) {
+  pdl_trigger();
+  pdl_wait();
+  const float* scale = scale_shift;
+  const float* shift = scale_shift + 8 * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8) * 8;
+    const uint4 v = __ldg(x + i);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_act2(u[j]);
+      const float a = fmaxf(fmaf(f.x, __ldg(scale + cg + 2 * j), __ldg(shift + cg + 2 * j)), 0.f);
+      const float b = fmaxf(fmaf(f.y, __ldg(scale + cg + 2 * j + 1), __ldg(shift + cg + 2 * j + 1)), 0.f);
+      o[j] = pack_act2(a, b);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static int affine_relu(const void* x, long long elems, int c, const float* scale_shift, void* out, cudaStream_t stream) {
+  MPX_REQUIRE(c % 8 == 0 && elems % c == 0, "affine_relu: C=%d", c);
+  if (elems == 0) return MPX_OK;
+  const long long n8 = elems / 8;
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  MPX_CHECK_CUDA(launch_pdl(affine_relu_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1,
+                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n8, c / 8, scale_shift));
+  ++g_launches;
+  return MPX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // global average pool + linear (fc and head folded into one [out_dim, C] matrix on the host)
 // one CTA (512 threads) per sample: the pixels are split over G = 512 / (C/4) thread groups (each thread sums
 // 4 channels over every G-th pixel, fixed order), the groups are combined through shared memory, then one warp per
@@ -164,6 +206,9 @@ struct GraphEntry {
 struct Net {
   int c_pad;
   int out_dim;
+  int preact = 0;            // 1: pre-activation WideResNet blocks (net_create_preact)
+  int layer_blocks[4] = {3, 4, 6, 3};
+  std::vector<const float*> block_affine;  // preact: per block [2, C_in] fp32 (scale, shift of bn1)
   std::vector<const void*> conv_w;
   std::vector<const float*> conv_b;
   const float* head_w;
@@ -196,6 +241,32 @@ int net_create(int c_pad, int out_dim, const void* const* conv_w, const float* c
   return MPX_OK;
 }
 
+int net_create_preact(int c_pad, int out_dim, const int* layer_blocks, const void* const* conv_w, const float* const* conv_b,
+                      int n_convs, const float* const* block_affine, int n_blocks, const float* head_w, const float* head_b,
+                      Net** out) {
+  MPX_REQUIRE(c_pad >= 16 && c_pad <= 256 && c_pad % 16 == 0, "net: c_pad=%d must be a multiple of 16 in [16, 256]", c_pad);
+  MPX_REQUIRE(out_dim >= 1 && out_dim <= 512, "net: out_dim=%d unsupported", out_dim);
+  int blocks = 0;
+  for (int l = 0; l < 4; ++l) {
+    MPX_REQUIRE(layer_blocks[l] >= 1 && layer_blocks[l] <= 64, "net: layer %d has %d blocks", l + 1, layer_blocks[l]);
+    blocks += layer_blocks[l];
+  }
+  MPX_REQUIRE(n_blocks == blocks && n_convs == 1 + 2 * blocks + 3, "net: expected %d blocks / %d conv tensors, got %d / %d",
+              blocks, 1 + 2 * blocks + 3, n_blocks, n_convs);
+  Net* net = new Net();
+  net->c_pad = c_pad;
+  net->out_dim = out_dim;
+  net->preact = 1;
+  for (int l = 0; l < 4; ++l) net->layer_blocks[l] = layer_blocks[l];
+  net->conv_w.assign(conv_w, conv_w + n_convs);
+  net->conv_b.assign(conv_b, conv_b + n_convs);
+  net->block_affine.assign(block_affine, block_affine + n_blocks);
+  net->head_w = head_w;
+  net->head_b = head_b;
+  *out = net;
+  return MPX_OK;
+}
+
 void net_destroy(Net* net) {
   if (!net) return;
   for (auto& g : net->graphs)
@@ -208,12 +279,12 @@ void net_destroy(Net* net) {
 
 static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-size_t net_workspace_bytes(int n, int h, int w) {
+size_t net_workspace_bytes(const Net* net, int n, int h, int w) {
   const size_t hs = h / 2, ws = w / 2;
   const size_t stem = align256(static_cast<size_t>(n) * hs * ws * 64 * 2);
   const size_t hp = (hs + 2 - 3) / 2 + 1, wp = (ws + 2 - 3) / 2 + 1;
   const size_t l1 = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
-  return stem + 3 * l1 + 1024;
+  return stem + (net != nullptr && net->preact ? 5 : 3) * l1 + 1024;
 }
 
 static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
@@ -279,10 +350,69 @@ int net_forward(const Net* cnet, const void* x, int n, int h, int w, float* out,
   return MPX_OK;
 }
 
+// WideResNet (pre-activation) schedule, models/wide_resnet.py:44-58, 106-115: stem 5x5/s2/p2 (a 3x3/s1/p1 convolution over
+// the space-to-depth input) + bn1 + relu, max-pool, then per block
+//   a = relu(bn1(x)) [affine_relu_kernel];  r = downsample(a) (bare 1x1/s2 convolution) or x;
+//   y = relu(bn2(conv1(a))) [bn2 folded into conv1];  x' = conv2(y) + r  [no bias, no ReLU]
+// and the spatial mean of the LAST block's raw output into the head (models/pose_rigid.py:323-328).
+static int net_forward_preact(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
+                              cudaStream_t stream) {
+  const int hs = h / 2, ws = w / 2;
+  const int hp = (hs + 2 - 3) / 2 + 1, wp = (ws + 2 - 3) / 2 + 1;
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  const size_t stem_bytes = align256(static_cast<size_t>(n) * hs * ws * 64 * 2);
+  const size_t l1_bytes = align256(static_cast<size_t>(n) * hp * wp * 64 * 2);
+  void* buf_stem = base;
+  void* bufs[5];
+  for (int i = 0; i < 5; ++i) bufs[i] = base + stem_bytes + i * l1_bytes;
+  const int sk = ((conv_get_mode() & 8) != 0 && n <= 64) ? -1 : 0;
+  int rc;
+  {
+    ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 3, 3, 1, 1, 1, 1, 1, 1, 0};
+    rc = conv_forward(d, x, net->conv_w[0], net->conv_b[0], nullptr, buf_stem, 0, 0, stream);
+    if (rc != MPX_OK) return rc;
+  }
+  rc = maxpool3x3s2(buf_stem, n, hs, ws, 64, bufs[0], stream);
+  if (rc != MPX_OK) return rc;
+  int ci = 1, blk_id = 0;
+  int cur = 0;  // buffer holding the block input x
+  int H = hp, W = wp, C = 64;
+  for (int layer = 0; layer < 4; ++layer) {
+    const int width = kLayerWidth[layer];
+    for (int blk = 0; blk < net->layer_blocks[layer]; ++blk, ++blk_id) {
+      const int stride = (blk == 0 && layer > 0) ? 2 : 1;
+      const bool has_ds = (blk == 0 && layer > 0);
+      const int ia = (cur + 1) % 5, iy = (cur + 2) % 5, ir = (cur + 3) % 5, io = (cur + 4) % 5;
+      const int Ho = conv_out_dim(H, 1, 1, 3, stride), Wo = conv_out_dim(W, 1, 1, 3, stride);
+      rc = affine_relu(bufs[cur], static_cast<long long>(n) * H * W * C, C, net->block_affine[blk_id], bufs[ia], stream);
+      if (rc != MPX_OK) return rc;
+      ConvDesc d1{n, H, W, C, width, 3, 3, stride, 1, 1, 1, 1, 1, 0};
+      rc = conv_forward(d1, bufs[ia], net->conv_w[ci], net->conv_b[ci], nullptr, bufs[iy], 0, 0, stream, sk);
+      if (rc != MPX_OK) return rc;
+      const void* residual = bufs[cur];
+      if (has_ds) {
+        ConvDesc dd{n, H, W, C, width, 1, 1, stride, 0, 0, 0, 0, 0, 0};
+        rc = conv_forward(dd, bufs[ia], net->conv_w[ci + 2], net->conv_b[ci + 2], nullptr, bufs[ir], 0, 0, stream, sk);
+        if (rc != MPX_OK) return rc;
+        residual = bufs[ir];
+      }
+      ConvDesc d2{n, Ho, Wo, width, width, 3, 3, 1, 1, 1, 1, 1, 0, 0};
+      rc = conv_forward(d2, bufs[iy], net->conv_w[ci + 1], net->conv_b[ci + 1], residual, bufs[io], 0, 0, stream, sk);
+      if (rc != MPX_OK) return rc;
+      ci += has_ds ? 3 : 2;
+      cur = io;
+      H = Ho;
+      W = Wo;
+      C = width;
+    }
+  }
+  return avgpool_linear(bufs[cur], n, H * W, C, net->head_w, net->head_b, net->out_dim, out, stream);
+}
+
 static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
                               size_t workspace_bytes, cudaStream_t stream) {
   MPX_REQUIRE(h % 2 == 0 && w % 2 == 0, "net: input %dx%d must be even", h, w);
-  MPX_REQUIRE(workspace_bytes >= net_workspace_bytes(n, h, w), "net: workspace too small");
+  MPX_REQUIRE(workspace_bytes >= net_workspace_bytes(net, n, h, w), "net: workspace too small");
   MPX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "net: workspace must be 256-B aligned");
   if (n == 0) return MPX_OK;
   const int hs = h / 2, ws = w / 2;
@@ -295,6 +425,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   // small batches (refiner iterations, final scoring): layers 2-4 split their K loop over a cluster
   const int sk = ((conv_get_mode() & 8) != 0 && n <= 64) ? -1 : 0;
 
+  if (net->preact) return net_forward_preact(net, x, n, h, w, out, workspace, stream);
   int ci = 0;
   int rc;
   // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input

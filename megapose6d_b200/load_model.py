@@ -149,11 +149,13 @@ def n_input_channels(cfg: Cfg) -> int:
 def create_model_pose(cfg: Cfg, renderer: BatchRenderer, mesh_db: BatchedMeshes,
                       state_dict: Dict[str, torch.Tensor], render_size: Tuple[int, int] = (240, 320)) -> PosePredictor:
     """training/pose_models_cfg.py:90-138 + load_state_dict; builds the engine from the checkpoint tensors."""
-    if cfg.backbone_str != "vanilla_resnet34":
-        raise NotImplementedError(f"backbone '{cfg.backbone_str}': only vanilla_resnet34 (all released models) is "
-                                  "implemented; the pre-activation WideResNet variants are listed as next in DESIGN.md")
+    if cfg.backbone_str not in ("vanilla_resnet34", "resnet34", "resnet18", "resnet34_width=1"):
+        # training/pose_models_cfg.py:106-118; wider WideResNets (resnet34_width=k, k > 1) have up to 2048 channels
+        raise NotImplementedError(f"backbone '{cfg.backbone_str}': vanilla_resnet34 (all released models), resnet34 and "
+                                  "resnet18 (WideResNet, width 1) are implemented")
     head = "pose_fc" if cfg.predict_pose_update else "views_logits_head"
-    expected = {head + ".weight", head + ".bias", "backbone.conv1.weight", "backbone.fc.weight"}
+    expected = {head + ".weight", head + ".bias", "backbone.conv1.weight"}
+    expected.add("backbone.fc.weight" if cfg.backbone_str == "vanilla_resnet34" else "backbone.layer1.0.bn1.weight")
     missing = expected - set(state_dict.keys())
     if missing:
         raise RuntimeError(f"checkpoint is missing keys {sorted(missing)}")

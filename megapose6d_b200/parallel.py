@@ -25,6 +25,7 @@ class HypothesisSharder:
         self.group = group
         self.rank = dist.get_rank(group) if self.enabled else 0
         self.world = dist.get_world_size(group) if self.enabled else 1
+        self._pad_bufs: dict = {}
 
     def span(self, n: int) -> Tuple[int, int]:
         """Contiguous slice [start, end) of n rows owned by this rank (ceil split, last ranks may be empty)."""
@@ -37,9 +38,21 @@ class HypothesisSharder:
         if self.world == 1:
             return local
         per = (n_total + self.world - 1) // self.world
-        tail = local.shape[1:]
-        padded = torch.zeros((per,) + tuple(tail), dtype=local.dtype, device=local.device)
-        padded[: local.shape[0]] = local
-        out = torch.empty((self.world * per,) + tuple(tail), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, padded.contiguous(), group=self.group)
+        tail = tuple(local.shape[1:])
+        out = torch.empty((self.world * per,) + tail, dtype=local.dtype, device=local.device)
+        if per * self.world == n_total:
+            # even split (576 rows over 1/2/4/8 ranks, one refiner row per rank, ...): one collective, nothing else -- the
+            # stage's three gathers are latency-bound, a memset + copy + slice per call was a third of their cost
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            return out
+        key = (per, tail, local.dtype, local.device)
+        padded = self._pad_bufs.get(key)
+        if padded is None:
+            if len(self._pad_bufs) >= 16:
+                self._pad_bufs.clear()
+            padded = self._pad_bufs[key] = torch.zeros((per,) + tail, dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local  # rows past the slice keep their zeros (a shorter slice is always the last one)
+        if local.shape[0] < per:
+            padded[local.shape[0]:] = 0
+        dist.all_gather_into_tensor(out, padded, group=self.group)
         return out[:n_total]

@@ -168,7 +168,7 @@ class RefPosePredictor:
         self.render_normals = cfg.get("render_normals", True)
         self.views_inplane_rotations = cfg.get("views_inplane_rotations", False)
         self.n_render_ch = 3 + (3 if self.render_normals else 0) + (1 if self.render_depth else 0)
-        self.net = net if net is not None else (lambda x: resnet_ref.forward(self.sd, x))
+        self.net = net if net is not None else (lambda x: resnet_ref.forward_any(self.sd, x))
 
     # pose_rigid.py:180-247
     def crop_inputs(self, images, K, TCO, tCR, labels):

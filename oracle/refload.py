@@ -191,6 +191,7 @@ def load():
     ns.cropping = _load("megapose.lib3d.cropping", "lib3d/cropping.py")
     ns.mesh_ops = _load("megapose.lib3d.mesh_ops", "lib3d/mesh_ops.py")
     ns.torchvision_resnet = _load("megapose.models.torchvision_resnet", "models/torchvision_resnet.py")
+    ns.wide_resnet = _load("megapose.models.wide_resnet", "models/wide_resnet.py")
     ns.tensor_collection = _load("megapose.utils.tensor_collection", "utils/tensor_collection.py")
     ns.timer = _load("megapose.utils.timer", "utils/timer.py")
     ns.types = _load("megapose.inference.types", "inference/types.py")

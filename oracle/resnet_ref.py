@@ -130,7 +130,7 @@ def act16_forward_error_bound(sd: Dict[str, torch.Tensor], x: torch.Tensor, eps:
     if eps is None:
         eps = ACT16_EPS[dtype]
     W, b = folded_head(sd)
-    pooled = pooled_features(sd, x).double()
+    pooled = (pooled_features_wide(sd, x) if is_wide(sd) else pooled_features(sd, x)).double()
     return (eps * (pooled.abs() @ W.abs().t() + b.abs())).float()
 
 
@@ -193,5 +193,131 @@ def folded_head(sd) -> Tuple[torch.Tensor, torch.Tensor]:
     """head o fc as one linear map (float64): W = Wh Wfc, b = Wh bfc + bh."""
     h = head_name(sd)
     Wh, bh = sd[h + ".weight"].double(), sd[h + ".bias"].double()
+    if "backbone.fc.weight" not in sd:  # WideResNet: the head sits directly on the pooled features
+        return Wh, bh
     Wf, bf = sd["backbone.fc.weight"].double(), sd["backbone.fc.bias"].double()
     return Wh @ Wf, Wh @ bf + bh
+
+
+# ---------------------------------------------------------------------------------------------
+# pre-activation backbone: WideResNet34 / WideResNet18 of models/wide_resnet.py:29-126 (backbone_str "resnet34" /
+# "resnet18", training/pose_models_cfg.py:110-116), width 1.  5x5 / stride-2 stem, BasicBlockV2
+# (relu(bn1(x)) -> [bare 1x1 downsample on the activated tensor] -> conv1 -> relu(bn2) -> conv2 -> + residual), the 4-D
+# output averaged in PosePredictor.net_forward (models/pose_rigid.py:323-328), no fc in front of the head.
+# ---------------------------------------------------------------------------------------------
+WIDE_LAYERS = {"resnet34": [3, 4, 6, 3], "resnet18": [2, 2, 2, 2]}
+
+
+def is_wide(sd) -> bool:
+    return "backbone.layer1.0.bn1.weight" in sd and "backbone.layer1.0.conv1.weight" in sd and "backbone.fc.weight" not in sd
+
+
+def wide_layers(sd) -> List[int]:
+    return [sum(1 for k in sd if k.startswith(f"backbone.layer{li}.") and k.endswith(".conv1.weight")) for li in (1, 2, 3, 4)]
+
+
+def init_state_dict_wide(n_inputs: int, head: str, head_dim: int, seed: int = 0, backbone_str: str = "resnet34"):
+    """Seeded random weights in the checkpoint layout of a WideResNet backbone + head."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, k):
+        sd[name + ".weight"] = torch.randn(co, ci, k, k, generator=g) * (2.0 / (co * k * k)) ** 0.5
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1)
+
+    conv("backbone.conv1", 64, n_inputs, 5)
+    bn("backbone.bn1", 64)
+    inplanes = 64
+    for li, (nb, width) in enumerate(zip(WIDE_LAYERS[backbone_str], WIDTHS)):
+        for b in range(nb):
+            p = f"backbone.layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            bn(p + ".bn1", inplanes)
+            conv(p + ".conv1", width, inplanes, 3)
+            bn(p + ".bn2", width)
+            conv(p + ".conv2", width, width, 3)
+            if stride != 1 or inplanes != width:
+                conv(p + ".downsample", width, inplanes, 1)
+            inplanes = width
+    sd[head + ".weight"] = torch.randn(head_dim, 512, generator=g) * (1.0 / 512) ** 0.5
+    sd[head + ".bias"] = 0.1 * torch.randn(head_dim, generator=g)
+    return sd
+
+
+def _wide_trunk(sd, x, q=lambda t: t, fold: bool = False, dev=None):
+    """Shared structure of the fp32 and the emulated forward: returns the last block's output [b, 512, h, w]."""
+    def cw(conv, bn=None):
+        if fold:
+            if bn is None:
+                w, b = sd[conv + ".weight"].double(), torch.zeros(sd[conv + ".weight"].shape[0], dtype=torch.float64)
+            else:
+                w, b = fold_bn(sd, conv, bn)
+            return q(w.float()).to(dev), b.float().to(dev)
+        return sd[conv + ".weight"], None
+
+    def affine(name):
+        scale = sd[name + ".weight"].double() / torch.sqrt(sd[name + ".running_var"].double() + BN_EPS)
+        shift = sd[name + ".bias"].double() - sd[name + ".running_mean"].double() * scale
+        return scale.float().view(1, -1, 1, 1).to(x.device), shift.float().view(1, -1, 1, 1).to(x.device)
+
+    if fold:
+        w, b = cw("backbone.conv1", "backbone.bn1")
+        x = q(F.relu(F.conv2d(q(x), w, b, stride=2, padding=2)))
+    else:
+        x = F.relu(_bn(F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=2), sd, "backbone.bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, nb in enumerate(wide_layers(sd)):
+        for bi in range(nb):
+            p = f"backbone.layer{li + 1}.{bi}"
+            stride = 2 if (bi == 0 and li > 0) else 1
+            if fold:
+                sc, sh = affine(p + ".bn1")
+                a = q(F.relu(x * sc + sh))  # the engine's elementwise pass: fp32 affine of the 16-bit tensor, one rounding
+                res = x
+                if (p + ".downsample.weight") in sd:
+                    wd, bd = cw(p + ".downsample")
+                    res = q(F.conv2d(a, wd, bd, stride=stride))
+                w1, b1 = cw(p + ".conv1", p + ".bn2")
+                y = q(F.relu(F.conv2d(a, w1, b1, stride=stride, padding=1)))
+                w2, b2 = cw(p + ".conv2")
+                x = q(F.conv2d(y, w2, b2, stride=1, padding=1) + res)
+            else:
+                a = F.relu(_bn(x, sd, p + ".bn1"))
+                res = F.conv2d(a, sd[p + ".downsample.weight"], stride=stride) if (p + ".downsample.weight") in sd else x
+                y = F.relu(_bn(F.conv2d(a, sd[p + ".conv1.weight"], stride=stride, padding=1), sd, p + ".bn2"))
+                x = F.conv2d(y, sd[p + ".conv2.weight"], stride=1, padding=1) + res
+    return x
+
+
+def forward_wide(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """fp32 forward of a WideResNet backbone + head: x [b,C,H,W] -> [b, 1|9]."""
+    feat = _wide_trunk(sd, x).flatten(2).mean(dim=-1)
+    h = head_name(sd)
+    return F.linear(feat, sd[h + ".weight"], sd[h + ".bias"])
+
+
+def pooled_features_wide(sd, x):
+    return _wide_trunk(sd, x).flatten(2).mean(dim=-1)
+
+
+def forward_wide_act16_emulated(sd, x, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """The engine's quantisation points for the pre-activation backbone (16-bit weights and stored tensors, fp32 math)."""
+    lim = float(torch.finfo(dtype).max)
+
+    def q(t):
+        return t.clamp(-lim, lim).to(dtype).float()
+
+    feat = _wide_trunk(sd, x, q=q, fold=True, dev=x.device).flatten(2).mean(dim=-1)
+    h = head_name(sd)
+    return F.linear(feat, sd[h + ".weight"].float().to(x.device), sd[h + ".bias"].float().to(x.device))
+
+
+def forward_any(sd, x):
+    """fp32 forward of either backbone family."""
+    return forward_wide(sd, x) if is_wide(sd) else forward(sd, x)

@@ -459,3 +459,24 @@ def test_stem_space_to_depth_skips_zero_slices(mode):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     ref = torch.relu(F.conv2d(x.float(), w7.float(), bias=bias, stride=2, padding=3)).permute(0, 2, 3, 1)
     assert (outs[0].float() - ref).abs().max() <= ULP * ref.abs().max().item() + ATOL
+
+
+@pytest.mark.parametrize("backbone_str", ["resnet34", "resnet18"])
+def test_wide_resnet_engine_vs_oracle(backbone_str):
+    """Pre-activation backbones (models/wide_resnet.py, backbone_str "resnet34" / "resnet18"): 5x5 stem as a 3x3 convolution
+    over the space-to-depth input, affine + ReLU pass per block, bare downsample, spatial mean into the head."""
+    cfg = dict(helpers.REFINER_CFG, backbone_str=backbone_str)
+    sd = helpers.make_state_dict(cfg, seed=4)
+    c = helpers.n_inputs(cfg)
+    eng = ResNet34Engine(sd, n_inputs=c, head="pose_fc")
+    for n, hh, ww in ((5, 240, 320), (3, 64, 96), (70, 64, 96)):
+        x = helpers._calibration_batch(c, 42 + n, n=n, h=hh, w=ww)
+        got = eng(x.cuda()).cpu()
+        emu = resnet_ref.forward_wide_act16_emulated(sd, x.cuda(), ACT).cpu()
+        with torch.no_grad():
+            fp32 = resnet_ref.forward_wide(sd, x)
+            bound = resnet_ref.act16_forward_error_bound(sd, x, dtype=ACT)
+        print(f"[{backbone_str} n={n}] max|engine-emulated|={(got - emu).abs().max():.4g} max|engine-fp32|={(got - fp32).abs().max():.4g} "
+              f"bound={bound.min():.4g}..{bound.max():.4g}")
+        assert ((got - emu).abs() <= 0.5 * bound + 1e-4).all()
+        assert ((got - fp32).abs() <= bound + 1e-4).all()

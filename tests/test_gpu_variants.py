@@ -78,6 +78,8 @@ VARIANTS = {
     "rgbd_tCR_center_clamp": dict(_rgbd=True, depth_normalization_type="tCR_center_clamp"),
     "rgbd_none": dict(_rgbd=True, depth_normalization_type="none"),
     "rgbd_no_normals": dict(_rgbd=True, render_normals=False),
+    "wide_resnet34": dict(backbone_str="resnet34"),
+    "wide_resnet18_rgbd": dict(_rgbd=True, backbone_str="resnet18"),
 }
 
 

@@ -98,6 +98,27 @@ def test_resnet_restatement_matches_reference_module(ref):
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("backbone_str,cls", [("resnet34", "WideResNet34"), ("resnet18", "WideResNet18")])
+def test_wide_resnet_restatement_matches_reference_module(ref, backbone_str, cls):
+    """models/wide_resnet.py:59-126 (pre-activation blocks, bare 1x1 downsample, no fc) + the spatial mean of
+    PosePredictor.net_forward (models/pose_rigid.py:323-328) + head."""
+    sd = resnet_ref.init_state_dict_wide(9, "views_logits_head", 2, seed=5, backbone_str=backbone_str)
+    net = getattr(ref.wide_resnet, cls)(n_inputs=9)
+    net.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")})
+    net.eval()
+    x = torch.rand(2, 9, 64, 96, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = torch.nn.functional.linear(net(x).flatten(2).mean(dim=-1), sd["views_logits_head.weight"], sd["views_logits_head.bias"])
+        got = resnet_ref.forward_wide(sd, x)
+        emu = resnet_ref.forward_wide_act16_emulated(sd, x)
+        bound = resnet_ref.act16_forward_error_bound(sd, x)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    assert ((emu - want).abs() <= 0.5 * bound).all()
+    from workloads import weights
+    sd_w = weights.init_state_dict_wide(9, "views_logits_head", 2, seed=5, backbone_str=backbone_str)
+    assert all(torch.equal(sd[k], sd_w[k]) for k in sd)  # the workload generator and the oracle agree on the layout
+
+
 class _MeshDbAdapter:
     """mesh_db.select(labels).{points, sample_points} as the reference's PosePredictor expects."""
 

@@ -94,6 +94,62 @@ def _pooled_features(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tens
     return torch.flatten(F.adaptive_avg_pool2d(x, (1, 1)), 1)
 
 
+WIDE_LAYERS = {"resnet34": [3, 4, 6, 3], "resnet18": [2, 2, 2, 2]}
+
+
+def init_state_dict_wide(n_inputs: int, head: str, head_dim: int, seed: int = 0, backbone_str: str = "resnet34"):
+    """Seeded random weights in the checkpoint layout of a WideResNet backbone (models/wide_resnet.py:59-126) + head."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, k):
+        sd[name + ".weight"] = torch.randn(co, ci, k, k, generator=g) * (2.0 / (co * k * k)) ** 0.5
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1)
+
+    conv("backbone.conv1", 64, n_inputs, 5)
+    bn("backbone.bn1", 64)
+    inplanes = 64
+    for li, (nb, width) in enumerate(zip(WIDE_LAYERS[backbone_str], WIDTHS)):
+        for b in range(nb):
+            p = f"backbone.layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            bn(p + ".bn1", inplanes)
+            conv(p + ".conv1", width, inplanes, 3)
+            bn(p + ".bn2", width)
+            conv(p + ".conv2", width, width, 3)
+            if stride != 1 or inplanes != width:
+                conv(p + ".downsample", width, inplanes, 1)
+            inplanes = width
+    sd[head + ".weight"] = torch.randn(head_dim, 512, generator=g) * (1.0 / 512) ** 0.5
+    sd[head + ".bias"] = 0.1 * torch.randn(head_dim, generator=g)
+    return sd
+
+
+def _pooled_features_wide(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """fp32 pre-activation backbone up to the spatial mean [b, 512] (calibration only)."""
+    x = F.relu(_bn(F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=2), sd, "backbone.bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    li = 0
+    while f"backbone.layer{li + 1}.0.conv1.weight" in sd:
+        b = 0
+        while f"backbone.layer{li + 1}.{b}.conv1.weight" in sd:
+            p = f"backbone.layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            a = F.relu(_bn(x, sd, p + ".bn1"))
+            res = F.conv2d(a, sd[p + ".downsample.weight"], stride=stride) if (p + ".downsample.weight") in sd else x
+            y = F.relu(_bn(F.conv2d(a, sd[p + ".conv1.weight"], stride=stride, padding=1), sd, p + ".bn2"))
+            x = F.conv2d(y, sd[p + ".conv2.weight"], stride=1, padding=1) + res
+            b += 1
+        li += 1
+    return x.flatten(2).mean(dim=-1)
+
+
 def calibration_batch(c, seed, n=4, h=240, w=320):
     """Smooth images in [0,1]; half of them with the render channels masked to a blob on black, like real inputs."""
     g = torch.Generator().manual_seed(1000 + seed)
@@ -118,10 +174,16 @@ def make_state_dict(cfg, seed=0):
     head = "pose_fc" if cfg["predict_pose_update"] else "views_logits_head"
     dim = 9 if cfg["predict_pose_update"] else cfg["n_rendered_views"]
     c = n_inputs(cfg)
-    sd = init_state_dict(c, head, dim, seed=seed)
-    with torch.no_grad():
-        pooled = _pooled_features(sd, calibration_batch(c, seed))
-        feats = torch.nn.functional.linear(pooled, sd["backbone.fc.weight"], sd["backbone.fc.bias"])
+    wide = cfg.get("backbone_str", "vanilla_resnet34") in ("resnet34", "resnet18")
+    if wide:
+        sd = init_state_dict_wide(c, head, dim, seed=seed, backbone_str=cfg["backbone_str"])
+        with torch.no_grad():
+            feats = _pooled_features_wide(sd, calibration_batch(c, seed))
+    else:
+        sd = init_state_dict(c, head, dim, seed=seed)
+        with torch.no_grad():
+            pooled = _pooled_features(sd, calibration_batch(c, seed))
+            feats = torch.nn.functional.linear(pooled, sd["backbone.fc.weight"], sd["backbone.fc.bias"])
     v = torch.linalg.svd(feats, full_matrices=False)[2][0]
     W = sd[head + ".weight"]
     W = W - (W @ v).unsqueeze(1) * v.unsqueeze(0)
