@@ -126,6 +126,31 @@ __device__ __forceinline__ void tc_commit_u(uint64_t* bar) {
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+
+// elected-lane forms of the remaining single-thread operations of the producer / issuer warps (see tc_mma_f16_u)
+#define MPX_ELECT_PRED "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+__device__ __forceinline__ void mbar_expect_tx_u(uint64_t* bar, uint32_t bytes) {
+  asm volatile(MPX_ELECT_PRED "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u(uint64_t* bar) {
+  asm volatile(MPX_ELECT_PRED "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(MPX_ELECT_PRED
+               "@e cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(smem_u32(smem)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_u(void* smem, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                     int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(MPX_ELECT_PRED
+               "@e cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}" ::"r"(smem_u32(smem)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+               : "memory");
+}
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -414,7 +439,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   float* bias_s = reinterpret_cast<float*>(bars + 32);  // [C_out] folded-BN bias, read by broadcast in the epilogue
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;  // work items: (tile, k-split)
   for (int i = threadIdx.x; i < p.C_out; i += blockDim.x) bias_s[i] = p.bias[i];
@@ -450,7 +475,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       int stage = 0;
       uint32_t phase = 0;
       const int pq = p.P * p.Q;
@@ -471,13 +496,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int tap = kb_begin / p.cblocks, cb = kb_begin - tap * p.cblocks;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_expect_tx_u(&full_bar[stage], Cfg::kStageBytes);
           const int r = tap / p.S;
           const int s = tap - r * p.S;
-          tma_load_im2col_4d(smem_a + stage * kATileBytes, &map_a, &full_bar[stage], cb * kBlockK,
+          tma_load_im2col_4d_u(smem_a + stage * kATileBytes, &map_a, &full_bar[stage], cb * kBlockK,
                              base_w, base_h, img, static_cast<uint16_t>(s),
                              static_cast<uint16_t>(r));
-          tma_load_2d(smem_b + stage * Cfg::kBTileBytes, &map_b, &full_bar[stage], kb * kBlockK,
+          tma_load_2d_u(smem_b + stage * Cfg::kBTileBytes, &map_b, &full_bar[stage], kb * kBlockK,
                       n_tile * BLOCK_N);
           if (++cb == p.cblocks) {
             cb = 0;
@@ -492,7 +517,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       // InstrDescriptor (cute/arch/mma_sm100_desc.hpp): c_format F32 [4,6)=1, a/b format
       // [7,10), [10,13) = kIdescAB (0 = F16, 1 = BF16), a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
       constexpr uint32_t idesc = (1u << 4) | kIdescAB |
@@ -518,16 +543,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_f16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+            tc_mma_f16_u(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                         idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          tc_commit_u(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        tc_commit_u(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
     }
   } else if (warp >= 4) {
@@ -860,7 +885,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 25);
   float* bias_s = reinterpret_cast<float*>(bars + 32);  // [64]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < kWinN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
 
@@ -897,17 +922,17 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       // resident weights: one [64 x 64] tile per tap
-      mbar_expect_tx(b_full, static_cast<uint32_t>(n_taps) * kWinBTile);
-      for (int t = 0; t < n_taps; ++t) tma_load_2d(smem_b + t * kWinBTile, &map_b, b_full, t * kBlockK, 0);
+      mbar_expect_tx_u(b_full, static_cast<uint32_t>(n_taps) * kWinBTile);
+      for (int t = 0; t < n_taps; ++t) tma_load_2d_u(smem_b + t * kWinBTile, &map_b, b_full, t * kBlockK, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         const long long q0 = p.q_base + static_cast<long long>(tile) * kBlockM;
         for (int wi = 0; wi < p.n_windows; ++wi) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.win_bytes));
+          mbar_expect_tx_u(&full_bar[stage], static_cast<uint32_t>(p.win_bytes));
           // window start in padded-linear space: rows of tap row-group wi start rg*wi rows of Wp further down
           long long qs = q0 - (static_cast<long long>(p.pl_h) * p.Wp + p.pl_w) + static_cast<long long>(wi) * p.rg * p.Wp;
           for (int ch = 0; ch < p.n_chunks; ++ch) {
@@ -915,7 +940,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int img = static_cast<int>(q / hpwp);
             const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
             const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-            tma_load_im2col_4d(smem_a + static_cast<size_t>(stage) * p.win_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
+            tma_load_im2col_4d_u(smem_a + static_cast<size_t>(stage) * p.win_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
                                &map_a, &full_bar[stage], 0, xp - p.pl_w, yp - p.pl_h, img, 0, 0);
           }
           if (++stage == stages) {
@@ -932,7 +957,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // which, not the tensor pipe, bounds a single issuer -- overlaps between two tiles.  mode bit 5 (32): warp 1 only.
     const int n_issuers = p.mma_issuers;
     const int which = warp == 1 ? 0 : (warp == 3 ? 1 : 2);  // warp 2 (TMEM allocator) doubles as the third issuer
-    if (lane == 0 && which < n_issuers) {
+    if (which < n_issuers) {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kWinN >> 3) << 17) |
                                  (static_cast<uint32_t>(kBlockM >> 4) << 24);
       mbar_wait(b_full, 0);
@@ -949,7 +974,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // which rules the case out by construction (always on since r02: no measurable cost, 13.42 vs 13.50 ms per step).
           for (int wi = 0; wi < p.n_windows; ++wi) {
             mbar_wait(&full_bar[stage], phase);
-            if (p.observers_arrive) mbar_arrive(&empty_bar[stage]);
+            if (p.observers_arrive) mbar_arrive_u(&empty_bar[stage]);
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
@@ -977,16 +1002,16 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int s = 0; s < p.S; ++s) {
               const unsigned sk = static_cast<unsigned>(p.kskip >> (4 * tap)) & 15u;
               if (sk == 0u) {
-                tc_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
-                tc_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
-                tc_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
-                tc_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
+                tc_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
+                tc_mma_f16_u(tmem_d, da + 2, db + 2, idesc, 1u);
+                tc_mma_f16_u(tmem_d, da + 4, db + 4, idesc, 1u);
+                tc_mma_f16_u(tmem_d, da + 6, db + 6, idesc, 1u);
                 first = 0;
               } else {  // structurally zero weight slices (7x7 stem inside its 8x8 space-to-depth footprint): not issued
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (((sk >> ks) & 1u) == 0u) {
-                    tc_mma_f16(tmem_d, da + 2 * ks, db + 2 * ks, idesc, first ? 0u : 1u);
+                    tc_mma_f16_u(tmem_d, da + 2 * ks, db + 2 * ks, idesc, first ? 0u : 1u);
                     first = 0;
                   }
               }
@@ -996,13 +1021,13 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             da_row += static_cast<uint64_t>(p.Wp) * 8;
           }
-          tc_commit(&empty_bar[stage]);
+          tc_commit_u(&empty_bar[stage]);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(&tmem_full[acc]);
+        tc_commit_u(&tmem_full[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -1263,7 +1288,7 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 28);
   float* bias_s = reinterpret_cast<float*>(bars + 32);  // [128]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < kW2N) bias_s[threadIdx.x] = p.bias[threadIdx.x];
 
@@ -1303,20 +1328,20 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     // ===================== window producer =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       int local = 0;
       for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++local) {
         const long long qs = p.q_base + static_cast<long long>(st) * 256 - (p.Wp + 1);  // first window row
         const uint32_t par = static_cast<uint32_t>(local & 1);
         for (int c = 0; c < 2; ++c) {
           mbar_wait(&a_empty[c], par ^ 1u);
-          mbar_expect_tx(&a_full[c], static_cast<uint32_t>(p.panel_bytes));
+          mbar_expect_tx_u(&a_full[c], static_cast<uint32_t>(p.panel_bytes));
           for (int ch = 0; ch < p.n_chunks; ++ch) {
             const long long q = qs + static_cast<long long>(ch) * p.chunk_rows;
             const int img = static_cast<int>(q / hpwp);
             const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
             const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-            tma_load_im2col_4d(smem_a + static_cast<size_t>(c) * p.panel_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
+            tma_load_im2col_4d_u(smem_a + static_cast<size_t>(c) * p.panel_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
                                &map_a, &a_full[c], c * 64, xp - 1, yp - 1, img, 0, 0);
           }
         }
@@ -1324,15 +1349,15 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 2) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       int stage = 0;
       uint32_t phase = 0;
       for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
         for (int c = 0; c < 2; ++c) {
           for (int t = 0; t < kW2Taps; ++t) {
             mbar_wait(&b_empty[stage], phase ^ 1u);
-            mbar_expect_tx(&b_full[stage], kW2BTile);
-            tma_load_2d(smem_b + stage * kW2BTile, &map_b, &b_full[stage], t * 128 + c * 64, 0);
+            mbar_expect_tx_u(&b_full[stage], kW2BTile);
+            tma_load_2d_u(smem_b + stage * kW2BTile, &map_b, &b_full[stage], t * 128 + c * 64, 0);
             if (++stage == kW2BStages) {
               stage = 0;
               phase ^= 1u;
@@ -1343,7 +1368,7 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers: warp 1 -> rows 0-127 of the super-tile, warp 3 -> rows 128-255 ==========
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       const int ti = warp == 1 ? 0 : 1;
       constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kW2N >> 3) << 17) |
                                  (static_cast<uint32_t>(kBlockM >> 4) << 24);
@@ -1370,12 +1395,12 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               mbar_wait(&b_full[stage], phase);
               tc_fence_after();
               const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * kW2BTile));
-              tc_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc_mma_f16_u(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc_mma_f16_u(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc_mma_f16_u(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
-              tc_commit(&b_empty[stage]);
+              tc_commit_u(&b_empty[stage]);
               if (++stage == kW2BStages) {
                 stage = 0;
                 phase ^= 1u;
@@ -1384,9 +1409,9 @@ conv_window2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             da_row += static_cast<uint64_t>(p.Wp) * 8;
           }
-          tc_commit(&a_empty[c]);  // this issuer is done with panel c
+          tc_commit_u(&a_empty[c]);  // this issuer is done with panel c
         }
-        tc_commit(&tmem_full[buf]);
+        tc_commit_u(&tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -1557,6 +1582,45 @@ __device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_remote_u(uint64_t* bar, uint32_t cta_rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta_rank));
+  asm volatile(MPX_ELECT_PRED "@e mbarrier.arrive.shared::cluster.b64 _, [%0];\n\t}" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d_u(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(MPX_ELECT_PRED
+               "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(smem_u32(smem)),
+               "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(kTmaCacheHintNormal)
+               : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d_u(void* smem, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                      int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(MPX_ELECT_PRED
+               "@e cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;\n\t}" ::"r"(smem_u32(smem)),
+               "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+               "l"(kTmaCacheHintNormal)
+               : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16_u(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc_u(uint64_t* bar) {
+  asm volatile(MPX_ELECT_PRED
+               "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
 template <int BLOCK_N>
 struct Conv2Cfg {
   static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;
@@ -1585,9 +1649,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   float* bias_s = reinterpret_cast<float*>(bars + 32);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x & 1u;  // = %cluster_ctarank for clusters of two along x; from blockIdx so that the compiler knows it is uniform
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
@@ -1624,7 +1688,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       int stage = 0;
       uint32_t phase = 0;
       const int pq = p.P * p.Q;
@@ -1641,13 +1705,13 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         int tap = 0, cb = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2u * Cfg::kStageBytes);
-          else mbar_arrive_remote(&full_bar[stage], 0);
+          if (leader) mbar_expect_tx_u(&full_bar[stage], 2u * Cfg::kStageBytes);
+          else mbar_arrive_remote_u(&full_bar[stage], 0);
           const int r = tap / p.S;
           const int s = tap - r * p.S;
-          tma2_load_im2col_4d(smem_a + stage * kATileBytes, &map_a, &full_bar[stage], cb * kBlockK, base_w, base_h, img,
+          tma2_load_im2col_4d_u(smem_a + stage * kATileBytes, &map_a, &full_bar[stage], cb * kBlockK, base_w, base_h, img,
                               static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          tma2_load_2d(smem_b + stage * Cfg::kBHalfBytes, &map_b, &full_bar[stage], kb * kBlockK,
+          tma2_load_2d_u(smem_b + stage * Cfg::kBHalfBytes, &map_b, &full_bar[stage], kb * kBlockK,
                        n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
           if (++cb == p.cblocks) {
             cb = 0;
@@ -1662,7 +1726,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       int stage = 0;
@@ -1681,16 +1745,16 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * Cfg::kBHalfBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            tc2_mma_f16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+            tc2_mma_f16_u(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc2_commit_mc(&empty_bar[stage]);
+          tc2_commit_mc_u(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc2_commit_mc(&tmem_full[acc]);
+        tc2_commit_mc_u(&tmem_full[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -1789,9 +1853,9 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 36);
   float* bias_s = reinterpret_cast<float*>(bars + 40);  // [128]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x & 1u;  // = %cluster_ctarank for clusters of two along x; from blockIdx so that the compiler knows it is uniform
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
@@ -1832,7 +1896,7 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (warp == 0) {
     // ===================== window producer (both CTAs: own super-tile) =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       int local = 0;
       for (int item = pair; item < n_items; item += n_pairs, ++local) {
         const long long st = 2LL * item + rank;
@@ -1840,14 +1904,14 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t par = static_cast<uint32_t>(local & 1);
         for (int c = 0; c < 2; ++c) {
           mbar_wait(&a_empty[c], par ^ 1u);
-          if (leader) mbar_expect_tx(&a_full[c], 2u * static_cast<uint32_t>(p.panel_bytes));
-          else mbar_arrive_remote(&a_full[c], 0);
+          if (leader) mbar_expect_tx_u(&a_full[c], 2u * static_cast<uint32_t>(p.panel_bytes));
+          else mbar_arrive_remote_u(&a_full[c], 0);
           for (int ch = 0; ch < p.n_chunks; ++ch) {
             const long long q = qs + static_cast<long long>(ch) * p.chunk_rows;
             const int img = static_cast<int>(q / hpwp);
             const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
             const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-            tma2_load_im2col_4d(smem_a + static_cast<size_t>(c) * p.panel_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
+            tma2_load_im2col_4d_u(smem_a + static_cast<size_t>(c) * p.panel_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
                                 &map_a, &a_full[c], c * 64, xp - 1, yp - 1, img, 0, 0);
           }
         }
@@ -1855,16 +1919,16 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else if (warp == 2) {
     // ===================== weight producer (both CTAs: own 64 output channels) =====================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       int stage = 0;
       uint32_t phase = 0;
       for (int item = pair; item < n_items; item += n_pairs) {
         for (int c = 0; c < 2; ++c) {
           for (int t = 0; t < kW2Taps; ++t) {
             mbar_wait(&b_empty[stage], phase ^ 1u);
-            if (leader) mbar_expect_tx(&b_full[stage], 2u * kW2qBHalf);
-            else mbar_arrive_remote(&b_full[stage], 0);
-            tma2_load_2d(smem_b + stage * kW2qBHalf, &map_b, &b_full[stage], t * 128 + c * 64,
+            if (leader) mbar_expect_tx_u(&b_full[stage], 2u * kW2qBHalf);
+            else mbar_arrive_remote_u(&b_full[stage], 0);
+            tma2_load_2d_u(smem_b + stage * kW2qBHalf, &map_b, &b_full[stage], t * 128 + c * 64,
                          static_cast<int>(rank) * (kW2N / 2));
             if (++stage == kW2qBStages) {
               stage = 0;
@@ -1876,7 +1940,7 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers (leader only): warp 1 -> rows 0-127 of both CTAs, warp 3 -> rows 128-255 ======
-    if (leader && lane == 0) {
+    if (leader) {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       const int ti = warp == 1 ? 0 : 1;
       constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kW2N >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
@@ -1902,12 +1966,12 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               mbar_wait(&b_full[stage], phase);
               tc_fence_after();
               const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * kW2qBHalf));
-              tc2_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
-              tc2_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
-              tc2_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
-              tc2_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
+              tc2_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc2_mma_f16_u(tmem_d, da + 2, db + 2, idesc, 1u);
+              tc2_mma_f16_u(tmem_d, da + 4, db + 4, idesc, 1u);
+              tc2_mma_f16_u(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
-              tc2_commit_mc(&b_empty[stage]);
+              tc2_commit_mc_u(&b_empty[stage]);
               if (++stage == kW2qBStages) {
                 stage = 0;
                 phase ^= 1u;
@@ -1916,9 +1980,9 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             da_row += static_cast<uint64_t>(p.Wp) * 8;
           }
-          tc2_commit_mc(&a_empty[c]);  // this issuer is done with panel c (in both CTAs)
+          tc2_commit_mc_u(&a_empty[c]);  // this issuer is done with panel c (in both CTAs)
         }
-        tc2_commit_mc(&tmem_full[buf]);
+        tc2_commit_mc_u(&tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -2073,9 +2137,9 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 25);
   float* bias_s = reinterpret_cast<float*>(bars + 32);  // [64]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x & 1u;  // = %cluster_ctarank for clusters of two along x; from blockIdx so that the compiler knows it is uniform
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
@@ -2115,26 +2179,26 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own windows, own half of the weights) =====================
-    if (lane == 0) {
-      if (leader) mbar_expect_tx(b_full, 2u * static_cast<uint32_t>(n_taps) * kWinqBHalf);
-      else mbar_arrive_remote(b_full, 0);
+    {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
+      if (leader) mbar_expect_tx_u(b_full, 2u * static_cast<uint32_t>(n_taps) * kWinqBHalf);
+      else mbar_arrive_remote_u(b_full, 0);
       for (int t = 0; t < n_taps; ++t)
-        tma2_load_2d(smem_b + t * kWinqBHalf, &map_b, b_full, t * kBlockK, static_cast<int>(rank) * (kWinN / 2));
+        tma2_load_2d_u(smem_b + t * kWinqBHalf, &map_b, b_full, t * kBlockK, static_cast<int>(rank) * (kWinN / 2));
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < n_ptiles; tile += n_pairs) {
         const long long q0 = p.q_base + (2LL * tile + rank) * kBlockM;
         for (int wi = 0; wi < p.n_windows; ++wi) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.win_bytes));
-          else mbar_arrive_remote(&full_bar[stage], 0);
+          if (leader) mbar_expect_tx_u(&full_bar[stage], 2u * static_cast<uint32_t>(p.win_bytes));
+          else mbar_arrive_remote_u(&full_bar[stage], 0);
           long long qs = q0 - (static_cast<long long>(p.pl_h) * p.Wp + p.pl_w) + static_cast<long long>(wi) * p.rg * p.Wp;
           for (int ch = 0; ch < p.n_chunks; ++ch) {
             const long long q = qs + static_cast<long long>(ch) * p.chunk_rows;
             const int img = static_cast<int>(q / hpwp);
             const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
             const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-            tma2_load_im2col_4d(smem_a + static_cast<size_t>(stage) * p.win_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
+            tma2_load_im2col_4d_u(smem_a + static_cast<size_t>(stage) * p.win_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
                                 &map_a, &full_bar[stage], 0, xp - p.pl_w, yp - p.pl_h, img, 0, 0);
           }
           if (++stage == stages) {
@@ -2147,7 +2211,7 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers (leader only), pair tiles alternately =====================
     const int which = warp == 1 ? 0 : 1;
-    if (leader && lane == 0) {
+    if (leader) {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
       constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kWinN >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
       mbar_wait(b_full, 0);
@@ -2184,16 +2248,16 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int s = 0; s < p.S; ++s) {
               const unsigned sk = static_cast<unsigned>(p.kskip >> (4 * tap)) & 15u;
               if (sk == 0u) {
-                tc2_mma_f16(tmem_d, da, db, idesc, first ? 0u : 1u);
-                tc2_mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
-                tc2_mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
-                tc2_mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
+                tc2_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
+                tc2_mma_f16_u(tmem_d, da + 2, db + 2, idesc, 1u);
+                tc2_mma_f16_u(tmem_d, da + 4, db + 4, idesc, 1u);
+                tc2_mma_f16_u(tmem_d, da + 6, db + 6, idesc, 1u);
                 first = 0;
               } else {  // structurally zero weight slices (7x7 stem inside its 8x8 space-to-depth footprint): not issued
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (((sk >> ks) & 1u) == 0u) {
-                    tc2_mma_f16(tmem_d, da + 2 * ks, db + 2 * ks, idesc, first ? 0u : 1u);
+                    tc2_mma_f16_u(tmem_d, da + 2 * ks, db + 2 * ks, idesc, first ? 0u : 1u);
                     first = 0;
                   }
               }
@@ -2203,13 +2267,13 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             da_row += static_cast<uint64_t>(p.Wp) * 8;
           }
-          tc2_commit_mc(&empty_bar[stage]);
+          tc2_commit_mc_u(&empty_bar[stage]);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc2_commit_mc(&tmem_full[acc]);
+        tc2_commit_mc_u(&tmem_full[acc]);
       }
     }
   } else if (warp >= 4) {
