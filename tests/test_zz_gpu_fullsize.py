@@ -10,7 +10,8 @@ oracle/raster_ref.c standing in for Panda3D) on the scenarios of workloads/scene
   fullsize_ycbv21   configs[3]: 21 objects x 576 hypotheses in one frame (12 096 coarse rows)
 
 Asserted, with the fp16-vs-fp32 tolerances stated here:
-  * every coarse logit within LOGIT_TOL_STD standard deviations of the reference's logits (max) and LOGIT_RMS_STD (rms);
+  * coarse logits: common offset within LOGIT_OFFSET_STD standard deviations of the reference's logits, every logit within
+    LOGIT_TOL_STD (max) and LOGIT_RMS_STD (rms) of the reference's about that offset;
   * per detection the same surviving hypothesis as the reference -- or, where the reference's own margin between its
     best candidates is inside twice the observed noise, one of those near-tied candidates (counted and bounded);
   * the refiner, iteration by iteration, each started from the REFERENCE's input pose of that iteration: output pose within
@@ -33,8 +34,10 @@ from workloads import scenes
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
-LOGIT_TOL_STD = 0.12   # max |logit error| / std of the reference's logits (observed with fp16: 0.08-0.10)
-LOGIT_RMS_STD = 0.04   # rms of the error about its mean (a common offset of ~0.06 std moves no ranking; it is printed)
+LOGIT_OFFSET_STD = 0.10  # |mean logit error| / std of the reference's logits: a common offset (observed -0.06 .. -0.07 std
+                         # on the RGB scenarios) moves no ranking and shifts every sigmoid score alike
+LOGIT_TOL_STD = 0.08     # max |logit error - mean error| / std (observed with fp16: 0.03-0.06 over 576 .. 12096 rows)
+LOGIT_RMS_STD = 0.03     # rms of the error about its mean (observed 0.010-0.015)
 ROT_TOL_DEG = 0.5      # SURVEY 8c (iv), per refiner iteration from the reference's input pose
 TRANS_TOL_MM = 1.0
 FREE_ROT_TOL_DEG = 2.0   # free-running 5 iterations, RGB scenarios (see the docstring)
@@ -105,11 +108,13 @@ def test_full_size_pipeline_matches_the_reference(name):
     rms_c = np.sqrt(((d - d.mean()) ** 2).mean())
     print(f"[{name}] coarse logits: max err {err.max():.4f} = {err.max() / std:.3f} std, mean offset {d.mean():+.4f}, rms about "
           f"the mean {rms_c:.4f} = {rms_c / std:.3f} std (reference std {std:.3f}, {B * M} rows)")
-    assert err.max() <= LOGIT_TOL_STD * std and rms_c <= LOGIT_RMS_STD * std
+    max_c = np.abs(d - d.mean()).max()
+    print(f"[{name}] coarse logits about the offset: max {max_c:.4f} = {max_c / std:.3f} std")
+    assert abs(d.mean()) <= LOGIT_OFFSET_STD * std and max_c <= LOGIT_TOL_STD * std and rms_c <= LOGIT_RMS_STD * std
 
     # ---- survivors
     kept = extra["coarse_filter"]["preds"].infos
-    noise = 2.0 * err.max()
+    noise = 2.0 * max_c  # ranking noise: the error about the common offset
     same, near_tie = [], 0
     for det in range(B):
         w = want[det * M:(det + 1) * M]
@@ -159,7 +164,7 @@ def test_full_size_pipeline_matches_the_reference(name):
     serr = np.abs(sl - g["scored_pose_logit"].astype(np.float64)[rows_g])
     print(f"[{name}] scoring logits (free-running poses): max err {serr.max():.4f}, median {np.median(serr):.4f}")
     if rgb_only:
-        assert serr.max() <= 2 * LOGIT_TOL_STD * std  # the refined poses differ on top of the network's own error
+        assert serr.max() <= (LOGIT_OFFSET_STD + 2 * LOGIT_TOL_STD) * std  # the refined poses differ on top of the network's own error
     labels_final = final.infos["label"].tolist()
     assert sorted(labels_final) == sorted(g["final_label"].tolist())
     for det in same:
