@@ -192,53 +192,67 @@ __device__ __forceinline__ void load_res_chunk(const act_t* res_row, int c, uint
   for (int i = 0; i < 4; ++i) r[i] = __ldg(r4 + i);
 }
 
+// +bias, +residual, ReLU, conversion and the four 16-byte stores of one 32-column chunk
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], act_t* out_c, const float* bias_c, bool has_res,
+                                               const uint4 (&res)[4], int relu) {
+  uint4* o4 = reinterpret_cast<uint4*>(out_c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_c + 8 * i);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_c + 8 * i + 4);
+    f[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
+    f[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
+    f[2] = __uint_as_float(v[8 * i + 2]) + b0.z;
+    f[3] = __uint_as_float(v[8 * i + 3]) + b0.w;
+    f[4] = __uint_as_float(v[8 * i + 4]) + b1.x;
+    f[5] = __uint_as_float(v[8 * i + 5]) + b1.y;
+    f[6] = __uint_as_float(v[8 * i + 6]) + b1.z;
+    f[7] = __uint_as_float(v[8 * i + 7]) + b1.w;
+    if (has_res) {
+      const uint32_t rr[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_act2(rr[j]);
+        f[2 * j] += t.x;
+        f[2 * j + 1] += t.y;
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_act2(f[0], f[1]);
+    o.y = pack_act2(f[2], f[3]);
+    o.z = pack_act2(f[4], f[5]);
+    o.w = pack_act2(f[6], f[7]);
+    o4[i] = o;
+  }
+}
+
+// The TMEM reads are double-buffered: the tcgen05.ld of chunk c + 1 is in flight while chunk c is converted and stored (r02
+// ncu: with one load + wait per chunk a quarter of the epilogue warps' samples sat on the first use of the loaded registers,
+// and the N = 64 kernels -- whose epilogue per MMA cycle is the largest -- ran at 37-54% tensor-pipe activity).
 template <int NCOLS>
 __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, act_t* out_row,
                                              const act_t* res_row, const float* bias_s, int relu,
                                              uint4 (&res_cur)[4]) {
   const bool has_res = valid && res_row != nullptr;
-#pragma unroll 1
-  for (int c = 0; c < NCOLS; c += 32) {
-    uint32_t v[32];
-    tc_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+  uint32_t va[32], vb[32];
+  tc_ld_32x32(taddr, va);
+#pragma unroll
+  for (int cc = 0; cc < NCOLS / 32; ++cc) {
+    const int c = cc * 32;
     uint4 res_nxt[4];
     if (has_res && c + 32 < NCOLS) load_res_chunk(res_row, c + 32, res_nxt);
-    tc_wait_ld();
-    if (valid) {
-      uint4* o4 = reinterpret_cast<uint4*>(out_row + c);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float f[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c + 8 * i);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 8 * i + 4);
-        f[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
-        f[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
-        f[2] = __uint_as_float(v[8 * i + 2]) + b0.z;
-        f[3] = __uint_as_float(v[8 * i + 3]) + b0.w;
-        f[4] = __uint_as_float(v[8 * i + 4]) + b1.x;
-        f[5] = __uint_as_float(v[8 * i + 5]) + b1.y;
-        f[6] = __uint_as_float(v[8 * i + 6]) + b1.z;
-        f[7] = __uint_as_float(v[8 * i + 7]) + b1.w;
-        if (has_res) {
-          const uint32_t rr[4] = {res_cur[i].x, res_cur[i].y, res_cur[i].z, res_cur[i].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 t = unpack_act2(rr[j]);
-            f[2 * j] += t.x;
-            f[2 * j + 1] += t.y;
-          }
-        }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        uint4 o;
-        o.x = pack_act2(f[0], f[1]);
-        o.y = pack_act2(f[2], f[3]);
-        o.z = pack_act2(f[4], f[5]);
-        o.w = pack_act2(f[6], f[7]);
-        o4[i] = o;
-      }
+    tc_wait_ld();  // chunk cc has landed (the only load in flight)
+    if ((cc & 1) == 0) {
+      if (c + 32 < NCOLS) tc_ld_32x32(taddr + static_cast<uint32_t>(c + 32), vb);
+      if (valid) epilogue_chunk(va, out_row + c, bias_s + c, has_res, res_cur, relu);
+    } else {
+      if (c + 32 < NCOLS) tc_ld_32x32(taddr + static_cast<uint32_t>(c + 32), va);
+      if (valid) epilogue_chunk(vb, out_row + c, bias_s + c, has_res, res_cur, relu);
     }
     if (has_res && c + 32 < NCOLS) {
 #pragma unroll
