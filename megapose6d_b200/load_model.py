@@ -214,8 +214,10 @@ def load_named_model(model_name: str, object_dataset: RigidObjectDataset, n_work
                                                       "n_workers": n_workers},
         models_root=models_root, render_size=render_size)
     depth_refiner = None
-    if model.get("depth_refiner") == "ICP":
-        raise NotImplementedError("the ICP depth refiner (OpenCV ppf_match_3d) is outside the hot path; SURVEY 8f")
+    if model.get("depth_refiner") == "ICP":  # utils/load_model.py:75-79
+        from .icp_refiner import ICPRefiner
+
+        depth_refiner = ICPRefiner(refiner_model.mesh_db, refiner_model.renderer)
     return PoseEstimator(refiner_model=refiner_model, coarse_model=coarse_model, detector_model=None,
                          depth_refiner=depth_refiner, bsz_objects=8, bsz_images=bsz_images)
 
