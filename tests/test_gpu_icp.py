@@ -32,14 +32,12 @@ def test_icp_refiner_pulls_perturbed_poses_back(tmp_path):
     labels = [ds[0].label, ds[1].label, ds[0].label]
     T_true = torch.from_numpy(procedural.random_poses(3, 23, z_range=(0.35, 0.6), xy_range=0.05)).float()
     Kn = K.repeat(3, 1, 1)
-    # "measured" depth of frame 0: the scene of the first two objects rendered by the ORACLE rasteriser at full resolution
+    # "measured" depth: one frame per object, rendered by the ORACLE rasteriser at full resolution
     rm = helpers.ref_meshes_from_dataset(ds)
     ref = pipeline_ref.RefRenderer(rm).render(labels, T_true, Kn, None, (480, 640), render_depth=True)["depths"][:, 0]
     got = est.depth_refiner.renderer.render(labels, T_true.cuda(), Kn.cuda(), None, (480, 640), render_depth=True).depths[:, 0]
     assert torch.equal(got.cpu(), ref)  # the depth render of the refiner is the contract's, bit for bit
-    depth0 = torch.where((ref[0] > 0) & ((ref[1] == 0) | (ref[0] < ref[1])), ref[0], ref[1])
-    depth1 = ref[2].clone()
-    depth = torch.stack((depth0, depth1)).cuda()                  # [B = 2, H, W] metres
+    depth = ref.clone().cuda()                                    # [B = 3, H, W] metres
     # predictions: the true poses perturbed by ~1.5 degrees and a few millimetres
     rng = np.random.RandomState(3)
     T_pred = T_true.clone()
@@ -49,17 +47,17 @@ def test_icp_refiner_pulls_perturbed_poses_back(tmp_path):
         Kx = torch.tensor([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
         T_pred[i, :3, :3] = torch.matrix_exp(Kx) @ T_true[i, :3, :3]
         T_pred[i, :3, 3] += torch.from_numpy(rng.uniform(-0.004, 0.004, 3)).float()
-    infos = pd.DataFrame(dict(label=labels, batch_im_id=[0, 0, 1], instance_id=[0, 0, 0]))
+    infos = pd.DataFrame(dict(label=labels, batch_im_id=[0, 1, 2], instance_id=[0, 0, 0]))
     preds = PandasTensorCollection(infos, poses=T_pred.cuda())
-    refined, extra = est.depth_refiner.refine_poses(preds, depth=depth, K=K.repeat(2, 1, 1).cuda())
+    refined, extra = est.depth_refiner.refine_poses(preds, depth=depth, K=K.repeat(3, 1, 1).cuda())
     assert torch.equal(refined.poses_input.cpu(), T_pred) and extra["n_accepted"] == 3
     for i in range(3):
         r0, t0 = _pose_err(T_pred[i], T_true[i])
         r1, t1 = _pose_err(refined.poses[i].cpu(), T_true[i])
         print(f"object {i}: {r0:.3f} deg / {t0:.2f} mm -> {r1:.3f} deg / {t1:.2f} mm")
-        assert t1 < 0.35 * t0 and t1 < 1.5 and r1 < 0.6 * r0 + 0.1
+        assert t1 < 0.35 * t0 and t1 < 1.0 and r1 < 0.6 * r0 + 0.1
     # too few valid points (depth image empty): poses stay, nothing accepted
-    empty, extra = est.depth_refiner.refine_poses(preds, depth=torch.zeros_like(depth), K=K.repeat(2, 1, 1).cuda())
+    empty, extra = est.depth_refiner.refine_poses(preds, depth=torch.zeros_like(depth), K=K.repeat(3, 1, 1).cuda())
     assert torch.equal(empty.poses.cpu(), T_pred) and extra["n_accepted"] == 0
     # the estimator's hook (inference/pose_estimator.py:485-508)
     m, _ = compute_masks("threshold", got[0], depth[0], 0.1)
