@@ -21,6 +21,10 @@ RASTER_NORMALS_GL = 2
 RASTER_POINT_LIGHTS = 4
 DEPTH_NORM_KINDS = {"tCR_scale_clamp_center": 0, "tCR_scale": 1, "tCR_center_clamp": 2, "none": 3, None: 3}
 DEPTH_NORM_SHIFT = 8
+# the four sample positions of 4x multisampling (standard pattern, sixteenths of a pixel about the pixel centre) -- what the
+# reference's offscreen buffer is configured with (framebuffer-multisample 1, multisamples 4:
+# panda3d_renderer/panda3d_scene_renderer.py:73-74)
+MSAA4_OFFSETS = ((-2 / 16, -6 / 16), (6 / 16, -2 / 16), (-6 / 16, 2 / 16), (2 / 16, 6 / 16))
 
 
 def is_scene_lights(lights) -> bool:
@@ -61,7 +65,8 @@ class BatchRenderOutput:
 class BatchRenderer:
     def __init__(self, object_dataset: Optional[RigidObjectDataset] = None, n_workers: int = 0,
                  preload_cache: bool = False, split_objects: bool = False,
-                 mesh_db: Optional[BatchedMeshes] = None, quantize8: bool = True, normals_gl_axes: bool = False):
+                 mesh_db: Optional[BatchedMeshes] = None, quantize8: bool = True, normals_gl_axes: bool = False,
+                 msaa4: bool = False):
         if mesh_db is None:
             assert object_dataset is not None
             mesh_db = MeshDataBase.from_object_ds(object_dataset).batched()
@@ -69,6 +74,9 @@ class BatchRenderer:
         self._object_dataset = object_dataset
         self.flags = (RASTER_QUANTIZE8 if quantize8 else 0) | (RASTER_NORMALS_GL if normals_gl_axes else 0)
         self._workspace: Optional[torch.Tensor] = None
+        # 4x anti-aliasing of the colour / normal outputs of `render` (see _render_msaa4); off by default: the fused
+        # network-input paths of the pipeline render one sample per pixel
+        self.msaa4 = msaa4
 
     def stop(self) -> None:  # the reference joins its worker processes here
         pass
@@ -104,6 +112,8 @@ class BatchRenderer:
                render_normals: bool = False) -> BatchRenderOutput:
         if render_mask:
             raise NotImplementedError
+        if self.msaa4:
+            return self._render_msaa4(labels, TCO, K, light_datas, resolution, render_depth, render_normals)
         flags = self.flags | self._light_flags(light_datas)
         n = TCO.shape[0]
         assert TCO.shape == (n, 4, 4) and K.shape == (n, 3, 3) and len(labels) == n
@@ -120,6 +130,39 @@ class BatchRenderer:
                                                 n, h, w, flags, _abi.ptr(rgbs), _abi.ptr(normals),
                                                 _abi.ptr(depths), _abi.ptr(ws), ws.numel(), _abi.stream_ptr()))
         return BatchRenderOutput(rgbs=rgbs, normals=normals, depths=depths)
+
+    def _render_msaa4(self, labels, TCO, K, light_datas, resolution, render_depth, render_normals) -> BatchRenderOutput:
+        """4x anti-aliased render (contract in oracle/pipeline_ref.py: RefRenderer.render(msaa4=True)): the view is rendered
+        once per sample position of the 4x multisample pattern -- pixel (i, j) sampled at (j + 0.5 + ox, i + 0.5 + oy), i.e.
+        with the principal point moved to (cx - ox, cy - oy) -- every sample shaded and quantised to 8 bits on its own, and
+        the pixel is the rounded mean of its four samples, (k0 + k1 + k2 + k3 + 2) >> 2 in 8-bit levels (GL's multisample
+        resolve).  Depth is the single-sample (pixel-centre) depth."""
+        self.msaa4 = False
+        try:
+            out = self.render(labels, TCO, K, light_datas, resolution, render_depth=render_depth, render_mask=False,
+                              render_normals=render_normals)
+            q8 = (self.flags & RASTER_QUANTIZE8) != 0
+            parts_rgb, parts_nrm = [], []
+            for ox, oy in MSAA4_OFFSETS:
+                Ks = K.detach().float().clone()
+                Ks[:, 0, 2] = Ks[:, 0, 2] - ox
+                Ks[:, 1, 2] = Ks[:, 1, 2] - oy
+                s = self.render(labels, TCO, Ks, light_datas, resolution, render_depth=False, render_mask=False,
+                                render_normals=render_normals)
+                parts_rgb.append(s.rgbs)
+                if render_normals:
+                    parts_nrm.append(s.normals)
+
+            def resolve(parts):
+                if q8:
+                    k = sum((p * 255.0).round().to(torch.int32) for p in parts)
+                    return ((k + 2) >> 2).float() / 255.0
+                return ((parts[0] + parts[1]) + (parts[2] + parts[3])) * 0.25
+
+            return BatchRenderOutput(rgbs=resolve(parts_rgb), normals=resolve(parts_nrm) if render_normals else None,
+                                     depths=out.depths)
+        finally:
+            self.msaa4 = True
 
     def render_fused(self, label_idx: torch.Tensor, TCO: torch.Tensor, K: torch.Tensor, views_per_sample: int,
                      resolution: Tuple[int, int], x: torch.Tensor, c_pad: int, ch_offset: int, ch_per_view: int,

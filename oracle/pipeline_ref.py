@@ -123,8 +123,39 @@ class RefRenderer:
         self.flags = (1 if quantize8 else 0) | (2 if normals_gl_axes else 0)
         self.n_threads = n_threads or os.cpu_count() or 1
 
+    MSAA4_OFFSETS = ((-2 / 16, -6 / 16), (6 / 16, -2 / 16), (-6 / 16, 2 / 16), (2 / 16, 6 / 16))
+
     def render(self, labels, TCO, K, light_datas=None, resolution=(240, 320), render_depth=False, render_mask=False,
-               render_normals=False, point_lights=False):
+               render_normals=False, point_lights=False, msaa4=False):
+        if msaa4:
+            return self._render_msaa4(labels, TCO, K, resolution, render_depth, render_normals, point_lights)
+        return self._render(labels, TCO, K, light_datas, resolution, render_depth, render_mask, render_normals, point_lights)
+
+    def _render_msaa4(self, labels, TCO, K, resolution, render_depth, render_normals, point_lights):
+        """Contract of the 4x anti-aliased render (the reference's offscreen buffer has 4x MSAA,
+        panda3d_scene_renderer.py:73-74; PARITY UNPINNED like the rest of the renderer): one render per sample position of
+        the standard 4x pattern (principal point moved by the sample offset, float32), every sample shaded and quantised on
+        its own, pixel = rounded mean of the four 8-bit samples ((k0 + k1 + k2 + k3 + 2) >> 2), or the float mean
+        ((s0 + s1) + (s2 + s3)) / 4 without quantisation; depth = the pixel-centre depth."""
+        centre = self._render(labels, TCO, K, None, resolution, render_depth, False, render_normals, point_lights)
+        parts = []
+        for ox, oy in self.MSAA4_OFFSETS:
+            Ks = K.detach().float().clone()
+            Ks[:, 0, 2] = Ks[:, 0, 2] - np.float32(ox)
+            Ks[:, 1, 2] = Ks[:, 1, 2] - np.float32(oy)
+            parts.append(self._render(labels, TCO, Ks, None, resolution, False, False, render_normals, point_lights))
+
+        def resolve(key):
+            ps = [p[key] for p in parts]
+            if self.flags & 1:
+                k = sum((p * 255.0).round().to(torch.int32) for p in ps)
+                return ((k + 2) >> 2).float() / 255.0
+            return ((ps[0] + ps[1]) + (ps[2] + ps[3])) * 0.25
+
+        return dict(rgbs=resolve("rgbs"), normals=resolve("normals") if render_normals else None, depths=centre["depths"])
+
+    def _render(self, labels, TCO, K, light_datas=None, resolution=(240, 320), render_depth=False, render_mask=False,
+                render_normals=False, point_lights=False):
         """`point_lights`: shade the albedo under make_scene_lights() (panda3d_scene_renderer.py:104-136) instead of white
         ambient light -- what models with render_normals=False are fed (models/pose_rigid.py:374-378)."""
         if render_mask:

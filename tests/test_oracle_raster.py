@@ -129,3 +129,29 @@ def test_oracle_point_lights_and_multiview_variants():
     assert W.shape == (3, 4, 4, 4)
     Rz = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
     assert torch.allclose(W[:, 1, :3, :3], Rz @ W[:, 0, :3, :3], atol=1e-6) and torch.equal(W[:, 1, :3, 3], W[:, 0, :3, 3])
+
+
+def test_oracle_msaa4_is_the_mean_of_four_offset_renders():
+    import torch
+
+    from megapose6d_b200 import procedural
+    from oracle import pipeline_ref
+    from tests import helpers
+
+    ds, _, _ = helpers.make_scene(1, seed=2)
+    rm = helpers.ref_meshes_from_dataset(ds)
+    T = torch.from_numpy(procedural.random_poses(1, 4, z_range=(0.3, 0.4), xy_range=0.01)).float()
+    K = torch.tensor([[600.0, 0, 80], [0, 600, 60], [0, 0, 1]]).unsqueeze(0)
+    r = pipeline_ref.RefRenderer(rm)
+    one = r.render([ds[0].label], T, K, None, (120, 160), render_normals=True, render_depth=True)
+    aa = r.render([ds[0].label], T, K, None, (120, 160), render_normals=True, render_depth=True, msaa4=True)
+    assert torch.equal(one["depths"], aa["depths"])
+    lv = aa["rgbs"] * 255
+    assert (lv - lv.round()).abs().max() < 1e-3  # 8-bit levels
+    inside = (one["depths"][0, 0] > 0)
+    # far from the silhouette the four samples see the same surface: within two 8-bit levels of the single-sample render
+    core = torch.nn.functional.avg_pool2d(inside[None, None].float(), 5, 1, 2)[0, 0] == 1
+    assert ((aa["rgbs"] - one["rgbs"])[0][:, core].abs().max() <= 3.5 / 255)
+    # on the silhouette the pixel is a blend with the black background
+    rim = inside & ~core
+    assert (aa["rgbs"][0].sum(0)[rim] < one["rgbs"][0].sum(0)[rim] - 1e-3).float().mean() > 0.2
