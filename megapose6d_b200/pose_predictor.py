@@ -292,7 +292,20 @@ class PosePredictor(nn.Module):
         nhwc4 = self._nhwc4(images)
         t_r = _Timer(cuda_timer)
         t_r.start()
-        if n_views == 1:
+        if getattr(self.renderer, "msaa4", False):
+            # anti-aliased renders (BatchRenderer(msaa4=True)): the un-fused form of the reference -- fp32 crops and renders,
+            # normalisation, concatenation (models/pose_rigid.py:546-567) -- then packed for the network
+            crops = lib3d.crop_images(nhwc4, boxes_crop, im_idx, c_in, self.render_size)
+            lights = [[Panda3dLightData("ambient", (1.0, 1.0, 1.0, 1.0))] if self.render_normals else make_scene_lights()]
+            data = self.renderer.render(None, TCV_O.reshape(-1, 4, 4).contiguous(), KV_crop.reshape(-1, 3, 3).contiguous(),
+                                        lights * lab_mv.shape[0], self.render_size, render_depth=self.render_depth,
+                                        render_normals=self.render_normals, label_idx=lab_mv)
+            cat = [data.rgbs] + ([data.normals] if self.render_normals else []) + ([data.depths] if self.render_depth else [])
+            renders = torch.cat(cat, dim=1)
+            renders = renders.view(n, n_views, renders.shape[1], h, w).flatten(1, 2)
+            crops, renders = self.normalize_images(crops, renders, tCR, images_inplace=True, renders_inplace=True)
+            x.copy_(self.backbone.pack_input(torch.cat((crops, renders), dim=1)))
+        elif n_views == 1:
             # one kernel: the rasteriser's resolve pass also crops the observation and stores whole pixel vectors
             self.renderer.render_crop_fused(lab_mv, TCV_O.reshape(-1, 4, 4).contiguous(),
                                             KV_crop.reshape(-1, 3, 3).contiguous(), self.render_size, nhwc4, im_idx,

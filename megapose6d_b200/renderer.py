@@ -109,19 +109,21 @@ class BatchRenderer:
 
     def render(self, labels: List[str], TCO: torch.Tensor, K: torch.Tensor, light_datas=None,
                resolution: Tuple[int, int] = (240, 320), render_depth: bool = False, render_mask: bool = False,
-               render_normals: bool = False) -> BatchRenderOutput:
+               render_normals: bool = False, label_idx: Optional[torch.Tensor] = None) -> BatchRenderOutput:
+        """`label_idx` (int32 mesh indices on the device) may be given instead of `labels` by callers that already hold it."""
         if render_mask:
             raise NotImplementedError
         if self.msaa4:
-            return self._render_msaa4(labels, TCO, K, light_datas, resolution, render_depth, render_normals)
+            return self._render_msaa4(labels, TCO, K, light_datas, resolution, render_depth, render_normals, label_idx)
         flags = self.flags | self._light_flags(light_datas)
         n = TCO.shape[0]
-        assert TCO.shape == (n, 4, 4) and K.shape == (n, 3, 3) and len(labels) == n
+        assert TCO.shape == (n, 4, 4) and K.shape == (n, 3, 3) and (label_idx is not None or len(labels) == n)
         h, w = resolution
         dev = TCO.device
         TCO = TCO.detach().float().contiguous()
         K = K.detach().float().contiguous()
-        label_idx = self.mesh_db.label_ids(labels, dev)
+        if label_idx is None:
+            label_idx = self.mesh_db.label_ids(labels, dev)
         rgbs = torch.empty(n, 3, h, w, device=dev, dtype=torch.float32)
         normals = torch.empty(n, 3, h, w, device=dev, dtype=torch.float32) if render_normals else None
         depths = torch.empty(n, 1, h, w, device=dev, dtype=torch.float32) if render_depth else None
@@ -131,7 +133,7 @@ class BatchRenderer:
                                                 _abi.ptr(depths), _abi.ptr(ws), ws.numel(), _abi.stream_ptr()))
         return BatchRenderOutput(rgbs=rgbs, normals=normals, depths=depths)
 
-    def _render_msaa4(self, labels, TCO, K, light_datas, resolution, render_depth, render_normals) -> BatchRenderOutput:
+    def _render_msaa4(self, labels, TCO, K, light_datas, resolution, render_depth, render_normals, label_idx=None) -> BatchRenderOutput:
         """4x anti-aliased render (contract in oracle/pipeline_ref.py: RefRenderer.render(msaa4=True)): the view is rendered
         once per sample position of the 4x multisample pattern -- pixel (i, j) sampled at (j + 0.5 + ox, i + 0.5 + oy), i.e.
         with the principal point moved to (cx - ox, cy - oy) -- every sample shaded and quantised to 8 bits on its own, and
@@ -140,7 +142,7 @@ class BatchRenderer:
         self.msaa4 = False
         try:
             out = self.render(labels, TCO, K, light_datas, resolution, render_depth=render_depth, render_mask=False,
-                              render_normals=render_normals)
+                              render_normals=render_normals, label_idx=label_idx)
             q8 = (self.flags & RASTER_QUANTIZE8) != 0
             parts_rgb, parts_nrm = [], []
             for ox, oy in MSAA4_OFFSETS:
@@ -148,7 +150,7 @@ class BatchRenderer:
                 Ks[:, 0, 2] = Ks[:, 0, 2] - ox
                 Ks[:, 1, 2] = Ks[:, 1, 2] - oy
                 s = self.render(labels, TCO, Ks, light_datas, resolution, render_depth=False, render_mask=False,
-                                render_normals=render_normals)
+                                render_normals=render_normals, label_idx=label_idx)
                 parts_rgb.append(s.rgbs)
                 if render_normals:
                     parts_nrm.append(s.normals)

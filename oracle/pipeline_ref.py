@@ -118,8 +118,10 @@ class RefMeshes:
 class RefRenderer:
     """`.render()` with the contract of Panda3dBatchRenderer.render (panda3d_batch_renderer.py:217-282)."""
 
-    def __init__(self, meshes: RefMeshes, quantize8: bool = True, normals_gl_axes: bool = False, n_threads: Optional[int] = None):
+    def __init__(self, meshes: RefMeshes, quantize8: bool = True, normals_gl_axes: bool = False, n_threads: Optional[int] = None,
+                 msaa4: bool = False):
         self.meshes = meshes
+        self.msaa4 = msaa4
         self.flags = (1 if quantize8 else 0) | (2 if normals_gl_axes else 0)
         self.n_threads = n_threads or os.cpu_count() or 1
 
@@ -127,7 +129,7 @@ class RefRenderer:
 
     def render(self, labels, TCO, K, light_datas=None, resolution=(240, 320), render_depth=False, render_mask=False,
                render_normals=False, point_lights=False, msaa4=False):
-        if msaa4:
+        if msaa4 or self.msaa4:
             return self._render_msaa4(labels, TCO, K, resolution, render_depth, render_normals, point_lights)
         return self._render(labels, TCO, K, light_datas, resolution, render_depth, render_mask, render_normals, point_lights)
 

@@ -136,3 +136,28 @@ def test_msaa4_render_bit_exact_vs_oracle(scene):
     # silhouette pixels are blends with the black background: strictly between 0 and the single-sample value somewhere
     edge = (ref["rgbs"].sum(1) > 0) & (one["depths"][:, 0] == 0)
     assert edge.sum() > 50
+
+
+def test_refiner_with_antialiased_renders_matches_oracle(scene, tmp_path):
+    """BatchRenderer(msaa4=True) switches the PosePredictor to the un-fused input path (fp32 crops and anti-aliased renders,
+    normalised, concatenated, packed): same outputs as the oracle predictor over the oracle's anti-aliased renderer."""
+    ds, images, K, rm = scene
+    model, _, cfg, sd = _variant_models(scene, tmp_path, dict(), seed=31)
+    model.renderer.msaa4 = True
+    try:
+        oracle = pipeline_ref.RefPosePredictor(sd, cfg, rm, pipeline_ref.RefRenderer(rm, msaa4=True))
+        n = 2
+        labels = [ds[i % 2].label for i in range(n)]
+        TCO = torch.from_numpy(procedural.random_poses(n, 29, z_range=(0.4, 0.8))).float()
+        imgs = images[:, :3].contiguous()
+        Kn = K.repeat(n, 1, 1)
+        model.keep_images = True
+        g = model(images=imgs.cuda(), K=Kn.cuda(), labels=labels, TCO=TCO.cuda(), n_iterations=1,
+                  batch_im_ids=torch.zeros(n, dtype=torch.long))["iteration=1"]
+        r = oracle.forward(imgs.repeat(n, 1, 1, 1), Kn, labels, TCO, n_iterations=1)["iteration=1"]
+        frac = (g.renders.cpu() != r["renders"]).float().mean().item()
+        assert frac < 0.05, f"anti-aliased renders: {frac:.3e} of values differ"
+        bound = resnet_ref.act16_forward_error_bound(sd, r["x"], dtype=ACT)
+        assert ((g.network_outputs["pose"].cpu() - r["network_output"]).abs() <= bound + 1e-3).all()
+    finally:
+        model.renderer.msaa4 = False
