@@ -158,7 +158,8 @@ class BatchRenderer:
             def resolve(parts):
                 if q8:
                     k = sum((p * 255.0).round().to(torch.int32) for p in parts)
-                    return ((k + 2) >> 2).float() / 255.0
+                    # a device-tensor divisor: CUDA torch turns `x / 255.0` into x * (1 / 255), not the IEEE quotient of the contract
+                    return ((k + 2) >> 2).float() / torch.full((1,), 255.0, device=k.device)
                 return ((parts[0] + parts[1]) + (parts[2] + parts[3])) * 0.25
 
             return BatchRenderOutput(rgbs=resolve(parts_rgb), normals=resolve(parts_nrm) if render_normals else None,
