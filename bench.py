@@ -9,7 +9,11 @@
 Workload (config.workload): BASELINE.json configs[1] "megapose-1.0-RGB: 1 object x 576 coarse hypotheses + 5
 refiner iters" at the reference's 240x320 render size (--render-size 224x224 for the size the metric's text names),
 synthetic 480x640 frame, procedural 10k-triangle mesh, seeded random vanilla_resnet34 weights in the model-zoo
-checkpoint format (workloads/scenes.py: bench_scene).  One step = one call of PoseEstimator.run_inference_pipeline.
+checkpoint format (workloads/scenes.py: bench_scene).  One step = one frame through PoseEstimator's inference pipeline.
+Frames are fed the way a stream of frames is served (--frames-in-flight 2, megapose6d_b200/frame_pipeline.py): two
+estimators on two CUDA streams, the latency-bound refiner iterations of frame i beside the coarse stage of frame i+1;
+every frame's result is produced and read exactly as by run_inference_pipeline (bit-identical, tested).  The line also
+carries `single_frame`: the same K steps with one blocking run_inference_pipeline call after the other.
 Weak scaling (default): a frame with one detection per rank, rows sharded by detection, one all-gather per stage.
 Strong scaling (--scaling strong): ONE frame (1 x 576, or --workload ycbv21: 21 x 576 = BASELINE configs[3]) whose
 rows are split over the N ranks.  The detection boxes change from step to step (a pool of jittered boxes), so a timed
@@ -54,6 +58,7 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--workload", default="rgb576", choices=["rgb576", "ycbv21"])
     ap.add_argument("--render-size", default="240x320")
+    ap.add_argument("--frames-in-flight", type=int, default=2, help="1: one blocking run_inference_pipeline call per step")
     ap.add_argument("--cpu-sample", type=int, default=32, help="coarse hypotheses in one bounded CPU step")
     ap.add_argument("--no-full-unit", action="store_true", help="CPU arm: skip the one complete 576-hypothesis unit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -83,6 +88,9 @@ def workload_config(args, sc, n_gpus: int):
             "parallelism": f"hypothesis rows sharded x{n_gpus}" + (" (one detection per rank)" if args.scaling == "weak" else
                                                                   " (one frame over all ranks)"),
             "inputs": "detection boxes jittered per step (pool of 4)",
+            "frames_in_flight": f"{max(1, args.frames_in_flight)} (megapose6d_b200/frame_pipeline.py: the refiner iterations of "
+                                "frame i overlap the coarse stage of frame i+1 on a second stream; every frame's result is "
+                                "produced and read; `single_frame` has the one-blocking-call-per-step numbers)",
             "l2": f"network input tensor ({2 * 64 * (h // 2) * (w // 2) * M_GRID * B / n_gpus / 1e9:.2f} GB per rank and "
                   "step) >> 126 MB L2, no explicit flush"}
 
@@ -307,7 +315,12 @@ def run_mpx_arm(args):
     n_gpus = world
     sc = build_scene(args, n_gpus)
     images, K, det_df = sc["images"], sc["K"], sc["det_df"]
-    est = scenes.build_estimator(sc, sharder=HypothesisSharder(enabled=world > 1))
+    from megapose6d_b200.frame_pipeline import FramePipeline
+
+    n_fif = max(1, args.frames_in_flight)
+    ests = [scenes.build_estimator(sc, sharder=HypothesisSharder(enabled=world > 1)) for _ in range(n_fif)]
+    est = ests[0]
+    pipe = FramePipeline(None, estimators=ests) if n_fif > 1 else None
     lib = _abi.lib()
     n_det = len(sc["labels"])
     h, w = sc["render_size"]
@@ -317,33 +330,57 @@ def run_mpx_arm(args):
     images_pin, K_pin, pool_pin = images.pin_memory(), K.pin_memory(), [b.pin_memory() for b in pool]
     counter = [0]
 
-    def step_device():
-        counter[0] += 1
-        obs = ObservationTensor(images_dev, K_dev)
-        det = PandasTensorCollection(det_df.copy(), bboxes=pool_dev[counter[0] % len(pool_dev)])
-        final, _ = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=N_REFINER_ITERS, n_pose_hypotheses=1)
-        return final
+    kw = dict(n_refiner_iterations=N_REFINER_ITERS, n_pose_hypotheses=1)
 
-    def step_e2e():
+    def frame_device():
+        counter[0] += 1
+        return ObservationTensor(images_dev, K_dev), PandasTensorCollection(det_df.copy(), bboxes=pool_dev[counter[0] % len(pool_dev)])
+
+    def frame_host():  # this step's inputs from pinned host memory
         counter[0] += 1
         obs = ObservationTensor(images_pin.cuda(non_blocking=True), K_pin.cuda(non_blocking=True))
-        det = PandasTensorCollection(det_df.copy(), bboxes=pool_pin[counter[0] % len(pool_pin)].cuda(non_blocking=True))
-        final, _ = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=N_REFINER_ITERS, n_pose_hypotheses=1)
-        poses = final.poses.cpu()
-        scores = final.infos["pose_score"].values
-        return poses, scores
+        return obs, PandasTensorCollection(det_df.copy(), bboxes=pool_pin[counter[0] % len(pool_pin)].cuda(non_blocking=True))
+
+    def read_back(final):  # the step's result on the host
+        return final.poses.cpu(), final.infos["pose_score"].values
+
+    def step_device(e=None):
+        obs, det = frame_device()
+        return (e or est).run_inference_pipeline(obs, detections=det, **kw)[0]
+
+    def run_single(steps, host: bool):  # one blocking call per step
+        for _ in range(steps):
+            if host:
+                obs, det = frame_host()
+                read_back(est.run_inference_pipeline(obs, detections=det, **kw)[0])
+            else:
+                step_device()
+
+    def run_in_flight(steps, host: bool):  # the same steps through the frame pipeline; every result is collected
+        n_done = 0
+        for _ in range(steps):
+            done = pipe.submit(*(frame_host() if host else frame_device()), **kw)
+            if done is not None:
+                n_done += 1
+                if host:
+                    read_back(done[0])
+        for done in pipe.drain():
+            n_done += 1
+            if host:
+                read_back(done[0])
+        pipe.join()
+        assert n_done == steps
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, host):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        fn(steps, host)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -352,16 +389,25 @@ def run_mpx_arm(args):
         return ms.item()
 
     warmup = max(3, args.warmup)
-    for _ in range(warmup + 2):  # first sight runs eagerly, the second captures the graphs, later ones replay
-        step_device()
+    for e in ests:
+        for _ in range(warmup + 2):  # first sight runs eagerly, the second captures the graphs, later ones replay
+            step_device(e)
+    run = run_in_flight if pipe is not None else run_single
+    run(2 * n_fif, False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms = timed(step_device, args.steps)
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
+    total_ms = timed(run, args.steps, False)
+    run(2 * n_fif, True)
+    e2e_ms = timed(run, args.steps, True)
+    single = None
+    if pipe is not None:  # the same steps, one blocking run_inference_pipeline call after the other
+        run_single(2, False)
+        s_ms = timed(run_single, args.steps, False)
+        run_single(2, True)
+        s_e2e_ms = timed(run_single, args.steps, True)
+        single = (s_ms, s_e2e_ms)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over all timed regions (device-resident and end-to-end)
 
     # roofline of the dominant kernels (the convolutions of the coarse forward): CUDA events around every conv launch, same
     # workload.  The coarse forward normally replays a CUDA graph (its launches cannot be timed one by one), so for this
@@ -391,6 +437,7 @@ def run_mpx_arm(args):
         dist.all_reduce(launches)
     barrier()
 
+    del pipe
     hyp_per_step = M_GRID * n_det
     ms_per_step = total_ms / args.steps
     value = hyp_per_step / (ms_per_step / 1000.0)
@@ -428,6 +475,11 @@ def run_mpx_arm(args):
                     "h2d_bytes_per_step": int(images.numel() * 4 + K.numel() * 4 + sc["bboxes"].numel() * 4),
                     "d2h_bytes_per_step": int(n_det * 16 * 4 + n_det * 4 * 2 + M_GRID * n_det * 8 * 3)},
             "gpu_launches": int(launches.item()),
+            "frames_in_flight": n_fif,
+            "single_frame": None if single is None else {
+                "note": "the same steps, one blocking run_inference_pipeline call per step (frame latency mode)",
+                "ms_per_step": single[0] / args.steps, "value": hyp_per_step / (single[0] / args.steps / 1000.0),
+                "e2e_value": hyp_per_step / (single[1] / args.steps / 1000.0), "unit": "hypotheses/s"},
             "clocks": clocks,
             "roofline": {"bound": "tensor",
                          "kernel": "tcgen05 implicit-GEMM convolutions (conv_window / conv_igemm / conv_igemm2): the "
@@ -446,7 +498,7 @@ def run_mpx_arm(args):
                          "whole_step_frac": gflop_per_hyp((h, w)) * hyp_per_step / n_gpus / ms_per_step / burst},
         }
         if n_gpus == 1 and not args.no_torch_baseline and args.workload == "rgb576":
-            del est
+            del est, ests
             torch.cuda.empty_cache()
             line["gpu_torch_baseline"] = torch_gpu_baseline(sc, quick=True)
         if n_gpus == 1 and not args.no_cpu_baseline and args.workload == "rgb576":

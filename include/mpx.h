@@ -36,6 +36,12 @@ int mpx_act_dtype(void);
 const char* mpx_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (host-side counter) */
 long long mpx_launch_count(void);
+/* Persistent grids (convolutions, the tiled rasteriser) are sized for mpx_sm_count() SMs: the device's count, or the even
+ * limit set here (0 = all).  A limit leaves SMs free for the latency-bound launches of another stream -- the refiner
+ * iterations of one frame beside the coarse stage of the next (megapose6d_b200/frame_pipeline.py).  Process-wide; set it
+ * before mesh databases are created and before CUDA graphs are captured (both record grid sizes). */
+int mpx_set_sm_limit(int n_sms);
+int mpx_sm_count(void);
 /* measurement aid for bench.py: when enabled every convolution launch is bracketed by CUDA events on
  * its stream; mpx_profile_summary synchronises the device, returns the summed duration (ms), the
  * algorithmic FLOPs (2*M*N*K per launch) and the launch count since enabling, and resets. */

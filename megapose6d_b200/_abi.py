@@ -70,6 +70,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_net_forward.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]
     lib.mpx_launch_count.restype = ctypes.c_longlong
     lib.mpx_profile_enable.argtypes = [c_int]
+    lib.mpx_set_sm_limit.argtypes = [c_int]
     lib.mpx_profile_summary.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                         POINTER(ctypes.c_longlong)]
     for name in EXPORTS:
@@ -82,7 +83,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 
 EXPORTS = [
-    "mpx_abi_version", "mpx_act_dtype", "mpx_last_error", "mpx_launch_count", "mpx_profile_enable", "mpx_profile_summary",
+    "mpx_abi_version", "mpx_act_dtype", "mpx_last_error", "mpx_launch_count", "mpx_set_sm_limit", "mpx_sm_count", "mpx_profile_enable", "mpx_profile_summary",
     "mpx_meshdb_create", "mpx_meshdb_destroy", "mpx_meshdb_set_textures",
     "mpx_raster_workspace_bytes", "mpx_raster_set_mode", "mpx_raster_render", "mpx_raster_render_fused", "mpx_render_crop_fused",
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",

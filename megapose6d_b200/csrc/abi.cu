@@ -6,6 +6,7 @@
 
 namespace mpx {
 long long g_launches = 0;
+int g_sm_limit = 0;
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -26,6 +27,12 @@ int mpx_act_dtype(void) { return kActIsFp16 ? 0 : 1; }
 const char* mpx_last_error(void) { return g_err; }
 
 long long mpx_launch_count(void) { return g_launches; }
+int mpx_set_sm_limit(int n_sms) {
+  MPX_REQUIRE(n_sms == 0 || (n_sms >= 16 && n_sms % 2 == 0), "mpx_set_sm_limit: %d is not 0 or an even number >= 16", n_sms);
+  g_sm_limit = n_sms;
+  return MPX_OK;
+}
+int mpx_sm_count(void) { return sm_count(); }
 int mpx_profile_enable(int on) {
   conv_profile_enable(on);
   return MPX_OK;

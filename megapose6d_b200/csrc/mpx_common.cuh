@@ -37,6 +37,10 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// Number of SMs the throughput kernels size their persistent grids for: the device's SM count, or the (even) limit set with
+// mpx_set_sm_limit -- the SMs left over stay free for latency-bound launches of another stream (two frames in flight:
+// the refiner iterations of one frame run beside the coarse stage of the next, see megapose6d_b200/frame_pipeline.py).
+extern int g_sm_limit;
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -45,7 +49,7 @@ inline int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -50,6 +50,23 @@ def filter_detections(detections: DetectionsType, labels=None, one_instance_per_
     return detections
 
 
+class PendingInference:
+    """Handle of PoseEstimator.submit_inference_pipeline: the frame's device work is enqueued, `.result()` waits for it."""
+
+    def __init__(self, finish, inputs, out):
+        self._finish, self._inputs, self._out = finish, inputs, out  # the inputs stay referenced until the device is done
+
+    @property
+    def done(self) -> bool:
+        return self._finish is None
+
+    def result(self):
+        if self._finish is not None:
+            self._out = self._finish()
+            self._finish = self._inputs = None
+        return self._out
+
+
 class PoseEstimator(torch.nn.Module):
     """Performs inference for pose estimation."""
 
@@ -309,6 +326,46 @@ class PoseEstimator(torch.nn.Module):
             extra_data["depth_refiner"] = {"preds": data_TCO_depth_refiner}
         return data_TCO_final, extra_data
 
+    def set_tail_priority(self, high: bool = True) -> None:
+        """Run everything after the coarse stage (refiner iterations, scoring, selection) on a high-priority stream, its
+        graphs captured at that priority: with a second frame in flight on another stream these few-CTA launches are then
+        scheduled ahead of the other frame's queued thread blocks.  Call before the first frame (graphs record the priority)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if high:
+            self._tail_stream = torch.cuda.Stream(device=dev, priority=-1)  # torch: -1 = high, 0 = default
+            cap = torch.cuda.Stream(device=dev, priority=-1)
+        else:
+            self._tail_stream, cap = None, None
+        for m in (self.coarse_model, self.refiner_model):
+            if m is not None:
+                m.graph_capture_stream = cap
+
+    @torch.no_grad()
+    def submit_inference_pipeline(self, observation: ObservationTensor, detections: DetectionsType,
+                                  n_refiner_iterations: int = 5, n_pose_hypotheses: int = 1,
+                                  detection_filter_kwargs: Optional[dict] = None) -> "PendingInference":
+        """run_inference_pipeline in two halves: this call enqueues the whole pipeline on the current stream and returns
+        without waiting for the device; `.result()` of the returned handle waits and builds what run_inference_pipeline
+        returns.  One frame per estimator may be in flight (its graphs and pinned buffers are single-buffered):
+        FramePipeline (frame_pipeline.py) alternates frames over two estimators on two streams, so that the latency-bound
+        refiner iterations of one frame overlap the coarse stage of the next."""
+        if self.__dict__.get("_in_flight") is not None and not self._in_flight.done:
+            raise RuntimeError("this estimator already has a frame in flight: call .result() of the pending handle first")
+        t_start = time.time()
+        kwargs = dict(n_refiner_iterations=n_refiner_iterations, n_pose_hypotheses=n_pose_hypotheses,
+                      detection_filter_kwargs=detection_filter_kwargs)
+        fused_ok = (self.fused_pipeline and self.refiner_model is not None and self.coarse_model is not None
+                    and len(detections) > 0 and n_refiner_iterations >= 1)
+        finish = self._run_pipeline_fused(observation, detections, n_refiner_iterations, n_pose_hypotheses,
+                                          detection_filter_kwargs, t_start, defer=True) if fused_ok else None
+        if finish is None:  # configurations the fused path does not take: computed here, the handle is already complete
+            out = self.run_inference_pipeline(observation, detections=detections, **kwargs)
+            pending = PendingInference(None, (observation, detections), out)
+        else:
+            pending = PendingInference(finish, (observation, detections), None)
+        self._in_flight = pending
+        return pending
+
     # ------------------------------------------------------------------------------------------
     def _pipeline_rows(self, df: pd.DataFrame, device) -> dict:
         """Index tensors of the coarse stage (row = detection * M + hypothesis): functions of the detections' image ids
@@ -451,14 +508,17 @@ class PoseEstimator(torch.nn.Module):
 
     @torch.no_grad()
     def _run_pipeline_fused(self, observation: ObservationTensor, detections: DetectionsType, n_refiner_iterations: int,
-                            n_pose_hypotheses: int, detection_filter_kwargs: Optional[dict], t_start: float):
+                            n_pose_hypotheses: int, detection_filter_kwargs: Optional[dict], t_start: float,
+                            defer: bool = False):
         """The same pipeline with every stage enqueued back to back.  The top-K selection between the stages and the
         final best-hypothesis selection run on the device (mpx_topk_per_group + stable sorts), so the host never waits
         for logits before it can launch the next stage.  The coarse logits come back on a side stream as soon as the
         coarse stage is done; all DataFrame bookkeeping of the reference's outputs is done while the refiner and the
         scoring pass run; after the last synchronisation only two columns are filled in.
         Returns None (caller falls back to the staged path) when two detections share a (batch_im_id, label,
-        instance_id) key, because then the reference's groupby merges their hypotheses."""
+        instance_id) key, because then the reference's groupby merges their hypotheses.
+        `defer`: return, right after the last launch, the function that waits for the device and builds the outputs
+        (submit_inference_pipeline) instead of calling it."""
         coarse_model, refiner = self.coarse_model, self.refiner_model
         device = observation.images.device
         detections = add_instance_id(detections)
@@ -505,8 +565,29 @@ class PoseEstimator(torch.nn.Module):
             else:
                 sel_user = {k: st[k] for k in ("TCO_sel", "K_sel", "bboxes_sel")}
         packed_c.record_stream(side)
-        TCO_sel, bim_sel, lab_sel, K_sel = st["TCO_sel"], st["bim_sel"], st["lab_sel"], st["K_sel"]
         # ---- refiner on the selected rows (sharded), then scoring, all enqueued without a host round trip
+        head, tail = main, self.__dict__.get("_tail_stream")
+        if tail is not None:  # set_tail_priority: the latency-bound rest of the frame on a high-priority stream
+            tail.wait_stream(head)
+            torch.cuda.set_stream(tail)
+            main = tail
+        head_vars = dict(observation=observation, refiner=refiner, device=device, df=df, B=B, M=M, Kh=Kh, n_sel=n_sel, t0=t0,
+                         t_start=t_start, main=main, side=side, st=st, rows=rows, out_c=out_c, pin_c=pin_c,
+                         ev_c_done=ev_c_done, K_rows=K_rows, bboxes=bboxes, TCO=TCO, logits=logits, scores=scores,
+                         sel_user=sel_user, n_refiner_iterations=n_refiner_iterations)
+        try:
+            return self._run_pipeline_tail(head_vars, defer)
+        finally:
+            if tail is not None:
+                torch.cuda.set_stream(head)
+                head.wait_stream(tail)
+
+    def _run_pipeline_tail(self, head_vars: dict, defer: bool):
+        (observation, refiner, device, df, B, M, Kh, n_sel, t0, t_start, main, side, st, rows, out_c, pin_c, ev_c_done,
+         K_rows, bboxes, TCO, logits, scores, sel_user, n_refiner_iterations) = (head_vars[k] for k in (
+             "observation", "refiner", "device", "df", "B", "M", "Kh", "n_sel", "t0", "t_start", "main", "side", "st", "rows",
+             "out_c", "pin_c", "ev_c_done", "K_rows", "bboxes", "TCO", "logits", "scores", "sel_user", "n_refiner_iterations"))
+        TCO_sel, bim_sel, lab_sel, K_sel = st["TCO_sel"], st["bim_sel"], st["lab_sel"], st["K_sel"]
         s0, s1 = self.sharder.span(n_sel)
         iters = refiner.refine_tensors(observation.images, bim_sel[s0:s1], K_sel[s0:s1], lab_sel[s0:s1], TCO_sel[s0:s1],
                                        n_refiner_iterations)
@@ -558,58 +639,61 @@ class PoseEstimator(torch.nn.Module):
         ev_f_done = torch.cuda.Event()
         ev_f_done.record(main)
 
-        # ---- host bookkeeping while the device works
-        df_hyp = df.loc[df.index.repeat(M)].copy()
-        df_hyp.index = pd.RangeIndex(B * M)
-        df_hyp["hypothesis_id"] = np.tile(np.arange(M), B)
-        df_hyp["bbox_id"] = np.repeat(df.index.values, M)
-        ev_c_done.synchronize()                                                # coarse stage done (refiner still running)
-        coarse_np = pin_c.numpy()
-        nBM = B * M
-        df_hyp["coarse_logit"] = coarse_np[:nBM].astype(np.float32)
-        df_hyp["coarse_score"] = coarse_np[nBM:2 * nBM].astype(np.float32)
-        rows_np = coarse_np[2 * nBM:].astype(np.int64)
-        data_TCO_coarse = PandasTensorCollection._wrap(df_hyp, dict(poses=TCO, bboxes=bboxes))
-        t_coarse = time.time() - t0
-        coarse_extra = {"render_time": out_c["render_time"], "model_time": out_c["model_time"], "time": t_coarse,
-                        "logits": logits.reshape(B, M), "scores": scores.reshape(B, M), "TCO": TCO.reshape(B, M, 4, 4),
-                        "debug": dict(), "n_batches": int(np.ceil(B * M / max(1, self.bsz_images))),
-                        "timing_str": f"time: {t_coarse:.2f}, model_time: {out_c['model_time']:.2f}, "
-                                      f"render_time: {out_c['render_time']:.2f}"}
-        df_sel = df_hyp.iloc[rows_np].copy()
-        df_sel.index = pd.RangeIndex(n_sel)
-        data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=sel_user["TCO_sel"], bboxes=sel_user["bboxes_sel"]))
-        df_ref = df_sel.copy()
-        df_ref["refiner_batch_idx"] = np.arange(n_sel) // max(1, self.bsz_objects)
-        df_ref["refiner_instance_idx"] = np.arange(n_sel) % max(1, self.bsz_objects)
-        preds = {f"iteration={n + 1}": PandasTensorCollection._wrap(df_ref.copy(), refined[n])
-                 for n in range(n_refiner_iterations)}
-        refiner_extra = {"n_iterations": n_refiner_iterations, "outputs": [], "model_time": max(0.0, t_ref - t0 - t_coarse),
-                         "time": max(0.0, t_ref - t0)}
-        data_TCO_scored = preds[f"iteration={n_refiner_iterations}"]
-        infos_scored = data_TCO_scored.infos
-        ev_f_done.synchronize()                                                # everything done
-        final_np = pin_f.numpy()
-        infos_scored["pose_logit"] = final_np[:n_sel].astype(np.float32)
-        infos_scored["pose_score"] = final_np[n_sel:2 * n_sel].astype(np.float32)
-        keep_np = final_np[2 * n_sel:].astype(np.int64)
-        df_final = infos_scored.iloc[keep_np].copy()
-        df_final.index = pd.RangeIndex(len(keep_np))
-        final = PandasTensorCollection._wrap(df_final, final_tensors)
-        scoring_extra = {"render_time": out_s["render_time"], "model_time": out_s["model_time"], "time": time.time() - t_ref,
-                         "logits": pose_logits, "scores": pose_scores, "debug": dict(),
-                         "n_batches": int(np.ceil(n_sel / max(1, self.bsz_images))), "timing_str": ""}
-        elapsed = time.time() - t_start
-        extra_data: dict = dict()
-        extra_data["coarse"] = {"preds": data_TCO_coarse, "data": coarse_extra}
-        extra_data["coarse_filter"] = {"preds": data_TCO_filtered}
-        extra_data["refiner_all_hypotheses"] = {"preds": preds, "data": refiner_extra}
-        extra_data["scoring"] = {"preds": data_TCO_scored, "data": scoring_extra}
-        extra_data["refiner"] = {"preds": final, "data": refiner_extra}
-        extra_data["timing_str"] = (f"total={elapsed:.2f}, coarse={t_coarse:.2f}, refiner={refiner_extra['time']:.2f}, "
-                                    f"scoring={scoring_extra['time']:.2f}, ")
-        extra_data["time"] = elapsed
-        return final, extra_data
+        def finish():
+            # ---- host bookkeeping while the device works
+            df_hyp = df.loc[df.index.repeat(M)].copy()
+            df_hyp.index = pd.RangeIndex(B * M)
+            df_hyp["hypothesis_id"] = np.tile(np.arange(M), B)
+            df_hyp["bbox_id"] = np.repeat(df.index.values, M)
+            ev_c_done.synchronize()                                                # coarse stage done (refiner still running)
+            coarse_np = pin_c.numpy()
+            nBM = B * M
+            df_hyp["coarse_logit"] = coarse_np[:nBM].astype(np.float32)
+            df_hyp["coarse_score"] = coarse_np[nBM:2 * nBM].astype(np.float32)
+            rows_np = coarse_np[2 * nBM:].astype(np.int64)
+            data_TCO_coarse = PandasTensorCollection._wrap(df_hyp, dict(poses=TCO, bboxes=bboxes))
+            t_coarse = time.time() - t0
+            coarse_extra = {"render_time": out_c["render_time"], "model_time": out_c["model_time"], "time": t_coarse,
+                            "logits": logits.reshape(B, M), "scores": scores.reshape(B, M), "TCO": TCO.reshape(B, M, 4, 4),
+                            "debug": dict(), "n_batches": int(np.ceil(B * M / max(1, self.bsz_images))),
+                            "timing_str": f"time: {t_coarse:.2f}, model_time: {out_c['model_time']:.2f}, "
+                                          f"render_time: {out_c['render_time']:.2f}"}
+            df_sel = df_hyp.iloc[rows_np].copy()
+            df_sel.index = pd.RangeIndex(n_sel)
+            data_TCO_filtered = PandasTensorCollection._wrap(df_sel, dict(poses=sel_user["TCO_sel"], bboxes=sel_user["bboxes_sel"]))
+            df_ref = df_sel.copy()
+            df_ref["refiner_batch_idx"] = np.arange(n_sel) // max(1, self.bsz_objects)
+            df_ref["refiner_instance_idx"] = np.arange(n_sel) % max(1, self.bsz_objects)
+            preds = {f"iteration={n + 1}": PandasTensorCollection._wrap(df_ref.copy(), refined[n])
+                     for n in range(n_refiner_iterations)}
+            refiner_extra = {"n_iterations": n_refiner_iterations, "outputs": [], "model_time": max(0.0, t_ref - t0 - t_coarse),
+                             "time": max(0.0, t_ref - t0)}
+            data_TCO_scored = preds[f"iteration={n_refiner_iterations}"]
+            infos_scored = data_TCO_scored.infos
+            ev_f_done.synchronize()                                                # everything done
+            final_np = pin_f.numpy()
+            infos_scored["pose_logit"] = final_np[:n_sel].astype(np.float32)
+            infos_scored["pose_score"] = final_np[n_sel:2 * n_sel].astype(np.float32)
+            keep_np = final_np[2 * n_sel:].astype(np.int64)
+            df_final = infos_scored.iloc[keep_np].copy()
+            df_final.index = pd.RangeIndex(len(keep_np))
+            final = PandasTensorCollection._wrap(df_final, final_tensors)
+            scoring_extra = {"render_time": out_s["render_time"], "model_time": out_s["model_time"], "time": time.time() - t_ref,
+                             "logits": pose_logits, "scores": pose_scores, "debug": dict(),
+                             "n_batches": int(np.ceil(n_sel / max(1, self.bsz_images))), "timing_str": ""}
+            elapsed = time.time() - t_start
+            extra_data: dict = dict()
+            extra_data["coarse"] = {"preds": data_TCO_coarse, "data": coarse_extra}
+            extra_data["coarse_filter"] = {"preds": data_TCO_filtered}
+            extra_data["refiner_all_hypotheses"] = {"preds": preds, "data": refiner_extra}
+            extra_data["scoring"] = {"preds": data_TCO_scored, "data": scoring_extra}
+            extra_data["refiner"] = {"preds": final, "data": refiner_extra}
+            extra_data["timing_str"] = (f"total={elapsed:.2f}, coarse={t_coarse:.2f}, refiner={refiner_extra['time']:.2f}, "
+                                        f"scoring={scoring_extra['time']:.2f}, ")
+            extra_data["time"] = elapsed
+            return final, extra_data
+
+        return finish if defer else finish()
 
     def filter_pose_estimates(self, data_TCO: PoseEstimatesType, top_K: int, filter_field: str,
                               ascending: bool = False) -> PoseEstimatesType:

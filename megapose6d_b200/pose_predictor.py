@@ -129,6 +129,9 @@ class PosePredictor(nn.Module):
         self._nhwc4_bufs: Dict[Tuple[int, ...], torch.Tensor] = {}
         self._graphs: Dict[Any, Dict[str, Any]] = {}
         self.use_cuda_graphs = True   # replay the refinement loop as one CUDA graph for small batches
+        # stream the small-batch graphs are captured on (None: torch's side stream).  Kernel nodes inherit its priority: a
+        # high-priority stream here makes the latency-bound launches schedule ahead of another frame's queued CTAs
+        self.graph_capture_stream = None
         self.graph_max_batch = 1024
         self._x_cache: Dict[Tuple[int, int, int], torch.Tensor] = {}
         self.graph_epoch = 0  # bumped whenever buffers that captured graphs point into are released
@@ -438,7 +441,7 @@ class PosePredictor(nn.Module):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=self.graph_capture_stream):
                     iters = self._iterate(images, static["im_idx"], static["K"], static["label_idx"], static["TCO"],
                                           n_iterations, defaultdict(float))
             except Exception:  # noqa: BLE001 -- capture not possible here: stay eager for this predictor

@@ -387,3 +387,52 @@ def test_graph_replay_survives_a_change_of_the_detection_count(setup):
     finally:
         lib.mpx_net_set_graphs(1)
     assert len(a.refiner_model.backbone._retired_workspaces) >= 1, "the scenario must grow the workspace after a capture"
+
+
+def test_frames_in_flight_equal_blocking_calls(setup):
+    """FramePipeline (two estimators, two streams, submit_inference_pipeline / result): every frame of a stream of frames with
+    changing detections and intrinsics comes back in order and bit-identical to a blocking run_inference_pipeline call, with
+    and without the high-priority tail; a second submit on a busy estimator is refused."""
+    from megapose6d_b200.frame_pipeline import FramePipeline
+
+    ds, images, K = setup["ds"], setup["images"][:, :3].contiguous(), setup["K"]
+    labels = [ds[0].label, ds[1].label]
+    TCO_gt = torch.from_numpy(procedural.random_poses(2, 37)).float()
+    TCO_gt[:, 2, 3] = torch.tensor([0.5, 0.75])
+    bboxes = torch.stack([helpers.detection_for_pose(K[0], TCO_gt[i], torch.from_numpy(ds.get_object_by_label(labels[i]).mesh.vertices).float())
+                          for i in range(2)])
+    det_df = pd.DataFrame(dict(label=labels, batch_im_id=0))
+    kw = dict(n_refiner_iterations=2, n_pose_hypotheses=2)
+
+    def frame(i):
+        bb = bboxes + (6.0 * torch.rand(bboxes.shape, generator=torch.Generator().manual_seed(100 + i)) - 3.0)
+        Kc = K.clone()
+        Kc[:, 0, 2] += float(i % 3)
+        return ObservationTensor(images.clone(), Kc).cuda(), PandasTensorCollection(det_df.copy(), bboxes=bb.cuda())
+
+    def make():
+        est = load_model.load_named_model("megapose-1.0-RGB-multi-hypothesis", ds, models_root=setup["root"])
+        est.load_SO3_grid(72)
+        return est
+
+    ref_est = make()
+    n = 9
+    want = []
+    for i in range(n):
+        obs, det = frame(i)
+        want.append(ref_est.run_inference_pipeline(obs, detections=det, **kw))
+    for prio in (False, True):
+        pipe = FramePipeline(make, n_slots=2, tail_priority=prio)
+        got = list(pipe.run((frame(i) for i in range(n)), **kw))
+        assert len(got) == n
+        for (f, e), (fw, ew) in zip(got, want):
+            assert torch.equal(f.poses, fw.poses)
+            pd.testing.assert_frame_equal(f.infos, fw.infos)
+            assert torch.equal(e["coarse"]["data"]["logits"], ew["coarse"]["data"]["logits"])
+            assert torch.equal(e["scoring"]["preds"].poses, ew["scoring"]["preds"].poses)
+    est = pipe.slots[0]["est"]
+    pending = est.submit_inference_pipeline(*frame(0), **kw)
+    with pytest.raises(RuntimeError):
+        est.submit_inference_pipeline(*frame(1), **kw)
+    f0, _ = pending.result()
+    assert torch.equal(f0.poses, want[0][0].poses) and pending.result()[0] is f0
