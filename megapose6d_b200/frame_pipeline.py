@@ -70,15 +70,14 @@ class FramePipeline:
         in flight), or None while the pipe is filling."""
         slot = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
-        done = None
-        if slot["pending"] is not None:
-            done = slot["pending"].result()
-            slot["pending"] = None
+        old = slot["pending"]
         caller = torch.cuda.current_stream(self.device)
         slot["stream"].wait_stream(caller)  # inputs produced (copied) on the caller's stream
         with torch.cuda.stream(slot["stream"]):
+            # enqueued BEFORE the older frame of this slot is waited for: the stream orders the two on the device, and the
+            # host-side bookkeeping of the older frame (a few ms of pandas) then runs while the device has work queued
             slot["pending"] = slot["est"].submit_inference_pipeline(observation, detections, **kwargs)
-        return done
+        return old.result() if old is not None else None
 
     def drain(self) -> List[Tuple]:
         """Wait for every frame in flight; results in submission order."""

@@ -346,11 +346,14 @@ class PoseEstimator(torch.nn.Module):
                                   detection_filter_kwargs: Optional[dict] = None) -> "PendingInference":
         """run_inference_pipeline in two halves: this call enqueues the whole pipeline on the current stream and returns
         without waiting for the device; `.result()` of the returned handle waits and builds what run_inference_pipeline
-        returns.  One frame per estimator may be in flight (its graphs and pinned buffers are single-buffered):
-        FramePipeline (frame_pipeline.py) alternates frames over two estimators on two streams, so that the latency-bound
-        refiner iterations of one frame overlap the coarse stage of the next."""
-        if self.__dict__.get("_in_flight") is not None and not self._in_flight.done:
-            raise RuntimeError("this estimator already has a frame in flight: call .result() of the pending handle first")
+        returns.  Frames of one estimator execute one after the other on the device (its graphs and workspaces are
+        single-buffered, the stream orders them); a second frame may be enqueued before the first one's `.result()` has been
+        taken so that the device never waits for the host, not more.  FramePipeline (frame_pipeline.py) alternates frames
+        over two estimators on two streams: the latency-bound refiner iterations of one frame overlap the coarse stage of
+        the next."""
+        pending_now = [p for p in self.__dict__.get("_in_flight", []) if not p.done]
+        if len(pending_now) >= 2:
+            raise RuntimeError("this estimator already has two frames enqueued: call .result() of the older handle first")
         t_start = time.time()
         kwargs = dict(n_refiner_iterations=n_refiner_iterations, n_pose_hypotheses=n_pose_hypotheses,
                       detection_filter_kwargs=detection_filter_kwargs)
@@ -363,7 +366,7 @@ class PoseEstimator(torch.nn.Module):
             pending = PendingInference(None, (observation, detections), out)
         else:
             pending = PendingInference(finish, (observation, detections), None)
-        self._in_flight = pending
+        self._in_flight = pending_now + [pending]
         return pending
 
     # ------------------------------------------------------------------------------------------
@@ -500,11 +503,10 @@ class PoseEstimator(torch.nn.Module):
         return dict(self._coarse_select(st, logits, rows_c, B, M, Kh), static=False)
 
     def _pinned(self, name: str, n: int) -> torch.Tensor:
-        bufs = self.__dict__.setdefault("_pinned_bufs", {})
-        buf = bufs.get(name)
-        if buf is None or buf.numel() < n:
-            buf = bufs[name] = torch.empty(max(n, 1024), dtype=torch.float64, pin_memory=True)
-        return buf[:n]
+        """Pinned staging buffer of one frame's read-back.  A fresh tensor per frame (torch's caching host allocator hands the
+        block back once the copy into it has completed and the frame has let go of it), so that a frame enqueued while an
+        older one is still being read on the host never shares its buffer."""
+        return torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)[:n]
 
     @torch.no_grad()
     def _run_pipeline_fused(self, observation: ObservationTensor, detections: DetectionsType, n_refiner_iterations: int,

@@ -392,7 +392,7 @@ def test_graph_replay_survives_a_change_of_the_detection_count(setup):
 def test_frames_in_flight_equal_blocking_calls(setup):
     """FramePipeline (two estimators, two streams, submit_inference_pipeline / result): every frame of a stream of frames with
     changing detections and intrinsics comes back in order and bit-identical to a blocking run_inference_pipeline call, with
-    and without the high-priority tail; a second submit on a busy estimator is refused."""
+    and without the high-priority tail; an estimator takes a second frame behind the one in flight, not a third."""
     from megapose6d_b200.frame_pipeline import FramePipeline
 
     ds, images, K = setup["ds"], setup["images"][:, :3].contiguous(), setup["K"]
@@ -432,7 +432,9 @@ def test_frames_in_flight_equal_blocking_calls(setup):
             assert torch.equal(e["scoring"]["preds"].poses, ew["scoring"]["preds"].poses)
     est = pipe.slots[0]["est"]
     pending = est.submit_inference_pipeline(*frame(0), **kw)
+    second = est.submit_inference_pipeline(*frame(1), **kw)  # enqueued behind the first (the stream orders them)
     with pytest.raises(RuntimeError):
-        est.submit_inference_pipeline(*frame(1), **kw)
+        est.submit_inference_pipeline(*frame(2), **kw)
     f0, _ = pending.result()
     assert torch.equal(f0.poses, want[0][0].poses) and pending.result()[0] is f0
+    assert torch.equal(second.result()[0].poses, want[1][0].poses)
