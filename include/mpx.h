@@ -237,6 +237,9 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
  *   512 launch without programmatic dependent launch;  1024 older row-group choice of the window kernel (diagnostic)
  *   16384 the layer2 window kernel on CTA pairs (cta_group::2, two MMA issuers in the leader): layer2 0.167 -> 0.153 ms
  *   32768 the 64 -> 64 window kernel (stem, layer1) on CTA pairs: layer1 0.255 -> 0.227 ms per convolution at batch 576
+ *   131072 do not skip the structurally zero K slices of the space-to-depth stem weights (diagnostic)
+ *   262144 / 524288 cap the automatic small-batch K split (bit 8) at 2 / 1 CTAs per tile: less SM time per layer at a higher
+ *       latency (set before graphs are captured; the trade for two frames in flight, frame_pipeline.py)
  * (r02 A/B, profiles/r02_layer_table_mode_bits.json; the other round-1 candidates -- pair-window kernels for layer3/4 and
  * 128-wide layer2 tiles, residual preload -- measured no gain and were removed.)
  * 0 = single-CTA TMA-im2col kernel only */

@@ -815,8 +815,11 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
       want = p.num_k_blocks / 4;
       if (want > sms / tiles) want = sms / tiles;
     }
+    // bits 18 / 19 of the mode cap the automatic split at 2 / 1: fewer, longer CTAs -- less SM time per layer at a higher
+    // latency, the better trade when another frame's kernels fill the device beside this one (frame_pipeline.py)
+    const int cap = (splitk < 0 && (conv_mode() & 524288)) ? 1 : ((splitk < 0 && (conv_mode() & 262144)) ? 2 : 8);
     int splits = 1;
-    while (splits * 2 <= want && splits * 2 <= 8 && splits * 2 <= p.num_k_blocks) splits *= 2;
+    while (splits * 2 <= want && splits * 2 <= cap && splits * 2 <= p.num_k_blocks) splits *= 2;
     p.splits = splits;
   }
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--slots", default="2")
     ap.add_argument("--priority", default="0,1")
+    ap.add_argument("--conv-modes", default="49163", help="comma-separated mpx_conv_set_mode values (set before building)")
     ap.add_argument("--out", type=Path, default=Path("gpurun_out/frames_in_flight.json"))
     args = ap.parse_args()
     sc = scenes.bench_scene(1)
@@ -48,9 +49,11 @@ def main():
     import itertools
     import time
     variants = itertools.product([int(v) for v in args.reserve.split(",")], [int(v) for v in args.slots.split(",")],
-                                 [int(v) for v in args.priority.split(",")])
-    for reserve, n_slots, prio in variants:
+                                 [int(v) for v in args.priority.split(",")], [int(v) for v in args.conv_modes.split(",")])
+    from megapose6d_b200 import _abi
+    for reserve, n_slots, prio, mode in variants:
         sms = FP.set_reserved_sms(reserve)
+        _abi.lib().mpx_conv_set_mode(mode)
         ests = [scenes.build_estimator(sc) for _ in range(n_slots)]
         pipe = FP.FramePipeline(None, estimators=ests, tail_priority=bool(prio))
         for est in ests:
@@ -88,7 +91,7 @@ def main():
         ms_pipe2 = timed(run_pipe)
         same = all(torch.equal(a.poses, b.poses) and a.infos["pose_logit"].tolist() == b.infos["pose_logit"].tolist()
                    for a, b in zip(seq_out, pipe_out)) and len(seq_out) == len(pipe_out) == args.steps
-        rec = dict(reserve_sms=reserve, sms_used=sms, slots=n_slots, tail_priority=prio, host_submit_ms=(t1 - t0) * 1e3,
+        rec = dict(conv_mode=mode, reserve_sms=reserve, sms_used=sms, slots=n_slots, tail_priority=prio, host_submit_ms=(t1 - t0) * 1e3,
                    host_result_ms=(t3 - t2) * 1e3, ms_per_frame_sequential=min(ms_seq, ms_seq2),
                    ms_per_frame_in_flight=min(ms_pipe, ms_pipe2), speedup=min(ms_seq, ms_seq2) / min(ms_pipe, ms_pipe2),
                    hyp_per_s_in_flight=576 / min(ms_pipe, ms_pipe2) * 1e3, results_identical=bool(same))
