@@ -45,7 +45,7 @@ def set_reserved_sms(reserve: int) -> int:
 
 class FramePipeline:
     def __init__(self, make_estimator: Callable[[], "torch.nn.Module"], n_slots: int = 2,
-                 estimators: Optional[Sequence["torch.nn.Module"]] = None, device=None, tail_priority: bool = True):
+                 estimators: Optional[Sequence["torch.nn.Module"]] = None, device=None, tail_priority="high"):
         """`make_estimator` is called once per slot (each call must build its own models and mesh database); or pass the
         estimators themselves (fresh ones: `tail_priority` -- PoseEstimator.set_tail_priority -- is recorded by the graphs
         they capture on their first frames)."""
@@ -59,7 +59,8 @@ class FramePipeline:
                     assert a.coarse_model is not b.coarse_model and a.refiner_model is not b.refiner_model, \
                         "the slots of a FramePipeline must not share models (their buffers and graphs are single-buffered)"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.slots = [dict(est=e, stream=torch.cuda.Stream(device=self.device), pending=None) for e in ests]
+        prio = -1 if tail_priority == "low" else 0
+        self.slots = [dict(est=e, stream=torch.cuda.Stream(device=self.device, priority=prio), pending=None) for e in ests]
         self._next = 0
 
     def __len__(self) -> int:

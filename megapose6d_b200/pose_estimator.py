@@ -326,16 +326,25 @@ class PoseEstimator(torch.nn.Module):
             extra_data["depth_refiner"] = {"preds": data_TCO_depth_refiner}
         return data_TCO_final, extra_data
 
-    def set_tail_priority(self, high: bool = True) -> None:
-        """Run everything after the coarse stage (refiner iterations, scoring, selection) on a high-priority stream, its
-        graphs captured at that priority: with a second frame in flight on another stream these few-CTA launches are then
-        scheduled ahead of the other frame's queued thread blocks.  Call before the first frame (graphs record the priority)."""
+    def set_tail_priority(self, mode=True) -> None:
+        """Stream priorities inside a frame, for two frames in flight (frame_pipeline.py).  Everything after the coarse stage
+        (refiner iterations, scoring, selection: a few hundred dependent few-CTA launches) runs on its own stream;
+          True / "high": that stream and the graphs captured on it have high priority -- its launches are scheduled ahead of
+                         the other frame's queued thread blocks (shortest frame latency);
+          "low":         the coarse stage's graph is captured at high priority and the tail keeps the default one -- the
+                         tail only takes SMs the other frame's coarse stage leaves idle;
+          False / None:  one stream, default priorities.
+        Call before the first frame (graphs record the priority of the stream they were captured on)."""
         dev = torch.device("cuda", torch.cuda.current_device())
-        if high:
+        mode = {True: "high", False: None}.get(mode, mode)
+        assert mode in ("high", "low", None)
+        self._tail_stream = self._head_capture_stream = cap = None
+        if mode == "high":
             self._tail_stream = torch.cuda.Stream(device=dev, priority=-1)  # torch: -1 = high, 0 = default
             cap = torch.cuda.Stream(device=dev, priority=-1)
-        else:
-            self._tail_stream, cap = None, None
+        elif mode == "low":
+            self._tail_stream = torch.cuda.Stream(device=dev, priority=0)
+            self._head_capture_stream = torch.cuda.Stream(device=dev, priority=-1)
         for m in (self.coarse_model, self.refiner_model):
             if m is not None:
                 m.graph_capture_stream = cap
@@ -479,7 +488,7 @@ class PoseEstimator(torch.nn.Module):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=self.__dict__.get("_head_capture_stream")):
                     out = self._coarse_stage(images, entry["K"], entry["bboxes"], rows_c, B, M, Kh, s0, s1, whole)
             except Exception:  # noqa: BLE001 -- capture not possible here: stay eager
                 torch.cuda.synchronize()

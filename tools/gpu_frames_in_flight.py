@@ -49,13 +49,13 @@ def main():
     import itertools
     import time
     variants = itertools.product([int(v) for v in args.reserve.split(",")], [int(v) for v in args.slots.split(",")],
-                                 [int(v) for v in args.priority.split(",")], [int(v) for v in args.conv_modes.split(",")])
+                                 [{"0": None, "1": "high"}.get(v, v) for v in args.priority.split(",")], [int(v) for v in args.conv_modes.split(",")])
     from megapose6d_b200 import _abi
     for reserve, n_slots, prio, mode in variants:
         sms = FP.set_reserved_sms(reserve)
         _abi.lib().mpx_conv_set_mode(mode)
         ests = [scenes.build_estimator(sc) for _ in range(n_slots)]
-        pipe = FP.FramePipeline(None, estimators=ests, tail_priority=bool(prio))
+        pipe = FP.FramePipeline(None, estimators=ests, tail_priority=prio)
         for est in ests:
             for i in range(5):
                 est.run_inference_pipeline(*frame(i), **kw)
