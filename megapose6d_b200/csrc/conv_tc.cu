@@ -261,6 +261,108 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, bool valid, act_t* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Staged epilogue of a 32-row x 64-column accumulator block (one warp), r02.  The row-per-thread form above stores 16 bytes
+// per lane into 32 different 128-byte lines per instruction (and loads the residual the same way): 32 L1 wavefronts per
+// instruction, 256 (512 with a residual) per warp and tile -- ncu on layer1: l1tex 67% / 86% busy, the epilogue warps never
+// waiting for an accumulator, the MMA issuers waiting for free TMEM.  Here the block goes through a 4 KB shared-memory tile
+// of the warp (rows of 128 B, 16-byte chunk c of row r at chunk position c ^ (r & 7): conflict-free both for "lane = row"
+// and for "8 lanes = one row" access), so that global loads and stores are whole 128-byte lines, 4 per instruction:
+//   stage_residual64   8 coalesced 16-byte loads per lane -> staging tile          (before the accumulator is waited for)
+//   epilogue_compute64 TMEM -> +bias -> +residual (staging) -> ReLU -> act16 -> staging tile (in place)
+//   store_staged64     staging tile -> 8 coalesced 16-byte stores per lane        (after the accumulator has been released)
+// `pix` = index of the lane's output pixel (row of the [M, 64] output matrix), -1 for rows that are not stored.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+constexpr int kStageTileBytes = 32 * 128;  // per epilogue warp
+
+__device__ __forceinline__ void stage_residual64(uint32_t stg, int lane, int pix, const act_t* residual) {
+  const int c = lane & 7;
+  uint4 t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = 4 * j + (lane >> 3);
+    const int pix_r = __shfl_sync(0xffffffffu, pix, r);
+    t[j] = pix_r >= 0 ? __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(pix_r) * 64) + c)
+                      : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = 4 * j + (lane >> 3);
+    sts128(stg + static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)), t[j]);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void epilogue_compute64(uint32_t taddr, uint32_t stg, int lane, bool has_res, uint32_t bias_smem,
+                                                   int relu) {
+  uint32_t va[32], vb[32];
+  tc_ld_32x32(taddr, va);
+  tc_ld_32x32(taddr + 32u, vb);
+  tc_wait_ld();
+  const uint32_t row_base = stg + static_cast<uint32_t>(lane * 128);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t* v = (i < 4) ? (va + 8 * i) : (vb + 8 * (i - 4));
+    const float4 b0 = lds_f4(bias_smem + static_cast<uint32_t>(32 * i));
+    const float4 b1 = lds_f4(bias_smem + static_cast<uint32_t>(32 * i + 16));
+    const uint32_t slot = row_base + static_cast<uint32_t>((i ^ (lane & 7)) << 4);
+    float f[8];
+    f[0] = __uint_as_float(v[0]) + b0.x;
+    f[1] = __uint_as_float(v[1]) + b0.y;
+    f[2] = __uint_as_float(v[2]) + b0.z;
+    f[3] = __uint_as_float(v[3]) + b0.w;
+    f[4] = __uint_as_float(v[4]) + b1.x;
+    f[5] = __uint_as_float(v[5]) + b1.y;
+    f[6] = __uint_as_float(v[6]) + b1.z;
+    f[7] = __uint_as_float(v[7]) + b1.w;
+    if (has_res) {
+      const uint4 rv = lds128(slot);
+      const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_act2(rr[j]);
+        f[2 * j] += t.x;
+        f[2 * j + 1] += t.y;
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_act2(f[0], f[1]);
+    o.y = pack_act2(f[2], f[3]);
+    o.z = pack_act2(f[4], f[5]);
+    o.w = pack_act2(f[6], f[7]);
+    sts128(slot, o);
+  }
+}
+
+__device__ __forceinline__ void store_staged64(uint32_t stg, int lane, int pix, act_t* out) {
+  const int c = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = 4 * j + (lane >> 3);
+    const int pix_r = __shfl_sync(0xffffffffu, pix, r);
+    const uint4 o = lds128(stg + static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)));
+    if (pix_r >= 0) *(reinterpret_cast<uint4*>(out + static_cast<size_t>(pix_r) * 64) + c) = o;
+  }
+  __syncwarp();  // the tile is free for the next residual
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -871,6 +973,7 @@ struct WinParams {
   int relu;
   int mma_issuers;     // 1 or 2 issuing threads (tiles alternate)
   int observers_arrive;  // 1: a stage is refilled only after EVERY issuer has seen its fill (empty count = issuers)
+  int row_epilogue;      // conv_windowq_kernel: 1 = row-per-thread epilogue (mode bit 20), 0 = staged / coalesced
   unsigned long long kskip;  // bit 4 * tap + ks set: K step ks (16 channels) of filter tap `tap` has all-zero weights
   const float* bias;
   const act_t* residual;
@@ -1186,6 +1289,7 @@ static int conv_window_try(const ConvDesc& d, const void* x, const void* w, cons
   p.relu = d.relu;
   p.mma_issuers = (g_conv_mode & 32) != 0 ? 1 : ((g_conv_mode & 64) != 0 ? 3 : 2);
   p.observers_arrive = 1;
+  p.row_epilogue = 0;
   p.kskip = stem_kskip(d);
   p.bias = bias;
   p.residual = reinterpret_cast<const act_t*>(residual);
@@ -2145,7 +2249,8 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_b = smem;                                  // n_taps resident half weight tiles
   uint8_t* smem_a = smem + n_taps * kWinqBHalf;            // `stages` windows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + static_cast<size_t>(stages) * p.win_bytes);
+  uint8_t* smem_stg = smem_a + static_cast<size_t>(stages) * p.win_bytes;  // 8 epilogue warps x 4 KB staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + 8 * kStageTileBytes);
   uint64_t* full_bar = bars;             // [stages <= 8] leader
   uint64_t* empty_bar = bars + 8;        // [stages]      per CTA
   uint64_t* tmem_full = bars + 16;       // [4]           per CTA
@@ -2315,18 +2420,34 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kWinN : 0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
-      const act_t* res_row = p.residual ? p.residual + off : nullptr;
-      uint4 res_cur[4];
-      if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
+      if (p.row_epilogue) {  // mode bit 20: one output row per thread, 16-byte accesses scattered over 32 lines (r01 form)
+        const act_t* res_row = p.residual ? p.residual + off : nullptr;
+        uint4 res_cur[4];
+        if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        epilogue_row<kWinN>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_remote(&tmem_empty[acc], 0);
+        }
+        continue;
+      }
+      const uint32_t stg = smem_u32(smem_stg) + static_cast<uint32_t>((warp - 4) * kStageTileBytes);
+      const int pix = valid ? static_cast<int>(off / kWinN) : -1;
+      if (p.residual) stage_residual64(stg, lane, pix, p.residual);  // in flight while the MMAs of this tile run
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_row<kWinN>(taddr, valid, p.out + off, res_row, bias_s, p.relu, res_cur);
+      epilogue_compute64(taddr, stg, lane, p.residual != nullptr, smem_u32(bias_s), p.relu);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0) {  // the accumulator is free before the global stores are issued
         if (leader) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_remote(&tmem_empty[acc], 0);
       }
+      store_staged64(stg, lane, pix, p.out);
     }
   }
 
@@ -2369,7 +2490,7 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
     const int n_chunks = (rows + 255) / 256;
     const int chunk = ((rows + n_chunks - 1) / n_chunks + 7) & ~7;
     const int win_bytes = chunk * n_chunks * 128;
-    int st = (smem_limit - b_bytes) / win_bytes;
+    int st = (smem_limit - b_bytes - 8 * kStageTileBytes) / win_bytes;
     if (st > 8) st = 8;
     if (st < 2) continue;
     double tiles = static_cast<double>(st) / (d.R / cand);
@@ -2392,10 +2513,12 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
   p.q_base = static_cast<long long>(p.pl_h) * p.Wp + p.pl_w;
   const long long m_tiles = (p.M_pad - p.q_base + kBlockM - 1) / kBlockM;
   if (m_tiles < 2 || m_tiles >= (1LL << 30)) return MPX_ERR_UNSUPPORTED;
+  if (static_cast<long long>(d.n_img) * d.H * d.W >= (1LL << 31)) return MPX_ERR_UNSUPPORTED;  // pixel indices are 32-bit
   p.m_tiles = static_cast<int>(m_tiles);
   p.relu = d.relu;
   p.mma_issuers = 2;
   p.observers_arrive = 0;
+  p.row_epilogue = (g_conv_mode & 1048576) ? 1 : 0;
   p.kskip = stem_kskip(d);
   p.bias = bias;
   p.residual = reinterpret_cast<const act_t*>(residual);
@@ -2431,7 +2554,7 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
   }
-  const int smem_bytes = 1024 + b_bytes + stages * p.win_bytes + 1024;
+  const int smem_bytes = 1024 + b_bytes + stages * p.win_bytes + 8 * kStageTileBytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MPX_CHECK_CUDA(cudaFuncSetAttribute(conv_windowq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
