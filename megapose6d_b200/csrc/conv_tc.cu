@@ -974,6 +974,7 @@ struct WinParams {
   int mma_issuers;     // 1 or 2 issuing threads (tiles alternate)
   int observers_arrive;  // 1: a stage is refilled only after EVERY issuer has seen its fill (empty count = issuers)
   int row_epilogue;      // conv_windowq_kernel: 1 = row-per-thread epilogue (mode bit 20), 0 = staged / coalesced
+  unsigned idesc;        // conv_windowq_kernel: the MMA instruction descriptor, as a parameter so that it lives in one uniform register
   unsigned long long kskip;  // bit 4 * tap + ks set: K step ks (16 channels) of filter tap `tap` has all-zero weights
   const float* bias;
   const act_t* residual;
@@ -1734,6 +1735,12 @@ __device__ __forceinline__ void tc2_mma_f16_u(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Advance a shared-memory descriptor by `inc` 16-byte units without touching its high word (SBO, version, layout): the start
+// address field never carries out of the low word (shared memory is < 256 KB), and a 32-bit add on the low register of the
+// uniform pair is half of the 64-bit add-with-carry the compiler emits for `desc + inc`.
+__device__ __forceinline__ uint64_t desc_add_lo(uint64_t d, uint32_t inc) {
+  return (d & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(static_cast<uint32_t>(d) + inc);
+}
 __device__ __forceinline__ void tc2_commit_mc_u(uint64_t* bar) {
   asm volatile(MPX_ELECT_PRED
                "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
@@ -2308,35 +2315,73 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tma2_load_2d_u(smem_b + t * kWinqBHalf, &map_b, b_full, t * kBlockK, static_cast<int>(rank) * (kWinN / 2));
       int stage = 0;
       uint32_t phase = 0;
+      // Window wi of a tile starts at padded-linear row (2 * tile + rank) * 128 + wi * rg * Wp; its position (img, y, x) in
+      // the padded image space is carried from tile to tile by additions (r02: with two 64-bit divisions per TMA
+      // instruction this warp executed ~120 instructions per window and never waited -- it paced the whole kernel)
+      const long long q_first = (2LL * pair + rank) * kBlockM;
+      int t_img = static_cast<int>(q_first / hpwp);
+      int t_y = static_cast<int>((q_first - static_cast<long long>(t_img) * hpwp) / p.Wp);
+      int t_x = static_cast<int>(q_first - static_cast<long long>(t_img) * hpwp - static_cast<long long>(t_y) * p.Wp);
+      const long long q_step = 2LL * n_pairs * kBlockM;
+      const int s_img = static_cast<int>(q_step / hpwp);
+      const int s_y = static_cast<int>((q_step - static_cast<long long>(s_img) * hpwp) / p.Wp);
+      const int s_x = static_cast<int>(q_step - static_cast<long long>(s_img) * hpwp - static_cast<long long>(s_y) * p.Wp);
+      const int c_y = p.chunk_rows / p.Wp, c_x = p.chunk_rows - c_y * p.Wp;
       for (int tile = pair; tile < n_ptiles; tile += n_pairs) {
-        const long long q0 = p.q_base + (2LL * tile + rank) * kBlockM;
+        int w_img = t_img, w_y = t_y;
         for (int wi = 0; wi < p.n_windows; ++wi) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (leader) mbar_expect_tx_u(&full_bar[stage], 2u * static_cast<uint32_t>(p.win_bytes));
           else mbar_arrive_remote_u(&full_bar[stage], 0);
-          long long qs = q0 - (static_cast<long long>(p.pl_h) * p.Wp + p.pl_w) + static_cast<long long>(wi) * p.rg * p.Wp;
+          int img = w_img, yp = w_y, xp = t_x;
           for (int ch = 0; ch < p.n_chunks; ++ch) {
-            const long long q = qs + static_cast<long long>(ch) * p.chunk_rows;
-            const int img = static_cast<int>(q / hpwp);
-            const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
-            const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
             tma2_load_im2col_4d_u(smem_a + static_cast<size_t>(stage) * p.win_bytes + static_cast<size_t>(ch) * p.chunk_rows * 128,
                                 &map_a, &full_bar[stage], 0, xp - p.pl_w, yp - p.pl_h, img, 0, 0);
+            xp += c_x;
+            if (xp >= p.Wp) {
+              xp -= p.Wp;
+              ++yp;
+            }
+            yp += c_y;
+            while (yp >= p.Hp) {
+              yp -= p.Hp;
+              ++img;
+            }
+          }
+          w_y += p.rg;
+          while (w_y >= p.Hp) {
+            w_y -= p.Hp;
+            ++w_img;
           }
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
+        t_x += s_x;
+        if (t_x >= p.Wp) {
+          t_x -= p.Wp;
+          ++t_y;
+        }
+        t_y += s_y;
+        while (t_y >= p.Hp) {
+          t_y -= p.Hp;
+          ++t_img;
+        }
+        t_img += s_img;
       }
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers (leader only), pair tiles alternately =====================
     const int which = warp == 1 ? 0 : 1;
     if (leader) {  // whole warp, warp-uniform operands; one lane is elected inside each instruction
-      constexpr uint32_t idesc = (1u << 4) | kIdescAB | (static_cast<uint32_t>(kWinN >> 3) << 17) |
-                                 (static_cast<uint32_t>(256 >> 4) << 24);
+      const uint32_t idesc = p.idesc;
       mbar_wait(b_full, 0);
+      // Every per-MMA operand below is a function of kernel parameters and loop counters only (tmem_base is known to be 0,
+      // checked above), so ptxas keeps the whole issue loop in uniform registers: ~5 instructions per MMA instead of ~10
+      // (r02 ncu: the two issuers executed 14-19 instructions per MMA and were busy 85-100% of the time).
+      const uint32_t row_step = static_cast<uint32_t>(p.Wp) * 8u - 8u * static_cast<uint32_t>(p.S);
+      const uint64_t b_base = make_sw128_desc(smem_u32(smem_b));
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -2356,38 +2401,44 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t acc_phase = (local / kWinAccBufs) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kWinN);
+        const uint32_t tmem_d = static_cast<uint32_t>(acc * kWinN);
         uint32_t first = 1;
+        uint64_t db = b_base;  // walks the resident half weight tiles: +2 per K step of 16 channels, 256 per tap
+        int tap = 0;
         for (int wi = 0; wi < p.n_windows; ++wi) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da_win = make_sw128_desc(smem_u32(smem_a + static_cast<size_t>(stage) * p.win_bytes));
-          uint64_t db = make_sw128_desc(smem_u32(smem_b + wi * p.taps_per_win * kWinqBHalf));
-          uint64_t da_row = da_win;
-          int tap = wi * p.taps_per_win;
+          uint64_t da = make_sw128_desc(smem_u32(smem_a + static_cast<size_t>(stage) * p.win_bytes));
           for (int r = 0; r < p.rg; ++r) {
-            uint64_t da = da_row;
             for (int s = 0; s < p.S; ++s) {
               const unsigned sk = static_cast<unsigned>(p.kskip >> (4 * tap)) & 15u;
               if (sk == 0u) {
                 tc2_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
-                tc2_mma_f16_u(tmem_d, da + 2, db + 2, idesc, 1u);
-                tc2_mma_f16_u(tmem_d, da + 4, db + 4, idesc, 1u);
-                tc2_mma_f16_u(tmem_d, da + 6, db + 6, idesc, 1u);
+                da = desc_add_lo(da, 2u);
+                db = desc_add_lo(db, 2u);
+                tc2_mma_f16_u(tmem_d, da, db, idesc, 1u);
+                da = desc_add_lo(da, 2u);
+                db = desc_add_lo(db, 2u);
+                tc2_mma_f16_u(tmem_d, da, db, idesc, 1u);
+                da = desc_add_lo(da, 2u);
+                db = desc_add_lo(db, 2u);
+                tc2_mma_f16_u(tmem_d, da, db, idesc, 1u);
+                da = desc_add_lo(da, 2u);                      // next tap: one pixel (128 B) further
+                db = desc_add_lo(db, kWinqBHalf / 16 - 6u);
                 first = 0;
               } else {  // structurally zero weight slices (7x7 stem inside its 8x8 space-to-depth footprint): not issued
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (((sk >> ks) & 1u) == 0u) {
-                    tc2_mma_f16_u(tmem_d, da + 2 * ks, db + 2 * ks, idesc, first ? 0u : 1u);
+                    tc2_mma_f16_u(tmem_d, desc_add_lo(da, 2u * ks), desc_add_lo(db, 2u * ks), idesc, first ? 0u : 1u);
                     first = 0;
                   }
+                da = desc_add_lo(da, 8u);
+                db = desc_add_lo(db, kWinqBHalf / 16);
               }
               ++tap;
-              da += 8;
-              db += kWinqBHalf / 16;
             }
-            da_row += static_cast<uint64_t>(p.Wp) * 8;
+            da = desc_add_lo(da, row_step);  // next filter row: Wp pixels further, minus the S taps already walked
           }
           tc2_commit_mc_u(&empty_bar[stage]);
           if (++stage == stages) {
@@ -2400,6 +2451,9 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows), two warp sets, tiles round-robin =====================
+    // The MMA issuers address the accumulators from column 0 (uniform-register arithmetic only): one allocation by a CTA
+    // that owns its SM (227 KB of shared memory) starts there; checked here, where tmem_base is a per-thread value anyway.
+    if (tmem_base != 0u) __trap();
     const int q4 = warp & 3;
     const int set = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
@@ -2519,6 +2573,7 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
   p.mma_issuers = 2;
   p.observers_arrive = 0;
   p.row_epilogue = (g_conv_mode & 1048576) ? 1 : 0;
+  p.idesc = (1u << 4) | kIdescAB | (static_cast<unsigned>(kWinN >> 3) << 17) | (static_cast<unsigned>(256 >> 4) << 24);
   p.kskip = stem_kskip(d);
   p.bias = bias;
   p.residual = reinterpret_cast<const act_t*>(residual);
