@@ -270,6 +270,10 @@ class PoseEstimator(torch.nn.Module):
             self.bsz_images = bsz_images
         if bsz_objects is not None:
             self.bsz_objects = bsz_objects
+        if coarse_estimates is None and detections is None and run_detector:  # pose_estimator.py:566-572
+            t0 = time.time()
+            detections = self.forward_detection_model(observation).cuda()
+            timing_str += f"detection={time.time() - t0:.2f}, "
         if (self.fused_pipeline and coarse_estimates is None and detections is not None and not run_depth_refiner
                 and not cuda_timer and not keep_all_refiner_outputs and self.refiner_model is not None
                 and self.coarse_model is not None and len(detections) > 0 and n_refiner_iterations >= 1):
@@ -279,10 +283,6 @@ class PoseEstimator(torch.nn.Module):
                 return out
         if coarse_estimates is None:
             assert detections is not None or run_detector, "You must either pass in `detections` or set run_detector=True"
-            if detections is None and run_detector:
-                t0 = time.time()
-                detections = self.forward_detection_model(observation).cuda()
-                timing_str += f"detection={time.time() - t0:.2f}, "
             assert detections is not None
             detections = add_instance_id(detections)
             if detection_filter_kwargs is not None:
