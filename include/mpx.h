@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MPX_ABI_VERSION 3
+#define MPX_ABI_VERSION 4
 
 /* ---- library ------------------------------------------------------------------------------ */
 int mpx_abi_version(void);
@@ -209,7 +209,10 @@ size_t mpx_net_input_bytes(int n, int h, int w, int c_pad);
  *   d_x [n,H,W,C_in] act16, d_w [C_out, R*S*C_in] act16, d_bias [C_out] fp32,
  *   d_residual / d_out [n,P,Q,C_out] act16 (residual may be NULL)
  *   relu: bit 0 = ReLU; bit 1 = the weights are the space-to-depth form of the 7x7 stem (4x4 taps over C_in = 64: the 15 of
- *   64 (tap, 16-channel) slices that are zero by construction are not multiplied, megapose6d_b200/backbone.py: _stem_s2d)
+ *   64 (tap, 16-channel) slices that are zero by construction are not multiplied, megapose6d_b200/backbone.py: _stem_s2d);
+ *   bit 2 = fused 3x3/s2/p1 max-pool (models/torchvision_resnet.py:197 `self.maxpool` right after the stem's ReLU): d_out is
+ *   then the ZEROED [n, (P-1)/2+1, (Q-1)/2+1, C_out] tensor and is max-reduced into; needs bit 0, no residual, and returns
+ *   MPX_ERR_UNSUPPORTED (nothing launched, no error text) for shapes the pair window kernel does not serve
  *   block_n: 0 = auto, else 64|128|256; max_ctas: 0 = one per SM */
 int mpx_conv2d(const void* d_x, int n, int h, int w, int c_in, const void* d_w,
                     const float* d_bias, int c_out, int r, int s, int stride, int pad_lo_h,
@@ -283,6 +286,11 @@ int mpx_net_destroy(mpx_net* net);
 /* mpx_net_forward replays a cached CUDA graph per (buffers, shape) after the first call; 0 disables that
  * (every launch is then issued eagerly on the caller's stream). Default: enabled. */
 int mpx_net_set_graphs(int on);
+/* Chunked front of the network: for batches of at least 2 * images the stem, the max-pool and layer1 run `images` samples
+ * at a time so that their tensors stay inside the L2 from one layer to the next (the reference only ever chunks whole forwards,
+ * bsz_images in inference/pose_estimator.py:139-141); layers 2-4 run on the whole batch.  Same kernels and per-element
+ * arithmetic: outputs are bit-identical.  0 = off.  Process-wide; recorded by graphs captured afterwards. */
+int mpx_net_set_chunk(int images);
 size_t mpx_net_workspace_bytes(const mpx_net* net, int n, int h, int w);
 /* d_x: network input tensor (see above) for n samples of size h x w; d_out [n, out_dim] fp32 */
 int mpx_net_forward(const mpx_net* net, const void* d_x, int n, int h, int w, float* d_out,

@@ -315,7 +315,7 @@ int mpx_conv2d(const void* d_x, int n, int h, int w, int c_in, const void* d_w, 
                   (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d_residual) & 15) == 0,
               "mpx_conv2d: pointers must be 16-byte aligned");
-  ConvDesc d{n, h, w, c_in, c_out, r, s, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w, relu & 1, (relu >> 1) & 1};
+  ConvDesc d{n, h, w, c_in, c_out, r, s, stride, pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w, relu & 1, (relu >> 1) & 1, (relu >> 2) & 1};
   return conv_forward(d, d_x, d_w, d_bias, d_residual, d_out, block_n, max_ctas,
                       static_cast<cudaStream_t>(stream));
 }
@@ -409,6 +409,11 @@ int mpx_net_create_preact(int c_pad, int out_dim, const int32_t* h_layer_blocks,
   int rc = net_create_preact(c_pad, out_dim, lb, h_conv_w, h_conv_b, n_convs, h_block_affine, n_blocks, d_head_w, d_head_b, &net);
   if (rc != MPX_OK) return rc;
   *out = new mpx_net{net};
+  return MPX_OK;
+}
+
+int mpx_net_set_chunk(int images) {
+  net_set_chunk(images);
   return MPX_OK;
 }
 

@@ -136,7 +136,17 @@ __device__ __forceinline__ float depth_norm(float d, float z, int kind) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Late trigger (mpx_conv_set_mode bit 22 = 4194304).  Every kernel of a chain triggering in its first instructions lets the
+// chain CASCADE: kernel k+1 is resident (parked in pdl_wait) as soon as k's CTAs have started, k+2 as soon as k+1's have,
+// ... as deep as the launch front end gets ahead -- several kernels' worth of CTAs hold shared memory and TMEM while only one
+// of them works.  Alone on the device that is free; beside another frame's persistent kernels (frame_pipeline.py) those parked
+// CTAs are SMs the other stream cannot use.  With `late` a CTA triggers only once its own wait has returned (its predecessor
+// has finished): at most the running kernel and ONE parked successor exist per chain, and the successor's set-up still
+// overlaps the running kernel.
+__device__ __forceinline__ void pdl_trigger(int late) { if (!late) pdl_trigger(); }
+__device__ __forceinline__ void pdl_wait(int late) { pdl_wait(); if (late) pdl_trigger(); }
 int conv_get_mode();
+inline int pdl_late_mode() { return (conv_get_mode() >> 22) & 1; }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               int cluster_x, Args&&... args) {
@@ -171,6 +181,8 @@ extern long long g_launches;  // kernels launched by this library (host-side cou
 void conv_profile_enable(int on);
 bool conv_profile_enabled();
 void net_set_graphs(int on);
+void net_set_chunk(int images);
+int net_get_chunk();
 void conv_set_mode(int mode);
 int conv_get_mode();
 int conv_profile_summary(double* total_ms, double* total_flops, long long* launches);
@@ -181,6 +193,9 @@ struct ConvDesc {
   int pad_lo_h, pad_lo_w, pad_hi_h, pad_hi_w;
   int relu;
   int s2d_stem;  // 1: the weights are the space-to-depth form of the 7x7 stem (zero slices are skipped), see conv_tc.cu
+  int pool;      // 1: `out` is the ZERO-INITIALISED [n, (H-1)/2+1, (W-1)/2+1, C_out] tensor and receives the 3x3/s2/p1 max-pool of
+                 //    the (ReLU'd) result through vector max-reductions; conv_forward returns MPX_ERR_UNSUPPORTED (no error set)
+                 //    when no kernel with that epilogue serves the shape
 };
 // splitk: 0 = never, -1 = heuristic (few output tiles, long K loop), 1|2|4|8 = that many k-splits (cluster size)
 int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* bias,

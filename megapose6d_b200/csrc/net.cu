@@ -16,9 +16,9 @@ namespace mpx {
 // one CTA per output row (img, oy): threads walk (ox, channel group) with 32-bit index math only -- the flat
 // grid-stride form spent most of its instructions on 64-bit div / mod of the element index
 __global__ void __launch_bounds__(512)
-maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int c8, int ho, int wo) {
-  pdl_trigger();
-  pdl_wait();
+maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int c8, int ho, int wo, int pdl_late) {
+  pdl_trigger(pdl_late);
+  pdl_wait(pdl_late);
   const int row_items = wo * c8;
   for (int row = blockIdx.x; row < n * ho; row += gridDim.x) {
     const int img = row / ho, oy = row - img * ho;
@@ -74,7 +74,7 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
   const long long cap = static_cast<long long>(sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   MPX_CHECK_CUDA(launch_pdl(maxpool3x3s2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, 1,
-                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo));
+                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo, pdl_late_mode()));
   ++g_launches;
   return MPX_OK;
 }
@@ -86,9 +86,9 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 affine_relu_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long n8, int c8,
-                   const float* __restrict__ scale_shift /* [2, C] */) {
-  pdl_trigger();
-  pdl_wait();
+                   const float* __restrict__ scale_shift /* [2, C] */, int pdl_late) {
+  pdl_trigger(pdl_late);
+  pdl_wait(pdl_late);
   const float* scale = scale_shift;
   const float* shift = scale_shift + 8 * c8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
@@ -116,7 +116,7 @@ static int affine_relu(const void* x, long long elems, int c, const float* scale
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   MPX_CHECK_CUDA(launch_pdl(affine_relu_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1,
-                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n8, c / 8, scale_shift));
+                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n8, c / 8, scale_shift, pdl_late_mode()));
   ++g_launches;
   return MPX_OK;
 }
@@ -131,12 +131,12 @@ static int affine_relu(const void* x, long long elems, int c, const float* scale
 constexpr int kPoolThreads = 512;
 __global__ void __launch_bounds__(kPoolThreads)
 avgpool_linear_kernel(const act_t* __restrict__ x, int hw, int c, const float* __restrict__ w,
-                      const float* __restrict__ b, int out_dim, float* __restrict__ out) {
+                      const float* __restrict__ b, int out_dim, float* __restrict__ out, int pdl_late) {
   extern __shared__ float smem_pool[];  // [G][c] partial sums, then [c] pooled
   const int img = blockIdx.x;
   const act_t* xi = x + static_cast<size_t>(img) * hw * c;
-  pdl_trigger();
-  pdl_wait();
+  pdl_trigger(pdl_late);
+  pdl_wait(pdl_late);
   const int nq = c >> 2;
   const int G = nq >= kPoolThreads ? 1 : kPoolThreads / nq;
   float* part = smem_pool;
@@ -183,7 +183,7 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
   const size_t smem = static_cast<size_t>(G + 1) * c * sizeof(float);
   MPX_REQUIRE(smem <= 48 * 1024, "avgpool_linear: C=%d needs %zu bytes of shared memory", c, smem);
   MPX_CHECK_CUDA(launch_pdl(avgpool_linear_kernel, dim3(n), dim3(kPoolThreads), smem, stream, 1,
-                            reinterpret_cast<const act_t*>(x), hw, c, w, b, out_dim, out));
+                            reinterpret_cast<const act_t*>(x), hw, c, w, b, out_dim, out, pdl_late_mode()));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;
@@ -350,6 +350,25 @@ int net_forward(const Net* cnet, const void* x, int n, int h, int w, float* out,
   return MPX_OK;
 }
 
+// Stem convolution + ReLU followed by the 3x3/s2/p1 max-pool.  With mode bit 21 (2097152) the pair window kernel pools in its
+// epilogue (max-reductions into the zeroed pooled tensor): the full-resolution stem output -- 2.46 MB per sample at 240x320,
+// written once and read once by nothing but the pool -- never exists.  Falls back to the two kernels when the shape is not
+// served (the memset is then wasted, nothing else).
+static int stem_and_pool(ConvDesc d, const void* x, const void* w, const float* b, void* buf_stem, void* buf_pool,
+                         cudaStream_t stream) {
+  const int hp = (d.H + 2 - 3) / 2 + 1, wp = (d.W + 2 - 3) / 2 + 1;
+  if ((conv_get_mode() & 2097152) != 0 && d.relu) {
+    MPX_CHECK_CUDA(cudaMemsetAsync(buf_pool, 0, static_cast<size_t>(d.n_img) * hp * wp * d.C_out * 2, stream));
+    d.pool = 1;
+    const int rc = conv_forward(d, x, w, b, nullptr, buf_pool, 0, 0, stream);
+    if (rc != MPX_ERR_UNSUPPORTED) return rc;
+    d.pool = 0;
+  }
+  const int rc = conv_forward(d, x, w, b, nullptr, buf_stem, 0, 0, stream);
+  if (rc != MPX_OK) return rc;
+  return maxpool3x3s2(buf_stem, d.n_img, d.H, d.W, d.C_out, buf_pool, stream);
+}
+
 // WideResNet (pre-activation) schedule, models/wide_resnet.py:44-58, 106-115: stem 5x5/s2/p2 (a 3x3/s1/p1 convolution over
 // the space-to-depth input) + bn1 + relu, max-pool, then per block
 //   a = relu(bn1(x)) [affine_relu_kernel];  r = downsample(a) (bare 1x1/s2 convolution) or x;
@@ -369,11 +388,9 @@ static int net_forward_preact(const Net* net, const void* x, int n, int h, int w
   int rc;
   {
     ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 3, 3, 1, 1, 1, 1, 1, 1, 0};
-    rc = conv_forward(d, x, net->conv_w[0], net->conv_b[0], nullptr, buf_stem, 0, 0, stream);
+    rc = stem_and_pool(d, x, net->conv_w[0], net->conv_b[0], buf_stem, bufs[0], stream);
     if (rc != MPX_OK) return rc;
   }
-  rc = maxpool3x3s2(buf_stem, n, hs, ws, 64, bufs[0], stream);
-  if (rc != MPX_OK) return rc;
   int ci = 1, blk_id = 0;
   int cur = 0;  // buffer holding the block input x
   int H = hp, W = wp, C = 64;
@@ -409,6 +426,66 @@ static int net_forward_preact(const Net* net, const void* x, int n, int h, int w
   return avgpool_linear(bufs[cur], n, H * W, C, net->head_w, net->head_b, net->out_dim, out, stream);
 }
 
+// Blocks of layers [layer_from, layer_to) of the post-activation ResNet on `n` images: bufs[cur] holds the input, the
+// three buffers rotate as in the reference's BasicBlock (conv1 -> t1; downsample -> t2; conv2 + residual -> out).  When
+// `final_dst` is given the LAST block writes its output there instead (the chunked schedule scatters chunk results into the
+// full-batch tensor).  Returns the buffer holding the result through *result.
+struct TrunkState {
+  int ci, H, W, C;
+};
+static int run_layers(const Net* net, int n, int layer_from, int layer_to, void* const bufs[3], int cur, TrunkState& st,
+                      void* final_dst, int sk, cudaStream_t stream, void** result) {
+  int rc;
+  void* cur_ptr = bufs[cur];
+  for (int layer = layer_from; layer < layer_to; ++layer) {
+    const int width = kLayerWidth[layer];
+    for (int blk = 0; blk < kLayerBlocks[layer]; ++blk) {
+      const int stride = (blk == 0 && layer > 0) ? 2 : 1;
+      const bool has_ds = (blk == 0 && layer > 0);
+      const bool last = final_dst != nullptr && layer == layer_to - 1 && blk == kLayerBlocks[layer] - 1;
+      const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
+      const int Ho = conv_out_dim(st.H, 1, 1, 3, stride), Wo = conv_out_dim(st.W, 1, 1, 3, stride);
+      // conv1 + bn1 + relu
+      ConvDesc d1{n, st.H, st.W, st.C, width, 3, 3, stride, 1, 1, 1, 1, 1};
+      rc = conv_forward(d1, bufs[cur], net->conv_w[st.ci], net->conv_b[st.ci], nullptr, bufs[t1], 0, 0, stream, sk);
+      if (rc != MPX_OK) return rc;
+      ++st.ci;
+      const void* residual = bufs[cur];
+      int out_buf = t2;
+      if (has_ds) {
+        // downsample: 1x1/s2 conv + bn (no relu) -> residual; conv_w order: conv1, conv2, downsample
+        ConvDesc dd{n, st.H, st.W, st.C, width, 1, 1, stride, 0, 0, 0, 0, 0};
+        rc = conv_forward(dd, bufs[cur], net->conv_w[st.ci + 1], net->conv_b[st.ci + 1], nullptr, bufs[t2], 0, 0, stream, sk);
+        if (rc != MPX_OK) return rc;
+        residual = bufs[t2];
+        out_buf = cur;  // block input is dead once conv1 and the downsample have consumed it
+      }
+      // conv2 + bn2 + residual + relu
+      ConvDesc d2{n, Ho, Wo, width, width, 3, 3, 1, 1, 1, 1, 1, 1};
+      cur_ptr = last ? final_dst : bufs[out_buf];
+      rc = conv_forward(d2, bufs[t1], net->conv_w[st.ci], net->conv_b[st.ci], residual, cur_ptr, 0, 0, stream, sk);
+      if (rc != MPX_OK) return rc;
+      st.ci += has_ds ? 2 : 1;
+      cur = out_buf;
+      st.H = Ho;
+      st.W = Wo;
+      st.C = width;
+    }
+  }
+  *result = cur_ptr;
+  return MPX_OK;
+}
+
+// Chunked front of the network (mpx_net_set_chunk): at batch 576 every tensor of the stem / layer1 is 0.35 - 1.4 GB, so each
+// of those layers streams its input from and its output to HBM and they run at the HBM roofline, not the tensor pipe's.
+// Taken `chunk` images at a time the same seven kernels keep their tensors (0.6 MB per image and layer) inside the 126 MB L2
+// from one layer to the next; only the network input and layer1's final output touch HBM.  Same kernels, same per-element
+// arithmetic: bit-identical outputs.  Layers 2-4 (tensor-bound, and coarser tiles that quantise badly on small batches) run
+// on the whole batch as before.
+static int g_net_chunk = 0;
+void net_set_chunk(int images) { g_net_chunk = images < 0 ? 0 : images; }
+int net_get_chunk() { return g_net_chunk; }
+
 static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
                               size_t workspace_bytes, cudaStream_t stream) {
   MPX_REQUIRE(h % 2 == 0 && w % 2 == 0, "net: input %dx%d must be even", h, w);
@@ -428,56 +505,45 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   if (net->preact) return net_forward_preact(net, x, n, h, w, out, workspace, stream);
   int ci = 0;
   int rc;
+  void* res = nullptr;
+  const int chunk = g_net_chunk;
+  if (chunk > 0 && n >= 2 * chunk) {
+    // stem + max-pool + layer1, `chunk` images at a time; the chunk's temporaries live in the (otherwise unused) full-batch
+    // stem buffer, layer1's result goes straight to its place in bufs[0]
+    const size_t in_img = static_cast<size_t>(hs) * ws * 4 * net->c_pad * 2;
+    const size_t stem_img = static_cast<size_t>(hs) * ws * 64 * 2, l1_img = static_cast<size_t>(hp) * wp * 64 * 2;
+    uint8_t* tmp = base;
+    void* c_stem = tmp;
+    void* c_bufs[3];
+    for (int i = 0; i < 3; ++i) c_bufs[i] = tmp + align256(chunk * stem_img) + i * align256(chunk * l1_img);
+    MPX_REQUIRE(align256(chunk * stem_img) + 3 * align256(chunk * l1_img) <= stem_bytes, "net: chunk temporaries do not fit");
+    TrunkState st{1, hp, wp, 64};
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+      const int nc = n - c0 < chunk ? n - c0 : chunk;
+      ConvDesc d{nc, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, 1};
+      rc = stem_and_pool(d, reinterpret_cast<const uint8_t*>(x) + c0 * in_img, net->conv_w[0], net->conv_b[0], c_stem, c_bufs[0],
+                         stream);
+      if (rc != MPX_OK) return rc;
+      st = TrunkState{1, hp, wp, 64};
+      rc = run_layers(net, nc, 0, 1, c_bufs, 0, st, reinterpret_cast<uint8_t*>(bufs[0]) + c0 * l1_img, 0, stream, &res);
+      if (rc != MPX_OK) return rc;
+    }
+    rc = run_layers(net, n, 1, 4, bufs, 0, st, nullptr, sk, stream, &res);
+    if (rc != MPX_OK) return rc;
+    return avgpool_linear(res, n, st.H * st.W, st.C, net->head_w, net->head_b, net->out_dim, out, stream);
+  }
   // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input
   {
     ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, 1};
-    rc = conv_forward(d, x, net->conv_w[ci], net->conv_b[ci], nullptr, buf_stem, 0, 0, stream);
+    rc = stem_and_pool(d, x, net->conv_w[ci], net->conv_b[ci], buf_stem, bufs[0], stream);
     if (rc != MPX_OK) return rc;
     ++ci;
   }
-  rc = maxpool3x3s2(buf_stem, n, hs, ws, 64, bufs[0], stream);
-  if (rc != MPX_OK) return rc;
 
-  int cur = 0;  // index of the buffer holding the block input
-  int H = hp, W = wp, C = 64;
-  for (int layer = 0; layer < 4; ++layer) {
-    const int width = kLayerWidth[layer];
-    for (int blk = 0; blk < kLayerBlocks[layer]; ++blk) {
-      const int stride = (blk == 0 && layer > 0) ? 2 : 1;
-      const bool has_ds = (blk == 0 && layer > 0);
-      const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
-      const int Ho = conv_out_dim(H, 1, 1, 3, stride), Wo = conv_out_dim(W, 1, 1, 3, stride);
-      // conv1 + bn1 + relu
-      ConvDesc d1{n, H, W, C, width, 3, 3, stride, 1, 1, 1, 1, 1};
-      rc = conv_forward(d1, bufs[cur], net->conv_w[ci], net->conv_b[ci], nullptr, bufs[t1], 0, 0, stream, sk);
-      if (rc != MPX_OK) return rc;
-      const int c1 = ci;
-      (void)c1;
-      ++ci;
-      const void* residual = bufs[cur];
-      int out_buf = t2;
-      if (has_ds) {
-        // downsample: 1x1/s2 conv + bn (no relu) -> residual; conv_w order: conv1, conv2, downsample
-        ConvDesc dd{n, H, W, C, width, 1, 1, stride, 0, 0, 0, 0, 0};
-        rc = conv_forward(dd, bufs[cur], net->conv_w[ci + 1], net->conv_b[ci + 1], nullptr, bufs[t2], 0, 0,
-                          stream, sk);
-        if (rc != MPX_OK) return rc;
-        residual = bufs[t2];
-        out_buf = cur;  // block input is dead once conv1 and the downsample have consumed it
-      }
-      // conv2 + bn2 + residual + relu
-      ConvDesc d2{n, Ho, Wo, width, width, 3, 3, 1, 1, 1, 1, 1, 1};
-      rc = conv_forward(d2, bufs[t1], net->conv_w[ci], net->conv_b[ci], residual, bufs[out_buf], 0, 0,
-                        stream, sk);
-      if (rc != MPX_OK) return rc;
-      ci += has_ds ? 2 : 1;
-      cur = out_buf;
-      H = Ho;
-      W = Wo;
-      C = width;
-    }
-  }
-  return avgpool_linear(bufs[cur], n, H * W, C, net->head_w, net->head_b, net->out_dim, out, stream);
+  TrunkState st{ci, hp, wp, 64};
+  rc = run_layers(net, n, 0, 4, bufs, 0, st, nullptr, sk, stream, &res);
+  if (rc != MPX_OK) return rc;
+  return avgpool_linear(res, n, st.H * st.W, st.C, net->head_w, net->head_b, net->out_dim, out, stream);
 }
 
 }  // namespace mpx
