@@ -228,7 +228,7 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                            void* d_out, int block_n, int splits, void* stream);
 
-/* kernel selection bits for block_n == 0 (auto), default 49163 = 1 + 2 + 8 + 16384 + 32768:
+/* kernel selection bits for block_n == 0 (auto), default 2146315 = 1 + 2 + 8 + 16384 + 32768 + 2097152:
  *   1   window kernels: 64->64 stride-1 convolutions (stem, layer1) and 128->128 3x3 (layer2) load their activations
  *       once per tile as a contiguous window and address the filter taps as row-shifted operand descriptors
  *   2   the CTA-pair (cta_group::2) kernel serves 256-wide tiles;  4  and 128-wide tiles
@@ -243,6 +243,11 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
  *   131072 do not skip the structurally zero K slices of the space-to-depth stem weights (diagnostic)
  *   262144 / 524288 cap the automatic small-batch K split (bit 8) at 2 / 1 CTAs per tile: less SM time per layer at a higher
  *       latency (set before graphs are captured; the trade for two frames in flight, frame_pipeline.py)
+ *   1048576 row-per-thread epilogue in the 64 -> 64 pair window kernel (round-1 form; default: staged, coalesced)
+ *   2097152 mpx_net_forward lets the stem's pair window kernel max-pool in its epilogue (mpx_conv2d relu bit 2): the
+ *       full-resolution stem output is never stored; network forward at batch 576: 6.51 -> 6.14 ms
+ *   4194304 late PDL trigger: a kernel of a chain releases its successor only once its own griddepcontrol.wait has returned,
+ *       so at most one successor is parked on the SMs (default: trigger in the prologue; A/B in DESIGN section 3.3)
  * (r02 A/B, profiles/r02_layer_table_mode_bits.json; the other round-1 candidates -- pair-window kernels for layer3/4 and
  * 128-wide layer2 tiles, residual preload -- measured no gain and were removed.)
  * 0 = single-CTA TMA-im2col kernel only */
@@ -286,11 +291,6 @@ int mpx_net_destroy(mpx_net* net);
 /* mpx_net_forward replays a cached CUDA graph per (buffers, shape) after the first call; 0 disables that
  * (every launch is then issued eagerly on the caller's stream). Default: enabled. */
 int mpx_net_set_graphs(int on);
-/* Chunked front of the network: for batches of at least 2 * images the stem, the max-pool and layer1 run `images` samples
- * at a time so that their tensors stay inside the L2 from one layer to the next (the reference only ever chunks whole forwards,
- * bsz_images in inference/pose_estimator.py:139-141); layers 2-4 run on the whole batch.  Same kernels and per-element
- * arithmetic: outputs are bit-identical.  0 = off.  Process-wide; recorded by graphs captured afterwards. */
-int mpx_net_set_chunk(int images);
 size_t mpx_net_workspace_bytes(const mpx_net* net, int n, int h, int w);
 /* d_x: network input tensor (see above) for n samples of size h x w; d_out [n, out_dim] fp32 */
 int mpx_net_forward(const mpx_net* net, const void* d_x, int n, int h, int w, float* d_out,

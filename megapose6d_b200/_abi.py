@@ -69,7 +69,6 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mpx_net_workspace_bytes.restype = c_size_t
     lib.mpx_net_forward.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]
     lib.mpx_launch_count.restype = ctypes.c_longlong
-    lib.mpx_net_set_chunk.argtypes = [c_int]
     lib.mpx_profile_enable.argtypes = [c_int]
     lib.mpx_set_sm_limit.argtypes = [c_int]
     lib.mpx_profile_summary.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double),
@@ -79,8 +78,6 @@ def _declare(lib: ctypes.CDLL) -> None:
     # diagnostic overrides of the kernel-selection bits (see include/mpx.h)
     if os.environ.get("MPX_CONV_MODE"):
         lib.mpx_conv_set_mode(int(os.environ["MPX_CONV_MODE"]))
-    if os.environ.get("MPX_NET_CHUNK"):
-        lib.mpx_net_set_chunk(int(os.environ["MPX_NET_CHUNK"]))
     if os.environ.get("MPX_RASTER_MODE"):
         lib.mpx_raster_set_mode(int(os.environ["MPX_RASTER_MODE"]))
 
@@ -92,7 +89,7 @@ EXPORTS = [
     "mpx_pose_init_autodepth", "mpx_normalize_T", "mpx_crop_geometry", "mpx_multiview_cameras",
     "mpx_pose_update", "mpx_topk_per_group", "mpx_image_to_nhwc4", "mpx_roi_align", "mpx_roi_align_fused",
     "mpx_net_input_bytes", "mpx_conv2d", "mpx_conv2d_splitk", "mpx_conv_set_mode", "mpx_debug_umma_rowshift", "mpx_debug_mma_probe", "mpx_maxpool3x3s2", "mpx_avgpool_linear",
-    "mpx_net_create", "mpx_net_create_preact", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_set_chunk", "mpx_net_workspace_bytes", "mpx_net_forward",
+    "mpx_net_create", "mpx_net_create_preact", "mpx_net_destroy", "mpx_net_set_graphs", "mpx_net_workspace_bytes", "mpx_net_forward",
 ]
 
 

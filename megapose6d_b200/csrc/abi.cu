@@ -412,11 +412,6 @@ int mpx_net_create_preact(int c_pad, int out_dim, const int32_t* h_layer_blocks,
   return MPX_OK;
 }
 
-int mpx_net_set_chunk(int images) {
-  net_set_chunk(images);
-  return MPX_OK;
-}
-
 int mpx_conv_set_mode(int mode) {
   conv_set_mode(mode);
   return MPX_OK;

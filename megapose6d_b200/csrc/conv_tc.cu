@@ -1246,7 +1246,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // bit 0: shared-memory window kernel for the 64 -> 64 stride-1 layers; bit 1: CTA-pair (cta_group::2) kernel for
 // C_out >= 128; 0 = single-CTA im2col kernel everywhere
-static int g_conv_mode = 49163;  // 11 + CTA-pair window kernels for layer2 (16384) and stem / layer1 (32768)
+static int g_conv_mode = 2146315;  // 11 + CTA-pair window kernels for layer2 (16384) and stem / layer1 (32768) + max-pool in the stem's epilogue (2097152)
 static int conv_mode() { return g_conv_mode; }
 int conv_get_mode() { return g_conv_mode; }
 void conv_set_mode(int mode) { g_conv_mode = mode; }

@@ -181,8 +181,6 @@ extern long long g_launches;  // kernels launched by this library (host-side cou
 void conv_profile_enable(int on);
 bool conv_profile_enabled();
 void net_set_graphs(int on);
-void net_set_chunk(int images);
-int net_get_chunk();
 void conv_set_mode(int mode);
 int conv_get_mode();
 int conv_profile_summary(double* total_ms, double* total_flops, long long* launches);

@@ -427,14 +427,13 @@ static int net_forward_preact(const Net* net, const void* x, int n, int h, int w
 }
 
 // Blocks of layers [layer_from, layer_to) of the post-activation ResNet on `n` images: bufs[cur] holds the input, the
-// three buffers rotate as in the reference's BasicBlock (conv1 -> t1; downsample -> t2; conv2 + residual -> out).  When
-// `final_dst` is given the LAST block writes its output there instead (the chunked schedule scatters chunk results into the
-// full-batch tensor).  Returns the buffer holding the result through *result.
+// three buffers rotate as in the reference's BasicBlock (conv1 -> t1; downsample -> t2; conv2 + residual -> out).  Returns the
+// buffer holding the result through *result.
 struct TrunkState {
   int ci, H, W, C;
 };
 static int run_layers(const Net* net, int n, int layer_from, int layer_to, void* const bufs[3], int cur, TrunkState& st,
-                      void* final_dst, int sk, cudaStream_t stream, void** result) {
+                      int sk, cudaStream_t stream, void** result) {
   int rc;
   void* cur_ptr = bufs[cur];
   for (int layer = layer_from; layer < layer_to; ++layer) {
@@ -442,7 +441,6 @@ static int run_layers(const Net* net, int n, int layer_from, int layer_to, void*
     for (int blk = 0; blk < kLayerBlocks[layer]; ++blk) {
       const int stride = (blk == 0 && layer > 0) ? 2 : 1;
       const bool has_ds = (blk == 0 && layer > 0);
-      const bool last = final_dst != nullptr && layer == layer_to - 1 && blk == kLayerBlocks[layer] - 1;
       const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
       const int Ho = conv_out_dim(st.H, 1, 1, 3, stride), Wo = conv_out_dim(st.W, 1, 1, 3, stride);
       // conv1 + bn1 + relu
@@ -462,7 +460,7 @@ static int run_layers(const Net* net, int n, int layer_from, int layer_to, void*
       }
       // conv2 + bn2 + residual + relu
       ConvDesc d2{n, Ho, Wo, width, width, 3, 3, 1, 1, 1, 1, 1, 1};
-      cur_ptr = last ? final_dst : bufs[out_buf];
+      cur_ptr = bufs[out_buf];
       rc = conv_forward(d2, bufs[t1], net->conv_w[st.ci], net->conv_b[st.ci], residual, cur_ptr, 0, 0, stream, sk);
       if (rc != MPX_OK) return rc;
       st.ci += has_ds ? 2 : 1;
@@ -475,16 +473,6 @@ static int run_layers(const Net* net, int n, int layer_from, int layer_to, void*
   *result = cur_ptr;
   return MPX_OK;
 }
-
-// Chunked front of the network (mpx_net_set_chunk): at batch 576 every tensor of the stem / layer1 is 0.35 - 1.4 GB, so each
-// of those layers streams its input from and its output to HBM and they run at the HBM roofline, not the tensor pipe's.
-// Taken `chunk` images at a time the same seven kernels keep their tensors (0.6 MB per image and layer) inside the 126 MB L2
-// from one layer to the next; only the network input and layer1's final output touch HBM.  Same kernels, same per-element
-// arithmetic: bit-identical outputs.  Layers 2-4 (tensor-bound, and coarser tiles that quantise badly on small batches) run
-// on the whole batch as before.
-static int g_net_chunk = 0;
-void net_set_chunk(int images) { g_net_chunk = images < 0 ? 0 : images; }
-int net_get_chunk() { return g_net_chunk; }
 
 static int net_forward_direct(const Net* net, const void* x, int n, int h, int w, float* out, void* workspace,
                               size_t workspace_bytes, cudaStream_t stream) {
@@ -506,32 +494,6 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   int ci = 0;
   int rc;
   void* res = nullptr;
-  const int chunk = g_net_chunk;
-  if (chunk > 0 && n >= 2 * chunk) {
-    // stem + max-pool + layer1, `chunk` images at a time; the chunk's temporaries live in the (otherwise unused) full-batch
-    // stem buffer, layer1's result goes straight to its place in bufs[0]
-    const size_t in_img = static_cast<size_t>(hs) * ws * 4 * net->c_pad * 2;
-    const size_t stem_img = static_cast<size_t>(hs) * ws * 64 * 2, l1_img = static_cast<size_t>(hp) * wp * 64 * 2;
-    uint8_t* tmp = base;
-    void* c_stem = tmp;
-    void* c_bufs[3];
-    for (int i = 0; i < 3; ++i) c_bufs[i] = tmp + align256(chunk * stem_img) + i * align256(chunk * l1_img);
-    MPX_REQUIRE(align256(chunk * stem_img) + 3 * align256(chunk * l1_img) <= stem_bytes, "net: chunk temporaries do not fit");
-    TrunkState st{1, hp, wp, 64};
-    for (int c0 = 0; c0 < n; c0 += chunk) {
-      const int nc = n - c0 < chunk ? n - c0 : chunk;
-      ConvDesc d{nc, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, 1};
-      rc = stem_and_pool(d, reinterpret_cast<const uint8_t*>(x) + c0 * in_img, net->conv_w[0], net->conv_b[0], c_stem, c_bufs[0],
-                         stream);
-      if (rc != MPX_OK) return rc;
-      st = TrunkState{1, hp, wp, 64};
-      rc = run_layers(net, nc, 0, 1, c_bufs, 0, st, reinterpret_cast<uint8_t*>(bufs[0]) + c0 * l1_img, 0, stream, &res);
-      if (rc != MPX_OK) return rc;
-    }
-    rc = run_layers(net, n, 1, 4, bufs, 0, st, nullptr, sk, stream, &res);
-    if (rc != MPX_OK) return rc;
-    return avgpool_linear(res, n, st.H * st.W, st.C, net->head_w, net->head_b, net->out_dim, out, stream);
-  }
   // stem: 7x7/s2/p3 conv expressed as 4x4/s1 (pad 2 low, 1 high) over the space-to-depth input
   {
     ConvDesc d{n, hs, ws, 4 * net->c_pad, 64, 4, 4, 1, 2, 2, 1, 1, 1, 1};
@@ -541,7 +503,7 @@ static int net_forward_direct(const Net* net, const void* x, int n, int h, int w
   }
 
   TrunkState st{ci, hp, wp, 64};
-  rc = run_layers(net, n, 0, 4, bufs, 0, st, nullptr, sk, stream, &res);
+  rc = run_layers(net, n, 0, 4, bufs, 0, st, sk, stream, &res);
   if (rc != MPX_OK) return rc;
   return avgpool_linear(res, n, st.H * st.W, st.C, net->head_w, net->head_b, net->out_dim, out, stream);
 }

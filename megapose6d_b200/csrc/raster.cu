@@ -12,8 +12,9 @@
 //   * vertices snapped to 1/256 pixel; coverage by exact 64-bit integer edge functions, edges
 //     inclusive, two-sided; the fragment with the largest interpolated 1/z wins, ties go to the lower
 //     triangle index;
-//   * triangles with a vertex in front of the near plane (z < 0.1) are dropped; fragments with 1/z
-//     outside [1/10, 1/0.1] are rejected;
+//   * fragments with 1/z outside [1/10, 1/0.1] are rejected: 1/z is linear in screen space, so this per-sample test clips
+//     every triangle exactly at the lens' near and far planes (types.py:63-64); only triangles with a vertex within 2^-10 m
+//     of the eye plane or behind it (no projection) are dropped;
 //   * barycentrics l_k = w_k * (1/area) from the integer edge values, 1/z interpolated linearly in
 //     screen space, attributes perspective-correctly (b_k = l_k/z_k * z);
 //   * rgb = interpolated vertex albedo (ambient light 1.0); normals = frac-wrapped eye normal
@@ -34,7 +35,7 @@
 
 namespace mpx {
 
-constexpr float kNear = 0.1f;
+constexpr float kProjMin = 0.0009765625f;  // 2^-10 m: nearer to the eye plane (or behind it) = not projectable; the near PLANE is the per-sample kIzMax test
 constexpr float kIzMax = 10.0f;  // 1 / near
 constexpr float kIzMin = 0.1f;   // 1 / far
 constexpr int kSubBits = 8;
@@ -141,7 +142,7 @@ struct TriSetup {
   bool ok;
 };
 
-// camera transform, projection and 1/256-pixel snapping of one model vertex: {X, Y, 1/z bits, behind-near-plane}
+// camera transform, projection and 1/256-pixel snapping of one model vertex: {X, Y, 1/z bits, not projectable}
 __device__ __forceinline__ int4 snap_vertex(const float* __restrict__ p, const float* sR, float fx, float cx, float fy,
                                             float cy) {
   const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
@@ -149,7 +150,7 @@ __device__ __forceinline__ int4 snap_vertex(const float* __restrict__ p, const f
   const float yc = __fmaf_rn(sR[4], px, __fmaf_rn(sR[5], py, __fmaf_rn(sR[6], pz, sR[7])));
   const float zc = __fmaf_rn(sR[8], px, __fmaf_rn(sR[9], py, __fmaf_rn(sR[10], pz, sR[11])));
   int4 o;
-  o.w = !(zc >= kNear);
+  o.w = !(zc >= kProjMin);
   const float zs = o.w ? 1.0f : zc;
   const float iz = __frcp_rn(zs);
   float u = __fmaf_rn(fx, __fmul_rn(xc, iz), cx);

@@ -19,8 +19,10 @@
  *   - pixel (i, j) sampled at (u, v) = (j + 0.5, i + 0.5), u = fx X/Z + cx, v = fy Y/Z + cy
  *   - vertices snapped to 1/256 pixel, exact integer edge functions, inclusive edges, two-sided
  *   - barycentrics l_k = w_k * (1/area); the fragment with the largest interpolated 1/z wins, ties -> lower
- *     triangle index; fragments with 1/z outside [1/10, 1/0.1] rejected; triangles with a vertex at z < 0.1
- *     are dropped (no near-plane clipping)
+ *     triangle index; fragments with 1/z outside [1/10, 1/0.1] rejected -- 1/z is linear in screen space, so this per-sample
+ *     test IS the clip against the near (z = 0.1) and far (z = 10) planes of the reference's lens (types.py:63-64, :77-80):
+ *     a triangle that straddles the near plane keeps exactly its part beyond it.  Only a triangle with a vertex within
+ *     2^-10 m (1 mm) of the eye plane, or behind it, has no projection and is dropped (the eye inside the surface)
  *   - 1/z linear in screen space, attributes perspective-correct (b_k = l_k/z_k * z, z = 1/(1/z))
  *   - single sample per pixel (the reference's 4x MSAA is not modelled)
  *   - textured meshes (panda3d_scene_renderer.py:195-208 loads the model with its material / texture): per-vertex
@@ -40,6 +42,7 @@
 #include <string.h>
 
 #define K_NEAR 0.1f
+#define K_PROJ_MIN 0.0009765625f /* 2^-10 m: vertices nearer to the eye plane than this (or behind it) cannot be projected */
 #define K_IZ_MAX 10.0f /* 1 / near */
 #define K_IZ_MIN 0.1f  /* 1 / far */
 #define K_SUB 256
@@ -194,7 +197,7 @@ static int render_view(const float* verts, const float* normals, const float* co
     const float yc = fmaf(R[4], px, fmaf(R[5], py, fmaf(R[6], pz, R[7])));
     const float zc = fmaf(R[8], px, fmaf(R[9], py, fmaf(R[10], pz, R[11])));
     vtx_t o;
-    o.behind = !(zc >= K_NEAR);
+    o.behind = !(zc >= K_PROJ_MIN);
     const float zs = o.behind ? 1.0f : zc;
     const float iz = 1.0f / zs;
     float u = fmaf(fx, xc * iz, cx);

@@ -164,6 +164,8 @@ def test_raster_big_batch_bit_exact_vs_oracle(scene, big_batch_mode):
     TCO[3, 2, 3] = 0.12
     TCO[4, 0, 3] = 0.35
     TCO[7, 1, 1] = float("nan")
+    TCO[9, 2, 3] = 0.06   # straddles the near plane: clipped per sample, screen-filling triangles
+    TCO[11, 2, 3] = 0.02  # the eye inside the mesh: vertices behind the eye plane (dropped), clamped projections
     Kc = torch.tensor([[1500.0, 0, 160], [0, 1500, 120], [0, 0, 1]]).repeat(n, 1, 1)
     Kc[5] = torch.tensor([[300.0, 0, 150.3], [0, 310, 118.9], [0, 0, 1]])
     out, ref = _render_both(ds, rm, labels, TCO, Kc, (240, 320))
@@ -190,8 +192,10 @@ def test_raster_bit_exact_vs_oracle(scene, raster_mode):
     n = 12
     labels = [ds[i % 3].label for i in range(n)]
     TCO = _poses(n, 21, z_range=(0.25, 0.9))
-    TCO[3, 2, 3] = 0.12   # very close: large triangles, near-plane drops
+    TCO[3, 2, 3] = 0.12   # very close: large triangles, samples clipped at the near plane
     TCO[4, 0, 3] = 0.35   # mostly outside the frustum
+    TCO[6, 2, 3] = 0.05   # straddles the near plane
+    TCO[8, 2, 3] = 0.015  # the eye inside the mesh
     Kc = torch.tensor([[1500.0, 0, 160], [0, 1500, 120], [0, 0, 1]]).repeat(n, 1, 1)
     Kc[5] = torch.tensor([[300.0, 0, 150.3], [0, 310, 118.9], [0, 0, 1]])
     out, ref = _render_both(ds, rm, labels, TCO, Kc, (240, 320))

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
 ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
 SINGLE_CTA_MODE = 11  # window | pair(256) | split-K, without the CTA-pair window kernels of bits 14 / 15
-DEFAULT_CONV_MODE = 49163  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15)
+DEFAULT_CONV_MODE = 2146315  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool (bit 21)
 
 
 def _conv_ref(x, w, bias, stride, pads, relu, residual):
@@ -482,7 +482,7 @@ def test_wide_resnet_engine_vs_oracle(backbone_str):
         assert ((got - fp32).abs() <= bound + 1e-4).all()
 
 
-FUSED_POOL_MODE = DEFAULT_CONV_MODE | 2097152  # bit 21: the stem's max-pool runs in the pair window kernel's epilogue
+SEPARATE_POOL_MODE = DEFAULT_CONV_MODE & ~2097152  # without bit 21: stem output stored, max-pool as its own kernel
 POOL_CASES = [
     # name, n, h, w, r, pads, max_ctas
     ("stem_4x4", 3, 120, 160, 4, (2, 2, 1, 1), 6),
@@ -523,7 +523,7 @@ def test_fused_maxpool_epilogue_equals_conv_then_maxpool(case):
 
 @pytest.mark.parametrize("cfg_name,n", [("coarse", 7), ("refiner", 1)])
 def test_network_with_fused_maxpool_equals_unfused(cfg_name, n):
-    """The whole forward with mode bit 21 (stem epilogue pools) against the default schedule (stem, then max-pool kernel):
+    """The whole forward with mode bit 21 (stem epilogue pools; the default) against the stem followed by the max-pool kernel:
     every later layer sees the same pooled tensor, so the outputs are identical."""
     cfg = dict(coarse=helpers.COARSE_CFG, refiner=helpers.REFINER_CFG)[cfg_name]
     sd = helpers.make_state_dict(cfg, seed=3)
@@ -531,7 +531,7 @@ def test_network_with_fused_maxpool_equals_unfused(cfg_name, n):
     x = helpers._calibration_batch(c, 42, n=n).cuda()
     outs = []
     try:
-        for mode in (DEFAULT_CONV_MODE, FUSED_POOL_MODE, FUSED_POOL_MODE):
+        for mode in (SEPARATE_POOL_MODE, DEFAULT_CONV_MODE, DEFAULT_CONV_MODE):
             _abi.lib().mpx_conv_set_mode(mode)
             eng = ResNet34Engine(sd, n_inputs=c, head=resnet_ref.head_name(sd))
             outs.append(eng(x).clone())  # first sight of a shape runs eagerly
@@ -540,31 +540,5 @@ def test_network_with_fused_maxpool_equals_unfused(cfg_name, n):
             torch.cuda.synchronize()
     finally:
         _abi.lib().mpx_conv_set_mode(DEFAULT_CONV_MODE)
-    for o in outs[1:]:
-        assert torch.equal(outs[0], o)
-
-
-@pytest.mark.parametrize("chunk,n", [(2, 7), (3, 6)])
-def test_chunked_front_of_the_network_is_bit_identical(chunk, n):
-    """mpx_net_set_chunk: stem + max-pool + layer1 run `chunk` images at a time (L2-resident tensors), layers 2-4 on the
-    whole batch.  Same kernels, same per-element arithmetic: identical outputs, ragged last chunk included, with and
-    without the fused max-pool epilogue, eager and replayed."""
-    cfg = helpers.COARSE_CFG
-    sd = helpers.make_state_dict(cfg, seed=4)
-    c = helpers.n_inputs(cfg)
-    x = helpers._calibration_batch(c, 43, n=n).cuda()
-    lib = _abi.lib()
-    outs = []
-    try:
-        for mode, ch in ((DEFAULT_CONV_MODE, 0), (DEFAULT_CONV_MODE, chunk), (FUSED_POOL_MODE, chunk)):
-            lib.mpx_conv_set_mode(mode)
-            lib.mpx_net_set_chunk(ch)
-            eng = ResNet34Engine(sd, n_inputs=c, head=resnet_ref.head_name(sd))
-            for _ in range(3):
-                outs.append(eng(x).clone())
-            torch.cuda.synchronize()
-    finally:
-        lib.mpx_conv_set_mode(DEFAULT_CONV_MODE)
-        lib.mpx_net_set_chunk(0)
     for o in outs[1:]:
         assert torch.equal(outs[0], o)

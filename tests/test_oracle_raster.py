@@ -155,3 +155,25 @@ def test_oracle_msaa4_is_the_mean_of_four_offset_renders():
     # on the silhouette the pixel is a blend with the black background
     rim = inside & ~core
     assert (aa["rgbs"][0].sum(0)[rim] < one["rgbs"][0].sum(0)[rim] - 1e-3).float().mean() > 0.2
+
+
+def test_near_plane_clips_per_sample_instead_of_dropping_triangles():
+    """A long quad receding from z = 0.04 to z = 0.5 crosses the lens' near plane (z = 0.1, types.py:63-64).  Its triangles
+    are kept and every sample nearer than the plane is rejected: depth is > 0 exactly where the surface lies beyond 0.1 m.
+    A triangle with a vertex behind the eye plane has no projection and is dropped."""
+    v = np.array([[-.03, .02, 0.04], [.03, .02, 0.04], [.03, -.25, 0.5], [-.03, -.25, 0.5]])
+    f = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    mesh = TriMesh(v, f, compute_vertex_normals(v, f), np.tile([0.2, 0.6, 1.0], (4, 1)))
+    rm = helpers.ref_meshes_from_dataset(RigidObjectDataset([RigidObject("q", mesh=mesh)]))
+    T = torch.eye(4).unsqueeze(0)
+    K = torch.tensor([[[300.0, 0, 160], [0, 300, 200], [0, 0, 1]]])
+    out = pipeline_ref.RefRenderer(rm).render(["q"], T, K, None, (240, 320), render_depth=True, render_normals=True)
+    d = out["depths"][0, 0]
+    assert (d > 0).sum() > 500, "the part beyond the near plane must be rendered"
+    assert d[d > 0].min() >= 0.1 - 1e-6 and d[d > 0].min() < 0.103  # cut at the plane, not at a triangle boundary
+    assert d.max() <= 0.5 + 1e-6
+    # the same quad pushed so that two vertices lie behind the eye: nothing can be projected, nothing is drawn
+    T2 = T.clone()
+    T2[0, 2, 3] = -0.05
+    out2 = pipeline_ref.RefRenderer(rm).render(["q"], T2, K, None, (240, 320), render_depth=True, render_normals=True)
+    assert out2["depths"].abs().sum() == 0

@@ -60,19 +60,15 @@ def main():
     torch.cuda.synchronize()
     rec["equal"] = bool(torch.equal(pooled.float(), pooled2.float()))
     sd = W.make_state_dict(W.COARSE_CFG, 1)
-    chunks = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
-    for name, mode in (("default", 49163), ("fused_pool", 49163 | 2097152)):
-        for chunk in chunks:
-            lib.mpx_conv_set_mode(mode)
-            lib.mpx_net_set_chunk(chunk)
-            eng = ResNet34Engine(sd, n_inputs=9, head="views_logits_head")
-            x = eng.alloc_input(n, h, w)
-            x.copy_(torch.rand(x.shape, device="cuda").to(act))
-            rec[f"network_{name}_chunk{chunk}_ms"] = time_ms(lambda: eng.forward(x, h, w), iters=8)
-            del eng, x
-            torch.cuda.empty_cache()
-    lib.mpx_conv_set_mode(49163)
-    lib.mpx_net_set_chunk(0)
+    for name, mode in (("separate_pool", 49163), ("fused_pool", 49163 | 2097152)):
+        lib.mpx_conv_set_mode(mode)
+        eng = ResNet34Engine(sd, n_inputs=9, head="views_logits_head")
+        x = eng.alloc_input(n, h, w)
+        x.copy_(torch.rand(x.shape, device="cuda").to(act))
+        rec[f"network_{name}_ms"] = time_ms(lambda: eng.forward(x, h, w), iters=8)
+        del eng, x
+        torch.cuda.empty_cache()
+    lib.mpx_conv_set_mode(49163 | 2097152)
     print(json.dumps(rec))
 
 
