@@ -838,6 +838,8 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
                              void* out, int max_ctas, cudaStream_t stream);
 static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
                             void* out, int max_ctas, cudaStream_t stream);
+static int conv_windows_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
+                            void* out, int max_ctas, cudaStream_t stream);
 static int conv_mode();
 struct ConvParams;
 template <int BLOCK_N>
@@ -860,9 +862,15 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
               d.S);
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
-  if (d.pool)  // fused max-pool epilogue: only the CTA-pair window kernel has one; the caller falls back to conv + max-pool
-    return block_n_override == 0 ? conv_windowq_try(d, x, w, bias, residual, out, max_ctas, stream) : MPX_ERR_UNSUPPORTED;
+  if (d.pool) {  // fused max-pool epilogue: only the CTA-pair window kernels have one; the caller falls back to conv + max-pool
+    if (block_n_override != 0) return MPX_ERR_UNSUPPORTED;
+    rc = conv_windows_try(d, x, w, bias, residual, out, max_ctas, stream);
+    if (rc != MPX_ERR_UNSUPPORTED) return rc;
+    return conv_windowq_try(d, x, w, bias, residual, out, max_ctas, stream);
+  }
   if (block_n_override == 0) {  // auto: the window kernel serves the 64 -> 64 stride-1 layers
+    rc = conv_windows_try(d, x, w, bias, residual, out, max_ctas, stream);  // CTA pairs, sliding window (bit 23)
+    if (rc != MPX_ERR_UNSUPPORTED) return rc;
     rc = conv_windowq_try(d, x, w, bias, residual, out, max_ctas, stream);  // CTA pairs (bit 15, default)
     if (rc != MPX_ERR_UNSUPPORTED) return rc;
     rc = conv_window_try(d, x, w, bias, residual, out, max_ctas, stream);
@@ -2704,6 +2712,379 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
   ProfileSlot* slot = profile_begin(stream);
   MPX_CHECK_CUDA(launch_pdl(conv_windowq_kernel, dim3(2 * pairs), dim3(384), smem_bytes, stream, 2, map_a, map_b, p, stages,
                             n_taps));
+  MPX_CHECK_CUDA(cudaGetLastError());
+  ++g_launches;
+  profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 64.0 * n_taps * 64.0);
+  return MPX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mode bit 23 = 8388608: the 64 -> 64 pair window kernel with a SLIDING window.  conv_windowq_kernel reloads the whole
+// window -- 128 output rows + (R-1) * Wp + S - 1 halo rows: 620 rows (79 KB) for the stem, 294 (38 KB) for layer1 -- for every
+// tile because its tiles are dealt out round-robin; at the N = 64 tensor rate that is 37 B/clk/SM of L2 -> SM traffic for the
+// stem plus the stores: beyond the ~43 B/clk/SM the L2 sustains chip-wide (B300_MICROARCH.md: LTS throughput cap), which --
+// not HBM and not the tensor pipe -- is what bounded the stem and layer1.  Here every CTA owns a CONTIGUOUS run of T blocks
+// of 128 padded-linear output rows; the activations live in a ring of 16 KB chunks (128 rows each) and block i reads chunks
+// i .. i + ncw - 1, so that each block costs ONE new chunk (16 KB) instead of a window.  The ring is addressed linearly by
+// the operand descriptors: an operand of 128 rows that starts in the last slot runs on into a shadow copy of slot 0 kept
+// behind it (chunks destined for slot 0 are loaded twice: + 1/slots traffic).  The two MMA issuers still alternate blocks; a
+// chunk is last read by blocks i and i - 1 (one per issuer), so its empty barrier takes two arrivals -- block i's commit
+// arrives on the barriers of chunk i and chunk i + 1.  Everything else (half weight tiles per CTA, accumulator ring, staged /
+// pooled epilogue) is conv_windowq_kernel's.  Results are bit-identical to it (same MMAs in the same order per output row).
+// ---------------------------------------------------------------------------------------------
+constexpr int kWsChunkBytes = kBlockM * 128;  // 128 rows x 64 channels x 2 B = 16 KB
+constexpr int kWsChunkUnits = kWsChunkBytes / 16;
+
+__global__ void __launch_bounds__(384, 1)
+conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_r, const WinParams p, int slots, int ncw, int T, int n_taps) {
+  constexpr int kEpiSets = 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem;                                   // n_taps resident half weight tiles
+  uint8_t* smem_ring = smem + n_taps * kWinqBHalf;          // `slots` chunks + the shadow of slot 0
+  // staging: 8 epilogue warps x 4 KB -- or, with a residual, four 16 KB blocks that TMA fills with the residual rows of blocks
+  // i, i+1, i+2, i+3 (same 128B-swizzled layout as the staging tiles) and the epilogue then overwrites in place
+  uint8_t* smem_stg = smem_ring + static_cast<size_t>(slots + 1) * kWsChunkBytes;
+  const bool has_res = p.residual != nullptr;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + (has_res ? kWinAccBufs * kWsChunkBytes : 8 * kStageTileBytes));
+  uint64_t* full_bar = bars;             // [slots <= 8] leader
+  uint64_t* empty_bar = bars + 8;        // [slots]      per CTA, two arrivals
+  uint64_t* tmem_full = bars + 16;       // [4]          per CTA
+  uint64_t* tmem_empty = bars + 20;      // [4]          leader, eight arrivals
+  uint64_t* b_full = bars + 24;          // [1]          leader
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* res_full = bars + 26;        // [4]          per CTA: residual rows of block i landed in buffer i % 4
+  float* bias_s = reinterpret_cast<float*>(bars + 32);  // [64]
+  uint64_t* res_empty = bars + 64;       // [4]          per CTA, the four warps of the set that owned the buffer
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = blockIdx.x & 1u;
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  if (threadIdx.x < kWinN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < slots; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 2);
+    }
+    for (int i = 0; i < kWinAccBufs; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 4);
+    }
+    mbar_init(b_full, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(kWinAccBufs * kWinN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_trigger(p.pdl_late);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int hpwp = p.Hp * p.Wp;
+  const long long run_start = (2LL * pair + rank) * T;  // first block of this CTA's run
+  pdl_wait(p.pdl_late);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own chunks, own half of the weights) =====================
+    if (leader) mbar_expect_tx_u(b_full, 2u * static_cast<uint32_t>(n_taps) * kWinqBHalf);
+    else mbar_arrive_remote_u(b_full, 0);
+    for (int t = 0; t < n_taps; ++t)
+      tma2_load_2d_u(smem_b + t * kWinqBHalf, &map_b, b_full, t * kBlockK, static_cast<int>(rank) * (kWinN / 2));
+    mbar_arrive_u(&empty_bar[0]);  // stands in for "the block before block 0" (see the issuer's double commit)
+    const long long l_first = run_start * kBlockM;  // padded-linear input row of chunk 0
+    int img = static_cast<int>(l_first / hpwp);
+    int yp = static_cast<int>((l_first - static_cast<long long>(img) * hpwp) / p.Wp);
+    int xp = static_cast<int>(l_first - static_cast<long long>(img) * hpwp - static_cast<long long>(yp) * p.Wp);
+    int slot = 0;
+    uint32_t phase = 0;
+    const int n_chunks = T + ncw - 1;
+    for (int j = 0; j < n_chunks; ++j) {
+      mbar_wait(&empty_bar[slot], phase ^ 1u);
+      const uint32_t bytes = slot == 0 ? 2u * kWsChunkBytes : static_cast<uint32_t>(kWsChunkBytes);
+      if (leader) mbar_expect_tx_u(&full_bar[slot], 2u * bytes);
+      else mbar_arrive_remote_u(&full_bar[slot], 0);
+      tma2_load_im2col_4d_u(smem_ring + static_cast<size_t>(slot) * kWsChunkBytes, &map_a, &full_bar[slot], 0, xp - p.pl_w,
+                            yp - p.pl_h, img, 0, 0);
+      if (slot == 0)
+        tma2_load_im2col_4d_u(smem_ring + static_cast<size_t>(slots) * kWsChunkBytes, &map_a, &full_bar[slot], 0, xp - p.pl_w,
+                              yp - p.pl_h, img, 0, 0);
+      xp += kBlockM;
+      while (xp >= p.Wp) {
+        xp -= p.Wp;
+        if (++yp == p.Hp) {
+          yp = 0;
+          ++img;
+        }
+      }
+      if (++slot == slots) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (leader only), blocks alternately =====================
+    const int which = warp == 1 ? 0 : 1;
+    if (leader) {
+      const uint32_t idesc = p.idesc;
+      mbar_wait(b_full, 0);
+      const uint32_t ring_units = static_cast<uint32_t>(slots) * kWsChunkUnits;
+      const uint32_t row_units = static_cast<uint32_t>(p.Wp) * 8u;
+      const uint64_t ring_desc = make_sw128_desc(smem_u32(smem_ring));
+      const uint64_t b_base = make_sw128_desc(smem_u32(smem_b));
+      const int R = n_taps / p.S;
+      for (int i = which; i < T; i += 2) {
+        const int acc = i % kWinAccBufs;
+        const uint32_t acc_phase = (i / kWinAccBufs) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        for (int k = 0; k < ncw; ++k) {  // the chunks of this block (all but the newest were awaited for earlier blocks)
+          const int j = i + k;
+          mbar_wait(&full_bar[j % slots], static_cast<uint32_t>(j / slots) & 1u);
+        }
+        tc_fence_after();
+        const uint32_t tmem_d = static_cast<uint32_t>(acc * kWinN);
+        uint32_t first = 1;
+        uint64_t db = b_base;
+        uint32_t pr = static_cast<uint32_t>(i % slots) * kWsChunkUnits;  // ring position (16-byte units) of filter row r
+        int tap = 0;
+        for (int r = 0; r < R; ++r) {
+          uint32_t pt = pr;
+          for (int s = 0; s < p.S; ++s) {
+            const uint64_t da = desc_add_lo(ring_desc, pt);
+            const unsigned sk = static_cast<unsigned>(p.kskip >> (4 * tap)) & 15u;
+            if (sk == 0u) {
+              tc2_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
+              tc2_mma_f16_u(tmem_d, desc_add_lo(da, 2u), desc_add_lo(db, 2u), idesc, 1u);
+              tc2_mma_f16_u(tmem_d, desc_add_lo(da, 4u), desc_add_lo(db, 4u), idesc, 1u);
+              tc2_mma_f16_u(tmem_d, desc_add_lo(da, 6u), desc_add_lo(db, 6u), idesc, 1u);
+              first = 0;
+            } else {  // structurally zero weight slices of the space-to-depth stem: not issued
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if (((sk >> ks) & 1u) == 0u) {
+                  tc2_mma_f16_u(tmem_d, desc_add_lo(da, 2u * ks), desc_add_lo(db, 2u * ks), idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+            }
+            db = desc_add_lo(db, kWinqBHalf / 16);
+            pt += 8u;  // next tap: one pixel (128 B) further
+            if (pt >= ring_units) pt -= ring_units;
+            ++tap;
+          }
+          pr += row_units;  // next filter row: Wp pixels further
+          if (pr >= ring_units) pr -= ring_units;
+        }
+        tc2_commit_mc_u(&empty_bar[i % slots]);        // chunk i: last read by this block and by block i - 1
+        tc2_commit_mc_u(&empty_bar[(i + 1) % slots]);  // chunk i + 1: last read by block i + 1 and by this one
+        tc2_commit_mc_u(&tmem_full[acc]);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== residual producer (both CTAs): TMA, four blocks ahead of the epilogue =====================
+    // The residual pixel of output row q sits at padded-linear position q of the residual tensor seen through the same
+    // image + padding-ring box as the activations: 128 consecutive positions = the block's rows, ring positions zero-filled.
+    // (Loaded by the epilogue warps with LDG + STS, as conv_windowq_kernel does, the global latency sat in the epilogue's
+    // dependent chain: ncu tensor-pipe activity 47% with a residual against 71% without.)
+    if (has_res) {
+      const long long q_first = p.q_base + run_start * kBlockM;
+      int img = static_cast<int>(q_first / hpwp);
+      int yp = static_cast<int>((q_first - static_cast<long long>(img) * hpwp) / p.Wp);
+      int xp = static_cast<int>(q_first - static_cast<long long>(img) * hpwp - static_cast<long long>(yp) * p.Wp);
+      for (int i = 0; i < T; ++i) {
+        const int b = i % kWinAccBufs;
+        mbar_wait(&res_empty[b], ((static_cast<uint32_t>(i) / kWinAccBufs) & 1u) ^ 1u);
+        mbar_expect_tx_u(&res_full[b], static_cast<uint32_t>(kWsChunkBytes));
+        tma_load_im2col_4d_u(smem_stg + static_cast<size_t>(b) * kWsChunkBytes, &map_r, &res_full[b], 0, xp - p.pl_w, yp - p.pl_h,
+                             img, 0, 0);
+        xp += kBlockM;
+        while (xp >= p.Wp) {
+          xp -= p.Wp;
+          if (++yp == p.Hp) {
+            yp = 0;
+            ++img;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows), two warp sets, blocks round-robin =====================
+    if (tmem_base != 0u) __trap();
+    const int q4 = warp & 3;
+    const int set = (warp - 4) >> 2;
+    const int row = q4 * 32 + lane;
+    const unsigned hpwp_u = static_cast<unsigned>(hpwp), Wp_u = static_cast<unsigned>(p.Wp);
+    int pool_info = 0, pool_base = 0;
+    auto pix_of = [&](int i) -> int {
+      pool_info = 0;
+      const long long q = p.q_base + (run_start + i) * kBlockM + row;
+      if (q >= p.M_pad) return -1;
+      const unsigned qu = static_cast<unsigned>(q);
+      const unsigned img = qu / hpwp_u;
+      const unsigned rem = qu - img * hpwp_u;
+      const unsigned yp = rem / Wp_u, xp = rem - yp * Wp_u;
+      const int y = static_cast<int>(yp) - p.pl_h, x = static_cast<int>(xp) - p.pl_w;
+      if (y < 0 || y >= p.H || x < 0 || x >= p.W) return -1;
+      if (p.pool) {  // see conv_windowq_kernel
+        int j = x >> 1;
+        if ((x & 1) == 0) {
+          pool_info = 1 | ((x > 0 && lane > 0) ? 4 : 0) | ((x + 1 < p.W && lane < 31) ? 8 : 0);
+        } else if (lane == 0) {
+          pool_info = 2;
+        } else if (lane == 31 && x + 1 < p.W) {
+          pool_info = 2;
+          j += 1;
+        }
+        if ((y & 1) && (y >> 1) + 1 < p.pool_H) pool_info |= 16;
+        pool_base = (static_cast<int>(img) * p.pool_H + (y >> 1)) * p.pool_W + j;
+      }
+      return (static_cast<int>(img) * p.H + y) * p.W + x;
+    };
+    for (int i = set; i < T; i += kEpiSets) {
+      const int acc = i % kWinAccBufs;
+      const uint32_t acc_phase = (i / kWinAccBufs) & 1;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(acc * kWinN);
+      const uint32_t stg = smem_u32(smem_stg) + (has_res ? static_cast<uint32_t>(acc * kWsChunkBytes + q4 * kStageTileBytes)
+                                                         : static_cast<uint32_t>((warp - 4) * kStageTileBytes));
+      const int pix = pix_of(i);
+      if (has_res) mbar_wait(&res_full[acc], acc_phase);  // written through the async proxy, complete_tx on the barrier
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_compute64(taddr, stg, lane, has_res, smem_u32(bias_s), p.relu);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(&tmem_empty[acc], 0);
+      }
+      if (p.pool) pool_staged64(stg, lane, pool_info, pool_base, p.pool_W * kWinN, p.out);
+      else store_staged64(stg, lane, pix, p.out);
+      if (has_res) {  // the buffer goes back to the residual producer: generic-proxy writes before the next TMA write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&res_empty[acc]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kWinAccBufs * kWinN)
+                 : "memory");
+  }
+}
+
+// Returns MPX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit or the mode bit is off.
+static int conv_windows_try(const ConvDesc& d, const void* x, const void* w, const float* bias, const void* residual,
+                            void* out, int max_ctas, cudaStream_t stream) {
+  if ((g_conv_mode & 8388608) == 0 || (g_conv_mode & 32768) == 0 || (g_conv_mode & 1048576) != 0) return MPX_ERR_UNSUPPORTED;
+  if (d.stride != 1 || d.C_in != 64 || d.C_out != 64) return MPX_ERR_UNSUPPORTED;
+  if (d.R > 4 || d.S > 4 || d.R * d.S > 16) return MPX_ERR_UNSUPPORTED;
+  if (d.pool && (residual != nullptr || !d.relu)) return MPX_ERR_UNSUPPORTED;
+  const int P = conv_out_dim(d.H, d.pad_lo_h, d.pad_hi_h, d.R, 1), Q = conv_out_dim(d.W, d.pad_lo_w, d.pad_hi_w, d.S, 1);
+  if (P != d.H || Q != d.W) return MPX_ERR_UNSUPPORTED;
+  WinParams p{};
+  p.Hp = d.H + d.pad_lo_h + d.pad_hi_h;
+  p.Wp = d.W + d.pad_lo_w + d.pad_hi_w;
+  p.H = d.H;
+  p.W = d.W;
+  p.pl_h = d.pad_lo_h;
+  p.pl_w = d.pad_lo_w;
+  p.n_img = d.n_img;
+  p.S = d.S;
+  const int n_taps = d.R * d.S;
+  const int b_bytes = n_taps * kWinqBHalf;
+  const int halo = (d.R - 1) * p.Wp + (d.S - 1);
+  const int ncw = (kBlockM + halo + kBlockM - 1) / kBlockM;
+  if (ncw < 2) return MPX_ERR_UNSUPPORTED;  // no halo, nothing to slide; also: block j + slots - 1 must need chunk j + slots (the
+                                            // release of slot j's previous occupant orders the arrivals of consecutive phases)
+  const int smem_limit = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers, bias*/;
+  const int stg_bytes = residual != nullptr ? kWinAccBufs * kWsChunkBytes : 8 * kStageTileBytes;
+  int slots = (smem_limit - b_bytes - stg_bytes) / kWsChunkBytes - 1;
+  if (slots > 8) slots = 8;
+  if (slots < ncw + 1) return MPX_ERR_UNSUPPORTED;
+  if (p.Wp * 8 >= slots * kWsChunkUnits) return MPX_ERR_UNSUPPORTED;
+  p.M_pad = static_cast<long long>(d.n_img) * p.Hp * p.Wp;
+  p.q_base = static_cast<long long>(p.pl_h) * p.Wp + p.pl_w;
+  const long long blocks = (p.M_pad - p.q_base + kBlockM - 1) / kBlockM;
+  int cap = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
+  if (cap < 1) cap = 1;
+  const long long T_ll = (blocks + 2LL * cap - 1) / (2LL * cap);
+  if (T_ll < 8) return MPX_ERR_UNSUPPORTED;  // short runs reload most of their window anyway: conv_windowq_kernel
+  const int T = static_cast<int>(T_ll);
+  const int pairs = static_cast<int>((blocks + 2LL * T - 1) / (2LL * T));
+  if (p.M_pad + (2LL * pairs * T + ncw + 2) * kBlockM >= (1LL << 31)) return MPX_ERR_UNSUPPORTED;
+  p.m_tiles = static_cast<int>(blocks);
+  p.relu = d.relu;
+  p.idesc = (1u << 4) | kIdescAB | (static_cast<unsigned>(kWinN >> 3) << 17) | (static_cast<unsigned>(256 >> 4) << 24);
+  p.kskip = stem_kskip(d);
+  p.bias = bias;
+  p.residual = reinterpret_cast<const act_t*>(residual);
+  p.out = reinterpret_cast<act_t*>(out);
+  p.pool = d.pool ? 1 : 0;
+  p.pool_H = (d.H - 1) / 2 + 1;
+  p.pool_W = (d.W - 1) / 2 + 1;
+  p.pdl_late = pdl_late_mode();
+
+  int rc = load_driver_entry_points();
+  if (rc != MPX_OK) return rc;
+  CUtensorMap map_a, map_b, map_r;
+  for (int which = 0; which < 2; ++which) {  // activations; residual (same geometry: both are [n, H, W, 64])
+    CUtensorMap& m = which == 0 ? map_a : map_r;
+    const void* base = which == 0 ? x : (residual != nullptr ? residual : x);
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.n_img)};
+    cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(d.W) * 128, static_cast<cuuint64_t>(d.H) * d.W * 128};
+    int lower[2] = {-d.pad_lo_w, -d.pad_lo_h};
+    int upper[2] = {d.pad_hi_w, d.pad_hi_h};  // the base pixel walks the whole padded image
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_im2col(&m, kTmaActType, 4, const_cast<void*>(base), dims, strides, lower, upper, kBlockK,
+                                 static_cast<cuuint32_t>(kBlockM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MPX_ERR_UNSUPPORTED;
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    const size_t bytes = static_cast<size_t>(d.n_img) * d.H * d.W * 128;
+    if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  }
+  {
+    const cuuint64_t K_total = static_cast<cuuint64_t>(n_taps) * 64;
+    cuuint64_t dims[2] = {K_total, 64};
+    cuuint64_t strides[1] = {K_total * 2};
+    cuuint32_t box[2] = {kBlockK, kWinN / 2};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&map_b, kTmaActType, 2, const_cast<void*>(w), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  }
+  const int smem_bytes = 1024 + b_bytes + (slots + 1) * kWsChunkBytes + stg_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MPX_CHECK_CUDA(cudaFuncSetAttribute(conv_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  ProfileSlot* slot = profile_begin(stream);
+  MPX_CHECK_CUDA(launch_pdl(conv_windows_kernel, dim3(2 * pairs), dim3(384), smem_bytes, stream, 2, map_a, map_b, map_r, p, slots,
+                            ncw, T, n_taps));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 64.0 * n_taps * 64.0);

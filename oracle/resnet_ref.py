@@ -170,6 +170,12 @@ def forward_act16_emulated(sd: Dict[str, torch.Tensor], x: torch.Tensor,
         w, b = fold_bn(sd, conv, bn)
         return _q(w.float()).to(dev), b.float().to(dev)
 
+    if dev.type == "cuda" and torch.backends.cudnn.allow_tf32:
+        # fp32 means fp32: with cuDNN's default TF32 convolutions the "exact" side of this comparison carries 2^-11 relative
+        # errors of its own -- as large as the 16-bit roundings it emulates -- and which algorithm cuDNN picks (TF32 or not)
+        # depends on the process' memory state, which made the comparison flaky at the stated half-bound
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return forward_act16_emulated(sd, x, dtype)
     x = _q(x)
     w, b = cw("backbone.conv1", "backbone.bn1")
     x = _q(F.relu(F.conv2d(x, w, b, stride=2, padding=3)))
@@ -310,6 +316,9 @@ def pooled_features_wide(sd, x):
 
 def forward_wide_act16_emulated(sd, x, dtype: torch.dtype = torch.float16) -> torch.Tensor:
     """The engine's quantisation points for the pre-activation backbone (16-bit weights and stored tensors, fp32 math)."""
+    if x.device.type == "cuda" and torch.backends.cudnn.allow_tf32:  # see forward_act16_emulated
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return forward_wide_act16_emulated(sd, x, dtype)
     lim = float(torch.finfo(dtype).max)
 
     def q(t):

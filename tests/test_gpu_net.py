@@ -22,6 +22,7 @@ from tests import helpers
 pytestmark = pytest.mark.gpu
 ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
 ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
+SLIDING_MODE = 2146315 | 8388608  # bit 23: the 64 -> 64 pair window kernel with a sliding window (conv_windows_kernel)
 SINGLE_CTA_MODE = 11  # window | pair(256) | split-K, without the CTA-pair window kernels of bits 14 / 15
 DEFAULT_CONV_MODE = 2146315  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool (bit 21)
 
@@ -396,6 +397,9 @@ PAIR_WINDOW64_CASES = [
     ("odd_size_odd_tiles", 3, 17, 23, 3, (1, 1, 1, 1), False, True, 2),
     ("two_tiles_one_pair", 1, 12, 16, 3, (1, 1, 1, 1), True, False, 2),
     ("one_by_one_taps", 4, 20, 24, 1, (0, 0, 0, 0), False, False, 4),
+    ("layer1_all_sms", 40, 60, 80, 3, (1, 1, 1, 1), True, True, 0),
+    ("stem_all_sms", 12, 120, 160, 4, (2, 2, 1, 1), True, False, 0),
+    ("ragged_runs", 9, 33, 47, 3, (1, 1, 1, 1), True, True, 10),
 ]
 
 
@@ -411,7 +415,7 @@ def test_pair_window64_kernel(case):
     res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        for mode in (DEFAULT_CONV_MODE, SINGLE_CTA_MODE):
+        for mode in (DEFAULT_CONV_MODE, SLIDING_MODE, SINGLE_CTA_MODE):
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
@@ -427,6 +431,7 @@ def test_pair_window64_kernel(case):
         assert not torch.isnan(o).any()
         assert (o - ref).abs().max() <= tol
         assert (o - outs[-1]).abs().max() <= ULP * ref.abs().max().item()
+    assert torch.equal(outs[0], outs[1])  # sliding window: the same MMAs in the same order per output row
 
 
 @pytest.mark.parametrize("mode", [DEFAULT_CONV_MODE, SINGLE_CTA_MODE], ids=["cta_pairs", "single_cta"])
@@ -490,6 +495,7 @@ POOL_CASES = [
     ("odd_rows_odd_cols", 3, 17, 23, 3, (1, 1, 1, 1), 2),
     ("odd_rows", 2, 31, 40, 3, (1, 1, 1, 1), 4),
     ("two_tiles_one_pair", 1, 12, 16, 3, (1, 1, 1, 1), 2),
+    ("stem_all_sms", 10, 120, 160, 4, (2, 2, 1, 1), 0),
 ]
 
 
@@ -510,12 +516,17 @@ def test_fused_maxpool_epilogue_equals_conv_then_maxpool(case):
                               _abi.ptr(full), 0, max_ctas, _abi.stream_ptr()))
     want = torch.empty(n, ho, wo, 64, device="cuda", dtype=ACT)
     _abi.check(lib.mpx_maxpool3x3s2(_abi.ptr(full), n, h, w, 64, _abi.ptr(want), _abi.stream_ptr()))
-    got = torch.zeros(n, ho, wo, 64, device="cuda", dtype=ACT)
-    _abi.check(lib.mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r, 1, *pads, 1 | 4, None,
-                              _abi.ptr(got), 0, max_ctas, _abi.stream_ptr()))
-    torch.cuda.synchronize()
     assert not torch.isnan(want.float()).any()
-    assert torch.equal(got.float(), want.float())
+    try:
+        for mode in (DEFAULT_CONV_MODE, SLIDING_MODE):
+            lib.mpx_conv_set_mode(mode)
+            got = torch.zeros(n, ho, wo, 64, device="cuda", dtype=ACT)
+            _abi.check(lib.mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r, 1, *pads, 1 | 4,
+                                      None, _abi.ptr(got), 0, max_ctas, _abi.stream_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(got.float(), want.float()), mode
+    finally:
+        lib.mpx_conv_set_mode(DEFAULT_CONV_MODE)
     # shapes without the epilogue are refused without launching anything (the network then runs conv + max-pool)
     assert lib.mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r, 1, *pads, 4, None,
                           _abi.ptr(got), 0, max_ctas, _abi.stream_ptr()) == -3  # no ReLU
