@@ -563,7 +563,6 @@ struct ConvParams {
   // split-K: the `splits` (1, 2, 4 or 8) CTAs of a cluster share one output tile, each accumulating a contiguous
   // range of k-blocks; reduction through distributed shared memory (see SplitKTile)
   int splits;
-  int pdl_late;  // mode bit 22: trigger the dependent launch after this kernel's own wait (see pdl_wait(int))
 };
 
 constexpr int kBlockM = 128;
@@ -626,12 +625,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  pdl_trigger(p.pdl_late);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait(p.pdl_late);  // activations / residual of the previous kernel are complete from here on
+  pdl_wait();  // activations / residual of the previous kernel are complete from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -962,7 +961,6 @@ int conv_forward(const ConvDesc& d, const void* x, const void* w, const float* b
   p.residual = reinterpret_cast<const act_t*>(residual);
   p.out = reinterpret_cast<act_t*>(out);
   p.splits = 1;
-  p.pdl_late = pdl_late_mode();
   if (splitk != 0 && !use_pair) {
     // Few output tiles and a long K loop (deep layers at batch 1: one 80-row tile, 72 k-blocks): split K over a cluster.
     const int tiles = p.m_tiles * p.n_tiles;
@@ -1036,7 +1034,6 @@ struct WinParams {
   act_t* out;
   int pool;            // conv_windowq_kernel: 1 = `out` is the zero-initialised [n, pool_H, pool_W, 64] max-pooled tensor (3x3/s2/p1)
   int pool_H, pool_W;
-  int pdl_late;        // mode bit 22 (see pdl_wait(int))
 };
 
 constexpr int kWinN = 64;          // C_out
@@ -1254,7 +1251,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // bit 0: shared-memory window kernel for the 64 -> 64 stride-1 layers; bit 1: CTA-pair (cta_group::2) kernel for
 // C_out >= 128; 0 = single-CTA im2col kernel everywhere
-static int g_conv_mode = 2146315;  // 11 + CTA-pair window kernels for layer2 (16384) and stem / layer1 (32768) + max-pool in the stem's epilogue (2097152)
+static int g_conv_mode = 10534923;  // 11 + CTA-pair window kernels for layer2 (16384) and stem / layer1 (32768) + max-pool in the stem's epilogue
+                                    // (2097152) + sliding window / TMA residual in the 64 -> 64 pair kernel (8388608)
 static int conv_mode() { return g_conv_mode; }
 int conv_get_mode() { return g_conv_mode; }
 void conv_set_mode(int mode) { g_conv_mode = mode; }
@@ -2355,14 +2353,14 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  pdl_trigger(p.pdl_late);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int hpwp = p.Hp * p.Wp;
-  pdl_wait(p.pdl_late);
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own windows, own half of the weights) =====================
@@ -2667,7 +2665,6 @@ static int conv_windowq_try(const ConvDesc& d, const void* x, const void* w, con
   p.pool = d.pool ? 1 : 0;
   p.pool_H = (d.H - 1) / 2 + 1;
   p.pool_W = (d.W - 1) / 2 + 1;
-  p.pdl_late = pdl_late_mode();
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
@@ -2791,7 +2788,7 @@ conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  pdl_trigger(p.pdl_late);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -2799,7 +2796,7 @@ conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int hpwp = p.Hp * p.Wp;
   const long long run_start = (2LL * pair + rank) * T;  // first block of this CTA's run
-  pdl_wait(p.pdl_late);
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own chunks, own half of the weights) =====================
@@ -3042,7 +3039,6 @@ static int conv_windows_try(const ConvDesc& d, const void* x, const void* w, con
   p.pool = d.pool ? 1 : 0;
   p.pool_H = (d.H - 1) / 2 + 1;
   p.pool_W = (d.W - 1) / 2 + 1;
-  p.pdl_late = pdl_late_mode();
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;

@@ -136,17 +136,7 @@ __device__ __forceinline__ float depth_norm(float d, float z, int kind) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Late trigger (mpx_conv_set_mode bit 22 = 4194304).  Every kernel of a chain triggering in its first instructions lets the
-// chain CASCADE: kernel k+1 is resident (parked in pdl_wait) as soon as k's CTAs have started, k+2 as soon as k+1's have,
-// ... as deep as the launch front end gets ahead -- several kernels' worth of CTAs hold shared memory and TMEM while only one
-// of them works.  Alone on the device that is free; beside another frame's persistent kernels (frame_pipeline.py) those parked
-// CTAs are SMs the other stream cannot use.  With `late` a CTA triggers only once its own wait has returned (its predecessor
-// has finished): at most the running kernel and ONE parked successor exist per chain, and the successor's set-up still
-// overlaps the running kernel.
-__device__ __forceinline__ void pdl_trigger(int late) { if (!late) pdl_trigger(); }
-__device__ __forceinline__ void pdl_wait(int late) { pdl_wait(); if (late) pdl_trigger(); }
 int conv_get_mode();
-inline int pdl_late_mode() { return (conv_get_mode() >> 22) & 1; }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               int cluster_x, Args&&... args) {

@@ -16,9 +16,9 @@ namespace mpx {
 // one CTA per output row (img, oy): threads walk (ox, channel group) with 32-bit index math only -- the flat
 // grid-stride form spent most of its instructions on 64-bit div / mod of the element index
 __global__ void __launch_bounds__(512)
-maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int c8, int ho, int wo, int pdl_late) {
-  pdl_trigger(pdl_late);
-  pdl_wait(pdl_late);
+maxpool3x3s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int c8, int ho, int wo) {
+  pdl_trigger();
+  pdl_wait();
   const int row_items = wo * c8;
   for (int row = blockIdx.x; row < n * ho; row += gridDim.x) {
     const int img = row / ho, oy = row - img * ho;
@@ -74,7 +74,7 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
   const long long cap = static_cast<long long>(sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   MPX_CHECK_CUDA(launch_pdl(maxpool3x3s2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, 1,
-                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo, pdl_late_mode()));
+                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n, h, w, c / 8, ho, wo));
   ++g_launches;
   return MPX_OK;
 }
@@ -86,9 +86,9 @@ int maxpool3x3s2(const void* x, int n, int h, int w, int c, void* out, cudaStrea
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 affine_relu_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long n8, int c8,
-                   const float* __restrict__ scale_shift /* [2, C] */, int pdl_late) {
-  pdl_trigger(pdl_late);
-  pdl_wait(pdl_late);
+                   const float* __restrict__ scale_shift /* [2, C] */) {
+  pdl_trigger();
+  pdl_wait();
   const float* scale = scale_shift;
   const float* shift = scale_shift + 8 * c8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
@@ -116,7 +116,7 @@ static int affine_relu(const void* x, long long elems, int c, const float* scale
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   MPX_CHECK_CUDA(launch_pdl(affine_relu_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1,
-                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n8, c / 8, scale_shift, pdl_late_mode()));
+                            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), n8, c / 8, scale_shift));
   ++g_launches;
   return MPX_OK;
 }
@@ -131,12 +131,12 @@ static int affine_relu(const void* x, long long elems, int c, const float* scale
 constexpr int kPoolThreads = 512;
 __global__ void __launch_bounds__(kPoolThreads)
 avgpool_linear_kernel(const act_t* __restrict__ x, int hw, int c, const float* __restrict__ w,
-                      const float* __restrict__ b, int out_dim, float* __restrict__ out, int pdl_late) {
+                      const float* __restrict__ b, int out_dim, float* __restrict__ out) {
   extern __shared__ float smem_pool[];  // [G][c] partial sums, then [c] pooled
   const int img = blockIdx.x;
   const act_t* xi = x + static_cast<size_t>(img) * hw * c;
-  pdl_trigger(pdl_late);
-  pdl_wait(pdl_late);
+  pdl_trigger();
+  pdl_wait();
   const int nq = c >> 2;
   const int G = nq >= kPoolThreads ? 1 : kPoolThreads / nq;
   float* part = smem_pool;
@@ -183,7 +183,7 @@ int avgpool_linear(const void* x, int n, int hw, int c, const float* w, const fl
   const size_t smem = static_cast<size_t>(G + 1) * c * sizeof(float);
   MPX_REQUIRE(smem <= 48 * 1024, "avgpool_linear: C=%d needs %zu bytes of shared memory", c, smem);
   MPX_CHECK_CUDA(launch_pdl(avgpool_linear_kernel, dim3(n), dim3(kPoolThreads), smem, stream, 1,
-                            reinterpret_cast<const act_t*>(x), hw, c, w, b, out_dim, out, pdl_late_mode()));
+                            reinterpret_cast<const act_t*>(x), hw, c, w, b, out_dim, out));
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   return MPX_OK;

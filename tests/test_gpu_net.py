@@ -22,9 +22,10 @@ from tests import helpers
 pytestmark = pytest.mark.gpu
 ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
 ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
-SLIDING_MODE = 2146315 | 8388608  # bit 23: the 64 -> 64 pair window kernel with a sliding window (conv_windows_kernel)
 SINGLE_CTA_MODE = 11  # window | pair(256) | split-K, without the CTA-pair window kernels of bits 14 / 15
-DEFAULT_CONV_MODE = 2146315  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool (bit 21)
+DEFAULT_CONV_MODE = 10534923  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool
+# (bit 21) | sliding window in the 64 -> 64 pair kernel (bit 23)
+RELOAD_MODE = DEFAULT_CONV_MODE & ~8388608  # without bit 23: conv_windowq_kernel (whole window reloaded per tile) everywhere
 
 
 def _conv_ref(x, w, bias, stride, pads, relu, residual):
@@ -415,7 +416,7 @@ def test_pair_window64_kernel(case):
     res = torch.randn(n, h, w, 64, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        for mode in (DEFAULT_CONV_MODE, SLIDING_MODE, SINGLE_CTA_MODE):
+        for mode in (DEFAULT_CONV_MODE, RELOAD_MODE, SINGLE_CTA_MODE):
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, 64), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r,
@@ -518,7 +519,7 @@ def test_fused_maxpool_epilogue_equals_conv_then_maxpool(case):
     _abi.check(lib.mpx_maxpool3x3s2(_abi.ptr(full), n, h, w, 64, _abi.ptr(want), _abi.stream_ptr()))
     assert not torch.isnan(want.float()).any()
     try:
-        for mode in (DEFAULT_CONV_MODE, SLIDING_MODE):
+        for mode in (DEFAULT_CONV_MODE, RELOAD_MODE):
             lib.mpx_conv_set_mode(mode)
             got = torch.zeros(n, ho, wo, 64, device="cuda", dtype=ACT)
             _abi.check(lib.mpx_conv2d(_abi.ptr(x), n, h, w, 64, _abi.ptr(wt.view(64, -1)), _abi.ptr(bias), 64, r, r, 1, *pads, 1 | 4,
