@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--workload", default="rgb576", choices=["rgb576", "ycbv21"])
     ap.add_argument("--render-size", default="240x320")
     ap.add_argument("--frames-in-flight", type=int, default=2, help="1: one blocking run_inference_pipeline call per step")
+    ap.add_argument("--overlap-heads", action="store_true", help="A/B: do not gate a frame's coarse stage on its predecessor's")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="size the persistent grids for (SMs - N): SMs left to the "
+                                                                "latency-bound tail of the other frame in flight (-1: default)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="coarse hypotheses in one bounded CPU step")
     ap.add_argument("--no-full-unit", action="store_true", help="CPU arm: skip the one complete 576-hypothesis unit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -318,9 +321,13 @@ def run_mpx_arm(args):
     from megapose6d_b200.frame_pipeline import FramePipeline
 
     n_fif = max(1, args.frames_in_flight)
+    if args.reserve_sms >= 0:
+        from megapose6d_b200 import frame_pipeline as _fp
+
+        _fp.set_reserved_sms(args.reserve_sms)
     ests = [scenes.build_estimator(sc, sharder=HypothesisSharder(enabled=world > 1)) for _ in range(n_fif)]
     est = ests[0]
-    pipe = FramePipeline(None, estimators=ests) if n_fif > 1 else None
+    pipe = FramePipeline(None, estimators=ests, serialize_heads=not args.overlap_heads) if n_fif > 1 else None
     lib = _abi.lib()
     n_det = len(sc["labels"])
     h, w = sc["render_size"]

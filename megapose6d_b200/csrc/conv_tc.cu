@@ -2175,32 +2175,22 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int ti = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
     int local = 0;
-    // element offset of this lane's output row in tile `ti` of the CTA's super-tile of `item`, or -1 (ring / out of range)
-    auto row_off = [&](int item) -> long long {
-      const long long q = p.q_base + (2LL * item + rank) * 256 + ti * 128 + row;
-      if (q >= p.M_pad) return -1;
-      const int img = static_cast<int>(q / hpwp);
-      const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
-      const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-      const int y = yp - 1, x = xp - 1;
-      if (y < 0 || y >= p.H || x < 0 || x >= p.W) return -1;
-      return ((static_cast<long long>(img) * p.H + y) * p.W + x) * kW2N;
-    };
     for (int item = pair; item < n_items; item += n_pairs, ++local) {
       const int buf = (local & 1) * 2 + ti;
-      const long long off_ll = row_off(item);
-      const bool valid = off_ll >= 0;
-      const size_t off = valid ? static_cast<size_t>(off_ll) : 0;
+      const long long q = p.q_base + (2LL * item + rank) * 256 + ti * 128 + row;
+      bool valid = q < p.M_pad;
+      size_t off = 0;
+      if (valid) {
+        const int img = static_cast<int>(q / hpwp);
+        const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+        const int y = yp - 1, x = xp - 1;
+        valid = (y >= 0) && (y < p.H) && (x >= 0) && (x < p.W);
+        off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kW2N : 0;
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * kW2N);
       const act_t* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
-      if (p.residual && item + n_pairs < n_items) {  // the NEXT item's residual row (256 B) is pulled into L2 now: its loads sit
-        const long long off_n = row_off(item + n_pairs);  // in the dependent chain of that item's epilogue
-        if (off_n >= 0) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off_n));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off_n + 64));
-        }
-      }
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
       mbar_wait(&tmem_full[buf], static_cast<uint32_t>(local >> 1) & 1u);
       tc_fence_after();

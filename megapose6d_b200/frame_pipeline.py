@@ -8,10 +8,10 @@ after the other, so the tail of frame i and the head of frame i+1 never overlap.
 
 FramePipeline alternates frames over `n_slots` PoseEstimators, each with its own CUDA stream, graphs, workspaces and mesh
 database (nothing on the device is shared, so no two frames ever touch the same buffer), using
-PoseEstimator.submit_inference_pipeline: the tail of one frame runs beside the head of the next.  For the small launches to
-find a free SM while persistent kernels of the other stream are resident, the persistent grids are sized for fewer than all
-SMs (`reserve_sms`, mpx_set_sm_limit): the head gets slower by reserve/148, the tail disappears from the critical path.
-Results come back in submission order and are, frame for frame, bit-identical to run_inference_pipeline's (same kernels,
+PoseEstimator.submit_inference_pipeline: the tail of one frame runs beside the head of the next, the heads themselves are
+gated one behind the other (`serialize_heads`), and the host-side bookkeeping of a frame runs while the device works on
+the next.  `set_reserved_sms` sizes the persistent grids for fewer than all SMs (measurement aid: it did not pay off,
+DESIGN.md section 3.3).  Results come back in submission order and are, frame for frame, bit-identical to run_inference_pipeline's (same kernels,
 same launch order within a frame).
 
     pipe = FramePipeline(lambda: build_estimator(...), n_slots=2)
@@ -45,7 +45,8 @@ def set_reserved_sms(reserve: int) -> int:
 
 class FramePipeline:
     def __init__(self, make_estimator: Callable[[], "torch.nn.Module"], n_slots: int = 2,
-                 estimators: Optional[Sequence["torch.nn.Module"]] = None, device=None, tail_priority="high"):
+                 estimators: Optional[Sequence["torch.nn.Module"]] = None, device=None, tail_priority="high",
+                 serialize_heads: bool = True):
         """`make_estimator` is called once per slot (each call must build its own models and mesh database); or pass the
         estimators themselves (fresh ones: `tail_priority` -- PoseEstimator.set_tail_priority -- is recorded by the graphs
         they capture on their first frames)."""
@@ -62,6 +63,13 @@ class FramePipeline:
         prio = -1 if tail_priority == "low" else 0
         self.slots = [dict(est=e, stream=torch.cuda.Stream(device=self.device, priority=prio), pending=None) for e in ests]
         self._next = 0
+        # `serialize_heads`: frame i+1's coarse stage waits (on the device) for frame i's.  Without the gate the head of frame
+        # i+2 -- enqueued behind the short tail of frame i on the same stream -- starts in the middle of frame i+1's head:
+        # two sets of persistent, statically scheduled kernels then take SMs from each other at every kernel boundary and
+        # each finishes when its most delayed CTA does.  Gated, the heads run back to back and each overlaps only the
+        # latency-bound tail of its predecessor, which is what the pipeline is for.
+        self.serialize_heads = bool(serialize_heads)
+        self._last_head_done = None
 
     def __len__(self) -> int:
         return len(self.slots)
@@ -77,7 +85,10 @@ class FramePipeline:
         with torch.cuda.stream(slot["stream"]):
             # enqueued BEFORE the older frame of this slot is waited for: the stream orders the two on the device, and the
             # host-side bookkeeping of the older frame (a few ms of pandas) then runs while the device has work queued
+            if self.serialize_heads and self._last_head_done is not None and len(self.slots) > 1:
+                slot["est"].__dict__["_head_gate"] = self._last_head_done
             slot["pending"] = slot["est"].submit_inference_pipeline(observation, detections, **kwargs)
+            self._last_head_done = slot["est"].__dict__.pop("_head_done", None)
         return old.result() if old is not None else None
 
     def drain(self) -> List[Tuple]:

@@ -547,6 +547,9 @@ class PoseEstimator(torch.nn.Module):
         side = self.__dict__.get("_copy_stream")
         if side is None:
             side = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=device)
+        gate = self.__dict__.pop("_head_gate", None)
+        if gate is not None:  # FramePipeline: this frame's coarse stage starts when the previous frame's (another estimator's,
+            main.wait_event(gate)  # another stream's) has finished -- two throughput-bound heads never share the device
         # ---- coarse: B*M rows, row = detection * M + hypothesis
         rows_c = self._pipeline_rows(df, device)
         batch_im_ids, label_idx = rows_c["batch_im_ids"], rows_c["label_idx"]
@@ -558,6 +561,7 @@ class PoseEstimator(torch.nn.Module):
         pin_c = self._pinned("coarse", packed_c.numel())
         ev_c = torch.cuda.Event()
         ev_c.record(main)
+        self.__dict__["_head_done"] = ev_c  # the throughput-bound part of this frame is enqueued up to here
         with torch.cuda.stream(side):
             side.wait_event(ev_c)
             pin_c.copy_(packed_c, non_blocking=True)
