@@ -228,7 +228,7 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                            void* d_out, int block_n, int splits, void* stream);
 
-/* kernel selection bits for block_n == 0 (auto), default 10534923 = 1 + 2 + 8 + 16384 + 32768 + 2097152 + 8388608:
+/* kernel selection bits for block_n == 0 (auto), default 27312139 = 1 + 2 + 8 + 16384 + 32768 + 2097152 + 8388608 + 16777216:
  *   1   window kernels: 64->64 stride-1 convolutions (stem, layer1) and 128->128 3x3 (layer2) load their activations
  *       once per tile as a contiguous window and address the filter taps as row-shifted operand descriptors
  *   2   the CTA-pair (cta_group::2) kernel serves 256-wide tiles;  4  and 128-wide tiles
@@ -250,6 +250,9 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
  *       the activations live in a ring of 16 KB chunks (one new chunk per block instead of a whole window: L2 -> SM reads 4x
  *       lower on the stem) and the residual rows arrive by TMA in the layout of the staging tiles: layer1 conv2 + residual
  *       0.246 -> 0.195 ms, bit-identical outputs; runs shorter than 8 blocks per CTA keep the reloading kernel (bit 15)
+ *   16777216 the layer2 pair window kernel stages its epilogue through shared memory: residual rows by TMA into 128B-swizzled
+ *       tiles, overwritten in place, stored as whole 128-byte lines (the weight ring gives up 3 of 12 stages for the 64 KB):
+ *       layer2 conv2 + residual 0.190 -> 0.163 ms, bit-identical outputs
  * (r02 A/B, profiles/r02_layer_table_mode_bits.json; the other round-1 candidates -- pair-window kernels for layer3/4 and
  * 128-wide layer2 tiles, residual preload -- measured no gain and were removed.)
  * 0 = single-CTA TMA-im2col kernel only */

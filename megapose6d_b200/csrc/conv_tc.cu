@@ -351,6 +351,7 @@ __device__ __forceinline__ void epilogue_compute64(uint32_t taddr, uint32_t stg,
   }
 }
 
+template <int ROW_ELEMS = 64>  // channels per output row (the staged tile holds 64 of them, at `out`)
 __device__ __forceinline__ void store_staged64(uint32_t stg, int lane, int pix, act_t* out) {
   const int c = lane & 7;
 #pragma unroll
@@ -358,7 +359,7 @@ __device__ __forceinline__ void store_staged64(uint32_t stg, int lane, int pix, 
     const int r = 4 * j + (lane >> 3);
     const int pix_r = __shfl_sync(0xffffffffu, pix, r);
     const uint4 o = lds128(stg + static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)));
-    if (pix_r >= 0) *(reinterpret_cast<uint4*>(out + static_cast<size_t>(pix_r) * 64) + c) = o;
+    if (pix_r >= 0) *(reinterpret_cast<uint4*>(out + static_cast<size_t>(pix_r) * ROW_ELEMS) + c) = o;
   }
   __syncwarp();  // the tile is free for the next residual
 }
@@ -1251,8 +1252,9 @@ conv_window_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // bit 0: shared-memory window kernel for the 64 -> 64 stride-1 layers; bit 1: CTA-pair (cta_group::2) kernel for
 // C_out >= 128; 0 = single-CTA im2col kernel everywhere
-static int g_conv_mode = 10534923;  // 11 + CTA-pair window kernels for layer2 (16384) and stem / layer1 (32768) + max-pool in the stem's epilogue
-                                    // (2097152) + sliding window / TMA residual in the 64 -> 64 pair kernel (8388608)
+static int g_conv_mode = 27312139;  // 11 + CTA-pair window kernels for layer2 (16384) and stem / layer1 (32768) + max-pool in the stem's epilogue
+                                    // (2097152) + sliding window / TMA residual in the 64 -> 64 pair kernel (8388608) + staged epilogue /
+                                    // TMA residual in the layer2 pair kernel (16777216)
 static int conv_mode() { return g_conv_mode; }
 int conv_get_mode() { return g_conv_mode; }
 void conv_set_mode(int mode) { g_conv_mode = mode; }
@@ -1441,6 +1443,8 @@ struct Win2Params {
   const float* bias;
   const act_t* residual;
   act_t* out;
+  int staged;      // conv_window2q_kernel: 1 = staged epilogue (coalesced stores, residual rows by TMA), mode bit 24
+  int b_stages;    // conv_window2q_kernel: depth of the weight ring (<= kW2qBStages)
 };
 
 constexpr int kW2N = 128;                 // C_out = C_in
@@ -1638,7 +1642,7 @@ static int conv_window2_try(const ConvDesc& d, const void* x, const void* w, con
   if ((g_conv_mode & 1) == 0 || (g_conv_mode & 256) != 0) return MPX_ERR_UNSUPPORTED;
   if (d.stride != 1 || d.C_in != 128 || d.C_out != 128 || d.R != 3 || d.S != 3) return MPX_ERR_UNSUPPORTED;
   if (d.pad_lo_h != 1 || d.pad_lo_w != 1 || d.pad_hi_h != 1 || d.pad_hi_w != 1) return MPX_ERR_UNSUPPORTED;
-  Win2Params p;
+  Win2Params p{};
   p.Hp = d.H + 2;
   p.Wp = d.W + 2;
   p.H = d.H;
@@ -2021,13 +2025,19 @@ constexpr int kW2qBHalf = (kW2N / 2) * 128;  // [64 c_out][64 c_in] bf16 = 8 KB 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const Win2Params p) {
+                     const __grid_constant__ CUtensorMap map_r, const Win2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_b = smem;                                         // weight ring (this CTA's half tiles)
-  uint8_t* smem_a = smem + kW2qBStages * kW2qBHalf;               // two window panels (this CTA's 256 rows + halo)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * static_cast<size_t>(p.panel_bytes));
+  const int b_stages = p.b_stages;
+  uint8_t* smem_a = smem + b_stages * kW2qBHalf;                  // two window panels (this CTA's 256 rows + halo)
+  // staged epilogue (p.staged): per tile of the super-tile two 64-channel panels of 128 rows x 128 B, 128B-swizzled -- the layout
+  // TMA writes the residual rows in and the epilogue overwrites in place before storing whole 128-byte lines
+  uint8_t* smem_stg = smem_a + 2 * static_cast<size_t>(p.panel_bytes);
+  const bool staged = p.staged != 0;
+  const bool has_res = p.residual != nullptr;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + (staged ? 2 * 2 * kBlockM * 128 : 0));
   uint64_t* b_full = bars;                 // [12] leader
   uint64_t* b_empty = bars + 12;           // [12] per CTA, two arrivals (one multicast commit per issuer)
   uint64_t* a_full = bars + 24;            // [2]  leader
@@ -2035,7 +2045,9 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* tmem_full = bars + 28;         // [4]  per CTA
   uint64_t* tmem_empty = bars + 32;        // [4]  leader, eight arrivals
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t* res_full = bars + 37;          // [2]  per CTA: residual rows of tile ti landed (staged epilogue)
   float* bias_s = reinterpret_cast<float*>(bars + 40);  // [128]
+  uint64_t* res_empty = bars + 104;        // [2]  per CTA, the four warps of tile ti
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction (role dispatch, UR operands)
   const int lane = threadIdx.x & 31;
@@ -2051,9 +2063,13 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kW2qBStages; ++i) {
+    for (int i = 0; i < b_stages; ++i) {
       mbar_init(&b_full[i], 2);
       mbar_init(&b_empty[i], 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 2);
@@ -2099,6 +2115,21 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                                 &map_a, &a_full[c], c * 64, xp - 1, yp - 1, img, 0, 0);
           }
         }
+        if (staged && has_res) {
+          // residual rows of the item's two tiles: the same 128 padded-linear positions of the residual tensor (ring
+          // positions zero-filled), both 64-channel panels, into the staging tiles the epilogue of the previous item has freed
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const long long q = p.q_base + st * 256 + t2 * 128;
+            const int img = static_cast<int>(q / hpwp);
+            const int rem = static_cast<int>(q - static_cast<long long>(img) * hpwp);
+            const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+            mbar_wait(&res_empty[t2], par ^ 1u);
+            mbar_expect_tx_u(&res_full[t2], 2u * kBlockM * 128u);
+            for (int c = 0; c < 2; ++c)
+              tma_load_im2col_4d_u(smem_stg + static_cast<size_t>(t2 * 2 + c) * kBlockM * 128, &map_r, &res_full[t2], c * 64,
+                                   xp - 1, yp - 1, img, 0, 0);
+          }
+        }
       }
     }
   } else if (warp == 2) {
@@ -2114,7 +2145,7 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             else mbar_arrive_remote_u(&b_full[stage], 0);
             tma2_load_2d_u(smem_b + stage * kW2qBHalf, &map_b, &b_full[stage], t * 128 + c * 64,
                          static_cast<int>(rank) * (kW2N / 2));
-            if (++stage == kW2qBStages) {
+            if (++stage == b_stages) {
               stage = 0;
               phase ^= 1u;
             }
@@ -2156,7 +2187,7 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               tc2_mma_f16_u(tmem_d, da + 6, db + 6, idesc, 1u);
               first = 0;
               tc2_commit_mc_u(&b_empty[stage]);
-              if (++stage == kW2qBStages) {
+              if (++stage == b_stages) {
                 stage = 0;
                 phase ^= 1u;
               }
@@ -2189,6 +2220,29 @@ conv_window2q_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         off = valid ? ((static_cast<size_t>(img) * p.H + y) * p.W + x) * kW2N : 0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(buf * kW2N);
+      if (staged) {
+        const int pix = valid ? static_cast<int>(off / kW2N) : -1;
+        const uint32_t stg = smem_u32(smem_stg) + static_cast<uint32_t>(ti * 2 * kBlockM * 128 + q4 * kStageTileBytes);
+        if (has_res) mbar_wait(&res_full[ti], static_cast<uint32_t>(local & 1));
+        mbar_wait(&tmem_full[buf], static_cast<uint32_t>(local >> 1) & 1u);
+        tc_fence_after();
+        epilogue_compute64(taddr, stg, lane, has_res, smem_u32(bias_s), p.relu);
+        epilogue_compute64(taddr + 64u, stg + kBlockM * 128u, lane, has_res, smem_u32(bias_s + 64), p.relu);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tmem_empty[buf]);
+          else mbar_arrive_remote(&tmem_empty[buf], 0);
+        }
+        store_staged64<kW2N>(stg, lane, pix, p.out);
+        store_staged64<kW2N>(stg + kBlockM * 128u, lane, pix, p.out + 64);
+        if (has_res) {  // generic-proxy writes into the tile before the next TMA write
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&res_empty[ti]);
+        }
+        continue;
+      }
       const act_t* res_row = p.residual ? p.residual + off : nullptr;
       uint4 res_cur[4];
       if (valid && res_row) load_res_chunk(res_row, 0, res_cur);
@@ -2219,7 +2273,7 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
   if ((g_conv_mode & 16384) == 0) return MPX_ERR_UNSUPPORTED;
   if (d.stride != 1 || d.C_in != 128 || d.C_out != 128 || d.R != 3 || d.S != 3) return MPX_ERR_UNSUPPORTED;
   if (d.pad_lo_h != 1 || d.pad_lo_w != 1 || d.pad_hi_h != 1 || d.pad_hi_w != 1) return MPX_ERR_UNSUPPORTED;
-  Win2Params p;
+  Win2Params p{};
   p.Hp = d.H + 2;
   p.Wp = d.W + 2;
   p.H = d.H;
@@ -2229,7 +2283,12 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
   p.n_chunks = (rows + 255) / 256;
   p.chunk_rows = ((rows + p.n_chunks - 1) / p.n_chunks + 7) & ~7;
   p.panel_bytes = p.chunk_rows * p.n_chunks * 128;
-  const int smem_bytes = 1024 + kW2qBStages * kW2qBHalf + 2 * p.panel_bytes + 1024;
+  // mode bit 24: staged epilogue (64 KB of staging tiles; the weight ring gives up stages for them)
+  p.staged = (g_conv_mode & 16777216) ? 1 : 0;
+  p.b_stages = kW2qBStages;
+  const int stg_bytes = p.staged ? 2 * 2 * kBlockM * 128 : 0;
+  while (p.b_stages > 6 && 1024 + p.b_stages * kW2qBHalf + 2 * p.panel_bytes + stg_bytes + 1024 > 227 * 1024) --p.b_stages;
+  const int smem_bytes = 1024 + p.b_stages * kW2qBHalf + 2 * p.panel_bytes + stg_bytes + 1024;
   if (smem_bytes > 227 * 1024) return MPX_ERR_UNSUPPORTED;
   p.M_pad = static_cast<long long>(d.n_img) * p.Hp * p.Wp;
   p.q_base = p.Wp + 1;
@@ -2244,22 +2303,24 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
 
   int rc = load_driver_entry_points();
   if (rc != MPX_OK) return rc;
-  CUtensorMap map_a, map_b;
-  {
+  CUtensorMap map_a, map_b, map_r;
+  for (int which = 0; which < 2; ++which) {  // activation windows (chunk_rows pixels per load); residual tiles (128 pixels)
+    CUtensorMap& m = which == 0 ? map_a : map_r;
+    const void* base = which == 0 ? x : (residual != nullptr ? residual : x);
     cuuint64_t dims[4] = {128, static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.n_img)};
     cuuint64_t strides[3] = {256, static_cast<cuuint64_t>(d.W) * 256, static_cast<cuuint64_t>(d.H) * d.W * 256};
     int lower[2] = {-1, -1};
     int upper[2] = {1, 1};  // the base pixel walks the whole padded image
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_im2col(&map_a, kTmaActType, 4, const_cast<void*>(x), dims, strides, lower,
-                                 upper, kBlockK, static_cast<cuuint32_t>(p.chunk_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = g_encode_im2col(&m, kTmaActType, 4, const_cast<void*>(base), dims, strides, lower, upper, kBlockK,
+                                 static_cast<cuuint32_t>(which == 0 ? p.chunk_rows : kBlockM), estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return MPX_ERR_UNSUPPORTED;
     int drv = 0;
     cudaDriverGetVersion(&drv);
     const size_t bytes = static_cast<size_t>(d.n_img) * d.H * d.W * 256;
-    if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&map_a)[1] &= ~(1ull << 21);
+    if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
   }
   {
     const cuuint64_t K_total = static_cast<cuuint64_t>(kW2Taps) * 128;
@@ -2282,7 +2343,7 @@ static int conv_window2q_try(const ConvDesc& d, const void* x, const void* w, co
   if (cap < 1) cap = 1;
   const int pairs = items < cap ? items : cap;
   ProfileSlot* slot = profile_begin(stream);
-  conv_window2q_kernel<<<2 * pairs, 384, smem_bytes, stream>>>(map_a, map_b, p);
+  conv_window2q_kernel<<<2 * pairs, 384, smem_bytes, stream>>>(map_a, map_b, map_r, p);
   MPX_CHECK_CUDA(cudaGetLastError());
   ++g_launches;
   profile_end(slot, stream, 2.0 * d.n_img * d.H * d.W * 128.0 * kW2Taps * 128.0);

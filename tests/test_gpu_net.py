@@ -23,8 +23,8 @@ pytestmark = pytest.mark.gpu
 ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
 ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
 SINGLE_CTA_MODE = 11  # window | pair(256) | split-K, without the CTA-pair window kernels of bits 14 / 15
-DEFAULT_CONV_MODE = 10534923  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool
-# (bit 21) | sliding window in the 64 -> 64 pair kernel (bit 23)
+DEFAULT_CONV_MODE = 27312139  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool
+# (bit 21) | sliding window in the 64 -> 64 pair kernel (bit 23) | staged epilogue in the layer2 pair kernel (bit 24)
 RELOAD_MODE = DEFAULT_CONV_MODE & ~8388608  # without bit 23: conv_windowq_kernel (whole window reloaded per tile) everywhere
 
 
@@ -357,6 +357,9 @@ PAIR_WINDOW_CASES = [
     ("l2_pairs_odd_size", 3, 17, 23, 128, 128, False, True, 2),
     ("l2_pairs_tiny_images", 11, 5, 7, 128, 128, True, True, 2),
     ("l2_pairs_one_item_peer_idle", 1, 12, 16, 128, 128, True, False, 1),
+    ("l2_pairs_all_sms_residual", 96, 30, 40, 128, 128, True, True, 0),
+    ("l2_pairs_all_sms", 80, 30, 40, 128, 128, True, False, 0),
+    ("l2_pairs_224", 24, 28, 28, 128, 128, True, True, 0),
 ]
 
 
@@ -372,7 +375,7 @@ def test_layer2_pair_window_kernel(case):
     res = torch.randn(n, h, w, cout, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        for mode in (DEFAULT_CONV_MODE, SINGLE_CTA_MODE):
+        for mode in (DEFAULT_CONV_MODE, DEFAULT_CONV_MODE ^ 16777216, SINGLE_CTA_MODE):  # bit 24 flipped: the other epilogue form
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, 3,
@@ -388,6 +391,7 @@ def test_layer2_pair_window_kernel(case):
         assert not torch.isnan(o).any()
         assert (o - ref).abs().max() <= tol
         assert (o - outs[-1]).abs().max() <= ULP * ref.abs().max().item()
+    assert torch.equal(outs[0], outs[1])  # staged (TMA residual, coalesced stores) vs row-per-thread epilogue: same arithmetic
 
 
 PAIR_WINDOW64_CASES = [
