@@ -228,7 +228,7 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
                            int pad_lo_w, int pad_hi_h, int pad_hi_w, int relu, const void* d_residual,
                            void* d_out, int block_n, int splits, void* stream);
 
-/* kernel selection bits for block_n == 0 (auto), default 27312139 = 1 + 2 + 8 + 16384 + 32768 + 2097152 + 8388608 + 16777216:
+/* kernel selection bits for block_n == 0 (auto), default 60866571 = 1 + 2 + 8 + 16384 + 32768 + 2097152 + 8388608 + 16777216 + 33554432:
  *   1   window kernels: 64->64 stride-1 convolutions (stem, layer1) and 128->128 3x3 (layer2) load their activations
  *       once per tile as a contiguous window and address the filter taps as row-shifted operand descriptors
  *   2   the CTA-pair (cta_group::2) kernel serves 256-wide tiles;  4  and 128-wide tiles
@@ -253,6 +253,9 @@ int mpx_conv2d_splitk(const void* d_x, int n, int h, int w, int c_in, const void
  *   16777216 the layer2 pair window kernel stages its epilogue through shared memory: residual rows by TMA into 128B-swizzled
  *       tiles, overwritten in place, stored as whole 128-byte lines (the weight ring gives up 3 of 12 stages for the 64 KB):
  *       layer2 conv2 + residual 0.190 -> 0.163 ms, bit-identical outputs
+ *   33554432 the same for the 256-wide CTA-pair im2col kernel (layers 3-4), one 128-channel half of the tile at a time through a
+ *       32 KB staging tile, bias read from global memory; only for K >= 768 (the 1x1 downsamples keep the row form):
+ *       layer3 conv2 + residual 0.151 -> 0.147 ms, bit-identical outputs
  * (r02 A/B, profiles/r02_layer_table_mode_bits.json; the other round-1 candidates -- pair-window kernels for layer3/4 and
  * 128-wide layer2 tiles, residual preload -- measured no gain and were removed.)
  * 0 = single-CTA TMA-im2col kernel only */

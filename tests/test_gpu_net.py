@@ -23,8 +23,8 @@ pytestmark = pytest.mark.gpu
 ACT = _abi.act_dtype() if torch.cuda.is_available() else torch.float16
 ULP, ATOL = (2 ** -10, 2e-3) if ACT == torch.float16 else (2 ** -7, 1e-2)
 SINGLE_CTA_MODE = 11  # window | pair(256) | split-K, without the CTA-pair window kernels of bits 14 / 15
-DEFAULT_CONV_MODE = 27312139  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool
-# (bit 21) | sliding window in the 64 -> 64 pair kernel (bit 23) | staged epilogue in the layer2 pair kernel (bit 24)
+DEFAULT_CONV_MODE = 60866571  # window | pair(256) | split-K in the network | CTA-pair window kernels (bits 14, 15) | fused max-pool
+# (bit 21) | sliding window in the 64 -> 64 pair kernel (bit 23) | staged epilogues in the layer2 (bit 24) and layer3-4 (bit 25) pair kernels
 RELOAD_MODE = DEFAULT_CONV_MODE & ~8388608  # without bit 23: conv_windowq_kernel (whole window reloaded per tile) everywhere
 
 
@@ -316,6 +316,9 @@ PAIR_CASES = [
     ("pair_ds_1x1", 3, 30, 40, 128, 256, 1, 1, 2, (0, 0, 0, 0), False, False),
     ("pair_single_tile", 1, 8, 10, 256, 256, 3, 3, 1, (1, 1, 1, 1), False, False),
     ("pair_forced_128", 4, 30, 40, 128, 128, 3, 3, 1, (1, 1, 1, 1), True, True),
+    ("pair_l3_all_sms", 96, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), True, True),
+    ("pair_l4_all_sms_ragged", 61, 8, 10, 512, 512, 3, 3, 1, (1, 1, 1, 1), True, True),
+    ("pair_l3_no_residual", 40, 15, 20, 256, 256, 3, 3, 1, (1, 1, 1, 1), True, False),
 ]
 
 
@@ -333,7 +336,7 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
     res = torch.randn(n, p, q, cout, device="cuda", generator=g).to(ACT) if use_res else None
     outs = []
     try:
-        for mode in (7, 1):
+        for mode in (7, 1, 7 | 33554432):  # pair kernel | single-CTA kernel | pair kernel with the staged epilogue (bit 25)
             _abi.lib().mpx_conv_set_mode(mode)
             out = torch.full((n, p, q, cout), float("nan"), device="cuda", dtype=ACT)
             _abi.check(_abi.lib().mpx_conv2d(_abi.ptr(x), n, h, w, cin, _abi.ptr(wt.view(cout, -1)), _abi.ptr(bias), cout, r, s,
@@ -347,6 +350,7 @@ def test_cta_pair_kernel_vs_torch_and_single_cta(case):
     tol = ULP * ref.abs().max().item() + ATOL
     assert (outs[0] - ref).abs().max() <= tol and (outs[1] - ref).abs().max() <= tol
     assert torch.equal(outs[0], outs[1])  # same products, same K order, fp32 accumulation in TMEM
+    assert torch.equal(outs[0], outs[2])  # staged epilogue (residual by TMA, bias from global memory): same arithmetic
 
 
 PAIR_WINDOW_CASES = [

@@ -58,7 +58,7 @@ def child(steps: int, warmup: int) -> None:
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--conv", default="27312139", help="comma-separated mpx_conv_set_mode values")
+    ap.add_argument("--conv", default="60866571", help="comma-separated mpx_conv_set_mode values")
     ap.add_argument("--raster", default="7", help="comma-separated mpx_raster_set_mode values")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)

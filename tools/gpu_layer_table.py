@@ -70,7 +70,7 @@ def main():
     act = _abi.act_dtype()
     torch.backends.cudnn.benchmark = True
     import os
-    default_mode = int(os.environ.get("MPX_CONV_MODE", "27312139"))
+    default_mode = int(os.environ.get("MPX_CONV_MODE", "60866571"))
     rows = []
     g = torch.Generator(device="cuda").manual_seed(0)
     for name, count, H, Wd, cin, cout, r, stride, pad, use_res in layers(h, w, 9):

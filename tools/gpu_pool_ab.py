@@ -60,7 +60,7 @@ def main():
     torch.cuda.synchronize()
     rec["equal"] = bool(torch.equal(pooled.float(), pooled2.float()))
     sd = W.make_state_dict(W.COARSE_CFG, 1)
-    for name, mode in (("separate_pool", 27312139 & ~2097152), ("fused_pool", 27312139)):
+    for name, mode in (("separate_pool", 60866571 & ~2097152), ("fused_pool", 60866571)):
         lib.mpx_conv_set_mode(mode)
         eng = ResNet34Engine(sd, n_inputs=9, head="views_logits_head")
         x = eng.alloc_input(n, h, w)
@@ -68,7 +68,7 @@ def main():
         rec[f"network_{name}_ms"] = time_ms(lambda: eng.forward(x, h, w), iters=8)
         del eng, x
         torch.cuda.empty_cache()
-    lib.mpx_conv_set_mode(27312139)
+    lib.mpx_conv_set_mode(60866571)
     print(json.dumps(rec))
 
 
