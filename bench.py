@@ -40,8 +40,9 @@ N_REFINER_ITERS = 5
 # SURVEY.md 8(d), FLOP = 2*MAC, conv + linear: {render size: (coarse/scoring forward, RGB refiner forward)} GFLOP per sample
 GFLOP = {(240, 320): (12.068, 14.236), (224, 224): (7.799, 9.215)}
 # 16-bit bytes the 36 convolutions of one coarse forward move at least once per hypothesis at 240x320 (each conv: input
-# read + output write + residual read; weights excluded): stem 2 x 2.46 MB, layer1 6 convs of 60x80x64, ... = 28.26 MB
-ALGO_CONV_BYTES_PER_HYP = 28.26e6
+# read + output write + residual read; weights excluded): stem 2.46 MB in + 0.61 MB pooled out (the max-pool runs in its
+# epilogue; 2 x 2.46 MB before), layer1 6 convs of 60x80x64, ... = 26.42 MB
+ALGO_CONV_BYTES_PER_HYP = 26.42e6
 
 
 def gflop_per_hyp(render_size, n_det=1):
