@@ -386,28 +386,43 @@ __device__ __forceinline__ uint32_t max_act2(uint32_t a, uint32_t b) {
   const act_t2 r = __hmax2(*reinterpret_cast<const act_t2*>(&a), *reinterpret_cast<const act_t2*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
-__device__ __forceinline__ void pool_staged64(uint32_t stg, int lane, int info, int base, int row_elems, act_t* pool) {
-  const int c = lane & 7;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int r = 4 * j + (lane >> 3);
-    const int info_r = __shfl_sync(0xffffffffu, info, r);
-    const int base_r = __shfl_sync(0xffffffffu, base, r);
-    if ((info_r & 3) == 0) continue;
-    uint4 o = lds128(stg + static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)));
+// Rows with work (centres and orphans: every other row of the tile, ~17 of 32) are compacted first -- rank by ballot / popc,
+// row index into a 32-byte list of the warp in shared memory (`list`) -- so that the 8-lane groups walk only those: ~5 fully
+// populated iterations instead of 8 half-empty ones (r02 ncu: the epilogue warps of the stem were busy 100% of the time, 56% of
+// it in this function, the tensor pipe waiting for them at 62%).
+__device__ __forceinline__ void pool_staged64(uint32_t stg, uint32_t list, int lane, int info, int base, int row_elems,
+                                              act_t* pool) {
+  const unsigned work = __ballot_sync(0xffffffffu, (info & 3) != 0);
+  const int count = __popc(work);
+  if ((info & 3) != 0) {
+    const uint32_t slot = list + static_cast<uint32_t>(__popc(work & ((1u << lane) - 1u)));
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(slot), "r"(lane) : "memory");
+  }
+  __syncwarp();
+  const int c = lane & 7, g = lane >> 3;
+  const int n_it = (count + 3) >> 2;
+  for (int it = 0; it < n_it; ++it) {
+    const int s = 4 * it + g;
+    const bool active = s < count;
+    uint32_t r = 0;
+    if (active) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(list + static_cast<uint32_t>(s)));
+    const int info_r = __shfl_sync(0xffffffffu, info, static_cast<int>(r));
+    const int base_r = __shfl_sync(0xffffffffu, base, static_cast<int>(r));
+    if (!active) continue;
+    uint4 o = lds128(stg + (r * 128u + ((static_cast<uint32_t>(c) ^ (r & 7u)) << 4)));
     if (info_r & 4) {
-      const uint4 t = lds128(stg + static_cast<uint32_t>((r - 1) * 128 + ((c ^ ((r - 1) & 7)) << 4)));
+      const uint4 t = lds128(stg + ((r - 1u) * 128u + ((static_cast<uint32_t>(c) ^ ((r - 1u) & 7u)) << 4)));
       o.x = max_act2(o.x, t.x); o.y = max_act2(o.y, t.y); o.z = max_act2(o.z, t.z); o.w = max_act2(o.w, t.w);
     }
     if (info_r & 8) {
-      const uint4 t = lds128(stg + static_cast<uint32_t>((r + 1) * 128 + ((c ^ ((r + 1) & 7)) << 4)));
+      const uint4 t = lds128(stg + ((r + 1u) * 128u + ((static_cast<uint32_t>(c) ^ ((r + 1u) & 7u)) << 4)));
       o.x = max_act2(o.x, t.x); o.y = max_act2(o.y, t.y); o.z = max_act2(o.z, t.z); o.w = max_act2(o.w, t.w);
     }
     act_t* dst = pool + static_cast<size_t>(base_r) * 64 + c * 8;
     red_max_act8(dst, o);
     if (info_r & 16) red_max_act8(dst + row_elems, o);
   }
-  __syncwarp();  // the tile is free for the next residual
+  __syncwarp();  // the tile (and the list) is free for the next block
 }
 
 // the same with the row length of the output matrix as a run-time value (conv_igemm2_kernel: C_out = 256 | 512)
@@ -2743,7 +2758,7 @@ conv_windowq_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (leader) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_remote(&tmem_empty[acc], 0);
       }
-      if (p.pool) pool_staged64(stg, lane, pool_info, pool_base, p.pool_W * kWinN, p.out);
+      if (p.pool) pool_staged64(stg, smem_u32(bars + 64) + static_cast<uint32_t>((warp - 4) * 32), lane, pool_info, pool_base, p.pool_W * kWinN, p.out);
       else store_staged64(stg, lane, pix, p.out);
     }
   }
@@ -3006,6 +3021,8 @@ conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint64_t ring_desc = make_sw128_desc(smem_u32(smem_ring));
       const uint64_t b_base = make_sw128_desc(smem_u32(smem_b));
       const int R = n_taps / p.S;
+      const unsigned ks_row0 = static_cast<unsigned>(p.kskip) & 15u;          // dead slices of the taps (0, s > 0) ...
+      const unsigned ks_col0 = static_cast<unsigned>(p.kskip >> 16) & 15u;    // ... and of the taps (r > 0, 0): see conv_windows_try
       for (int i = which; i < T; i += 2) {
         const int acc = i % kWinAccBufs;
         const uint32_t acc_phase = (i / kWinAccBufs) & 1;
@@ -3019,12 +3036,15 @@ conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t first = 1;
         uint64_t db = b_base;
         uint32_t pr = static_cast<uint32_t>(i % slots) * kWsChunkUnits;  // ring position (16-byte units) of filter row r
-        int tap = 0;
         for (int r = 0; r < R; ++r) {
           uint32_t pt = pr;
           for (int s = 0; s < p.S; ++s) {
             const uint64_t da = desc_add_lo(ring_desc, pt);
-            const unsigned sk = static_cast<unsigned>(p.kskip >> (4 * tap)) & 15u;
+            // structurally zero K slices of the space-to-depth stem: the (dy, dx) sub-pixels that fall into the filter's
+            // padding on its first row / first column -- a function of (r == 0, s == 0) only, kept in uniform registers
+            // (the per-tap 64-bit shift of conv_windowq_kernel ran on the vector pipe: the two issuers were busy all the time
+            // at ~12 instructions x ~10 cycles per MMA, and the stem -- 44% of whose taps take the slow path -- was issue-bound)
+            const unsigned sk = (r == 0 ? ks_row0 : 0u) | (s == 0 ? ks_col0 : 0u);
             if (sk == 0u) {
               tc2_mma_f16_u(tmem_d, da, db, idesc, first ? 0u : 1u);
               tc2_mma_f16_u(tmem_d, desc_add_lo(da, 2u), desc_add_lo(db, 2u), idesc, 1u);
@@ -3042,7 +3062,6 @@ conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             db = desc_add_lo(db, kWinqBHalf / 16);
             pt += 8u;  // next tap: one pixel (128 B) further
             if (pt >= ring_units) pt -= ring_units;
-            ++tap;
           }
           pr += row_units;  // next filter row: Wp pixels further
           if (pr >= ring_units) pr -= ring_units;
@@ -3129,7 +3148,7 @@ conv_windows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (leader) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_remote(&tmem_empty[acc], 0);
       }
-      if (p.pool) pool_staged64(stg, lane, pool_info, pool_base, p.pool_W * kWinN, p.out);
+      if (p.pool) pool_staged64(stg, smem_u32(bars + 72) + static_cast<uint32_t>((warp - 4) * 32), lane, pool_info, pool_base, p.pool_W * kWinN, p.out);
       else store_staged64(stg, lane, pix, p.out);
       if (has_res) {  // the buffer goes back to the residual producer: generic-proxy writes before the next TMA write
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -3192,7 +3211,22 @@ static int conv_windows_try(const ConvDesc& d, const void* x, const void* w, con
   p.m_tiles = static_cast<int>(blocks);
   p.relu = d.relu;
   p.idesc = (1u << 4) | kIdescAB | (static_cast<unsigned>(kWinN >> 3) << 17) | (static_cast<unsigned>(256 >> 4) << 24);
-  p.kskip = stem_kskip(d);
+  {
+    // the kernel takes the zero slices in structured form: dead (dy, dx) slices of the first filter row (tap (0, 1)) and of
+    // the first filter column (tap (1, 0)); any other pattern goes to conv_windowq_kernel
+    const unsigned long long full = stem_kskip(d);
+    unsigned long long packed = 0;
+    if (full != 0) {
+      const unsigned row0 = static_cast<unsigned>(full >> (4 * 1)) & 15u, col0 = static_cast<unsigned>(full >> (4 * d.S)) & 15u;
+      unsigned long long expect = 0;
+      for (int r = 0; r < d.R; ++r)
+        for (int sx = 0; sx < d.S; ++sx)
+          expect |= static_cast<unsigned long long>((r == 0 ? row0 : 0u) | (sx == 0 ? col0 : 0u)) << (4 * (r * d.S + sx));
+      if (expect != full) return MPX_ERR_UNSUPPORTED;
+      packed = row0 | (static_cast<unsigned long long>(col0) << 16);
+    }
+    p.kskip = packed;
+  }
   p.bias = bias;
   p.residual = reinterpret_cast<const act_t*>(residual);
   p.out = reinterpret_cast<act_t*>(out);
