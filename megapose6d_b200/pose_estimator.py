@@ -463,6 +463,11 @@ class PoseEstimator(torch.nn.Module):
 
         def finish(st: dict, static: bool) -> dict:
             if not whole:
+                # the throughput-bound part of the frame ends here: the next frame in flight (FramePipeline.serialize_heads) may
+                # start its coarse stage while this one's logits are gathered over the ranks and the survivors selected
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(images.device))
+                self.__dict__["_head_done"] = ev
                 st = self._coarse_select(st, self.sharder.gather_rows(st["logits_local"], n), rows_c, B, M, Kh)
             return dict(st, static=static)
 
@@ -547,6 +552,7 @@ class PoseEstimator(torch.nn.Module):
         side = self.__dict__.get("_copy_stream")
         if side is None:
             side = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=device)
+        self.__dict__.pop("_head_done", None)  # (an event of an earlier frame that nobody collected)
         gate = self.__dict__.pop("_head_gate", None)
         if gate is not None:  # FramePipeline: this frame's coarse stage starts when the previous frame's (another estimator's,
             main.wait_event(gate)  # another stream's) has finished -- two throughput-bound heads never share the device
@@ -561,7 +567,8 @@ class PoseEstimator(torch.nn.Module):
         pin_c = self._pinned("coarse", packed_c.numel())
         ev_c = torch.cuda.Event()
         ev_c.record(main)
-        self.__dict__["_head_done"] = ev_c  # the throughput-bound part of this frame is enqueued up to here
+        self.__dict__.setdefault("_head_done", ev_c)  # the throughput-bound part of this frame is enqueued up to here (with
+        # several ranks: up to the all-gather of the coarse logits, recorded in _coarse_stage_graphed)
         with torch.cuda.stream(side):
             side.wait_event(ev_c)
             pin_c.copy_(packed_c, non_blocking=True)
