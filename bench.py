@@ -508,7 +508,10 @@ def run_mpx_arm(args):
         if n_gpus == 1 and not args.no_torch_baseline and args.workload == "rgb576":
             del est, ests
             torch.cuda.empty_cache()
-            line["gpu_torch_baseline"] = torch_gpu_baseline(sc, quick=True)
+            try:
+                line["gpu_torch_baseline"] = torch_gpu_baseline(sc, quick=True)
+            except Exception as exc:  # noqa: BLE001 -- a side measurement, never a reason to lose the bench line
+                line["gpu_torch_baseline"] = {"failed": repr(exc)[:300]}
         if n_gpus == 1 and not args.no_cpu_baseline and args.workload == "rgb576":
             line["cpu_baseline"] = cpu_baseline_subprocess(args)
         print(json.dumps(line))
