@@ -168,3 +168,25 @@ def test_procedural_mesh_counts():
     assert np.allclose(np.linalg.norm(m.vertex_normals, axis=1), 1, atol=1e-6)
     # outward orientation: normals point away from the centre
     assert (np.einsum("ij,ij->i", m.vertex_normals, m.vertices) > 0).mean() > 0.99
+
+
+def test_so3_grid_rotations_agree_with_an_independent_quaternion_library():
+    """load_SO3_grid turns the (x, y, z, w) quaternions of data_<N>.qua into matrices with roma.unitquat_to_rotmat
+    (utils/transform_utils.py:27-50); roma is not installable here, so the restated formula (product: so3.py, oracle:
+    lib3d_ref.unitquat_to_rotmat) is held against scipy's scalar-last Rotation.from_quat, an independent implementation of
+    the same convention."""
+    import numpy as np
+    import torch
+    from scipy.spatial.transform import Rotation
+
+    from megapose6d_b200 import so3
+    from oracle import lib3d_ref
+
+    for n in (72, 576):
+        q = np.load(so3._DATA / f"so3_grid_{n}.npy").astype(np.float64)
+        assert q.shape == (n, 4) and np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
+        want = Rotation.from_quat(q).as_matrix()  # (x, y, z, w)
+        got = so3.load_SO3_grid(n).double().numpy()
+        ora = lib3d_ref.unitquat_to_rotmat(torch.tensor(q)).numpy()
+        assert np.abs(got - want).max() < 1e-5 and np.abs(ora - want).max() < 1e-5  # fp32 grid, file quaternions unit to 1e-6
+        assert np.allclose(got @ got.transpose(0, 2, 1), np.eye(3), atol=1e-5) and np.allclose(np.linalg.det(got), 1.0, atol=1e-5)
